@@ -1,0 +1,147 @@
+/* suta_b200 -- C ABI of the B200-native SUTA adaptation engine (libsuta_b200.so).
+ *
+ * The reference (ishine/Test-time-adaptation-ASR-SUTA) has no FFI of its own: its boundary is the Python
+ * function surface of main.py plus the torch / transformers calls underneath.  Each entry point below names
+ * the reference interface it replaces (REF = reference repo, HF = transformers/models/wav2vec2).
+ *
+ * Conventions: plain C, plain pointers and sizes; every pointer marked DEV is a CUDA device pointer owned by
+ * the caller; every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates device
+ * memory, and returns 0 on success or a SUTA_ERR_* code (text via suta_last_error()).
+ * There is no CPU implementation behind this ABI: without a CUDA device every compute call fails.
+ */
+#ifndef SUTA_B200_H
+#define SUTA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUTA_MAX_LAYERS 48
+#define SUTA_MAX_CONV 8
+#define SUTA_ABI_VERSION 1
+
+typedef struct suta_engine suta_engine;
+
+/* HF/configuration_wav2vec2.py:165-211 (the fields the hot path reads) */
+typedef struct suta_model_cfg {
+  int32_t hidden, layers, heads, intermediate, vocab;
+  int32_t n_conv;
+  int32_t conv_dim[SUTA_MAX_CONV], conv_kernel[SUTA_MAX_CONV], conv_stride[SUTA_MAX_CONV];
+  int32_t pos_k, pos_groups;
+  float ln_eps;
+} suta_model_cfg;
+
+/* Frozen weights, already in the engine's operand formats (see INTEGRATION.md for the packing recipe).
+ * bf16 matrices are row-major [out, in] ("W") and their transposes [in, out] ("W_t", used by the backward). */
+typedef struct suta_layer_weights {
+  const void *wqkv, *wqkv_t;     /* DEV bf16 [3H,H] (q|k|v rows), [H,3H]     HF:500-507 */
+  const void *wo, *wo_t;         /* DEV bf16 [H,H]                            HF:546     */
+  const void *w1, *w1_t;         /* DEV bf16 [I,H], [H,I]                     HF:565     */
+  const void *w2, *w2_t;         /* DEV bf16 [H,I], [I,H]                     HF:569     */
+  const float *bqkv, *bo, *b1, *b2; /* DEV fp32 */
+} suta_layer_weights;
+
+typedef struct suta_weights {
+  const float* conv0_w;                  /* DEV fp32 [C0,k0]                                  HF:319 */
+  const float *gn_g, *gn_b;              /* DEV fp32 [C0] GroupNorm affine                    HF:320 */
+  const void* conv_w[SUTA_MAX_CONV];     /* DEV bf16 [C_l, k_l*C_{l-1}], K order (tap,cin)    HF:269 */
+  const void* conv_w_t[SUTA_MAX_CONV];   /* DEV bf16 [k_l*C_{l-1}, C_l] (train_feature dgrad)        */
+  const void *proj_w, *proj_w_t;         /* DEV bf16 [H,C], [C,H]                             HF:431 */
+  const float* proj_b;                   /* DEV fp32 [H] */
+  const void *pos_w, *pos_w_t;           /* DEV bf16 [H, K*(H/G)] weight-normed, (tap,cin);   HF:360-368
+                                            transposed-flipped [H(g,cin), K*(H/G)] (tap',cout) for dgrad */
+  const float* pos_b;                    /* DEV fp32 [H] */
+  suta_layer_weights layer[SUTA_MAX_LAYERS];
+  const void *lm_w, *lm_w_t;             /* DEV bf16 [V,H], [H,V]                             HF:1708 */
+  const float* lm_b;                     /* DEV fp32 [V] */
+  const float* params0;                  /* DEV fp32 [n_params] pristine trainable vector (episodic snapshot) */
+  const uint8_t* mult;                   /* DEV u8   [n_params] how many times REF/main.py:62-103 lists each element */
+} suta_weights;
+
+/* One segment of the per-utterance trainable vector. kind: 0 LN gamma, 1 LN beta, 2 GroupNorm gamma, 3 GroupNorm beta,
+ * 4 conv weight (layer index in `index`), 5 projection weight, 6 projection bias.
+ * module: 0 feature_projection.layer_norm, 1 encoder.layer_norm, 2 layers[index].layer_norm,
+ *         3 layers[index].final_layer_norm, 4 feature_extractor.conv_layers[index], 5 feature_projection.projection */
+typedef struct suta_param_seg {
+  int32_t kind, module, index;
+  int64_t offset, size;
+} suta_param_seg;
+
+/* REF/main.py:172 forward_and_adapt's hyper-parameters + REF/main.py:8 setup_optimizer's */
+typedef struct suta_hyper {
+  float em_coef, temp;
+  int32_t reweight, not_blank;
+  int32_t opt_kind;                      /* 0 Adam/AdamW, 1 SGD */
+  float lr, beta1, beta2, eps, weight_decay;
+} suta_hyper;
+
+const char* suta_last_error(void);
+int suta_abi_version(void);
+int suta_device_sm_count(void);
+
+/* ---- engine lifecycle (replaces Wav2Vec2ForCTC.from_pretrained(...).eval().cuda() + configure_model +
+ *      collect_params, REF/main.py:302-307; train_feature as REF/main.py:88-94) ---------------------------- */
+int suta_engine_create(const suta_model_cfg* cfg, int train_feature, suta_engine** out);
+void suta_engine_destroy(suta_engine* e);
+int64_t suta_engine_param_count(const suta_engine* e);
+int suta_engine_param_layout(const suta_engine* e, suta_param_seg* segs, int max_segs, int* n_segs);
+int suta_engine_set_weights(suta_engine* e, const suta_weights* w);
+
+/* ---- batch of independent utterances (the reference's per-utterance loop body, REF/main.py:319-402,
+ *      executed for n_utts utterances at once, each with its own adapted parameters) ---------------------- */
+int64_t suta_batch_workspace_bytes(suta_engine* e, int n_utts, const int32_t* n_samples);
+int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_samples, void* workspace /*DEV*/, int64_t bytes,
+                     void* stream);
+int suta_batch_info(const suta_engine* e, int64_t* total_frames, int32_t* frames /*[U]*/, int64_t* frame_off /*[U]*/,
+                    int64_t* sample_off /*[U]*/, int64_t* total_samples);
+/* raw waveform, packed at sample_off; `is_host` selects the copy kind (pinned host memory recommended) */
+int suta_batch_set_audio(suta_engine* e, const float* wav, int is_host, void* stream);
+
+int suta_reset(suta_engine* e, void* stream);                       /* load_model_and_optimizer, REF/main.py:147-155 */
+int suta_frontend(suta_engine* e, void* stream);                    /* HF/feature_extraction_wav2vec2.py:95 + HF:409-419 */
+int suta_forward(suta_engine* e, void* stream);                     /* model(x).logits, REF/main.py:181/:214/:332 */
+int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* stream);   /* REF/main.py:183-205 */
+int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* stream);  /* optimizer.step(), REF/main.py:206 */
+int suta_decode(suta_engine* e, void* stream);                      /* argmax + batch_decode collapse, REF/main.py:333-334 */
+/* one whole forward_and_adapt (REF/main.py:172-215): loss+backward on the current logits, update, forward again */
+int suta_adapt_step(suta_engine* e, const suta_hyper* h, void* stream);
+
+/* device views into the workspace (valid until the next suta_batch_begin) */
+float* suta_logits(const suta_engine* e);        /* DEV fp32 [total_frames, V] */
+float* suta_dlogits(const suta_engine* e);       /* DEV fp32 [total_frames, V] */
+float* suta_losses(const suta_engine* e);        /* DEV fp32 [3][U]: total, entropy, mcc */
+float* suta_params(const suta_engine* e);        /* DEV fp32 [U][n_params] */
+float* suta_grads(const suta_engine* e);         /* DEV fp32 [U][n_params] */
+int32_t* suta_argmax_ids(const suta_engine* e);  /* DEV i32 [total_frames] */
+int32_t* suta_collapsed_ids(const suta_engine* e); /* DEV i32 [total_frames], utterance u at frame_off[u] */
+int32_t* suta_collapsed_len(const suta_engine* e); /* DEV i32 [U] */
+const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype);
+int64_t suta_launch_count(const suta_engine* e); /* kernels launched by this engine since creation */
+
+/* ---- single operators (the kernels behind the calls above, exposed for parity tests) ------------------- */
+/* D[M,N] = A[M,K] B[N,K]^T (+bias)(gelu / gelu')(+residual), tcgen05 GEMM; out_f32 and/or out_bf16 */
+int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride, const void* b, int64_t b_rows, int64_t b_row_stride,
+                 int M, int N, int K, float* out_f32, void* out_bf16, int out_ld, const float* bias,
+                 const float* residual, int res_ld, int act, const void* aux_in, void* aux_out, int aux_ld, void* stream);
+int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P, int64_t pstride,
+                          int g_off, int b_off, float* y_f32, void* y_bf16, float* mean, float* rstd, int64_t M, int N,
+                          float eps, void* stream);
+int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const void* x_bf16, const float* mean, const float* rstd,
+                          const int32_t* row_utt, const float* P, int64_t pstride, int g_off, int b_off, float* G,
+                          float* dx_f32, void* dx_bf16, int64_t M, int N, void* stream);
+int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
+                          int64_t M, void* stream);
+int suta_op_attention_bwd(const void* qkv, const void* O, const void* dO, const float* lse, float* D, void* dqkv,
+                          const int32_t* blk_tab, int n_blk, int H, int heads, int64_t M, void* stream);
+int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef, float temp,
+                 int reweight, int not_blank, float* loss /*[3U]*/, float* dlogits_f32, void* dlogits_bf16, void* stream);
+int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,
+                 int step_index, const suta_hyper* h, void* shadow_bf16, void* stream);
+int suta_op_decode(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, int V, int32_t* ids,
+                   int32_t* collapsed, int32_t* out_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUTA_B200_H */

@@ -1,0 +1,721 @@
+// suta_b200 engine: host-side orchestration of one batched SUTA adaptation (C ABI in include/suta_b200.h).
+//
+// The reference adapts ONE utterance at a time (REF/main.py:319-402): reset -> forward -> {loss, backward,
+// optimizer step, forward} x steps.  This engine runs the same arithmetic for a batch of independent utterances
+// at once: frozen weights are shared, every utterance owns a private copy of the trainable vector (LayerNorm
+// affine; plus the CNN front end under train_feature), tokens of all utterances are packed on one M axis so the
+// tcgen05 GEMMs see M = sum(T_u), and every cross-frame operator (GroupNorm statistics, positional conv padding,
+// attention, loss reductions) is confined to its own utterance.
+//
+// Work per adaptation step = 1 backward + 1 forward (the reference's "repeat_inference" forward of step i IS the
+// training forward of step i+1, REF/main.py:181 vs :212-214); LayerNorm-only mode runs the CNN once per utterance.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/suta_b200.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+static thread_local char g_err[1024] = "";
+extern "C" void suta_set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* suta_last_error(void) { return g_err; }
+extern "C" int suta_abi_version(void) { return SUTA_ABI_VERSION; }
+extern "C" int suta_device_sm_count(void) { return gemm_num_sms(); }
+
+namespace {
+
+struct Bump {            // bump allocator over the caller's workspace (pass 1: base == nullptr just sizes it)
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct LayerBufs {
+  bf16* qkv;      // [M,3H]
+  bf16* attn;     // [M,H]
+  float* lse;     // [heads,M]
+  float* h1;      // [M,H] pre-LN1
+  float *mean1, *rstd1;
+  bf16* pre;      // [M,I] FFN pre-activation
+  float* h2;      // [M,H] pre-LN2
+  float *mean2, *rstd2;
+};
+
+struct Seg { int kind, module, index; long long off, size; };
+
+}  // namespace
+
+struct suta_engine {
+  suta_model_cfg cfg{};
+  int train_feature = 0;
+  suta_weights w{};
+  bool have_weights = false;
+  std::vector<Seg> segs;
+  long long n_params = 0;
+  // segment offsets
+  long long fp_g = 0, fp_b = 0, enc_g = 0, enc_b = 0;
+  std::vector<long long> ln1_g, ln1_b, ln2_g, ln2_b;
+  long long launches = 0;
+
+  // ---- batch state ----
+  int U = 0;
+  long long M = 0, S = 0, R = 0, Rm = 0;
+  int max_samples = 0, max_L0 = 0;
+  std::vector<int> n_samples;
+  std::vector<std::vector<int>> L;                 // [layer][u]
+  std::vector<std::vector<long long>> off;         // [layer][u] first row in layer output
+  std::vector<long long> rows_total;               // [layer]
+  std::vector<long long> samp_off, tok_off, pad_off;
+  std::vector<int> T;
+  std::vector<int> n_mblk;                         // [layer]
+  int n_attn_blk = 0;
+  bool frontend_done = false;
+  int opt_steps = 0;
+
+  // device tables
+  long long *d_samp_off = nullptr, *d_tok_off = nullptr, *d_pad_off = nullptr, *d_off0 = nullptr;
+  int *d_n_samples = nullptr, *d_T = nullptr, *d_L0 = nullptr, *d_row_utt = nullptr;
+  int4* d_mblk[SUTA_MAX_CONV] = {};
+  int4* d_attn_tab = nullptr;
+  // device buffers
+  float *wav = nullptr, *wav_norm = nullptr;
+  double* stats = nullptr;
+  bf16* conv_out[SUTA_MAX_CONV] = {};
+  float *fp_mean = nullptr, *fp_rstd = nullptr;
+  bf16* y_fp = nullptr;
+  float* h0 = nullptr;
+  bf16* xg = nullptr;
+  float *cpos = nullptr, *dcpos = nullptr;
+  float* hE = nullptr;
+  float *enc_mean = nullptr, *enc_rstd = nullptr;
+  float *fa = nullptr, *fb = nullptr;
+  bf16 *b16 = nullptr, *gelu16 = nullptr, *dpre16 = nullptr, *dqkv16 = nullptr, *dO16 = nullptr;
+  float* Dbuf = nullptr;
+  float* d_yfp = nullptr;
+  std::vector<LayerBufs> lb;
+  float *logits = nullptr, *dlogits = nullptr, *losses = nullptr;
+  bf16* dlogits16 = nullptr;
+  float *P = nullptr, *G = nullptr, *Mom = nullptr, *Var = nullptr;
+  int *ids = nullptr, *collapsed = nullptr, *out_len = nullptr;
+  std::vector<uint8_t> host_tables;
+};
+
+namespace {
+
+int build_layout(suta_engine* e) {
+  const suta_model_cfg& c = e->cfg;
+  e->segs.clear();
+  long long o = 0;
+  auto add = [&](int kind, int module, int index, long long size) {
+    e->segs.push_back({kind, module, index, o, size});
+    long long r = o;
+    o += size;
+    return r;
+  };
+  const int C = c.conv_dim[c.n_conv - 1], H = c.hidden;
+  e->fp_g = add(0, 0, 0, C);
+  e->fp_b = add(1, 0, 0, C);
+  e->enc_g = add(0, 1, 0, H);
+  e->enc_b = add(1, 1, 0, H);
+  e->ln1_g.resize(c.layers); e->ln1_b.resize(c.layers); e->ln2_g.resize(c.layers); e->ln2_b.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    e->ln1_g[l] = add(0, 2, l, H);
+    e->ln1_b[l] = add(1, 2, l, H);
+    e->ln2_g[l] = add(0, 3, l, H);
+    e->ln2_b[l] = add(1, 3, l, H);
+  }
+  e->n_params = o;
+  return SUTA_OK;
+}
+
+int check_cfg(const suta_model_cfg& c) {
+  SUTA_CHECK_ARG(c.hidden > 0 && c.hidden % 64 == 0 && c.heads * 64 == c.hidden);
+  SUTA_CHECK_ARG(c.layers > 0 && c.layers <= SUTA_MAX_LAYERS && c.intermediate % 64 == 0);
+  SUTA_CHECK_ARG(c.vocab == 32);
+  SUTA_CHECK_ARG(c.n_conv >= 2 && c.n_conv <= SUTA_MAX_CONV);
+  for (int l = 0; l < c.n_conv; ++l) SUTA_CHECK_ARG(c.conv_dim[l] % 64 == 0 && c.conv_kernel[l] > 0 && c.conv_stride[l] > 0);
+  SUTA_CHECK_ARG(c.pos_k > 0 && c.pos_k % 2 == 0 && c.pos_groups > 0 && c.hidden % c.pos_groups == 0);
+  SUTA_CHECK_ARG((c.hidden / c.pos_groups) % 16 == 0);
+  return SUTA_OK;
+}
+
+// geometry of a batch; fills host vectors, returns workspace size through the bump allocator
+int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
+  const suta_model_cfg& c = e->cfg;
+  SUTA_CHECK_ARG(U > 0 && n_samples);
+  e->U = U;
+  e->n_samples.assign(n_samples, n_samples + U);
+  e->L.assign(c.n_conv, std::vector<int>(U));
+  e->off.assign(c.n_conv, std::vector<long long>(U));
+  e->rows_total.assign(c.n_conv, 0);
+  e->samp_off.resize(U); e->tok_off.resize(U); e->pad_off.resize(U); e->T.resize(U);
+  e->n_mblk.assign(c.n_conv, 0);
+  long long s = 0;
+  e->max_samples = 0; e->max_L0 = 0;
+  for (int u = 0; u < U; ++u) {
+    int n = n_samples[u];
+    int Lc = n;
+    for (int l = 0; l < c.n_conv; ++l) {
+      Lc = (Lc - c.conv_kernel[l]) / c.conv_stride[l] + 1;
+      if (Lc < 1 || (l == 0 && n < c.conv_kernel[0])) {
+        suta_set_last_error("utterance %d with %d samples is too short for the feature extractor", u, n);
+        return SUTA_ERR_ARG;
+      }
+      e->L[l][u] = Lc;
+    }
+    e->samp_off[u] = s;
+    s += (n + 3) & ~3;
+    e->max_samples = n > e->max_samples ? n : e->max_samples;
+    e->max_L0 = e->L[0][u] > e->max_L0 ? e->L[0][u] : e->max_L0;
+  }
+  e->S = s;
+  for (int l = 0; l < c.n_conv; ++l) {
+    long long r = 0;
+    const bool last = l == c.n_conv - 1;
+    for (int u = 0; u < U; ++u) {
+      e->off[l][u] = r;
+      // rows of the next layer's implicit-GEMM view start at off/stride: keep offsets multiples of 8
+      r += last ? e->L[l][u] : ((e->L[l][u] + 7) & ~7);
+      if (l >= 1) e->n_mblk[l] += ceil_div(e->L[l][u], 128);
+    }
+    e->rows_total[l] = r;
+    if (!last) SUTA_CHECK_ARG(8 % c.conv_stride[l + 1] == 0);
+  }
+  long long m = 0, p = c.pos_k / 2;
+  int nblk = 0;
+  for (int u = 0; u < U; ++u) {
+    e->T[u] = e->L[c.n_conv - 1][u];
+    e->tok_off[u] = m;
+    e->pad_off[u] = p;
+    m += e->T[u];
+    p += e->T[u] + c.pos_k / 2;
+    nblk += ceil_div(e->T[u], 64);
+  }
+  e->M = m;
+  e->R = p;                       // padded rows per group slab (leading, between-utterance and trailing zero rows)
+  e->Rm = e->R - c.pos_k + 1;     // number of K-tap windows
+  e->n_attn_blk = nblk;
+  return SUTA_OK;
+}
+
+void carve(suta_engine* e, Bump& b) {
+  const suta_model_cfg& c = e->cfg;
+  const int U = e->U, H = c.hidden, I = c.intermediate, C = c.conv_dim[c.n_conv - 1], V = c.vocab;
+  const long long M = e->M;
+  e->d_samp_off = b.take<long long>(U); e->d_tok_off = b.take<long long>(U); e->d_pad_off = b.take<long long>(U);
+  e->d_off0 = b.take<long long>(U);
+  e->d_n_samples = b.take<int>(U); e->d_T = b.take<int>(U); e->d_L0 = b.take<int>(U);
+  e->d_row_utt = b.take<int>(M);
+  for (int l = 1; l < c.n_conv; ++l) e->d_mblk[l] = b.take<int4>(e->n_mblk[l]);
+  e->d_attn_tab = b.take<int4>(e->n_attn_blk);
+  e->wav = b.take<float>(e->S); e->wav_norm = b.take<float>(e->S + 64);
+  e->stats = b.take<double>((size_t)2 * U * (c.conv_dim[0] > 1 ? c.conv_dim[0] : 1) + 2 * U);
+  for (int l = 0; l < c.n_conv; ++l) e->conv_out[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
+  e->fp_mean = b.take<float>(M); e->fp_rstd = b.take<float>(M);
+  e->y_fp = b.take<bf16>((size_t)M * C);
+  e->h0 = b.take<float>((size_t)M * H);
+  e->xg = b.take<bf16>((size_t)(e->R + 8) * H);
+  e->cpos = b.take<float>((size_t)e->Rm * H);
+  e->dcpos = b.take<float>((size_t)e->Rm * H);
+  e->hE = b.take<float>((size_t)M * H);
+  e->enc_mean = b.take<float>(M); e->enc_rstd = b.take<float>(M);
+  e->fa = b.take<float>((size_t)M * H); e->fb = b.take<float>((size_t)M * H);
+  e->b16 = b.take<bf16>((size_t)M * H);
+  e->gelu16 = b.take<bf16>((size_t)M * I);
+  e->dpre16 = b.take<bf16>((size_t)M * I);
+  e->dqkv16 = b.take<bf16>((size_t)M * 3 * H);
+  e->dO16 = b.take<bf16>((size_t)M * H);
+  e->Dbuf = b.take<float>((size_t)M * c.heads);
+  e->d_yfp = b.take<float>((size_t)M * C);
+  e->lb.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    LayerBufs& x = e->lb[l];
+    x.qkv = b.take<bf16>((size_t)M * 3 * H);
+    x.attn = b.take<bf16>((size_t)M * H);
+    x.lse = b.take<float>((size_t)M * c.heads);
+    x.h1 = b.take<float>((size_t)M * H);
+    x.mean1 = b.take<float>(M); x.rstd1 = b.take<float>(M);
+    x.pre = b.take<bf16>((size_t)M * I);
+    x.h2 = b.take<float>((size_t)M * H);
+    x.mean2 = b.take<float>(M); x.rstd2 = b.take<float>(M);
+  }
+  e->logits = b.take<float>((size_t)M * V); e->dlogits = b.take<float>((size_t)M * V);
+  e->dlogits16 = b.take<bf16>((size_t)M * V);
+  e->losses = b.take<float>(3 * U);
+  e->P = b.take<float>((size_t)U * e->n_params); e->G = b.take<float>((size_t)U * e->n_params);
+  e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
+  e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
+  b.off = align_up(b.off, 256);
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
+  e->launches += 1;
+  return gemm_bf16_tc(p, st);
+}
+
+GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
+  GemmProblem p;
+  p.a = {A, M, K};
+  p.b = {B, N, K};
+  p.M = (int)M; p.N = N; p.K = K;
+  return p;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int suta_engine_create(const suta_model_cfg* cfg, int train_feature, suta_engine** out) {
+  SUTA_CHECK_ARG(cfg && out);
+  SUTA_TRY(check_cfg(*cfg));
+  if (train_feature) {
+    suta_set_last_error("train_feature (per-utterance CNN weights) is not implemented in this build");
+    return SUTA_ERR_ARG;
+  }
+  suta_engine* e = new suta_engine();
+  e->cfg = *cfg;
+  e->train_feature = train_feature;
+  build_layout(e);
+  *out = e;
+  return SUTA_OK;
+}
+extern "C" void suta_engine_destroy(suta_engine* e) { delete e; }
+extern "C" int64_t suta_engine_param_count(const suta_engine* e) { return e ? e->n_params : 0; }
+extern "C" int suta_engine_param_layout(const suta_engine* e, suta_param_seg* segs, int max_segs, int* n_segs) {
+  SUTA_CHECK_ARG(e && n_segs);
+  *n_segs = (int)e->segs.size();
+  if (segs) {
+    SUTA_CHECK_ARG(max_segs >= (int)e->segs.size());
+    for (size_t i = 0; i < e->segs.size(); ++i)
+      segs[i] = {e->segs[i].kind, e->segs[i].module, e->segs[i].index, e->segs[i].off, e->segs[i].size};
+  }
+  return SUTA_OK;
+}
+extern "C" int suta_engine_set_weights(suta_engine* e, const suta_weights* w) {
+  SUTA_CHECK_ARG(e && w);
+  const suta_model_cfg& c = e->cfg;
+  SUTA_CHECK_ARG(w->conv0_w && w->gn_g && w->gn_b && w->proj_w && w->proj_w_t && w->proj_b);
+  SUTA_CHECK_ARG(w->pos_w && w->pos_w_t && w->pos_b && w->lm_w && w->lm_w_t && w->lm_b && w->params0 && w->mult);
+  for (int l = 1; l < c.n_conv; ++l) SUTA_CHECK_ARG(w->conv_w[l]);
+  for (int l = 0; l < c.layers; ++l) {
+    const suta_layer_weights& x = w->layer[l];
+    SUTA_CHECK_ARG(x.wqkv && x.wqkv_t && x.wo && x.wo_t && x.w1 && x.w1_t && x.w2 && x.w2_t && x.bqkv && x.bo && x.b1 && x.b2);
+  }
+  e->w = *w;
+  e->have_weights = true;
+  return SUTA_OK;
+}
+
+extern "C" int64_t suta_batch_workspace_bytes(suta_engine* e, int n_utts, const int32_t* n_samples) {
+  if (!e || plan_batch(e, n_utts, n_samples) != SUTA_OK) return -1;
+  Bump b;
+  carve(e, b);
+  e->U = 0;   // planning only: the batch is not live until suta_batch_begin
+  return (int64_t)b.off + 256;
+}
+
+extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_samples, void* workspace, int64_t bytes,
+                                void* stream) {
+  SUTA_CHECK_ARG(e && workspace && e->have_weights);
+  SUTA_TRY(plan_batch(e, n_utts, n_samples));
+  Bump b;
+  b.base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  carve(e, b);
+  if ((int64_t)(b.off + (b.base - reinterpret_cast<uint8_t*>(workspace))) > bytes) {
+    suta_set_last_error("workspace too small: need %zu bytes, got %lld", b.off + 256, (long long)bytes);
+    e->U = 0;
+    return SUTA_ERR_NOMEM;
+  }
+  const suta_model_cfg& c = e->cfg;
+  const int U = e->U;
+  cudaStream_t st = S(stream);
+  // ---- host tables -> device (one staging vector kept alive in the engine) ----
+  std::vector<int> row_utt(e->M);
+  for (int u = 0; u < U; ++u)
+    for (int t = 0; t < e->T[u]; ++t) row_utt[e->tok_off[u] + t] = u;
+  std::vector<int4> attn_tab;
+  attn_tab.reserve(e->n_attn_blk);
+  for (int u = 0; u < U; ++u)
+    for (int m0 = 0; m0 < e->T[u]; m0 += 64) attn_tab.push_back(make_int4((int)e->tok_off[u], e->T[u], m0, 0));
+  auto up = [&](void* dst, const void* src, size_t n) { return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st); };
+  CUDA_TRY(up(e->d_samp_off, e->samp_off.data(), sizeof(long long) * U));
+  CUDA_TRY(up(e->d_tok_off, e->tok_off.data(), sizeof(long long) * U));
+  CUDA_TRY(up(e->d_pad_off, e->pad_off.data(), sizeof(long long) * U));
+  CUDA_TRY(up(e->d_off0, e->off[0].data(), sizeof(long long) * U));
+  CUDA_TRY(up(e->d_n_samples, e->n_samples.data(), sizeof(int) * U));
+  CUDA_TRY(up(e->d_T, e->T.data(), sizeof(int) * U));
+  CUDA_TRY(up(e->d_L0, e->L[0].data(), sizeof(int) * U));
+  CUDA_TRY(up(e->d_row_utt, row_utt.data(), sizeof(int) * e->M));
+  CUDA_TRY(up(e->d_attn_tab, attn_tab.data(), sizeof(int4) * attn_tab.size()));
+  for (int l = 1; l < c.n_conv; ++l) {
+    std::vector<int4> tab;
+    tab.reserve(e->n_mblk[l]);
+    const int s = c.conv_stride[l];
+    for (int u = 0; u < U; ++u)
+      for (int m0 = 0; m0 < e->L[l][u]; m0 += 128) {
+        int rows = e->L[l][u] - m0 < 128 ? e->L[l][u] - m0 : 128;
+        tab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0), rows, 0));
+      }
+    CUDA_TRY(up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size()));
+    CUDA_TRY(cudaStreamSynchronize(st));   // `tab` is pageable stack-owned memory
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // zero rows of the padded positional-conv slabs never get written afterwards
+  CUDA_TRY(cudaMemsetAsync(e->xg, 0, sizeof(bf16) * (size_t)(e->R + 8) * c.hidden, st));
+  // conv buffers carry 128 slack rows read (never used) by partial implicit-GEMM tiles
+  for (int l = 0; l < c.n_conv; ++l)
+    CUDA_TRY(cudaMemsetAsync(e->conv_out[l] + (size_t)e->rows_total[l] * c.conv_dim[l], 0, sizeof(bf16) * 128 * c.conv_dim[l], st));
+  e->frontend_done = false;
+  e->opt_steps = 0;
+  return SUTA_OK;
+}
+
+extern "C" int suta_batch_info(const suta_engine* e, int64_t* total_frames, int32_t* frames, int64_t* frame_off,
+                               int64_t* sample_off, int64_t* total_samples) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  if (total_frames) *total_frames = e->M;
+  if (total_samples) *total_samples = e->S;
+  for (int u = 0; u < e->U; ++u) {
+    if (frames) frames[u] = e->T[u];
+    if (frame_off) frame_off[u] = e->tok_off[u];
+    if (sample_off) sample_off[u] = e->samp_off[u];
+  }
+  return SUTA_OK;
+}
+
+extern "C" int suta_batch_set_audio(suta_engine* e, const float* wav, int is_host, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0 && wav);
+  CUDA_TRY(cudaMemcpyAsync(e->wav, wav, sizeof(float) * e->S, is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                           S(stream)));
+  e->frontend_done = false;
+  return SUTA_OK;
+}
+
+extern "C" int suta_reset(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  e->launches += 1;
+  e->opt_steps = 0;
+  return params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, S(stream));
+}
+
+extern "C" int suta_frontend(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  const suta_model_cfg& c = e->cfg;
+  cudaStream_t st = S(stream);
+  SUTA_TRY(normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
+  Conv0Args a{};
+  a.x = e->wav_norm; a.samp_off = e->d_samp_off; a.L0 = e->d_L0; a.out_off = e->d_off0;
+  a.w = e->w.conv0_w; a.w_stride = 0;
+  a.gn_shared_g = e->w.gn_g; a.gn_shared_b = e->w.gn_b;
+  a.stats = e->stats + 2 * e->U;
+  a.out = e->conv_out[0]; a.pre_out = nullptr;
+  a.n_utts = e->U; a.C = c.conv_dim[0]; a.k = c.conv_kernel[0]; a.stride = c.conv_stride[0]; a.max_L0 = e->max_L0;
+  SUTA_TRY(conv0_groupnorm_gelu(a, st));
+  e->launches += 4;
+  for (int l = 1; l < c.n_conv; ++l) {
+    const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l], s = c.conv_stride[l];
+    GemmProblem p;
+    // overlapping-row view: row r = input rows [s*r, s*r + k) flattened = k*Cin contiguous elements
+    long long rows_in = e->rows_total[l - 1] + 128;
+    p.a = {e->conv_out[l - 1], (rows_in - k) / s + 1, (long long)s * Cin};
+    p.b = {reinterpret_cast<const bf16*>(e->w.conv_w[l]), Cout, (long long)k * Cin};
+    p.M = 0; p.N = Cout; p.K = k * Cin;
+    p.mblk = e->d_mblk[l]; p.num_mblk = e->n_mblk[l];
+    p.M = e->n_mblk[l] * 128;
+    p.epi.act = 1;
+    p.epi.out_bf16 = e->conv_out[l]; p.epi.out_ld = Cout;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  e->frontend_done = true;
+  return SUTA_OK;
+}
+
+extern "C" int suta_forward(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  if (!e->frontend_done) SUTA_TRY(suta_frontend(e, stream));
+  const suta_model_cfg& c = e->cfg;
+  cudaStream_t st = S(stream);
+  const int H = c.hidden, I = c.intermediate, C = c.conv_dim[c.n_conv - 1], V = c.vocab, G = c.pos_groups, CG = H / G;
+  const long long M = e->M;
+  UttParams prm{e->P, e->n_params};
+  const bf16* feat = e->conv_out[c.n_conv - 1];
+
+  // feature projection: LayerNorm(C) -> Linear(C->H)        HF/modeling_wav2vec2.py:429-434
+  SUTA_TRY(layernorm_forward(nullptr, feat, e->d_row_utt, prm, (int)e->fp_g, (int)e->fp_b, nullptr, e->y_fp, e->fp_mean,
+                             e->fp_rstd, M, C, c.ln_eps, st));
+  {
+    GemmProblem p = dense(e->y_fp, M, C, reinterpret_cast<const bf16*>(e->w.proj_w), H);
+    p.epi.bias = e->w.proj_b; p.epi.out_f32 = e->h0; p.epi.out_ld = H;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  // positional conv embedding + GELU + residual               HF/modeling_wav2vec2.py:360-368, :690-691
+  SUTA_TRY(posconv_pack(e->h0, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, st));
+  {
+    GemmProblem p;
+    p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
+    p.b = {reinterpret_cast<const bf16*>(e->w.pos_w), H, (long long)c.pos_k * CG};
+    p.M = (int)e->Rm; p.N = CG; p.K = c.pos_k * CG;
+    p.nz = G; p.a_z_rows = e->R; p.b_z_rows = CG; p.c_z_cols = CG;
+    p.epi.bias = e->w.pos_b; p.epi.out_f32 = e->cpos; p.epi.out_ld = H;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  SUTA_TRY(posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->hE, M, H, -(c.pos_k / 2), st));
+  // encoder.layer_norm                                          HF/modeling_wav2vec2.py:692
+  SUTA_TRY(layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->fa, e->b16, e->enc_mean,
+                             e->enc_rstd, M, H, c.ln_eps, st));
+  e->launches += 5;
+  for (int l = 0; l < c.layers; ++l) {
+    const suta_layer_weights& w = e->w.layer[l];
+    LayerBufs& x = e->lb[l];
+    {  // q,k,v projections fused to one N=3H GEMM            HF:500-507
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
+      p.epi.bias = w.bqkv; p.epi.out_bf16 = x.qkv; p.epi.out_ld = 3 * H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    SUTA_TRY(attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+    {  // out_proj + residual                                    HF:546, :597
+      GemmProblem p = dense(x.attn, M, H, reinterpret_cast<const bf16*>(w.wo), H);
+      p.epi.bias = w.bo; p.epi.residual = e->fa; p.epi.res_ld = H; p.epi.out_f32 = x.h1; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    SUTA_TRY(layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], e->fb, e->b16,
+                               x.mean1, x.rstd1, M, H, c.ln_eps, st));
+    {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
+      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->gelu16; p.epi.out_ld = I;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    {  // output_dense + residual                                HF:569, :600
+      GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
+      p.epi.bias = w.b2; p.epi.residual = e->fb; p.epi.res_ld = H; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    SUTA_TRY(layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], e->fa, e->b16,
+                               x.mean2, x.rstd2, M, H, c.ln_eps, st));
+    e->launches += 3;
+  }
+  {  // lm_head                                                   HF:1708
+    GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.lm_w), V);
+    p.epi.bias = e->w.lm_b; p.epi.out_f32 = e->logits; p.epi.out_ld = V;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  return SUTA_OK;
+}
+
+extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0 && h);
+  const suta_model_cfg& c = e->cfg;
+  cudaStream_t st = S(stream);
+  const int H = c.hidden, I = c.intermediate, C = c.conv_dim[c.n_conv - 1], V = c.vocab, G = c.pos_groups, CG = H / G;
+  const long long M = e->M;
+  UttParams prm{e->P, e->n_params};
+
+  LossArgs la{};
+  la.logits = e->logits; la.tok_off = e->d_tok_off; la.T = e->d_T;
+  la.dlogits_f32 = e->dlogits; la.dlogits_bf16 = e->dlogits16; la.loss = e->losses; la.n_utts = e->U;
+  la.em_coef = h->em_coef; la.temp = h->temp; la.reweight = h->reweight; la.not_blank = h->not_blank;
+  SUTA_TRY(suta_loss_forward_backward(la, st));
+  CUDA_TRY(cudaMemsetAsync(e->G, 0, sizeof(float) * (size_t)e->U * e->n_params, st));
+  e->launches += 2;
+
+  float* da = e->fa;   // gradient w.r.t. the current LayerNorm output
+  float* db = e->fb;   // gradient w.r.t. the pre-LayerNorm sum
+  {  // lm_head dgrad
+    GemmProblem p = dense(e->dlogits16, M, V, reinterpret_cast<const bf16*>(e->w.lm_w_t), H);
+    p.epi.out_f32 = da; p.epi.out_ld = H;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  for (int l = c.layers - 1; l >= 0; --l) {
+    const suta_layer_weights& w = e->w.layer[l];
+    LayerBufs& x = e->lb[l];
+    SUTA_TRY(layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+                                e->G, db, e->b16, M, H, st));
+    {  // output_dense dgrad, times GELU'(pre)
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
+      p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    {  // intermediate_dense dgrad + residual path
+      GemmProblem p = dense(e->dpre16, M, I, reinterpret_cast<const bf16*>(w.w1_t), H);
+      p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    SUTA_TRY(layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
+                                e->G, db, e->b16, M, H, st));
+    {  // out_proj dgrad
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
+      p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    SUTA_TRY(attention_backward(x.qkv, x.attn, e->dO16, x.lse, e->Dbuf, e->dqkv16, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+    {  // q,k,v dgrad + residual path
+      GemmProblem p = dense(e->dqkv16, M, 3 * H, reinterpret_cast<const bf16*>(w.wqkv_t), H);
+      p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    e->launches += 5;
+  }
+  // encoder.layer_norm
+  SUTA_TRY(layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
+                              e->G, db, nullptr, M, H, st));
+  // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
+  SUTA_TRY(posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
+  {
+    GemmProblem p;
+    p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
+    p.b = {reinterpret_cast<const bf16*>(e->w.pos_w_t), H, (long long)c.pos_k * CG};
+    p.M = (int)e->Rm; p.N = CG; p.K = c.pos_k * CG;
+    p.nz = G; p.a_z_rows = e->R; p.b_z_rows = CG; p.c_z_cols = CG;
+    p.epi.out_f32 = e->dcpos; p.epi.out_ld = H;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  SUTA_TRY(posconv_combine_grad(db, e->dcpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, nullptr, e->b16, M, H,
+                                -(c.pos_k / 2 - 1), st));
+  {  // projection dgrad
+    GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.proj_w_t), C);
+    p.epi.out_f32 = e->d_yfp; p.epi.out_ld = C;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
+  SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
+                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, st));
+  e->launches += 4;
+  return SUTA_OK;
+}
+
+extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0 && h);
+  AdamArgs a{};
+  a.P = e->P; a.G = e->G; a.Mom = e->Mom; a.Var = e->Var; a.mult = e->w.mult;
+  a.n = e->n_params; a.n_utts = e->U; a.step_index = e->opt_steps;
+  a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps; a.weight_decay = h->weight_decay;
+  a.kind = h->opt_kind; a.shadow = nullptr;
+  SUTA_TRY(optimizer_step(a, S(stream)));
+  e->opt_steps += 1;
+  e->launches += 1;
+  return SUTA_OK;
+}
+
+extern "C" int suta_adapt_step(suta_engine* e, const suta_hyper* h, void* stream) {
+  SUTA_TRY(suta_loss_backward(e, h, stream));
+  SUTA_TRY(suta_optimizer_step(e, h, stream));
+  return suta_forward(e, stream);
+}
+
+extern "C" int suta_decode(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  e->launches += 1;
+  return ctc_greedy_decode(e->logits, e->d_tok_off, e->d_T, e->ids, e->collapsed, e->out_len, e->U, e->cfg.vocab, S(stream));
+}
+
+extern "C" float* suta_logits(const suta_engine* e) { return e->logits; }
+extern "C" float* suta_dlogits(const suta_engine* e) { return e->dlogits; }
+extern "C" float* suta_losses(const suta_engine* e) { return e->losses; }
+extern "C" float* suta_params(const suta_engine* e) { return e->P; }
+extern "C" float* suta_grads(const suta_engine* e) { return e->G; }
+extern "C" int32_t* suta_argmax_ids(const suta_engine* e) { return e->ids; }
+extern "C" int32_t* suta_collapsed_ids(const suta_engine* e) { return e->collapsed; }
+extern "C" int32_t* suta_collapsed_len(const suta_engine* e) { return e->out_len; }
+extern "C" int64_t suta_launch_count(const suta_engine* e) { return e->launches; }
+
+// dtype: 0 fp32, 1 bf16
+extern "C" const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype) {
+  if (!e || e->U <= 0 || !name) return nullptr;
+  const suta_model_cfg& c = e->cfg;
+  const int H = c.hidden, C = c.conv_dim[c.n_conv - 1];
+  auto ret = [&](const void* p, long long r, long long k, int dt) { *rows = r; *cols = k; *dtype = dt; return p; };
+  std::string n(name);
+  if (n == "wav_norm") return ret(e->wav_norm, 1, e->S, 0);
+  if (n == "feat") return ret(e->conv_out[c.n_conv - 1], e->M, C, 1);
+  if (n == "h0") return ret(e->h0, e->M, H, 0);
+  if (n == "cpos") return ret(e->cpos, e->Rm, H, 0);
+  if (n == "hE") return ret(e->hE, e->M, H, 0);
+  if (n == "x_final") return ret(e->fa, e->M, H, 0);
+  if (n == "d_yfp") return ret(e->d_yfp, e->M, C, 0);
+  if (n.rfind("conv", 0) == 0) {
+    int l = atoi(n.c_str() + 4);
+    if (l >= 0 && l < c.n_conv) return ret(e->conv_out[l], e->rows_total[l], c.conv_dim[l], 1);
+  }
+  if (n.rfind("h1_", 0) == 0) { int l = atoi(n.c_str() + 3); if (l >= 0 && l < c.layers) return ret(e->lb[l].h1, e->M, H, 0); }
+  if (n.rfind("h2_", 0) == 0) { int l = atoi(n.c_str() + 3); if (l >= 0 && l < c.layers) return ret(e->lb[l].h2, e->M, H, 0); }
+  if (n.rfind("qkv_", 0) == 0) { int l = atoi(n.c_str() + 4); if (l >= 0 && l < c.layers) return ret(e->lb[l].qkv, e->M, 3 * H, 1); }
+  if (n.rfind("attn_", 0) == 0) { int l = atoi(n.c_str() + 5); if (l >= 0 && l < c.layers) return ret(e->lb[l].attn, e->M, H, 1); }
+  return nullptr;
+}
+
+// ---- single operators ----------------------------------------------------------------------------------
+extern "C" int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride, const void* b, int64_t b_rows,
+                            int64_t b_row_stride, int M, int N, int K, float* out_f32, void* out_bf16, int out_ld,
+                            const float* bias, const float* residual, int res_ld, int act, const void* aux_in, void* aux_out,
+                            int aux_ld, void* stream) {
+  GemmProblem p;
+  p.a = {reinterpret_cast<const bf16*>(a), a_rows, a_row_stride};
+  p.b = {reinterpret_cast<const bf16*>(b), b_rows, b_row_stride};
+  p.M = M; p.N = N; p.K = K;
+  p.epi.out_f32 = out_f32; p.epi.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.epi.out_ld = out_ld;
+  p.epi.bias = bias; p.epi.residual = residual; p.epi.res_ld = res_ld; p.epi.act = act;
+  p.epi.aux_in = reinterpret_cast<const bf16*>(aux_in); p.epi.aux_out = reinterpret_cast<bf16*>(aux_out); p.epi.aux_ld = aux_ld;
+  return gemm_bf16_tc(p, S(stream));
+}
+extern "C" int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P,
+                                     int64_t pstride, int g_off, int b_off, float* y_f32, void* y_bf16, float* mean,
+                                     float* rstd, int64_t M, int N, float eps, void* stream) {
+  return layernorm_forward(x_f32, reinterpret_cast<const bf16*>(x_bf16), row_utt, UttParams{P, pstride}, g_off, b_off, y_f32,
+                           reinterpret_cast<bf16*>(y_bf16), mean, rstd, M, N, eps, S(stream));
+}
+extern "C" int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const void* x_bf16, const float* mean,
+                                     const float* rstd, const int32_t* row_utt, const float* P, int64_t pstride, int g_off,
+                                     int b_off, float* G, float* dx_f32, void* dx_bf16, int64_t M, int N, void* stream) {
+  return layernorm_backward(dy, x_f32, reinterpret_cast<const bf16*>(x_bf16), mean, rstd, row_utt, UttParams{P, pstride}, g_off,
+                            b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N, S(stream));
+}
+extern "C" int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
+                                     int64_t M, void* stream) {
+  return attention_forward(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(O), lse,
+                           reinterpret_cast<const int4*>(blk_tab), n_blk, H, heads, M, S(stream));
+}
+extern "C" int suta_op_attention_bwd(const void* qkv, const void* O, const void* dO, const float* lse, float* D, void* dqkv,
+                                     const int32_t* blk_tab, int n_blk, int H, int heads, int64_t M, void* stream) {
+  return attention_backward(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(O),
+                            reinterpret_cast<const bf16*>(dO), lse, D, reinterpret_cast<bf16*>(dqkv),
+                            reinterpret_cast<const int4*>(blk_tab), n_blk, H, heads, M, S(stream));
+}
+extern "C" int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef,
+                            float temp, int reweight, int not_blank, float* loss, float* dlogits_f32, void* dlogits_bf16,
+                            void* stream) {
+  LossArgs la{};
+  la.logits = logits; la.tok_off = reinterpret_cast<const long long*>(tok_off); la.T = T; la.n_utts = n_utts;
+  la.em_coef = em_coef; la.temp = temp; la.reweight = reweight; la.not_blank = not_blank;
+  la.loss = loss; la.dlogits_f32 = dlogits_f32; la.dlogits_bf16 = reinterpret_cast<bf16*>(dlogits_bf16);
+  return suta_loss_forward_backward(la, S(stream));
+}
+extern "C" int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,
+                            int step_index, const suta_hyper* h, void* shadow_bf16, void* stream) {
+  SUTA_CHECK_ARG(h);
+  AdamArgs a{};
+  a.P = P; a.G = G; a.Mom = Mom; a.Var = Var; a.mult = mult; a.n = n; a.n_utts = n_utts; a.step_index = step_index;
+  a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps; a.weight_decay = h->weight_decay;
+  a.kind = h->opt_kind; a.shadow = reinterpret_cast<bf16*>(shadow_bf16);
+  return optimizer_step(a, S(stream));
+}
+extern "C" int suta_op_decode(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, int V, int32_t* ids,
+                              int32_t* collapsed, int32_t* out_len, void* stream) {
+  return ctc_greedy_decode(logits, reinterpret_cast<const long long*>(tok_off), T, ids, collapsed, out_len, n_utts, V, S(stream));
+}

@@ -1,0 +1,149 @@
+// Waveform front end: per-utterance input normalisation and the first feature-extractor layer.
+//   normalize_audio       HF/feature_extraction_wav2vec2.py:95   (x - mean) / sqrt(var + 1e-7)
+//   conv0_groupnorm_gelu  HF/modeling_wav2vec2.py:319-323        Conv1d(1->C,k=10,s=5,no bias) + GroupNorm(C groups,
+//                         i.e. per-channel statistics over TIME) + erf-GELU      
+// Cin = 1, so this layer is HBM-bound (writes L0*C bf16, reads 4 B per sample): direct convolution on CUDA cores,
+// channels-last bf16 output so the next layer's implicit GEMM can read overlapping rows straight through TMA.
+// In a batch, GroupNorm statistics are taken over each utterance's own valid frames only.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int NORM_CHUNK = 16384;
+
+__global__ void audio_stats_kernel(const float* __restrict__ wav, const long long* __restrict__ samp_off,
+                                   const int* __restrict__ n_samples, double* __restrict__ stats) {
+  const int u = blockIdx.y;
+  const int n = n_samples[u];
+  const int i0 = blockIdx.x * NORM_CHUNK;
+  if (i0 >= n) return;
+  const float* x = wav + samp_off[u];
+  double s = 0.0, ss = 0.0;
+  for (int i = i0 + threadIdx.x; i < min(n, i0 + NORM_CHUNK); i += blockDim.x) {
+    float v = x[i];
+    s += v;
+    ss += (double)v * v;
+  }
+  __shared__ double sh[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; }
+    atomicAdd(&stats[2 * u], a);
+    atomicAdd(&stats[2 * u + 1], b);
+  }
+}
+
+__global__ void audio_apply_kernel(const float* __restrict__ wav, float* __restrict__ out,
+                                   const long long* __restrict__ samp_off, const int* __restrict__ n_samples,
+                                   const double* __restrict__ stats) {
+  const int u = blockIdx.y;
+  const int n = n_samples[u];
+  const int i0 = blockIdx.x * NORM_CHUNK;
+  if (i0 >= n) return;
+  const double mean = stats[2 * u] / n;
+  const double var = stats[2 * u + 1] / n - mean * mean;
+  const float m = (float)mean, r = (float)(1.0 / sqrt(var + 1e-7));
+  const float* x = wav + samp_off[u];
+  float* y = out + samp_off[u];
+  for (int i = i0 + threadIdx.x; i < min(n, i0 + NORM_CHUNK); i += blockDim.x) y[i] = (x[i] - m) * r;
+}
+
+constexpr int C0_TT = 128;      // frames per CTA
+constexpr int C0_MAXK = 16;
+
+// MODE 0: accumulate per-channel sum / sum of squares;  MODE 1: normalise + GELU + store
+template <int MODE>
+__global__ void __launch_bounds__(256)
+conv0_kernel(Conv0Args a, double* __restrict__ stats) {
+  extern __shared__ float sx[];                  // C0_TT*stride + k samples
+  const int u = blockIdx.y;
+  const int L0 = a.L0[u];
+  const int t0 = blockIdx.x * C0_TT;
+  if (t0 >= L0) return;
+  const int nt = min(C0_TT, L0 - t0);
+  const float* x = a.x + a.samp_off[u] + (long long)t0 * a.stride;
+  const int nx = (nt - 1) * a.stride + a.k;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = x[i];
+  __syncthreads();
+  const float* w = a.w + (a.w_stride ? (long long)u * a.w_stride : 0);
+  for (int cp = threadIdx.x; 2 * cp < a.C; cp += blockDim.x) {
+    const int c = 2 * cp;
+    float w0[C0_MAXK], w1[C0_MAXK];
+#pragma unroll
+    for (int j = 0; j < C0_MAXK; ++j) {
+      w0[j] = j < a.k ? w[(long long)c * a.k + j] : 0.f;
+      w1[j] = j < a.k ? w[(long long)(c + 1) * a.k + j] : 0.f;
+    }
+    if (MODE == 0) {
+      float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+      for (int t = 0; t < nt; ++t) {
+        const float* xs = sx + t * a.stride;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < C0_MAXK; ++j)
+          if (j < a.k) { y0 += w0[j] * xs[j]; y1 += w1[j] * xs[j]; }
+        s0 += y0; q0 += y0 * y0; s1 += y1; q1 += y1 * y1;
+      }
+      double* st = stats + ((long long)u * a.C + c) * 2;
+      atomicAdd(st + 0, (double)s0); atomicAdd(st + 1, (double)q0);
+      atomicAdd(st + 2, (double)s1); atomicAdd(st + 3, (double)q1);
+    } else {
+      const double* st = stats + ((long long)u * a.C + c) * 2;
+      const double m0 = st[0] / L0, m1 = st[2] / L0;
+      const float mean0 = (float)m0, mean1 = (float)m1;
+      const float r0 = (float)(1.0 / sqrt(st[1] / L0 - m0 * m0 + 1e-5));
+      const float r1 = (float)(1.0 / sqrt(st[3] / L0 - m1 * m1 + 1e-5));
+      float g0, g1, b0, b1;
+      if (a.gn.P) {
+        const float* P = a.gn.P + (long long)u * a.gn.stride;
+        g0 = P[a.g_off + c]; g1 = P[a.g_off + c + 1]; b0 = P[a.b_off + c]; b1 = P[a.b_off + c + 1];
+      } else {
+        g0 = a.gn_shared_g[c]; g1 = a.gn_shared_g[c + 1]; b0 = a.gn_shared_b[c]; b1 = a.gn_shared_b[c + 1];
+      }
+      const long long row0 = a.out_off[u] + t0;
+      for (int t = 0; t < nt; ++t) {
+        const float* xs = sx + t * a.stride;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < C0_MAXK; ++j)
+          if (j < a.k) { y0 += w0[j] * xs[j]; y1 += w1[j] * xs[j]; }
+        y0 = (y0 - mean0) * r0 * g0 + b0;
+        y1 = (y1 - mean1) * r1 * g1 + b1;
+        const long long o = (row0 + t) * a.C + c;
+        if (a.pre_out) *reinterpret_cast<uint32_t*>(a.pre_out + o) = pack_bf16x2(y0, y1);
+        *reinterpret_cast<uint32_t*>(a.out + o) = pack_bf16x2(gelu_erf(y0), gelu_erf(y1));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int normalize_audio(const float* wav, float* out, const long long* samp_off, const int* n_samples, int n_utts,
+                    int max_samples, double* stats_scratch, cudaStream_t stream) {
+  SUTA_CHECK_ARG(n_utts > 0 && max_samples > 0 && stats_scratch);
+  CUDA_TRY(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 2 * n_utts, stream));
+  dim3 grid(ceil_div(max_samples, NORM_CHUNK), n_utts);
+  audio_stats_kernel<<<grid, 256, 0, stream>>>(wav, samp_off, n_samples, stats_scratch);
+  audio_apply_kernel<<<grid, 256, 0, stream>>>(wav, out, samp_off, n_samples, stats_scratch);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream) {
+  SUTA_CHECK_ARG(a.k <= C0_MAXK && a.C % 2 == 0 && a.n_utts > 0);
+  double* stats = a.stats;
+  CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * a.C * a.n_utts, stream));
+  dim3 grid(ceil_div(a.max_L0, C0_TT), a.n_utts);
+  size_t smem = sizeof(float) * (C0_TT * a.stride + a.k);
+  conv0_kernel<0><<<grid, 256, smem, stream>>>(a, stats);
+  conv0_kernel<1><<<grid, 256, smem, stream>>>(a, stats);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}

@@ -1,0 +1,43 @@
+// tcgen05/TMEM GEMM:  D[M,N] = A[M,K] * B[N,K]^T  (bf16 operands, fp32 accumulate in tensor memory)
+// with a fused epilogue (bias / GELU / GELU' / fp32 residual / fp32+bf16 stores).
+// One kernel serves every dense contraction of the path (SURVEY.md 2.3 K2,K3,K4,K6,K8,K10):
+//   * encoder linears forward  (A = activations, B = W)           HF/modeling_wav2vec2.py:500-573
+//   * encoder linears backward (A = dY,          B = W^T)         autograd dgrad of the same
+//   * strided conv layers as implicit GEMM: A is an overlapping-row TMA view of the channels-last input
+//     (row t = x[s*t : s*t+k, :] flattened, which is contiguous)   HF/modeling_wav2vec2.py:269-272
+//   * positional grouped conv: same trick per group, groups on the z axis  HF/modeling_wav2vec2.py:360-368
+#pragma once
+#include "common.cuh"
+
+struct GemmOperand {
+  const bf16* ptr;         // first element of row 0
+  long long rows;          // number of addressable rows (TMA zero-fills beyond)
+  long long row_stride;    // elements between consecutive rows (may be < K: overlapping conv windows)
+};
+
+struct GemmEpilogue {
+  float* out_f32 = nullptr;        // optional fp32 output
+  bf16* out_bf16 = nullptr;        // optional bf16 output (same leading dim)
+  int out_ld = 0;
+  const float* bias = nullptr;     // indexed [b_row_off + out_col]
+  const float* residual = nullptr; // fp32 [rows, res_ld], added last
+  int res_ld = 0;
+  int act = 0;                     // 0 none, 1 GELU(erf), 2 multiply by GELU'(aux_in)
+  const bf16* aux_in = nullptr;    // pre-activation saved by the forward (act == 2)
+  bf16* aux_out = nullptr;         // where to save the pre-activation (act == 1), may be null
+  int aux_ld = 0;
+};
+
+struct GemmProblem {
+  GemmOperand a, b;
+  int M = 0, N = 0, K = 0;         // per-z problem; N % 16 == 0
+  int nz = 1;                      // batch (z) count: A rows += z*a_z_rows, B rows += z*b_z_rows, out cols += z*c_z_cols
+  long long a_z_rows = 0, b_z_rows = 0;
+  int c_z_cols = 0;
+  const int4* mblk = nullptr;      // optional per-M-block table {a_row0, out_row0, rows_valid, b_row_off}
+  int num_mblk = 0;                // = ceil(M/128) when mblk == nullptr
+  GemmEpilogue epi;
+};
+
+int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream);
+int gemm_num_sms();

@@ -1,0 +1,101 @@
+// Host-callable launchers of the non-GEMM kernels (all asynchronous on `stream`, return SUTA_* status).
+#pragma once
+#include "common.cuh"
+
+// Per-utterance trainable vector: parameter `off` of utterance u lives at P + u*stride + off.
+struct UttParams {
+  const float* P = nullptr;
+  long long stride = 0;
+};
+
+// ---- attention.cu ---------------------------------------------------------------------------
+int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
+                      cudaStream_t stream);
+int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const float* LSE, float* D, bf16* dqkv,
+                       const int4* blk_tab, int n_blk, int H, int heads, long long M, cudaStream_t stream);
+
+// ---- norm.cu --------------------------------------------------------------------------------
+// y = LayerNorm(x) * gamma[u] + beta[u]; x is fp32 (x_f32) or bf16 (x_bf16), exactly one non-null.
+int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
+                      float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
+                      cudaStream_t stream);
+// dgamma/dbeta are accumulated (atomicAdd) into G (same layout as the parameter vector); dx outputs optional.
+int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
+                       const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
+                       long long M, int N, cudaStream_t stream);
+
+// ---- frontend.cu ----------------------------------------------------------------------------
+// per-utterance (x - mean) / sqrt(var + 1e-7), optional additive noise is applied by the caller beforehand
+int normalize_audio(const float* wav, float* out, const long long* samp_off, const int* n_samples, int n_utts,
+                    int max_samples, double* stats_scratch /*[2*n_utts]*/, cudaStream_t stream);
+// conv0 (Cin=1) + GroupNorm(per channel over time) + GELU -> channels-last bf16
+struct Conv0Args {
+  const float* x;              // normalised audio, packed
+  const long long* samp_off;   // [U]
+  const int* L0;               // [U] output frames per utterance
+  const long long* out_off;    // [U] first output row per utterance
+  const float* w;              // [C, k] fp32 (shared) or per-utterance [U][C*k] when w_stride != 0
+  long long w_stride;
+  UttParams gn;                // GroupNorm affine via the trainable vector (gn.stride == 0 => shared)
+  const float* gn_shared_g;    // used when gn.P == nullptr
+  const float* gn_shared_b;
+  int g_off, b_off;
+  double* stats;               // [U][C][2] sum, sumsq scratch (zeroed by the launcher)
+  bf16* out;                   // [rows, C]
+  bf16* pre_out;               // optional: pre-GELU normalised value (train_feature backward)
+  int n_utts, C, k, stride, max_L0;
+};
+int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
+
+// ---- posconv.cu -----------------------------------------------------------------------------
+// scatter fp32 [M,H] tokens into the zero-padded per-group bf16 layout [G][R][CGP] used as the implicit-GEMM A operand
+int posconv_pack(const float* h, const int* row_utt, const long long* tok_off, const long long* pad_off, bf16* xg,
+                 long long M, int H, int G, int CGP, long long R, cudaStream_t stream);
+// h_out = h + GELU(conv[pad_row(u,t)])   (conv already contains the bias)
+int posconv_combine(const float* h, const float* conv, const int* row_utt, const long long* tok_off,
+                    const long long* pad_off, float* h_out, long long M, int H, int row_shift, cudaStream_t stream);
+// dC = d_out * GELU'(conv) scattered into the padded per-group layout (backward A operand)
+int posconv_pack_grad(const float* d_out, const float* conv, const int* row_utt, const long long* tok_off,
+                      const long long* pad_off, bf16* dg, long long M, int H, int G, int CGP, long long R, int row_shift,
+                      cudaStream_t stream);
+// d_h = d_out + dconv[pad_row(u,t)]   (residual path + conv path)
+int posconv_combine_grad(const float* d_out, const float* dconv, const int* row_utt, const long long* tok_off,
+                         const long long* pad_off, float* d_h, bf16* d_h_bf16, long long M, int H, int row_shift,
+                         cudaStream_t stream);
+
+// ---- loss.cu --------------------------------------------------------------------------------
+struct LossArgs {
+  const float* logits;         // [M, 32]
+  const long long* tok_off;    // [U]
+  const int* T;                // [U]
+  float* dlogits_f32;          // optional [M,32]
+  bf16* dlogits_bf16;          // optional [M,32]
+  float* loss;                 // [U] total, then [U] entropy term, then [U] mcc term
+  int n_utts;
+  float em_coef, temp;
+  int reweight, not_blank;
+};
+int suta_loss_forward_backward(const LossArgs& a, cudaStream_t stream);
+
+// ---- optim.cu -------------------------------------------------------------------------------
+struct AdamArgs {
+  float* P;                    // [U][n]
+  const float* G;              // [U][n]
+  float* Mom;                  // [U][n]
+  float* Var;                  // [U][n]
+  const unsigned char* mult;   // [n] multiplicity k of each element (REF/main.py:62-103 duplicates), 1..4
+  long long n;
+  int n_utts;
+  int step_index;              // number of optimizer.step() calls already applied since reset
+  float lr, beta1, beta2, eps, weight_decay;
+  int kind;                    // 0 Adam/AdamW, 1 SGD
+  bf16* shadow;                // optional bf16 copy of P (GEMM operands of trainable weights), same layout
+};
+int optimizer_step(const AdamArgs& a, cudaStream_t stream);
+int params_reset(float* P, const float* P0, float* Mom, float* Var, bf16* shadow, long long n, int n_utts,
+                 cudaStream_t stream);
+
+// ---- decode.cu ------------------------------------------------------------------------------
+// ids[row] = argmax(logits[row]); collapsed[u_off + j] = j-th kept id (repeat-collapsed, blank dropped); out_len[u]
+int ctc_greedy_decode(const float* logits, const long long* tok_off, const int* T, int* ids, int* collapsed,
+                      int* out_len, int n_utts, int V, cudaStream_t stream);

@@ -1,0 +1,283 @@
+"""Python host side of the B200 engine: weight packing, workspace ownership, and the batched adaptation calls.
+
+PyTorch is used here for device memory (the workspace and the packed weights are torch tensors), streams and the
+one-off layout transforms of the frozen weights.  All arithmetic of the hot path happens in libsuta_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Hyper, ModelCfg, ParamSeg, Weights, check
+from .config import ModelConfig
+
+CHECKPOINT_STEPS = (1, 3, 5, 10, 20, 40)       # REF/main.py:350-398
+
+_MODULE_NAMES = {0: "wav2vec2.feature_projection.layer_norm", 1: "wav2vec2.encoder.layer_norm",
+                 2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm"}
+_KIND_LEAF = {0: "weight", 1: "bias"}
+
+
+@dataclass
+class AdaptHyper:
+    """REF/main.py:172 (forward_and_adapt) + :8 (setup_optimizer); defaults = REF/scripts/LS.sh preset."""
+    em_coef: float = 0.3
+    temp: float = 2.5
+    reweight: bool = True
+    not_blank: bool = True
+    opt: str = "AdamW"
+    lr: float = 2e-5
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    weight_decay: float = 0.0
+
+    def to_c(self) -> Hyper:
+        if self.opt not in ("AdamW", "Adam", "SGD"):
+            raise ValueError(f"unsupported optimizer {self.opt!r} (AdamW, Adam, SGD)")
+        return Hyper(self.em_coef, self.temp, int(self.reweight), int(self.not_blank), 1 if self.opt == "SGD" else 0,
+                     self.lr, self.beta1, self.beta2, self.eps, self.weight_decay)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class SutaEngine:
+    """One frozen wav2vec2-CTC model on one GPU + the batched SUTA loop over independent utterances."""
+
+    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False,
+                 trainable_mult: Optional[Dict[str, int]] = None, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise _lib.SutaError("suta_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = ModelConfig.from_any(cfg)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.train_feature = bool(train_feature)
+        c = self.cfg
+        cc = ModelCfg()
+        cc.hidden, cc.layers, cc.heads, cc.intermediate, cc.vocab = (c.hidden_size, c.num_hidden_layers,
+                                                                      c.num_attention_heads, c.intermediate_size, c.vocab_size)
+        cc.n_conv = len(c.conv_dim)
+        for i in range(cc.n_conv):
+            cc.conv_dim[i], cc.conv_kernel[i], cc.conv_stride[i] = c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i]
+        cc.pos_k, cc.pos_groups, cc.ln_eps = c.num_conv_pos_embeddings, c.num_conv_pos_embedding_groups, c.layer_norm_eps
+        h = C.c_void_p()
+        check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature), C.byref(h)))
+        self._h = h
+        self.n_params = int(self.lib.suta_engine_param_count(h))
+        n = C.c_int()
+        check(self.lib.suta_engine_param_layout(h, None, 0, C.byref(n)))
+        segs = (ParamSeg * n.value)()
+        check(self.lib.suta_engine_param_layout(h, segs, n.value, C.byref(n)))
+        self.segments = []      # (hf name, offset, size)
+        for s in segs:
+            name = _MODULE_NAMES[s.module].format(i=s.index) + "." + _KIND_LEAF[s.kind]
+            self.segments.append((name, int(s.offset), int(s.size)))
+        self._keep: List[torch.Tensor] = []
+        self._pack_weights(state_dict, trainable_mult)
+        self._ws: Optional[torch.Tensor] = None
+        self.n_utts = 0
+
+    # ------------------------------------------------------------------ weights
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _pack_weights(self, sd: Dict[str, torch.Tensor], trainable_mult: Optional[Dict[str, int]]):
+        c = self.cfg
+        bf, f32 = torch.bfloat16, torch.float32
+        w = Weights()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        g = lambda k: sd[k].detach().to(torch.float32)
+
+        def mat(t):       # [out,in] fp32 -> (bf16 W, bf16 W^T)
+            t = t.to(self.device)
+            return self._dev(t, bf), self._dev(t.t(), bf)
+
+        fe = "wav2vec2.feature_extractor.conv_layers."
+        w.conv0_w = p(self._dev(g(fe + "0.conv.weight").reshape(c.conv_dim[0], c.conv_kernel[0]), f32))
+        w.gn_g = p(self._dev(g(fe + "0.layer_norm.weight"), f32))
+        w.gn_b = p(self._dev(g(fe + "0.layer_norm.bias"), f32))
+        for l in range(1, len(c.conv_dim)):
+            cw = g(fe + f"{l}.conv.weight")                       # [Cout, Cin, k] -> [Cout, (k, Cin)]
+            w.conv_w[l] = p(self._dev(cw.permute(0, 2, 1).reshape(cw.shape[0], -1), bf))
+        pw, pwt = mat(g("wav2vec2.feature_projection.projection.weight"))
+        w.proj_w, w.proj_w_t = p(pw), p(pwt)
+        w.proj_b = p(self._dev(g("wav2vec2.feature_projection.projection.bias"), f32))
+        # positional conv: fold weight_norm once (frozen), HF/modeling_wav2vec2.py:344-352
+        pre = "wav2vec2.encoder.pos_conv_embed.conv."
+        if pre + "weight" in sd:
+            pcw = g(pre + "weight")
+        else:
+            wg, wv = g(pre + "parametrizations.weight.original0"), g(pre + "parametrizations.weight.original1")
+            pcw = wv * (wg / wv.norm(dim=(0, 1), keepdim=True))
+        H, G, K = c.hidden_size, c.num_conv_pos_embedding_groups, c.num_conv_pos_embeddings
+        CG = H // G
+        w.pos_w = p(self._dev(pcw.permute(0, 2, 1).reshape(H, K * CG), bf))                 # [co, (tap, ci)]
+        wf = pcw.view(G, CG, CG, K).flip(-1).permute(0, 2, 3, 1)                              # [g, ci, tap', co]
+        w.pos_w_t = p(self._dev(wf.reshape(H, K * CG), bf))
+        w.pos_b = p(self._dev(g(pre + "bias"), f32))
+        for l in range(c.num_hidden_layers):
+            b = f"wav2vec2.encoder.layers.{l}."
+            lw = w.layer[l]
+            qkv = torch.cat([g(b + f"attention.{n}_proj.weight") for n in ("q", "k", "v")], 0)
+            a, at = mat(qkv); lw.wqkv, lw.wqkv_t = p(a), p(at)
+            a, at = mat(g(b + "attention.out_proj.weight")); lw.wo, lw.wo_t = p(a), p(at)
+            a, at = mat(g(b + "feed_forward.intermediate_dense.weight")); lw.w1, lw.w1_t = p(a), p(at)
+            a, at = mat(g(b + "feed_forward.output_dense.weight")); lw.w2, lw.w2_t = p(a), p(at)
+            lw.bqkv = p(self._dev(torch.cat([g(b + f"attention.{n}_proj.bias") for n in ("q", "k", "v")], 0), f32))
+            lw.bo = p(self._dev(g(b + "attention.out_proj.bias"), f32))
+            lw.b1 = p(self._dev(g(b + "feed_forward.intermediate_dense.bias"), f32))
+            lw.b2 = p(self._dev(g(b + "feed_forward.output_dense.bias"), f32))
+        a, at = mat(g("lm_head.weight")); w.lm_w, w.lm_w_t = p(a), p(at)
+        w.lm_b = p(self._dev(g("lm_head.bias"), f32))
+        # pristine trainable vector + per-element multiplicity (REF/main.py:62-103 lists some tensors several times)
+        p0 = torch.empty(self.n_params, dtype=f32)
+        mult = torch.zeros(self.n_params, dtype=torch.uint8)
+        for name, off, size in self.segments:
+            p0[off:off + size] = g(name).reshape(-1)
+            mult[off:off + size] = 1 if trainable_mult is None else int(trainable_mult.get(name, 0))
+        self.params0 = self._dev(p0, f32)
+        self.mult = self._dev(mult, torch.uint8)
+        w.params0, w.mult = p(self.params0), p(self.mult)
+        self._weights = w
+        check(self.lib.suta_engine_set_weights(self._h, C.byref(w)))
+
+    def set_trainable(self, mult_by_name: Dict[str, int]):
+        """Re-select what the optimizer updates (collect_params' result): name -> multiplicity (0 = frozen)."""
+        m = torch.zeros(self.n_params, dtype=torch.uint8)
+        for name, off, size in self.segments:
+            m[off:off + size] = int(mult_by_name.get(name, 0))
+        self.mult.copy_(m.to(self.device))
+
+    # ------------------------------------------------------------------ batches
+    def begin_batch(self, wavs: Sequence[np.ndarray]):
+        """Start adapting a batch of raw (un-normalised) fp32 waveforms; copies them to the device."""
+        lens = np.asarray([len(w) for w in wavs], dtype=np.int32)
+        self.begin_batch_lengths(lens)
+        host = torch.zeros(self.total_samples, dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for w, o in zip(wavs, self.sample_off):
+            hv[o:o + len(w)] = np.asarray(w, dtype=np.float32)
+        self.set_audio(host)
+
+    def begin_batch_lengths(self, lens: np.ndarray):
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        U = len(lens)
+        lp = lens.ctypes.data_as(C.POINTER(C.c_int32))
+        need = int(self.lib.suta_batch_workspace_bytes(self._h, U, lp))
+        if need < 0:
+            check(2)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        check(self.lib.suta_batch_begin(self._h, U, lp, C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream_ptr()))
+        M, S = C.c_int64(), C.c_int64()
+        frames = (C.c_int32 * U)()
+        foff = (C.c_int64 * U)()
+        soff = (C.c_int64 * U)()
+        check(self.lib.suta_batch_info(self._h, C.byref(M), frames, foff, soff, C.byref(S)))
+        self.n_utts, self.total_frames, self.total_samples = U, M.value, S.value
+        self.frames = np.asarray(frames[:], dtype=np.int64)
+        self.frame_off = np.asarray(foff[:], dtype=np.int64)
+        self.sample_off = np.asarray(soff[:], dtype=np.int64)
+        self.lengths = lens.copy()
+
+    def set_audio(self, packed: torch.Tensor):
+        """packed: fp32 [total_samples] (pinned host or device), utterance u at sample_off[u]."""
+        assert packed.dtype == torch.float32 and packed.numel() >= self.total_samples
+        self._audio_keep = packed
+        check(self.lib.suta_batch_set_audio(self._h, C.c_void_p(packed.data_ptr()), int(not packed.is_cuda), _stream_ptr()))
+
+    def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
+        off = ptr - self._ws.data_ptr()
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self._ws[off:off + n].view(dtype).view(*shape)
+
+    # ------------------------------------------------------------------ the path
+    def reset(self):
+        check(self.lib.suta_reset(self._h, _stream_ptr()))
+
+    def frontend(self):
+        check(self.lib.suta_frontend(self._h, _stream_ptr()))
+
+    def forward(self) -> torch.Tensor:
+        check(self.lib.suta_forward(self._h, _stream_ptr()))
+        return self.logits()
+
+    def loss_backward(self, hp: AdaptHyper):
+        h = hp.to_c()
+        check(self.lib.suta_loss_backward(self._h, C.byref(h), _stream_ptr()))
+
+    def optimizer_step(self, hp: AdaptHyper):
+        h = hp.to_c()
+        check(self.lib.suta_optimizer_step(self._h, C.byref(h), _stream_ptr()))
+
+    def adapt_step(self, hp: AdaptHyper) -> torch.Tensor:
+        h = hp.to_c()
+        check(self.lib.suta_adapt_step(self._h, C.byref(h), _stream_ptr()))
+        return self.logits()
+
+    def decode_ids(self) -> List[List[int]]:
+        """Greedy CTC on the device; returns the collapsed id sequence per utterance (one D2H copy)."""
+        check(self.lib.suta_decode(self._h, _stream_ptr()))
+        ids = self._view(self.lib.suta_collapsed_ids(self._h), (self.total_frames,), torch.int32)
+        lens = self._view(self.lib.suta_collapsed_len(self._h), (self.n_utts,), torch.int32)
+        ids_h, lens_h = ids.cpu().numpy(), lens.cpu().numpy()
+        return [ids_h[o:o + n].tolist() for o, n in zip(self.frame_off, lens_h)]
+
+    # ------------------------------------------------------------------ views
+    def logits(self) -> torch.Tensor:
+        return self._view(self.lib.suta_logits(self._h), (self.total_frames, self.cfg.vocab_size), torch.float32)
+
+    def dlogits(self) -> torch.Tensor:
+        return self._view(self.lib.suta_dlogits(self._h), (self.total_frames, self.cfg.vocab_size), torch.float32)
+
+    def losses(self) -> torch.Tensor:
+        return self._view(self.lib.suta_losses(self._h), (3, self.n_utts), torch.float32)
+
+    def params(self) -> torch.Tensor:
+        return self._view(self.lib.suta_params(self._h), (self.n_utts, self.n_params), torch.float32)
+
+    def grads(self) -> torch.Tensor:
+        return self._view(self.lib.suta_grads(self._h), (self.n_utts, self.n_params), torch.float32)
+
+    def argmax_ids(self) -> torch.Tensor:
+        return self._view(self.lib.suta_argmax_ids(self._h), (self.total_frames,), torch.int32)
+
+    def utt_logits(self, u: int) -> torch.Tensor:
+        o, t = int(self.frame_off[u]), int(self.frames[u])
+        return self.logits()[o:o + t]
+
+    def utt_params(self, u: int) -> Dict[str, torch.Tensor]:
+        P = self.params()[u]
+        return {name: P[off:off + size] for name, off, size in self.segments}
+
+    def debug_buffer(self, name: str) -> torch.Tensor:
+        r, c, dt = C.c_int64(), C.c_int64(), C.c_int()
+        ptr = self.lib.suta_debug_buffer(self._h, name.encode(), C.byref(r), C.byref(c), C.byref(dt))
+        if not ptr:
+            raise KeyError(name)
+        return self._view(ptr, (r.value, c.value), torch.bfloat16 if dt.value == 1 else torch.float32)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.suta_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.suta_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
