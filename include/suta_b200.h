@@ -95,8 +95,9 @@ int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_samples, void*
                      void* stream);
 int suta_batch_info(const suta_engine* e, int64_t* total_frames, int32_t* frames /*[U]*/, int64_t* frame_off /*[U]*/,
                     int64_t* sample_off /*[U]*/, int64_t* total_samples);
-/* raw waveform, packed at sample_off; `is_host` selects the copy kind (pinned host memory recommended) */
-int suta_batch_set_audio(suta_engine* e, const float* wav, int is_host, void* stream);
+/* waveform packed at sample_off. flags: bit0 = `wav` is host memory (pinned recommended), bit1 = already normalised
+ * by the caller (HF processor output, REF/main.py:322) so the device normalisation is skipped */
+int suta_batch_set_audio(suta_engine* e, const float* wav, int flags, void* stream);
 
 int suta_reset(suta_engine* e, void* stream);                       /* load_model_and_optimizer, REF/main.py:147-155 */
 int suta_frontend(suta_engine* e, void* stream);                    /* HF/feature_extraction_wav2vec2.py:95 + HF:409-419 */
@@ -118,6 +119,9 @@ int32_t* suta_collapsed_ids(const suta_engine* e); /* DEV i32 [total_frames], ut
 int32_t* suta_collapsed_len(const suta_engine* e); /* DEV i32 [U] */
 const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype);
 int64_t suta_launch_count(const suta_engine* e); /* kernels launched by this engine since creation */
+/* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg). Reads and clears the counters collected
+ * so far (any pointer may be NULL), then switches collection on/off. */
+int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
 /* ---- single operators (the kernels behind the calls above, exposed for parity tests) ------------------- */
 /* D[M,N] = A[M,K] B[N,K]^T (+bias)(gelu / gelu')(+residual), tcgen05 GEMM; out_f32 and/or out_bf16 */
@@ -136,6 +140,8 @@ int suta_op_attention_bwd(const void* qkv, const void* O, const void* dO, const 
                           const int32_t* blk_tab, int n_blk, int H, int heads, int64_t M, void* stream);
 int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef, float temp,
                  int reweight, int not_blank, float* loss /*[3U]*/, float* dlogits_f32, void* dlogits_bf16, void* stream);
+/* out[row] = entropy(softmax(logits[row]/temp)), V = 32: softmax_entropy, REF/main.py:26-28 */
+int suta_op_softmax_entropy(const float* logits, int64_t rows, float temp, float* out, void* stream);
 int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,
                  int step_index, const suta_hyper* h, void* shadow_bf16, void* stream);
 int suta_op_decode(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, int V, int32_t* ids,

@@ -70,6 +70,12 @@ struct suta_engine {
   long long fp_g = 0, fp_b = 0, enc_g = 0, enc_b = 0;
   std::vector<long long> ln1_g, ln1_b, ln2_g, ln2_b;
   long long launches = 0;
+  // optional per-launch GEMM timing (bench.py roofline leg): CUDA event pairs around every tcgen05 GEMM launch
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double prof_flops = 0.0;
+  bool audio_normalized = false;
 
   // ---- batch state ----
   int U = 0;
@@ -266,7 +272,20 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   e->launches += 1;
-  return gemm_bf16_tc(p, st);
+  if (!e->profile) return gemm_bf16_tc(p, st);
+  if (e->ev_used + 2 > e->ev_pool.size()) {
+    size_t old = e->ev_pool.size();
+    e->ev_pool.resize(old + 512);
+    for (size_t i = old; i < e->ev_pool.size(); ++i) CUDA_TRY(cudaEventCreate(&e->ev_pool[i]));
+  }
+  CUDA_TRY(cudaEventRecord(e->ev_pool[e->ev_used], st));
+  int r = gemm_bf16_tc(p, st);
+  CUDA_TRY(cudaEventRecord(e->ev_pool[e->ev_used + 1], st));
+  e->ev_used += 2;
+  // algorithmic FLOPs of this launch: valid rows only (the M-block table may pad), all z slices
+  double rows = p.M;
+  e->prof_flops += 2.0 * rows * p.N * p.K * p.nz;
+  return r;
 }
 
 GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
@@ -296,7 +315,11 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int train_feature, 
   *out = e;
   return SUTA_OK;
 }
-extern "C" void suta_engine_destroy(suta_engine* e) { delete e; }
+extern "C" void suta_engine_destroy(suta_engine* e) {
+  if (!e) return;
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  delete e;
+}
 extern "C" int64_t suta_engine_param_count(const suta_engine* e) { return e ? e->n_params : 0; }
 extern "C" int suta_engine_param_layout(const suta_engine* e, suta_param_seg* segs, int max_segs, int* n_segs) {
   SUTA_CHECK_ARG(e && n_segs);
@@ -400,11 +423,33 @@ extern "C" int suta_batch_info(const suta_engine* e, int64_t* total_frames, int3
   return SUTA_OK;
 }
 
-extern "C" int suta_batch_set_audio(suta_engine* e, const float* wav, int is_host, void* stream) {
+extern "C" int suta_batch_set_audio(suta_engine* e, const float* wav, int flags, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0 && wav);
-  CUDA_TRY(cudaMemcpyAsync(e->wav, wav, sizeof(float) * e->S, is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                           S(stream)));
+  const bool is_host = flags & 1;
+  e->audio_normalized = (flags & 2) != 0;
+  CUDA_TRY(cudaMemcpyAsync(e->audio_normalized ? e->wav_norm : e->wav, wav, sizeof(float) * e->S,
+                           is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, S(stream)));
   e->frontend_done = false;
+  return SUTA_OK;
+}
+
+extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops) {
+  SUTA_CHECK_ARG(e);
+  if (gemm_ms || gemm_launches || gemm_flops) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, e->ev_pool[i], e->ev_pool[i + 1]));
+      ms += t;
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_launches) *gemm_launches = (int64_t)(e->ev_used / 2);
+    if (gemm_flops) *gemm_flops = e->prof_flops;
+  }
+  e->ev_used = 0;
+  e->prof_flops = 0.0;
+  e->profile = enable != 0;
   return SUTA_OK;
 }
 
@@ -419,7 +464,8 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   const suta_model_cfg& c = e->cfg;
   cudaStream_t st = S(stream);
-  SUTA_TRY(normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
+  if (!e->audio_normalized)
+    SUTA_TRY(normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
   Conv0Args a{};
   a.x = e->wav_norm; a.samp_off = e->d_samp_off; a.L0 = e->d_L0; a.out_off = e->d_off0;
   a.w = e->w.conv0_w; a.w_stride = 0;
@@ -438,7 +484,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     p.b = {reinterpret_cast<const bf16*>(e->w.conv_w[l]), Cout, (long long)k * Cin};
     p.M = 0; p.N = Cout; p.K = k * Cin;
     p.mblk = e->d_mblk[l]; p.num_mblk = e->n_mblk[l];
-    p.M = e->n_mblk[l] * 128;
+    { long long rows = 0; for (int u = 0; u < e->U; ++u) rows += e->L[l][u]; p.M = (int)rows; }   // valid rows (FLOP accounting); tiles come from the table
     p.epi.act = 1;
     p.epi.out_bf16 = e->conv_out[l]; p.epi.out_ld = Cout;
     SUTA_TRY(gemm(e, p, st));
@@ -705,6 +751,9 @@ extern "C" int suta_op_loss(const float* logits, const int64_t* tok_off, const i
   la.em_coef = em_coef; la.temp = temp; la.reweight = reweight; la.not_blank = not_blank;
   la.loss = loss; la.dlogits_f32 = dlogits_f32; la.dlogits_bf16 = reinterpret_cast<bf16*>(dlogits_bf16);
   return suta_loss_forward_backward(la, S(stream));
+}
+extern "C" int suta_op_softmax_entropy(const float* logits, int64_t rows, float temp, float* out, void* stream) {
+  return softmax_entropy_rows(logits, rows, temp, out, S(stream));
 }
 extern "C" int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,
                             int step_index, const suta_hyper* h, void* shadow_bf16, void* stream) {

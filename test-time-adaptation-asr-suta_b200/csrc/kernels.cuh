@@ -76,6 +76,8 @@ struct LossArgs {
   int reweight, not_blank;
 };
 int suta_loss_forward_backward(const LossArgs& a, cudaStream_t stream);
+// out[row] = entropy of softmax(logits[row] / temp)   (REF/main.py:26-28), V = 32
+int softmax_entropy_rows(const float* logits, long long rows, float temp, float* out, cudaStream_t stream);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 struct AdamArgs {

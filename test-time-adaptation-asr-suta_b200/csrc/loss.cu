@@ -166,7 +166,23 @@ suta_loss_kernel(LossArgs a) {
   }
 }
 
+__global__ void entropy_rows_kernel(const float* __restrict__ logits, long long rows, float inv_temp, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowStats r = row_softmax(logits[row * V + lane], inv_temp, lane);
+  if (lane == 0) out[row] = r.H;
+}
+
 }  // namespace
+
+int softmax_entropy_rows(const float* logits, long long rows, float temp, float* out, cudaStream_t stream) {
+  SUTA_CHECK_ARG(logits && out && temp > 0.f);
+  if (rows <= 0) return SUTA_OK;
+  entropy_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(logits, rows, 1.0f / temp, out);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
 
 int suta_loss_forward_backward(const LossArgs& a, cudaStream_t stream) {
   SUTA_CHECK_ARG(a.n_utts > 0 && a.logits && a.loss && a.temp > 0.f);

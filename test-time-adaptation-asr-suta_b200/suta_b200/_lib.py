@@ -81,6 +81,7 @@ SIGNATURES = {
     "suta_collapsed_len": (c_void_p, [c_void_p]),
     "suta_debug_buffer": (c_void_p, [c_void_p, C.c_char_p, C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(c_int)]),
     "suta_launch_count": (c_int64, [c_void_p]),
+    "suta_profile": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
     "suta_op_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
                              c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "suta_op_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
@@ -92,6 +93,7 @@ SIGNATURES = {
                                       c_int, c_int64, c_void_p]),
     "suta_op_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
+    "suta_op_softmax_entropy": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "suta_op_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, C.POINTER(Hyper),
                              c_void_p, c_void_p]),
     "suta_op_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

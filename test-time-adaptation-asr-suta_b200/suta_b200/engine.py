@@ -190,11 +190,20 @@ class SutaEngine:
         self.sample_off = np.asarray(soff[:], dtype=np.int64)
         self.lengths = lens.copy()
 
-    def set_audio(self, packed: torch.Tensor):
-        """packed: fp32 [total_samples] (pinned host or device), utterance u at sample_off[u]."""
+    def set_audio(self, packed: torch.Tensor, normalized: bool = False):
+        """packed: fp32 [total_samples] (pinned host or device), utterance u at sample_off[u].
+        normalized=True: the caller already applied the HF processor's zero-mean/unit-variance (REF/main.py:322)."""
         assert packed.dtype == torch.float32 and packed.numel() >= self.total_samples
         self._audio_keep = packed
-        check(self.lib.suta_batch_set_audio(self._h, C.c_void_p(packed.data_ptr()), int(not packed.is_cuda), _stream_ptr()))
+        flags = int(not packed.is_cuda) | (2 if normalized else 0)
+        check(self.lib.suta_batch_set_audio(self._h, C.c_void_p(packed.data_ptr()), flags, _stream_ptr()))
+
+    def profile(self, enable: bool):
+        """Read-and-clear the per-launch GEMM timers, then switch collection on/off.
+        Returns (gemm_ms, gemm_launches, gemm_flops) accumulated since the previous call."""
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        check(self.lib.suta_profile(self._h, int(enable), C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
 
     def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
         off = ptr - self._ws.data_ptr()

@@ -1,0 +1,76 @@
+"""GPU: every CUDA operator, called through the C ABI, against fp32 torch / the oracle (tolerances stated here).
+fp32 outputs of bf16-operand GEMMs must match an fp32 reference on the same bf16 inputs to accumulation-order noise
+(1e-5 relative); bf16 outputs carry one bf16 rounding (2^-9 relative per element, < 4e-3 in norm)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+F32, BF16 = 1e-5, 4e-3
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import gpu_checks
+    return gpu_checks
+
+
+def test_gemm_plain(K):
+    r = K.check_gemm_plain()
+    assert r["nan"] == 0 and r["rel"] < F32
+
+
+def test_gemm_epilogues(K):
+    r = K.check_gemm_epilogue()
+    assert r["res_rel"] < F32 and r["gelu_bwd_rel"] < F32
+    assert r["gelu_rel"] < BF16 and r["aux_rel"] < BF16 and r["res16_rel"] < BF16
+
+
+def test_gemm_shapes_of_the_path(K):
+    for name, rel in K.check_gemm_shapes().items():
+        assert rel < 2e-5, name
+
+
+def test_gemm_overlapping_window_operand(K):
+    assert K.check_gemm_window()["rel"] < 2e-5
+    assert K.check_gemm_window(R=300, CG=64, Kp=16, N=64)["rel"] < 2e-5
+    assert K.check_gemm_strided_conv()["rel"] < F32
+    assert K.check_gemm_strided_conv(L=4003, C=512, k=2, s=2, N=512)["rel"] < F32
+
+
+@pytest.mark.parametrize("N,bf16_in", [(768, False), (512, True), (1024, False), (128, False), (64, True)])
+def test_layernorm_forward_backward(K, N, bf16_in):
+    r = K.check_layernorm(N, (70, 3, 129, 64), 5 + N, bf16_in)
+    assert r["y_rel"] < F32 and r["dx_rel"] < F32 and r["dparam_rel"] < F32
+    assert r["y16_rel"] < BF16 and r["dx16_rel"] < BF16
+
+
+@pytest.mark.parametrize("Ts,heads", [((249, 64, 1, 130), 2), ((1749,), 1), ((63, 65, 128, 129), 12)])
+def test_attention_forward_backward(K, Ts, heads):
+    r = K.check_attention(Ts, heads)
+    assert r["nan"] == 0
+    assert r["o_rel"] < 6e-3 and r["dq_rel"] < 8e-3 and r["dk_rel"] < 8e-3 and r["dv_rel"] < 8e-3
+
+
+@pytest.mark.parametrize("em,rew,nb", [(0.3, True, True), (0.3, False, False), (1.0, False, True), (0.0, True, False)])
+def test_fused_loss_matches_reference_formulas(K, em, rew, nb):
+    r = K.check_loss(em_coef=em, reweight=rew, not_blank=nb)
+    assert r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4 and r["bf16_rel"] < BF16
+
+
+def test_fused_loss_all_blank_and_single_frame(K):
+    r = K.check_loss(Ts=(1, 2, 1874), blank_bias=0.5)
+    assert r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4
+
+
+def test_adam_with_multiplicities(K):
+    r = K.check_adam()
+    assert r["frozen_moved"] == 0.0 and r["delta_rel"] < 1e-4 and r["m_rel"] < 1e-5 and r["v_rel"] < 1e-4
+
+
+def test_ctc_decode_bit_exact(K):
+    r = K.check_decode()
+    assert r == {"argmax_mismatch": 0, "collapse_mismatch": 0}
+    assert K.check_decode(Ts=(1, 1, 1874, 2), seed=3) == {"argmax_mismatch": 0, "collapse_mismatch": 0}

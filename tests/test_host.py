@@ -1,0 +1,90 @@
+"""CPU: host-side logic of the package (no CUDA calls)."""
+import re
+import types
+
+import numpy as np
+import pytest
+
+from oracle import suta_oracle as O
+from suta_b200 import ModelConfig
+from suta_b200.data import librispeech_shaped
+from suta_b200.shard import bucket_batches, shard_lpt, utterance_cost
+from suta_b200.text import CTCVocab
+from suta_b200.wer import wer, wer_counts
+
+
+def test_frames_formula_matches_oracle_and_survey():
+    for cfg, o in ((ModelConfig.base(), O.W2V2Config.base()), (ModelConfig.tiny(), O.W2V2Config.tiny())):
+        for n in (400, 2000, 80000, 104000, 480000, 560000, 123457):
+            assert cfg.frames(n) == o.frames(n)
+    b = ModelConfig.base()
+    assert (b.frames(80000), b.frames(104000), b.frames(480000), b.frames(560000)) == (249, 324, 1499, 1749)
+    assert b.frames(b.min_samples) == 1 and b.frames(b.min_samples - 1) < 1
+
+
+def test_text_and_wer_agree_with_oracle():
+    v = CTCVocab()
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        ids = rng.integers(0, 32, rng.integers(0, 60)).tolist()
+        col = O.ctc_collapse(ids)
+        assert v.ids_to_text(col) == O.ctc_ids_to_text(col)
+    words = ["A", "B", "C", "D", "E"]
+    for _ in range(50):
+        r = " ".join(rng.choice(words, rng.integers(1, 12)))
+        h = " ".join(rng.choice(words, rng.integers(0, 12)))
+        assert wer_counts([r], [h]) == O.wer_counts([r], [h])
+    assert wer("a b c d", "a x c") == 0.5
+    with pytest.raises(ValueError):
+        wer_counts(["a"], [])
+
+
+def test_vocab_matches_reference_table():
+    assert CTCVocab().id_to_tok == O.VOCAB
+
+
+def test_shard_lpt_is_a_balanced_partition():
+    utts = librispeech_shaped(500)
+    cfg = ModelConfig.base()
+    costs = [utterance_cost(cfg.frames(u.n_samples)) for u in utts]
+    for w in (1, 2, 4, 8):
+        shards = shard_lpt(costs, w)
+        assert sorted(i for s in shards for i in s) == list(range(500))
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) / (sum(loads) / w) < 1.05
+
+
+def test_bucket_batches_respect_limits_and_cover():
+    utts = librispeech_shaped(300)
+    cfg = ModelConfig.base()
+    frames = [cfg.frames(u.n_samples) for u in utts]
+    batches = bucket_batches(frames, list(range(300)), 64, 20000)
+    assert sorted(i for b in batches for i in b) == list(range(300))
+    for b in batches:
+        assert len(b) <= 64 and (len(b) == 1 or sum(frames[i] for i in b) <= 20000)
+        assert [frames[i] for i in b] == sorted((frames[i] for i in b), reverse=True)
+
+
+def test_synthetic_set_shape():
+    utts = librispeech_shaped(2939)
+    d = np.array([u.duration for u in utts])
+    assert len(utts) == 2939 and d.min() >= 2.0 and d.max() <= 35.0
+    assert 5.0 < d.sum() / 3600 < 5.6          # LibriSpeech test-other is ~5.3 h
+    a, b = utts[3].audio(), utts[3].audio()
+    assert a.dtype == np.float32 and len(a) == utts[3].n_samples and np.array_equal(a, b)
+
+
+def test_collect_params_names_and_duplicates_match_reference_walk(capsys):
+    from suta_b200 import api
+    for cfg, ocfg in ((ModelConfig.base(), O.W2V2Config.base()), (ModelConfig.tiny(), O.W2V2Config.tiny())):
+        names_all = {f"{nm}.{leaf}" for nm, _k, leaves in api._module_order(cfg) for leaf in leaves}
+        model = types.SimpleNamespace(cfg=cfg, engine=types.SimpleNamespace(train_feature=True),
+                                      _params={n: types.SimpleNamespace(name=n, requires_grad=False) for n in names_all})
+        for tf in (False, True):
+            for bias_only in (False, True):
+                params, names = api.collect_params(model, bias_only, tf, False, True)
+                assert sorted(names) == sorted(O.collect_param_names(ocfg, bias_only=bias_only, train_feature=tf))
+                assert [p.name for p in params] == names
+    capsys.readouterr()
+    with pytest.raises(NotImplementedError):
+        api.collect_params(model, False, False, True, True)

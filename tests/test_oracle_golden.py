@@ -1,0 +1,98 @@
+"""CPU: the oracle restatement against the golden vectors produced by the unmodified reference (make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import suta_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["tiny_ln", "tiny_feat", "tiny_short", "base_ln_5s", "base_ln_5s_noblank", "base_feat_2s"]
+
+
+def load(case):
+    z = np.load(os.path.join(GOLD, case + ".npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_decode_of_reference_logits_matches_reference_transcripts(case):
+    z, meta = load(case)
+    for k, text in meta["texts"].items():
+        assert O.ctc_greedy_decode(z[f"logits_{k}"]) == text
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_loss_and_closed_form_gradient_on_reference_logits(case):
+    z, meta = load(case)
+    h = meta["hyper"]
+    lg = z["logits_0"]
+    val, grad = O.suta_loss_grad_closed(lg, h["em_coef"], h["reweight"], h["temp"], h["not_blank"])
+    assert abs(val - z["losses"][0]) / abs(z["losses"][0]) < 1e-5          # loss of step 1's training forward
+    t = torch.tensor(lg[None], dtype=torch.float64, requires_grad=True)
+    O.suta_loss(t, h["em_coef"], h["reweight"], h["temp"], h["not_blank"]).backward()
+    np.testing.assert_allclose(grad, t.grad[0].numpy(), rtol=1e-7, atol=1e-14)
+
+
+@pytest.mark.parametrize("case", ["tiny_ln", "tiny_feat", "tiny_short"])
+def test_oracle_adaptation_reproduces_reference(case):
+    z, meta = load(case)
+    cfg = getattr(O.W2V2Config, meta["cfg"])()
+    sd = O.init_weights(cfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"])
+    x = O.normalize_audio(O.synth_audio(meta["n_samples"], meta["audio_seed"]))
+    res = O.adapt_utterance(cfg, sd, x, steps=meta["steps"], train_feature=meta["train_feature"], **meta["hyper"])
+    np.testing.assert_allclose(res.logits0, z["logits_0"], atol=5e-5)
+    np.testing.assert_allclose(res.losses, z["losses"], rtol=2e-5)
+    for k, text in meta["texts"].items():
+        if int(k):
+            np.testing.assert_allclose(res.logits[int(k)], z[f"logits_{k}"], atol=3e-4)
+            assert res.texts[int(k)] == text
+    names = O.collect_param_names(cfg, train_feature=meta["train_feature"])
+    assert sorted(names) == sorted(meta["names"])                           # same duplicates as REF/main.py:62-103
+    for n in set(names):
+        ref = z["param:" + n]
+        if ref.dtype == np.float32:
+            d_ref, d_got = ref - sd[n].numpy(), res.params[n] - sd[n].numpy()
+            assert np.abs(d_ref - d_got).max() <= 0.05 * np.abs(d_ref).max() + 1e-9
+
+
+def test_param_multiplicities_match_survey():
+    names = O.collect_param_names(O.W2V2Config.base(), train_feature=True)
+    mult = {}
+    for n in names:
+        mult[n] = mult.get(n, 0) + 1
+    assert len(names) == 96 and len(mult) == 63
+    assert mult["wav2vec2.feature_extractor.conv_layers.3.conv.weight"] == 4
+    assert mult["wav2vec2.feature_extractor.conv_layers.0.layer_norm.weight"] == 4
+    assert mult["wav2vec2.feature_projection.layer_norm.bias"] == 3
+    assert mult["wav2vec2.feature_projection.projection.weight"] == 2
+    assert mult["wav2vec2.encoder.layers.5.final_layer_norm.weight"] == 1
+    assert len(O.collect_param_names(O.W2V2Config.base())) == 52
+
+
+def test_adam_multiplicity_equals_sequential_substeps():
+    rng = np.random.default_rng(0)
+    g = rng.standard_normal(50).astype(np.float32)
+    p1 = rng.standard_normal(50).astype(np.float32)
+    p4 = p1.copy()
+    m1, v1, m4, v4 = (np.zeros(50, np.float32) for _ in range(4))
+    s = 0
+    for _ in range(4):
+        s = O.adam_update(p1, g, m1, v1, s, 1e-3, k=1)
+    O.adam_update(p4, g, m4, v4, 0, 1e-3, k=4)
+    np.testing.assert_allclose(p1, p4, rtol=0, atol=0)
+
+
+def test_decode_known_answer():
+    ids = [0, 11, 11, 0, 5, 15, 15, 0, 15, 8, 4, 4, 18, 8, 13, 15, 14, 0, 1, 2, 3]
+    assert O.ctc_ids_to_text(O.ctc_collapse(ids)) == "HELLO WORLD<s></s><unk>"
+    assert O.ctc_ids_to_text(O.ctc_collapse([0, 0, 0])) == ""
+    assert O.ctc_ids_to_text(O.ctc_collapse([])) == ""
+
+
+def test_wer_known_answers():
+    assert O.wer(["a b c d"], ["a x c"]) == 0.5
+    assert O.wer_counts(["a b", "c"], ["a b", ""]) == (1, 3)
+    assert O.wer(["hello world"], ["hello world"]) == 0.0
