@@ -128,6 +128,10 @@ int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_laun
 int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride, const void* b, int64_t b_rows, int64_t b_row_stride,
                  int M, int N, int K, float* out_f32, void* out_bf16, int out_ld, const float* bias,
                  const float* residual, int res_ld, int act, const void* aux_in, void* aux_out, int aux_ld, void* stream);
+/* same contraction with per-operand memory order: a_mn / b_mn = 1 -> operand stored [K rows][M|N contiguous]
+ * (weight-gradient GEMMs reduce over time, so both operands are naturally in that order); fp32 output */
+int suta_op_gemm_mn(const void* a, int64_t a_rows, int64_t a_row_stride, int a_mn, const void* b, int64_t b_rows,
+                    int64_t b_row_stride, int b_mn, int M, int N, int K, float* out_f32, int out_ld, void* stream);
 int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P, int64_t pstride,
                           int g_off, int b_off, float* y_f32, void* y_bf16, float* mean, float* rstd, int64_t M, int N,
                           float eps, void* stream);

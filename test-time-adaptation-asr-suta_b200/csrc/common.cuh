@@ -54,10 +54,22 @@ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of erff's
+// branchy polynomial -- the GEMM epilogues evaluate it for every element of the FFN / conv activations.
+__device__ __forceinline__ float erf_fast(float z) {
+  const float a = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = 1.0f - p * t * __expf(-a * a);
+  return copysignf(y, z);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 // d/dx [ x * Phi(x) ] = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
   float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
@@ -190,6 +202,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version 1 bits [46,48)
   d |= (uint64_t)2 << 61;                               // SWIZZLE_128B         bits [61,64)
+  return d;
+}
+// MN-major, 128-byte-swizzled: 64 M|N elements per 128-byte row, 8 k-rows per 1024-byte atom; atoms along M|N are
+// `lbo` bytes apart (here 8192: one 64x64 TMA box), atoms along K 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;                     // leading byte offset: next 64 M|N elements
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: next 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128.

@@ -1,0 +1,225 @@
+// Backward pieces of the CNN feature extractor for --train_feature (REF/main.py:88-94 makes every parameter of
+// feature_extractor / feature_projection trainable, so autograd reaches the waveform-side layers):
+//   cast_params_bf16        refresh the bf16 GEMM-operand copy of per-utterance trainable weights after an update
+//   conv_col2im_gelu_grad   gather the dgrad GEMM result Z[t,(j,ci)] back to input rows r = s*t + j and multiply by
+//                           GELU'(pre-activation of the layer below)                 (backward of HF:269-272)
+//   gelu_grad_to_padded     dX * GELU'(pre) written into a per-utterance 64-row-aligned slab (zero rows between
+//                           utterances) so the weight-gradient GEMM can reduce over time in 64-row steps
+//   conv0_groupnorm_backward  backward of Conv1d(1->C,k,s) + GroupNorm(per channel over time)  (HF:319-323)
+//   colsum_per_utt          bias gradient of the per-utterance projection
+// The contractions themselves (dgrad, wgrad) run on the tcgen05 GEMM with MN-major operands (gemm_tc.cu).
+#include "kernels.cuh"
+
+namespace {
+
+__global__ void cast_kernel(const float* __restrict__ P, long long pstride, long long seg_off, long long size, int U,
+                            bf16* __restrict__ out) {
+  const long long total = size * U;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long u = i / size, e = i - u * size;
+    out[i] = __float2bfloat16(P[u * pstride + seg_off + e]);
+  }
+}
+
+__global__ void gelu_grad_pad_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
+                                     const int* __restrict__ row_utt, const long long* __restrict__ tok_off,
+                                     const long long* __restrict__ pad_off, long long M, int C) {
+  const int c8 = C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * c8) return;
+  const long long row = idx / c8;
+  const int c = (int)(idx - row * c8) * 8;
+  const int u = row_utt[row];
+  const long long prow = pad_off[u] + (row - tok_off[u]);
+  float4 a = *reinterpret_cast<const float4*>(d + row * C + c), b = *reinterpret_cast<const float4*>(d + row * C + c + 4);
+  if (pre) {
+    uint4 p = *reinterpret_cast<const uint4*>(pre + row * C + c);
+    float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y), p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
+    a.x *= gelu_erf_grad(p0.x); a.y *= gelu_erf_grad(p0.y); a.z *= gelu_erf_grad(p1.x); a.w *= gelu_erf_grad(p1.y);
+    b.x *= gelu_erf_grad(p2.x); b.y *= gelu_erf_grad(p2.y); b.z *= gelu_erf_grad(p3.x); b.w *= gelu_erf_grad(p3.y);
+  }
+  *reinterpret_cast<uint4*>(out + prow * C + c) =
+      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
+constexpr int C2I_ROWS = 16;
+
+__global__ void __launch_bounds__(256)
+col2im_kernel(Col2imArgs a) {
+  const int u = blockIdx.y;
+  const int Lo = a.L_out[u], Li = a.L_in[u];
+  const int c8n = a.C >> 3;
+  const long long oo = a.off_out[u], oi = a.off_in[u];
+  const int ldz = a.k * a.C;
+  for (int idx = threadIdx.x; idx < C2I_ROWS * c8n; idx += blockDim.x) {
+    const int r = blockIdx.x * C2I_ROWS + idx / c8n;
+    if (r >= Lo) continue;
+    const int c = (idx % c8n) * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < a.k; ++j) {
+      const int rj = r - j;
+      if (rj < 0 || rj % a.s != 0) continue;
+      const int t = rj / a.s;
+      if (t >= Li) continue;
+      uint4 z = *reinterpret_cast<const uint4*>(a.Z + (oi + t) * ldz + j * a.C + c);
+      float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y), z2 = unpack_bf16x2(z.z), z3 = unpack_bf16x2(z.w);
+      acc[0] += z0.x; acc[1] += z0.y; acc[2] += z1.x; acc[3] += z1.y;
+      acc[4] += z2.x; acc[5] += z2.y; acc[6] += z3.x; acc[7] += z3.y;
+    }
+    uint4 p = *reinterpret_cast<const uint4*>(a.pre + (oo + r) * a.C + c);
+    float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y), p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
+    acc[0] *= gelu_erf_grad(p0.x); acc[1] *= gelu_erf_grad(p0.y); acc[2] *= gelu_erf_grad(p1.x); acc[3] *= gelu_erf_grad(p1.y);
+    acc[4] *= gelu_erf_grad(p2.x); acc[5] *= gelu_erf_grad(p2.y); acc[6] *= gelu_erf_grad(p3.x); acc[7] *= gelu_erf_grad(p3.y);
+    *reinterpret_cast<uint4*>(a.out + (oo + r) * a.C + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// ---- conv0 + GroupNorm backward -------------------------------------------------------------------------------
+// y = gamma * zhat + beta, zhat = (z - mu) * rstd, z[t] = sum_j w[j] x[s t + j]; given dy (already times GELU'):
+//   dbeta = S1 = sum_t dy,  dgamma = S2 = sum_t dy zhat,
+//   dz[t] = rstd*gamma*(dy[t] - S1/L - zhat[t]*S2/L),  dw[j] = sum_t dz[t] x[s t + j]
+//         = rstd*gamma*(A_j - (S1/L) B_j - (S2/L) C_j),  A_j = sum dy x, B_j = sum x, C_j = sum zhat x.
+constexpr int C0B_TT = 512;
+constexpr int C0B_MAXK = 16;
+constexpr int C0B_ACC = 2 + 2 * C0B_MAXK;   // S1, S2, A[16], C[16] per channel (B_j is channel independent)
+
+__global__ void __launch_bounds__(256)
+conv0_bwd_accum_kernel(Conv0BwdArgs a) {
+  extern __shared__ float sx[];
+  const int u = blockIdx.y;
+  const int L0 = a.L0[u];
+  const int t0 = blockIdx.x * C0B_TT;
+  if (t0 >= L0) return;
+  const int nt = min(C0B_TT, L0 - t0);
+  const float* x = a.x + a.samp_off[u] + (long long)t0 * a.stride;
+  const int nx = (nt - 1) * a.stride + a.k;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = x[i];
+  __syncthreads();
+  if (threadIdx.x < a.k) {     // B_j = sum_t x[s t + j]
+    float b = 0.f;
+    for (int t = 0; t < nt; ++t) b += sx[t * a.stride + threadIdx.x];
+    atomicAdd(a.acc_x + (long long)u * C0B_MAXK + threadIdx.x, (double)b);
+  }
+  const float* w = a.w + (long long)u * a.w_stride;
+  const long long row0 = a.out_off[u] + t0;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float wj[C0B_MAXK];
+#pragma unroll
+    for (int j = 0; j < C0B_MAXK; ++j) wj[j] = j < a.k ? w[(long long)c * a.k + j] : 0.f;
+    const double* st = a.stats + ((long long)u * a.C + c) * 2;
+    const double m = st[0] / L0;
+    const float mean = (float)m, rstd = (float)(1.0 / sqrt(st[1] / L0 - m * m + 1e-5));
+    float s1 = 0.f, s2 = 0.f, A[C0B_MAXK], Cc[C0B_MAXK];
+#pragma unroll
+    for (int j = 0; j < C0B_MAXK; ++j) A[j] = Cc[j] = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const float* xs = sx + t * a.stride;
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j < C0B_MAXK; ++j)
+        if (j < a.k) z += wj[j] * xs[j];
+      const float zh = (z - mean) * rstd;
+      const float dy = __bfloat162float(a.dy[(row0 + t) * a.C + c]);
+      s1 += dy;
+      s2 += dy * zh;
+#pragma unroll
+      for (int j = 0; j < C0B_MAXK; ++j)
+        if (j < a.k) { A[j] += dy * xs[j]; Cc[j] += zh * xs[j]; }
+    }
+    double* acc = a.acc + ((long long)u * a.C + c) * C0B_ACC;
+    atomicAdd(acc + 0, (double)s1);
+    atomicAdd(acc + 1, (double)s2);
+    for (int j = 0; j < a.k; ++j) {
+      atomicAdd(acc + 2 + j, (double)A[j]);
+      atomicAdd(acc + 2 + C0B_MAXK + j, (double)Cc[j]);
+    }
+  }
+}
+
+__global__ void conv0_bwd_finalize_kernel(Conv0BwdArgs a) {
+  const int u = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const int L0 = a.L0[u];
+  const double* st = a.stats + ((long long)u * a.C + c) * 2;
+  const double m = st[0] / L0;
+  const double rstd = 1.0 / sqrt(st[1] / L0 - m * m + 1e-5);
+  const double* acc = a.acc + ((long long)u * a.C + c) * C0B_ACC;
+  const double s1 = acc[0], s2 = acc[1];
+  const double gamma = a.P[(long long)u * a.pstride + a.g_off + c];
+  float* G = a.G + (long long)u * a.pstride;
+  G[a.b_off + c] = (float)s1;
+  G[a.g_off + c] = (float)s2;
+  for (int j = 0; j < a.k; ++j) {
+    const double bj = a.acc_x[(long long)u * C0B_MAXK + j];
+    G[a.w_off + (long long)c * a.k + j] = (float)(rstd * gamma * (acc[2 + j] - s1 / L0 * bj - s2 / L0 * acc[2 + C0B_MAXK + j]));
+  }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ x, const long long* __restrict__ tok_off, const int* __restrict__ T,
+                              float* __restrict__ G, long long gstride, long long g_off, int C) {
+  const int u = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* p = x + tok_off[u] * C + c;
+  float s = 0.f;
+  for (int t = 0; t < T[u]; ++t) s += p[(long long)t * C];
+  G[(long long)u * gstride + g_off + c] = s;
+}
+
+int grid_for(long long total) {
+  long long b = (total + 255) / 256, cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,
+                     cudaStream_t stream) {
+  SUTA_CHECK_ARG(P && out && size > 0 && n_utts > 0);
+  cast_kernel<<<grid_for(size * n_utts), 256, 0, stream>>>(P, pstride, seg_off, size, n_utts, out);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int gelu_grad_to_padded(const float* d, const bf16* pre, bf16* out, const int* row_utt, const long long* tok_off,
+                        const long long* pad_off, long long M, int C, cudaStream_t stream) {
+  SUTA_CHECK_ARG(C % 8 == 0);
+  long long n = M * (C >> 3);
+  if (n <= 0) return SUTA_OK;
+  gelu_grad_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, pre, out, row_utt, tok_off, pad_off, M, C);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int conv_col2im_gelu_grad(const Col2imArgs& a, cudaStream_t stream) {
+  SUTA_CHECK_ARG(a.C % 8 == 0 && a.n_utts > 0 && a.max_L_out > 0);
+  dim3 grid(ceil_div(a.max_L_out, C2I_ROWS), a.n_utts);
+  col2im_kernel<<<grid, 256, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream) {
+  SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0);
+  CUDA_TRY(cudaMemsetAsync(a.acc, 0, sizeof(double) * (size_t)a.n_utts * a.C * C0B_ACC, stream));
+  CUDA_TRY(cudaMemsetAsync(a.acc_x, 0, sizeof(double) * (size_t)a.n_utts * C0B_MAXK, stream));
+  dim3 grid(ceil_div(a.max_L0, C0B_TT), a.n_utts);
+  size_t smem = sizeof(float) * (C0B_TT * a.stride + a.k);
+  conv0_bwd_accum_kernel<<<grid, 256, smem, stream>>>(a);
+  conv0_bwd_finalize_kernel<<<dim3(ceil_div(a.C, 128), a.n_utts), 128, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
+                   int C, int n_utts, cudaStream_t stream) {
+  colsum_kernel<<<dim3(ceil_div(C, 128), n_utts), 128, 0, stream>>>(x, tok_off, T, G, gstride, g_off, C);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+long long conv0_bwd_scratch_doubles(int n_utts, int C) { return (long long)n_utts * C * C0B_ACC + (long long)n_utts * C0B_MAXK; }

@@ -69,6 +69,11 @@ struct suta_engine {
   // segment offsets
   long long fp_g = 0, fp_b = 0, enc_g = 0, enc_b = 0;
   std::vector<long long> ln1_g, ln1_b, ln2_g, ln2_b;
+  // train_feature segments (REF/main.py:88-94): GroupNorm affine, every conv weight, projection weight + bias
+  long long ln_params = 0;                         // size of the LayerNorm-only prefix of the trainable vector
+  long long gn_g = 0, gn_b = 0, proj_w_off = 0, proj_b_off = 0;
+  long long conv_w_off[SUTA_MAX_CONV] = {};
+  long long conv_w_size[SUTA_MAX_CONV] = {};
   long long launches = 0;
   // optional per-launch GEMM timing (bench.py roofline leg): CUDA event pairs around every tcgen05 GEMM launch
   bool profile = false;
@@ -97,6 +102,25 @@ struct suta_engine {
   int *d_n_samples = nullptr, *d_T = nullptr, *d_L0 = nullptr, *d_row_utt = nullptr;
   int4* d_mblk[SUTA_MAX_CONV] = {};
   int4* d_attn_tab = nullptr;
+  // train_feature only
+  std::vector<long long> off64;                    // [u] first row of utterance u in the 64-row-aligned token slabs
+  long long R64 = 0;
+  int n_tok_mblk = 0;
+  int4* d_tok_mblk = nullptr;                      // per-utterance M-blocks over packed tokens (per-utterance projection)
+  int4* d_dgrad_mblk[SUTA_MAX_CONV] = {};          // per-utterance M-blocks over layer-l rows (conv dgrad)
+  int4* d_ztab[SUTA_MAX_CONV + 1] = {};            // per-utterance reduction ranges of the wgrad GEMMs ([n_conv] = projection)
+  long long* d_off[SUTA_MAX_CONV] = {};            // [U] row offsets per layer
+  long long* d_dpre_off_last = nullptr;            // = off64 on device
+  int* d_L[SUTA_MAX_CONV] = {};                    // [U] valid rows per layer
+  bf16* conv_pre[SUTA_MAX_CONV] = {};              // pre-GELU activations (bf16)
+  bf16* conv_dpre[SUTA_MAX_CONV] = {};             // d(pre-activation), zero outside valid rows
+  bf16* w_shadow[SUTA_MAX_CONV] = {};              // bf16 copies of the per-utterance conv weights [U][Cout][k*Cin]
+  bf16* proj_shadow = nullptr;                     // [U][H][C]
+  bf16* zbuf = nullptr;                            // dgrad GEMM output [rows_l, k*Cin]
+  bf16* dh0_pad = nullptr;                         // [R64, H]
+  float* d_feat = nullptr;                         // [M, C]
+  double* c0_scratch = nullptr;
+  int max_L[SUTA_MAX_CONV] = {};
   // device buffers
   float *wav = nullptr, *wav_norm = nullptr;
   double* stats = nullptr;
@@ -143,6 +167,17 @@ int build_layout(suta_engine* e) {
     e->ln1_b[l] = add(1, 2, l, H);
     e->ln2_g[l] = add(0, 3, l, H);
     e->ln2_b[l] = add(1, 3, l, H);
+  }
+  e->ln_params = o;
+  if (e->train_feature) {
+    e->gn_g = add(2, 4, 0, c.conv_dim[0]);
+    e->gn_b = add(3, 4, 0, c.conv_dim[0]);
+    for (int l = 0; l < c.n_conv; ++l) {
+      e->conv_w_size[l] = (long long)c.conv_dim[l] * c.conv_kernel[l] * (l ? c.conv_dim[l - 1] : 1);
+      e->conv_w_off[l] = add(4, 4, l, e->conv_w_size[l]);     // packed [Cout][(tap, Cin)]
+    }
+    e->proj_w_off = add(5, 5, 0, (long long)H * C);
+    e->proj_b_off = add(6, 5, 0, H);
   }
   e->n_params = o;
   return SUTA_OK;
@@ -194,9 +229,12 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
     const bool last = l == c.n_conv - 1;
     for (int u = 0; u < U; ++u) {
       e->off[l][u] = r;
-      // rows of the next layer's implicit-GEMM view start at off/stride: keep offsets multiples of 8
-      r += last ? e->L[l][u] : ((e->L[l][u] + 7) & ~7);
+      // rows of the next layer's implicit-GEMM view start at off/stride: keep offsets multiples of 8; under
+      // train_feature the weight-gradient GEMMs reduce over time in 64-row steps, so utterances are 64-row aligned
+      const int al = e->train_feature ? 63 : 7;
+      r += last ? e->L[l][u] : ((e->L[l][u] + al) & ~al);
       if (l >= 1) e->n_mblk[l] += ceil_div(e->L[l][u], 128);
+      e->max_L[l] = u == 0 ? e->L[l][u] : (e->L[l][u] > e->max_L[l] ? e->L[l][u] : e->max_L[l]);
     }
     e->rows_total[l] = r;
     if (!last) SUTA_CHECK_ARG(8 % c.conv_stride[l + 1] == 0);
@@ -212,6 +250,15 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
     nblk += ceil_div(e->T[u], 64);
   }
   e->M = m;
+  e->off64.assign(U, 0);
+  e->n_tok_mblk = 0;
+  long long r64 = 0;
+  for (int u = 0; u < U; ++u) {
+    e->off64[u] = r64;
+    r64 += (e->T[u] + 63) & ~63;
+    e->n_tok_mblk += ceil_div(e->T[u], 128);
+  }
+  e->R64 = r64;
   e->R = p;                       // padded rows per group slab (leading, between-utterance and trailing zero rows)
   e->Rm = e->R - c.pos_k + 1;     // number of K-tap windows
   e->n_attn_blk = nblk;
@@ -265,6 +312,32 @@ void carve(suta_engine* e, Bump& b) {
   e->P = b.take<float>((size_t)U * e->n_params); e->G = b.take<float>((size_t)U * e->n_params);
   e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
   e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
+  if (e->train_feature) {
+    e->d_tok_mblk = b.take<int4>(e->n_tok_mblk);
+    e->d_dpre_off_last = b.take<long long>(U);
+    e->d_ztab[c.n_conv] = b.take<int4>(U);
+    size_t zmax = 0;
+    for (int l = 0; l < c.n_conv; ++l) {
+      const bool last = l == c.n_conv - 1;
+      const long long rows = last ? e->R64 : e->rows_total[l];
+      e->d_off[l] = b.take<long long>(U);
+      e->d_L[l] = b.take<int>(U);
+      e->conv_pre[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
+      e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 128) * c.conv_dim[l]);
+      if (l >= 1) {
+        e->d_dgrad_mblk[l] = b.take<int4>(e->n_mblk[l]);
+        e->d_ztab[l] = b.take<int4>(U);
+        e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
+        size_t z = (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
+        zmax = z > zmax ? z : zmax;
+      }
+    }
+    e->zbuf = b.take<bf16>(zmax);
+    e->proj_shadow = b.take<bf16>((size_t)U * H * C);
+    e->dh0_pad = b.take<bf16>((size_t)(e->R64 + 128) * H);
+    e->d_feat = b.take<float>((size_t)M * C);
+    e->c0_scratch = b.take<double>((size_t)conv0_bwd_scratch_doubles(U, c.conv_dim[0]));
+  }
   b.off = align_up(b.off, 256);
 }
 
@@ -284,7 +357,7 @@ int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   e->ev_used += 2;
   // algorithmic FLOPs of this launch: valid rows only (the M-block table may pad), all z slices
   double rows = p.M;
-  e->prof_flops += 2.0 * rows * p.N * p.K * p.nz;
+  e->prof_flops += p.flops > 0.0 ? p.flops : 2.0 * rows * p.N * p.K * p.nz;
   return r;
 }
 
@@ -304,13 +377,9 @@ GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
 extern "C" int suta_engine_create(const suta_model_cfg* cfg, int train_feature, suta_engine** out) {
   SUTA_CHECK_ARG(cfg && out);
   SUTA_TRY(check_cfg(*cfg));
-  if (train_feature) {
-    suta_set_last_error("train_feature (per-utterance CNN weights) is not implemented in this build");
-    return SUTA_ERR_ARG;
-  }
   suta_engine* e = new suta_engine();
   e->cfg = *cfg;
-  e->train_feature = train_feature;
+  e->train_feature = train_feature ? 1 : 0;
   build_layout(e);
   *out = e;
   return SUTA_OK;
@@ -394,10 +463,50 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
     for (int u = 0; u < U; ++u)
       for (int m0 = 0; m0 < e->L[l][u]; m0 += 128) {
         int rows = e->L[l][u] - m0 < 128 ? e->L[l][u] - m0 : 128;
-        tab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0), rows, 0));
+        // b_row_off selects the utterance's own weights under train_feature (stacked [U][Cout] rows)
+        tab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0), rows,
+                                e->train_feature ? u * c.conv_dim[l] : 0));
       }
     CUDA_TRY(up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size()));
     CUDA_TRY(cudaStreamSynchronize(st));   // `tab` is pageable stack-owned memory
+  }
+  if (e->train_feature) {
+    const int last = c.n_conv - 1;
+    std::vector<int4> tab;
+    for (int u = 0; u < U; ++u)
+      for (int m0 = 0; m0 < e->T[u]; m0 += 128)
+        tab.push_back(make_int4((int)(e->tok_off[u] + m0), (int)(e->tok_off[u] + m0), e->T[u] - m0 < 128 ? e->T[u] - m0 : 128,
+                                u * c.hidden));
+    CUDA_TRY(up(e->d_tok_mblk, tab.data(), sizeof(int4) * tab.size()));
+    CUDA_TRY(up(e->d_dpre_off_last, e->off64.data(), sizeof(long long) * U));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int l = 0; l < c.n_conv; ++l) {
+      CUDA_TRY(up(e->d_off[l], e->off[l].data(), sizeof(long long) * U));
+      CUDA_TRY(up(e->d_L[l], e->L[l].data(), sizeof(int) * U));
+      if (l >= 1) {
+        // rows of d(pre-activation) of layer l: own 64-aligned layout, except the last layer (token slab off64)
+        std::vector<int4> dg, zt;
+        for (int u = 0; u < U; ++u) {
+          const long long dro = l == last ? e->off64[u] : e->off[l][u];
+          for (int m0 = 0; m0 < e->L[l][u]; m0 += 128)
+            dg.push_back(make_int4((int)(dro + m0), (int)(dro + m0), e->L[l][u] - m0 < 128 ? e->L[l][u] - m0 : 128,
+                                   u * c.conv_dim[l]));
+          zt.push_back(make_int4((int)dro, (int)(e->off[l - 1][u] / c.conv_stride[l]), e->L[l][u], 0));
+        }
+        CUDA_TRY(up(e->d_dgrad_mblk[l], dg.data(), sizeof(int4) * dg.size()));
+        CUDA_TRY(up(e->d_ztab[l], zt.data(), sizeof(int4) * zt.size()));
+      }
+      CUDA_TRY(cudaStreamSynchronize(st));
+      // gap rows between utterances must be exact zeros: they are reduced over by the weight-gradient GEMMs
+      const long long rows = l == last ? e->R64 : e->rows_total[l];
+      CUDA_TRY(cudaMemsetAsync(e->conv_out[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
+      CUDA_TRY(cudaMemsetAsync(e->conv_dpre[l], 0, sizeof(bf16) * (size_t)(rows + 128) * c.conv_dim[l], st));
+    }
+    std::vector<int4> zt;
+    for (int u = 0; u < U; ++u) zt.push_back(make_int4((int)e->off64[u], (int)e->tok_off[u], e->T[u], 0));
+    CUDA_TRY(up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size()));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemsetAsync(e->dh0_pad, 0, sizeof(bf16) * (size_t)(e->R64 + 128) * c.hidden, st));
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   // zero rows of the padded positional-conv slabs never get written afterwards
@@ -453,11 +562,27 @@ extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t
   return SUTA_OK;
 }
 
+// bf16 GEMM-operand copies of the per-utterance trainable matrices (train_feature): refreshed after every update
+static int refresh_shadows(suta_engine* e, cudaStream_t st) {
+  if (!e->train_feature) return SUTA_OK;
+  const suta_model_cfg& c = e->cfg;
+  for (int l = 1; l < c.n_conv; ++l) {
+    SUTA_TRY(cast_params_bf16(e->P, e->n_params, e->conv_w_off[l], e->conv_w_size[l], e->U, e->w_shadow[l], st));
+    e->launches += 1;
+  }
+  SUTA_TRY(cast_params_bf16(e->P, e->n_params, e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->U,
+                            e->proj_shadow, st));
+  e->launches += 1;
+  e->frontend_done = false;      // the CNN output depends on the updated weights
+  return SUTA_OK;
+}
+
 extern "C" int suta_reset(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   e->launches += 1;
   e->opt_steps = 0;
-  return params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, S(stream));
+  SUTA_TRY(params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, S(stream)));
+  return refresh_shadows(e, S(stream));
 }
 
 extern "C" int suta_frontend(suta_engine* e, void* stream) {
@@ -472,6 +597,11 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   a.gn_shared_g = e->w.gn_g; a.gn_shared_b = e->w.gn_b;
   a.stats = e->stats + 2 * e->U;
   a.out = e->conv_out[0]; a.pre_out = nullptr;
+  if (e->train_feature) {        // per-utterance conv0 weight and GroupNorm affine live in the trainable vector
+    a.w = e->P + e->conv_w_off[0]; a.w_stride = e->n_params;
+    a.gn = UttParams{e->P, e->n_params}; a.g_off = (int)e->gn_g; a.b_off = (int)e->gn_b;
+    a.pre_out = e->conv_pre[0];
+  }
   a.n_utts = e->U; a.C = c.conv_dim[0]; a.k = c.conv_kernel[0]; a.stride = c.conv_stride[0]; a.max_L0 = e->max_L0;
   SUTA_TRY(conv0_groupnorm_gelu(a, st));
   e->launches += 4;
@@ -487,6 +617,10 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     { long long rows = 0; for (int u = 0; u < e->U; ++u) rows += e->L[l][u]; p.M = (int)rows; }   // valid rows (FLOP accounting); tiles come from the table
     p.epi.act = 1;
     p.epi.out_bf16 = e->conv_out[l]; p.epi.out_ld = Cout;
+    if (e->train_feature) {
+      p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin};
+      p.epi.aux_out = e->conv_pre[l]; p.epi.aux_ld = Cout;
+    }
     SUTA_TRY(gemm(e, p, st));
   }
   e->frontend_done = true;
@@ -509,6 +643,11 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   {
     GemmProblem p = dense(e->y_fp, M, C, reinterpret_cast<const bf16*>(e->w.proj_w), H);
     p.epi.bias = e->w.proj_b; p.epi.out_f32 = e->h0; p.epi.out_ld = H;
+    if (e->train_feature) {      // per-utterance projection weight / bias
+      p.b = {e->proj_shadow, (long long)e->U * H, C};
+      p.mblk = e->d_tok_mblk; p.num_mblk = e->n_tok_mblk;
+      p.epi.bias = e->P + e->proj_b_off; p.epi.bias_utt_stride = e->n_params;
+    }
     SUTA_TRY(gemm(e, p, st));
   }
   // positional conv embedding + GELU + residual               HF/modeling_wav2vec2.py:360-368, :690-691
@@ -578,7 +717,8 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   la.dlogits_f32 = e->dlogits; la.dlogits_bf16 = e->dlogits16; la.loss = e->losses; la.n_utts = e->U;
   la.em_coef = h->em_coef; la.temp = h->temp; la.reweight = h->reweight; la.not_blank = h->not_blank;
   SUTA_TRY(suta_loss_forward_backward(la, st));
-  CUDA_TRY(cudaMemsetAsync(e->G, 0, sizeof(float) * (size_t)e->U * e->n_params, st));
+  // only the LayerNorm segments are accumulated with atomics; every other gradient segment is written whole
+  CUDA_TRY(cudaMemset2DAsync(e->G, sizeof(float) * e->n_params, 0, sizeof(float) * e->ln_params, e->U, st));
   e->launches += 2;
 
   float* da = e->fa;   // gradient w.r.t. the current LayerNorm output
@@ -632,17 +772,87 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     p.epi.out_f32 = e->dcpos; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
-  SUTA_TRY(posconv_combine_grad(db, e->dcpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, nullptr, e->b16, M, H,
-                                -(c.pos_k / 2 - 1), st));
+  SUTA_TRY(posconv_combine_grad(db, e->dcpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->train_feature ? da : nullptr,
+                                e->b16, M, H, -(c.pos_k / 2 - 1), st));
   {  // projection dgrad
     GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.proj_w_t), C);
     p.epi.out_f32 = e->d_yfp; p.epi.out_ld = C;
+    if (e->train_feature) {      // d y = d h0 * W_u : W_u [H (reduction rows), C] is MN-major for this product
+      p.b = {e->proj_shadow, (long long)e->U * H, C, 1, C};
+      p.mblk = e->d_tok_mblk; p.num_mblk = e->n_tok_mblk;
+    }
     SUTA_TRY(gemm(e, p, st));
   }
-  // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
-  SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
-                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, st));
   e->launches += 4;
+  if (!e->train_feature) {
+    // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
+    return layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
+                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, st);
+  }
+
+  // ================= train_feature: projection weight/bias, then the whole CNN (REF/main.py:88-94) =================
+  const int last = c.n_conv - 1;
+  {  // d W_proj[u] = d h0[u]^T y_fp[u]  (reduction over the utterance's frames; both operands MN-major)
+    SUTA_TRY(gelu_grad_to_padded(da, nullptr, e->dh0_pad, e->d_row_utt, e->d_tok_off, e->d_dpre_off_last, M, H, st));
+    GemmProblem p;
+    p.a = {e->dh0_pad, e->R64 + 128, H, 1, H};
+    p.b = {e->y_fp, M, C, 1, C};
+    p.M = H; p.N = C; p.K = 0; p.nz = e->U;
+    p.ztab = e->d_ztab[c.n_conv];
+    p.epi.out_f32 = e->G + e->proj_w_off; p.epi.out_ld = C; p.out_z_stride = e->n_params;
+    p.flops = 2.0 * H * C * (double)M;
+    SUTA_TRY(gemm(e, p, st));
+    SUTA_TRY(colsum_per_utt(da, e->d_tok_off, e->d_T, e->G, e->n_params, e->proj_b_off, H, e->U, st));
+  }
+  // feature_projection.layer_norm with input gradient
+  SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
+                              (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, st));
+  // d(pre-activation) of the last conv layer, in the 64-row-aligned token slab
+  SUTA_TRY(gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
+                               e->d_dpre_off_last, M, C, st));
+  e->launches += 4;
+  for (int l = last; l >= 1; --l) {
+    const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l], s = c.conv_stride[l];
+    const long long dpre_rows = (l == last ? e->R64 : e->rows_total[l]) + 128;
+    long long rows_valid = 0;
+    for (int u = 0; u < e->U; ++u) rows_valid += e->L[l][u];
+    {  // d W_l[u] = d pre_l[u]^T  im2col(x_{l-1}[u])   (reduction over time)
+      GemmProblem p;
+      p.a = {e->conv_dpre[l], dpre_rows, Cout, 1, Cout};
+      p.b = {e->conv_out[l - 1], (e->rows_total[l - 1] + 128 - k) / s + 1, (long long)s * Cin, 1, (long long)k * Cin};
+      p.M = Cout; p.N = k * Cin; p.K = 0; p.nz = e->U;
+      p.ztab = e->d_ztab[l];
+      p.epi.out_f32 = e->G + e->conv_w_off[l]; p.epi.out_ld = k * Cin; p.out_z_stride = e->n_params;
+      p.flops = 2.0 * Cout * k * Cin * (double)rows_valid;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    {  // Z = d pre_l * W_l[u]  -> [rows_l, (tap, Cin)]
+      GemmProblem p;
+      p.a = {e->conv_dpre[l], dpre_rows, Cout};
+      p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin, 1, (long long)k * Cin};
+      p.M = (int)rows_valid; p.N = k * Cin; p.K = Cout;
+      p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_mblk[l];
+      p.epi.out_bf16 = e->zbuf; p.epi.out_ld = k * Cin;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    Col2imArgs ca{};
+    ca.Z = e->zbuf; ca.pre = e->conv_pre[l - 1]; ca.out = e->conv_dpre[l - 1];
+    ca.off_out = e->d_off[l - 1]; ca.off_in = l == last ? e->d_dpre_off_last : e->d_off[l];
+    ca.L_out = e->d_L[l - 1]; ca.L_in = e->d_L[l];
+    ca.C = Cin; ca.k = k; ca.s = s; ca.n_utts = e->U; ca.max_L_out = e->max_L[l - 1];
+    SUTA_TRY(conv_col2im_gelu_grad(ca, st));
+    e->launches += 1;
+  }
+  Conv0BwdArgs ba{};
+  ba.x = e->wav_norm; ba.samp_off = e->d_samp_off; ba.L0 = e->d_L0; ba.out_off = e->d_off0;
+  ba.w = e->P + e->conv_w_off[0]; ba.w_stride = e->n_params;
+  ba.dy = e->conv_dpre[0]; ba.stats = e->stats + 2 * e->U;
+  ba.acc = e->c0_scratch; ba.acc_x = e->c0_scratch + (size_t)e->U * c.conv_dim[0] * 34;
+  ba.P = e->P; ba.G = e->G; ba.pstride = e->n_params;
+  ba.g_off = e->gn_g; ba.b_off = e->gn_b; ba.w_off = e->conv_w_off[0];
+  ba.n_utts = e->U; ba.C = c.conv_dim[0]; ba.k = c.conv_kernel[0]; ba.stride = c.conv_stride[0]; ba.max_L0 = e->max_L0;
+  SUTA_TRY(conv0_groupnorm_backward(ba, st));
+  e->launches += 2;
   return SUTA_OK;
 }
 
@@ -656,7 +866,7 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
   SUTA_TRY(optimizer_step(a, S(stream)));
   e->opt_steps += 1;
   e->launches += 1;
-  return SUTA_OK;
+  return refresh_shadows(e, S(stream));
 }
 
 extern "C" int suta_adapt_step(suta_engine* e, const suta_hyper* h, void* stream) {
@@ -718,6 +928,17 @@ extern "C" int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride,
   p.epi.out_f32 = out_f32; p.epi.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.epi.out_ld = out_ld;
   p.epi.bias = bias; p.epi.residual = residual; p.epi.res_ld = res_ld; p.epi.act = act;
   p.epi.aux_in = reinterpret_cast<const bf16*>(aux_in); p.epi.aux_out = reinterpret_cast<bf16*>(aux_out); p.epi.aux_ld = aux_ld;
+  return gemm_bf16_tc(p, S(stream));
+}
+// D[M,N] = A * B^T-style contraction with per-operand memory order: a_mn / b_mn = 1 means the operand is stored
+// [K rows][M|N contiguous] (the layouts of weight-gradient GEMMs); fp32 output.
+extern "C" int suta_op_gemm_mn(const void* a, int64_t a_rows, int64_t a_row_stride, int a_mn, const void* b, int64_t b_rows,
+                               int64_t b_row_stride, int b_mn, int M, int N, int K, float* out_f32, int out_ld, void* stream) {
+  GemmProblem p;
+  p.a = {reinterpret_cast<const bf16*>(a), a_rows, a_row_stride, a_mn, a_mn ? M : 0};
+  p.b = {reinterpret_cast<const bf16*>(b), b_rows, b_row_stride, b_mn, b_mn ? N : 0};
+  p.M = M; p.N = N; p.K = K;
+  p.epi.out_f32 = out_f32; p.epi.out_ld = out_ld;
   return gemm_bf16_tc(p, S(stream));
 }
 extern "C" int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P,

@@ -12,14 +12,20 @@
 struct GemmOperand {
   const bf16* ptr;         // first element of row 0
   long long rows;          // number of addressable rows (TMA zero-fills beyond)
-  long long row_stride;    // elements between consecutive rows (may be < K: overlapping conv windows)
+  long long row_stride;    // elements between consecutive rows (may be < row length: overlapping conv windows)
+  // K-major (default): memory is [M or N rows][K contiguous].
+  // MN-major (mn_major = 1): memory is [K rows][M or N contiguous] -- the natural layout of both operands of a
+  // weight-gradient GEMM (reduction over time) and of W when computing dY * W; `cols` = extent of the M/N axis.
+  int mn_major = 0;
+  long long cols = 0;
 };
 
 struct GemmEpilogue {
   float* out_f32 = nullptr;        // optional fp32 output
   bf16* out_bf16 = nullptr;        // optional bf16 output (same leading dim)
   int out_ld = 0;
-  const float* bias = nullptr;     // indexed [b_row_off + out_col]
+  const float* bias = nullptr;     // indexed [b_row_off + out_col], or [(b_row_off / N) * bias_utt_stride + out_col]
+  long long bias_utt_stride = 0;   //   when bias_utt_stride != 0 (per-utterance bias inside the trainable vector)
   const float* residual = nullptr; // fp32 [rows, res_ld], added last
   int res_ld = 0;
   int act = 0;                     // 0 none, 1 GELU(erf), 2 multiply by GELU'(aux_in)
@@ -36,6 +42,10 @@ struct GemmProblem {
   int c_z_cols = 0;
   const int4* mblk = nullptr;      // optional per-M-block table {a_row0, out_row0, rows_valid, b_row_off}
   int num_mblk = 0;                // = ceil(M/128) when mblk == nullptr
+  const int4* ztab = nullptr;      // optional per-z table {a_k_row0, b_k_row0, k_len, 0} (MN-major operands: the
+                                   // reduction runs over rows [k_row0, k_row0 + k_len) of each operand)
+  long long out_z_stride = 0;      // elements added to the output pointers per z (per-utterance gradient slabs)
+  double flops = 0.0;              // algorithmic FLOPs of this launch when it cannot be derived from M,N,K,nz
   GemmEpilogue epi;
 };
 

@@ -47,6 +47,43 @@ struct Conv0Args {
 };
 int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
 
+// ---- convbwd.cu (train_feature backward of the CNN front end) ---------------------------------
+int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,
+                     cudaStream_t stream);
+// out[pad_off[u] + t] = d[row] * GELU'(pre[row]) (pre may be null: plain cast) into a 64-row-aligned, zero-gapped slab
+int gelu_grad_to_padded(const float* d, const bf16* pre, bf16* out, const int* row_utt, const long long* tok_off,
+                        const long long* pad_off, long long M, int C, cudaStream_t stream);
+struct Col2imArgs {
+  const bf16* Z;               // [rows_in, k*C] dgrad GEMM output of the layer above, (tap, cin) column order
+  const bf16* pre;             // [rows_out, C] pre-activation of this layer's output
+  bf16* out;                   // [rows_out, C] d(pre-activation)
+  const long long *off_out, *off_in;   // [U] first row of each utterance in this / the upper layer
+  const int *L_out, *L_in;     // [U] valid rows
+  int C, k, s, n_utts, max_L_out;
+};
+int conv_col2im_gelu_grad(const Col2imArgs& a, cudaStream_t stream);
+struct Conv0BwdArgs {
+  const float* x;              // normalised audio
+  const long long* samp_off;
+  const int* L0;
+  const long long* out_off;
+  const float* w;              // per-utterance conv0 weight inside the trainable vector: w + u*w_stride
+  long long w_stride;
+  const bf16* dy;              // [rows0, C] d(GroupNorm output) (already multiplied by GELU')
+  const double* stats;         // [U][C][2] forward sum / sumsq
+  double* acc;                 // scratch [U][C][34]
+  double* acc_x;               // scratch [U][16]
+  const float* P;              // trainable vectors (for gamma)
+  float* G;                    // gradient vectors (same layout)
+  long long pstride;
+  long long g_off, b_off, w_off;
+  int n_utts, C, k, stride, max_L0;
+};
+int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream);
+long long conv0_bwd_scratch_doubles(int n_utts, int C);
+int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
+                   int C, int n_utts, cudaStream_t stream);
+
 // ---- posconv.cu -----------------------------------------------------------------------------
 // scatter fp32 [M,H] tokens into the zero-padded per-group bf16 layout [G][R][CGP] used as the implicit-GEMM A operand
 int posconv_pack(const float* h, const int* row_utt, const long long* tok_off, const long long* pad_off, bf16* xg,

@@ -19,8 +19,9 @@ from .config import ModelConfig
 CHECKPOINT_STEPS = (1, 3, 5, 10, 20, 40)       # REF/main.py:350-398
 
 _MODULE_NAMES = {0: "wav2vec2.feature_projection.layer_norm", 1: "wav2vec2.encoder.layer_norm",
-                 2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm"}
-_KIND_LEAF = {0: "weight", 1: "bias"}
+                 2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm",
+                 4: "wav2vec2.feature_extractor.conv_layers.{i}", 5: "wav2vec2.feature_projection.projection"}
+_KIND_LEAF = {0: "weight", 1: "bias", 2: "layer_norm.weight", 3: "layer_norm.bias", 4: "conv.weight", 5: "weight", 6: "bias"}
 
 
 @dataclass
@@ -76,9 +77,11 @@ class SutaEngine:
         segs = (ParamSeg * n.value)()
         check(self.lib.suta_engine_param_layout(h, segs, n.value, C.byref(n)))
         self.segments = []      # (hf name, offset, size)
+        self.seg_kind = {}      # hf name -> kind (4 = conv weight stored as [Cout, tap, Cin])
         for s in segs:
             name = _MODULE_NAMES[s.module].format(i=s.index) + "." + _KIND_LEAF[s.kind]
             self.segments.append((name, int(s.offset), int(s.size)))
+            self.seg_kind[name] = int(s.kind)
         self._keep: List[torch.Tensor] = []
         self._pack_weights(state_dict, trainable_mult)
         self._ws: Optional[torch.Tensor] = None
@@ -141,14 +144,28 @@ class SutaEngine:
         # pristine trainable vector + per-element multiplicity (REF/main.py:62-103 lists some tensors several times)
         p0 = torch.empty(self.n_params, dtype=f32)
         mult = torch.zeros(self.n_params, dtype=torch.uint8)
+        self._hf_shapes = {name: tuple(sd[name].shape) for name, _o, _s in self.segments}
         for name, off, size in self.segments:
-            p0[off:off + size] = g(name).reshape(-1)
+            p0[off:off + size] = self.to_engine_layout(name, g(name))
             mult[off:off + size] = 1 if trainable_mult is None else int(trainable_mult.get(name, 0))
         self.params0 = self._dev(p0, f32)
         self.mult = self._dev(mult, torch.uint8)
         w.params0, w.mult = p(self.params0), p(self.mult)
         self._weights = w
         check(self.lib.suta_engine_set_weights(self._h, C.byref(w)))
+
+    def to_engine_layout(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """HF tensor -> flat segment of the trainable vector (conv weights go [Cout, Cin, k] -> [Cout, k, Cin])."""
+        if self.seg_kind[name] == 4:
+            t = t.permute(0, 2, 1)
+        return t.reshape(-1)
+
+    def from_engine_layout(self, name: str, flat: torch.Tensor) -> torch.Tensor:
+        """Flat segment -> tensor of the HF parameter's shape."""
+        shp = self._hf_shapes[name]
+        if self.seg_kind[name] == 4:
+            return flat.view(shp[0], shp[2], shp[1]).permute(0, 2, 1)
+        return flat.view(*shp)
 
     def set_trainable(self, mult_by_name: Dict[str, int]):
         """Re-select what the optimizer updates (collect_params' result): name -> multiplicity (0 = frozen)."""
@@ -266,8 +283,9 @@ class SutaEngine:
         return self.logits()[o:o + t]
 
     def utt_params(self, u: int) -> Dict[str, torch.Tensor]:
+        """Adapted trainables of utterance u, keyed by HF parameter name, in the HF tensor shapes."""
         P = self.params()[u]
-        return {name: P[off:off + size] for name, off, size in self.segments}
+        return {name: self.from_engine_layout(name, P[off:off + size]) for name, off, size in self.segments}
 
     def debug_buffer(self, name: str) -> torch.Tensor:
         r, c, dt = C.c_int64(), C.c_int64(), C.c_int()

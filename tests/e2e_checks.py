@@ -27,11 +27,11 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
-def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False):
+def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False, train_feature=False, mult=None):
     """Batched SUTA on the GPU: returns per-utterance dicts (logits at checkpoints, losses, params, ids)."""
     _, mcfg = _cfgs(cfg_name)
     hp = hp or AdaptHyper()
-    eng = SutaEngine(mcfg, sd)
+    eng = SutaEngine(mcfg, sd, train_feature=train_feature, trainable_mult=mult)
     eng.begin_batch(wavs)
     eng.reset()
     res = [dict(logits={}, losses=[], ids={}) for _ in wavs]
@@ -57,9 +57,8 @@ def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False):
             for u in range(len(wavs)):
                 res[u]["logits"][i + 1] = eng.utt_logits(u).cpu().numpy().copy()
                 res[u]["ids"][i + 1] = ids[u]
-    Pm = eng.params().cpu().numpy()
     for u in range(len(wavs)):
-        res[u]["params"] = {name: Pm[u, off:off + size].copy() for name, off, size in eng.segments}
+        res[u]["params"] = {name: t.detach().cpu().contiguous().numpy().copy().reshape(-1) for name, t in eng.utt_params(u).items()}
     res[0]["segments"] = eng.segments
     res[0]["launches"] = eng.launch_count
     eng.close()
@@ -110,6 +109,40 @@ def check_tiny_batch(steps=10):
     return out
 
 
+def _mult(ocfg, train_feature):
+    m = {}
+    for n in O.collect_param_names(ocfg, train_feature=train_feature):
+        m[n] = m.get(n, 0) + 1
+    return m
+
+
+def check_tiny_feat_batch(steps=5):
+    """train_feature: per-utterance CNN + projection weights, duplicate-parameter Adam semantics (REF/main.py:88-94)."""
+    ocfg, _ = _cfgs("tiny")
+    sd = O.init_weights(ocfg, 4, blank_bias=0.35, ln_jitter=0.1)
+    lens, seeds = [9000, 12000, 3000], [12, 15, 16]
+    wavs = [O.synth_audio(n, s) for n, s in zip(lens, seeds)]
+    res = run_engine("tiny", sd, wavs, steps, keep_grads=True, train_feature=True, mult=_mult(ocfg, True))
+    out = {}
+    for u, w in enumerate(wavs):
+        ora = O.adapt_utterance(ocfg, sd, O.normalize_audio(w), steps=steps, train_feature=True)
+        ref_logits = dict(ora.logits); ref_logits[0] = ora.logits0
+        m = compare(res[u], ref_logits, ora.losses, ora.params, sd, ref_ids=True)
+        # per-group delta errors localise a broken gradient
+        for grp in ("conv_layers.0.conv", "conv_layers.0.layer_norm", "conv_layers.3.conv", "conv_layers.6.conv",
+                    "feature_projection.projection.weight", "feature_projection.projection.bias", "feature_projection.layer_norm",
+                    "encoder.layers.0.layer_norm"):
+            num = den = 0.0
+            for name, p in ora.params.items():
+                if grp in name:
+                    p0 = sd[name].numpy().reshape(-1)
+                    num += float(np.sum((res[u]["params"][name] - p.reshape(-1)) ** 2))
+                    den += float(np.sum((p.reshape(-1) - p0) ** 2))
+            m["delta:" + grp] = float(np.sqrt(num / max(den, 1e-30)))
+        out[f"utt{u}_T{ora.logits0.shape[0]}"] = m
+    return out
+
+
 def check_tiny_stages():
     """Intermediate activations of the forward vs the oracle's taps (localises a broken stage)."""
     ocfg, mcfg = _cfgs("tiny")
@@ -143,7 +176,8 @@ def check_golden(case):
     sd = O.init_weights(ocfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"])
     wav = O.synth_audio(meta["n_samples"], meta["audio_seed"])
     hp = AdaptHyper(**{k: meta["hyper"][k] for k in ("lr", "em_coef", "reweight", "temp", "not_blank")})
-    res = run_engine(meta["cfg"], sd, [wav], meta["steps"], hp)[0]
+    tf = bool(meta["train_feature"])
+    res = run_engine(meta["cfg"], sd, [wav], meta["steps"], hp, train_feature=tf, mult=_mult(ocfg, tf))[0]
     ref_logits = {int(k.split("_")[1]): z[k] for k in z.files if k.startswith("logits_")}
     ref_params = {k[6:]: z[k] for k in z.files if k.startswith("param:") and z[k].dtype == np.float32}
     m = compare(res, ref_logits, z["losses"], ref_params, sd, ref_ids=True)
@@ -154,7 +188,8 @@ def check_golden(case):
     return m
 
 
-ALL = [("tiny_stages", check_tiny_stages), ("tiny_batch", check_tiny_batch),
+ALL = [("tiny_stages", check_tiny_stages), ("tiny_batch", check_tiny_batch), ("tiny_feat_batch", check_tiny_feat_batch),
+       ("golden_tiny_feat", lambda: check_golden("tiny_feat")), ("golden_base_feat_2s", lambda: check_golden("base_feat_2s")),
        ("golden_tiny_ln", lambda: check_golden("tiny_ln")), ("golden_tiny_short", lambda: check_golden("tiny_short")),
        ("golden_base_ln_5s", lambda: check_golden("base_ln_5s")),
        ("golden_base_ln_5s_noblank", lambda: check_golden("base_ln_5s_noblank"))]

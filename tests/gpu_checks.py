@@ -113,6 +113,26 @@ def check_gemm_strided_conv(L=1001, C=64, k=3, s=2, N=64, seed=4):
     return dict(rel=relerr(out, ref))
 
 
+def check_gemm_mn(M=256, N=512, K=1000, seed=13):
+    """MN-major operands: (A K-major, B [K,N]) and (A [K,M], B [K,N]) -- the dgrad-through-W and wgrad layouts."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    at = a.t().contiguous()                                   # [K, M]
+    bt = torch.randn(K, N, device=DEV, generator=g).bfloat16()    # [K, N]
+    ref = a.float() @ bt.float()
+    out = {}
+    o = torch.zeros(M, N, device=DEV)
+    check(lib.suta_op_gemm_mn(P(a), M, K, 0, P(bt), K, N, 1, M, N, K, P(o), N, stream()))
+    torch.cuda.synchronize()
+    out["kmajorA_mnB"] = relerr(o, ref)
+    o2 = torch.zeros(M, N, device=DEV)
+    check(lib.suta_op_gemm_mn(P(at), K, M, 1, P(bt), K, N, 1, M, N, K, P(o2), N, stream()))
+    torch.cuda.synchronize()
+    out["mnA_mnB"] = relerr(o2, ref)
+    return out
+
+
 def _row_utt(Ts):
     return torch.tensor(np.repeat(np.arange(len(Ts)), Ts), dtype=torch.int32, device=DEV)
 
@@ -274,6 +294,7 @@ def check_decode(Ts=(249, 37, 1, 700), seed=9):
 
 
 ALL = [("gemm_plain", check_gemm_plain), ("gemm_epilogue", check_gemm_epilogue), ("gemm_shapes", check_gemm_shapes),
+       ("gemm_mn", check_gemm_mn), ("gemm_mn2", lambda: check_gemm_mn(128, 64, 64, 14)),
        ("gemm_window", check_gemm_window), ("gemm_strided_conv", check_gemm_strided_conv),
        ("layernorm", check_layernorm), ("layernorm_bf16in_512", lambda: check_layernorm(512, (33, 70), 11, True)),
        ("layernorm_64", lambda: check_layernorm(64, (33, 70), 12, True)),
