@@ -32,6 +32,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
+    ap.add_argument("--mode", default="feature", choices=["feature", "ln"],
+                    help="feature = BASELINE.json configs[1] (--train_feature preset of REF/scripts/LS.sh); ln = LayerNorm-only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=5.0, help="duration of the CPU-baseline utterance")
     return ap.parse_args()
@@ -82,7 +84,7 @@ class ClockSampler:
                     samples=len(self.samples))
 
 
-def utt_flops(cfg, n_samples, steps):
+def utt_flops(cfg, n_samples, steps, train_feature=False):
     H, I, NL, V = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size
     Ls, L = [], n_samples
     for k, s in zip(cfg.conv_kernel, cfg.conv_stride):
@@ -99,6 +101,9 @@ def utt_flops(cfg, n_samples, steps):
     f_head = 2.0 * T * H * V
     enc_f = f_proj + f_pos + NL * (f_lin + 4.0 * T * T * H) + f_head
     enc_b = f_proj + f_pos + NL * (f_lin + 8.0 * T * T * H) + f_head
+    if train_feature:   # CNN forward every step, dgrad (no input grad for conv0) + wgrad in every backward
+        f_conv0 = 2.0 * cfg.conv_dim[0] * cfg.conv_kernel[0] * Ls[0]
+        return (steps + 1) * (f_conv + enc_f) + steps * (enc_b + f_proj + 2 * f_conv - f_conv0)
     return f_conv + (steps + 1) * enc_f + steps * enc_b
 
 
@@ -128,7 +133,12 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = getattr(ModelConfig, args.model)()
-    eng = SutaEngine(cfg, random_state_dict(cfg, seed=0, blank_bias=1.75))
+    tf = args.mode == "feature"
+    mult = None
+    if tf:              # multiplicities of REF/main.py:62-103 with train_feature (conv x4, proj LN x3, projection x2)
+        from suta_b200.api import reference_multiplicities
+        mult = reference_multiplicities(cfg, train_feature=True)
+    eng = SutaEngine(cfg, random_state_dict(cfg, seed=0, blank_bias=1.75), train_feature=tf, trainable_mult=mult)
     hp, vocab = AdaptHyper(), CTCVocab()
     utts = librispeech_shaped(2939, seed=rank)           # weak scaling: every rank adapts its own draw of the set
     K, W = args.steps, max(args.warmup, 0)
@@ -189,7 +199,7 @@ def run_b200(args):
 
     audio_s = sum(u.duration for b in timed for u in b)
     tot = torch.tensor([audio_s, float(sum(len(b) for b in timed)),
-                        sum(utt_flops(cfg, u.n_samples, SUTA_STEPS) for b in timed for u in b)], device="cuda", dtype=torch.float64)
+                        sum(utt_flops(cfg, u.n_samples, SUTA_STEPS, tf) for b in timed for u in b)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     audio_all, utts_all, flops_all = (float(x) for x in tot.tolist())
@@ -201,7 +211,8 @@ def run_b200(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (0.1*randn audio, random-init wav2vec2-base weights; no checkpoint/dataset offline)",
         "config": {"workload": f"wav2vec2-{args.model} CTC, LibriSpeech-test-other-shaped synthetic set (2939 utts, 2-35 s), "
-                               f"{SUTA_STEPS}-step EM+MCC SUTA, LayerNorm-only (train_feature not built yet), "
+                               f"{SUTA_STEPS}-step EM+MCC SUTA, " + ("train_feature (LayerNorm + CNN front end + projection adapted per utterance)"
+                                                                if tf else "LayerNorm-only") + ", "
                                f"<= {MAX_UTTS} utts / {MAX_FRAMES} frames per adaptation batch, length-bucketed",
                    "utts_per_step": utts_all / K / world, "audio_s_per_step": audio_all / K / world,
                    "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2",

@@ -73,6 +73,27 @@ def _module_order(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
     return mods
 
 
+def reference_multiplicities(cfg, bias_only: bool = False, train_feature: bool = False, train_LN: bool = True) -> Dict[str, int]:
+    """How many times REF/main.py:62-103 would list each parameter (0 = not trainable): LayerNorm affine once, and under
+    train_feature every parameter of feature_extractor / feature_projection once per enclosing module (recursive
+    named_parameters), e.g. conv weights x4, feature_projection.layer_norm x3, projection x2."""
+    cfg = ModelConfig.from_any(cfg)
+    trainable = ['bias'] if bias_only else ['weight', 'bias']
+    tree = _module_order(cfg)
+    mult: Dict[str, int] = {f"{nm}.{leaf}": 0 for nm, _k, leaves in tree for leaf in leaves}
+    for nm, kind, leaves in tree:
+        if train_LN and kind == "layernorm":
+            for leaf in leaves:
+                if leaf in trainable:
+                    mult[f"{nm}.{leaf}"] += 1
+        if train_feature and len(nm.split('.')) > 1 and nm.split('.')[1] in ('feature_extractor', 'feature_projection'):
+            for nm2, _k2, leaves2 in tree:
+                if nm2 == nm or nm2.startswith(nm + "."):
+                    for leaf in leaves2:
+                        mult[f"{nm2}.{leaf}"] += 1
+    return mult
+
+
 class SutaModel:
     """Engine-backed stand-in for the HF model object the reference functions touch."""
 
