@@ -196,6 +196,11 @@ def run_b200(args):
     for (l, _), a in zip(staged, dev_audio):
         one_step(l, a)
     gemm_ms, gemm_n, gemm_fl = eng.profile(False)
+    rep = eng.profile_report()
+    tot_ms = sum(v[0] for v in rep.values()) or 1.0
+    breakdown = [{"kernel": k, "share": round(v[0] / tot_ms, 4), "ms_per_step": round(v[0] / K, 3), "launches_per_step": v[2] / K,
+                  "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] else None}
+                 for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])]
 
     audio_s = sum(u.duration for b in timed for u in b)
     tot = torch.tensor([audio_s, float(sum(len(b) for b in timed)),
@@ -231,6 +236,7 @@ def run_b200(args):
                  "achieved_tflops": flops_all / (ms_dev * 1e-3) / 1e12 / world,
                  "frac_of_peak": flops_all / (ms_dev * 1e-3) / 1e12 / world / peaks["tflops"]},
         "rtf_p50": None,
+        "breakdown": breakdown,
     }
     # p50 RTF: per-utterance latency (wall time of the batch that carried it, end to end) / its duration, this rank
     rtfs = sorted((t / 1e3) / u.duration for b, t in zip(timed, step_ms_e2e) for u in b)

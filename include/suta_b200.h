@@ -122,6 +122,8 @@ int64_t suta_launch_count(const suta_engine* e); /* kernels launched by this eng
 /* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg). Reads and clears the counters collected
  * so far (any pointer may be NULL), then switches collection on/off. */
 int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+/* per-kernel-class breakdown of the last read-out: lines "tag<TAB>ms<TAB>flops<TAB>launches" */
+const char* suta_profile_report(const suta_engine* e);
 
 /* ---- single operators (the kernels behind the calls above, exposed for parity tests) ------------------- */
 /* D[M,N] = A[M,K] B[N,K]^T (+bias)(gelu / gelu')(+residual), tcgen05 GEMM; out_f32 and/or out_bf16 */

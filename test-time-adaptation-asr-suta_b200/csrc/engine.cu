@@ -79,8 +79,11 @@ struct suta_engine {
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  double prof_flops = 0.0;
+  struct ProfRec { std::string tag; double flops; bool is_gemm; };
+  std::vector<ProfRec> prof_recs;
+  std::string prof_report;
   bool audio_normalized = false;
+  double sumT2 = 0.0;                              // sum over utterances of T_u^2 (attention FLOP accounting)
 
   // ---- batch state ----
   int U = 0;
@@ -249,6 +252,8 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
     p += e->T[u] + c.pos_k / 2;
     nblk += ceil_div(e->T[u], 64);
   }
+  e->sumT2 = 0.0;
+  for (int u = 0; u < U; ++u) e->sumT2 += (double)e->T[u] * e->T[u];
   e->M = m;
   e->off64.assign(U, 0);
   e->n_tok_mblk = 0;
@@ -343,22 +348,45 @@ void carve(suta_engine* e, Bump& b) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// CUDA-event pair around one launch (or group of launches) when profiling is on; records (tag, flops) for the report
+struct ProfScope {
+  suta_engine* e;
+  cudaStream_t st;
+  bool on;
+  ProfScope(suta_engine* e_, cudaStream_t st_, const std::string& tag, double flops, bool is_gemm) : e(e_), st(st_), on(e_->profile) {
+    if (!on) return;
+    if (e->ev_used + 2 > e->ev_pool.size()) {
+      size_t old = e->ev_pool.size();
+      e->ev_pool.resize(old + 1024);
+      for (size_t i = old; i < e->ev_pool.size(); ++i) cudaEventCreate(&e->ev_pool[i]);
+    }
+    e->prof_recs.push_back({tag, flops, is_gemm});
+    cudaEventRecord(e->ev_pool[e->ev_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(e->ev_pool[e->ev_used + 1], st);
+    e->ev_used += 2;
+  }
+};
+#define PROF_F(tag, flops, expr)                \
+  do {                                          \
+    ProfScope _ps(e, st, tag, flops, false);    \
+    SUTA_TRY(expr);                             \
+  } while (0)
+#define PROF(tag, expr) PROF_F(tag, 0.0, expr)
+
 int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   e->launches += 1;
   if (!e->profile) return gemm_bf16_tc(p, st);
-  if (e->ev_used + 2 > e->ev_pool.size()) {
-    size_t old = e->ev_pool.size();
-    e->ev_pool.resize(old + 512);
-    for (size_t i = old; i < e->ev_pool.size(); ++i) CUDA_TRY(cudaEventCreate(&e->ev_pool[i]));
-  }
-  CUDA_TRY(cudaEventRecord(e->ev_pool[e->ev_used], st));
-  int r = gemm_bf16_tc(p, st);
-  CUDA_TRY(cudaEventRecord(e->ev_pool[e->ev_used + 1], st));
-  e->ev_used += 2;
   // algorithmic FLOPs of this launch: valid rows only (the M-block table may pad), all z slices
-  double rows = p.M;
-  e->prof_flops += p.flops > 0.0 ? p.flops : 2.0 * rows * p.N * p.K * p.nz;
-  return r;
+  const double flops = p.flops > 0.0 ? p.flops : 2.0 * (double)p.M * p.N * p.K * p.nz;
+  char tag[96];
+  snprintf(tag, sizeof(tag), "gemm N%d K%d%s%s%s%s%s%s", p.N, p.K, p.nz > 1 ? " batched" : "", p.a.mn_major ? " wgrad" : "",
+           (!p.a.mn_major && p.b.mn_major) ? " Bmn" : "", p.epi.act == 1 ? " gelu" : (p.epi.act == 2 ? " gelu'" : ""),
+           p.epi.residual ? " +res" : "", p.epi.bias ? " +bias" : "");
+  ProfScope ps(e, st, tag, flops, true);
+  return gemm_bf16_tc(p, st);
 }
 
 GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
@@ -546,31 +574,48 @@ extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t
   SUTA_CHECK_ARG(e);
   if (gemm_ms || gemm_launches || gemm_flops) {
     CUDA_TRY(cudaDeviceSynchronize());
-    double ms = 0.0;
-    for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    double ms = 0.0, fl = 0.0;
+    int64_t n = 0;
+    e->prof_report.clear();
+    std::vector<std::string> tags;
+    std::vector<double> tms, tfl;
+    std::vector<long long> tn;
+    for (size_t i = 0; i < e->prof_recs.size() && 2 * i + 1 < e->ev_used; ++i) {
       float t = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&t, e->ev_pool[i], e->ev_pool[i + 1]));
-      ms += t;
+      CUDA_TRY(cudaEventElapsedTime(&t, e->ev_pool[2 * i], e->ev_pool[2 * i + 1]));
+      const auto& r = e->prof_recs[i];
+      if (r.is_gemm) { ms += t; fl += r.flops; n += 1; }
+      size_t k = 0;
+      while (k < tags.size() && tags[k] != r.tag) ++k;
+      if (k == tags.size()) { tags.push_back(r.tag); tms.push_back(0); tfl.push_back(0); tn.push_back(0); }
+      tms[k] += t; tfl[k] += r.flops; tn[k] += 1;
+    }
+    for (size_t k = 0; k < tags.size(); ++k) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s\t%.4f\t%.6g\t%lld\n", tags[k].c_str(), tms[k], tfl[k], tn[k]);
+      e->prof_report += line;
     }
     if (gemm_ms) *gemm_ms = ms;
-    if (gemm_launches) *gemm_launches = (int64_t)(e->ev_used / 2);
-    if (gemm_flops) *gemm_flops = e->prof_flops;
+    if (gemm_launches) *gemm_launches = n;
+    if (gemm_flops) *gemm_flops = fl;
   }
   e->ev_used = 0;
-  e->prof_flops = 0.0;
+  e->prof_recs.clear();
   e->profile = enable != 0;
   return SUTA_OK;
 }
+// per-tag breakdown of the last suta_profile read-out: lines "tag<TAB>ms<TAB>flops<TAB>launches"
+extern "C" const char* suta_profile_report(const suta_engine* e) { return e ? e->prof_report.c_str() : ""; }
 
 // bf16 GEMM-operand copies of the per-utterance trainable matrices (train_feature): refreshed after every update
 static int refresh_shadows(suta_engine* e, cudaStream_t st) {
   if (!e->train_feature) return SUTA_OK;
   const suta_model_cfg& c = e->cfg;
   for (int l = 1; l < c.n_conv; ++l) {
-    SUTA_TRY(cast_params_bf16(e->P, e->n_params, e->conv_w_off[l], e->conv_w_size[l], e->U, e->w_shadow[l], st));
+    PROF("cast_shadow", cast_params_bf16(e->P, e->n_params, e->conv_w_off[l], e->conv_w_size[l], e->U, e->w_shadow[l], st));
     e->launches += 1;
   }
-  SUTA_TRY(cast_params_bf16(e->P, e->n_params, e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->U,
+  PROF("cast_shadow", cast_params_bf16(e->P, e->n_params, e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->U,
                             e->proj_shadow, st));
   e->launches += 1;
   e->frontend_done = false;      // the CNN output depends on the updated weights
@@ -581,7 +626,8 @@ extern "C" int suta_reset(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   e->launches += 1;
   e->opt_steps = 0;
-  SUTA_TRY(params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, S(stream)));
+  cudaStream_t st = S(stream);
+  PROF("reset", params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, st));
   return refresh_shadows(e, S(stream));
 }
 
@@ -590,7 +636,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   const suta_model_cfg& c = e->cfg;
   cudaStream_t st = S(stream);
   if (!e->audio_normalized)
-    SUTA_TRY(normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
+    PROF("normalize", normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
   Conv0Args a{};
   a.x = e->wav_norm; a.samp_off = e->d_samp_off; a.L0 = e->d_L0; a.out_off = e->d_off0;
   a.w = e->w.conv0_w; a.w_stride = 0;
@@ -603,7 +649,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     a.pre_out = e->conv_pre[0];
   }
   a.n_utts = e->U; a.C = c.conv_dim[0]; a.k = c.conv_kernel[0]; a.stride = c.conv_stride[0]; a.max_L0 = e->max_L0;
-  SUTA_TRY(conv0_groupnorm_gelu(a, st));
+  PROF("conv0_fwd", conv0_groupnorm_gelu(a, st));
   e->launches += 4;
   for (int l = 1; l < c.n_conv; ++l) {
     const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l], s = c.conv_stride[l];
@@ -638,7 +684,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   const bf16* feat = e->conv_out[c.n_conv - 1];
 
   // feature projection: LayerNorm(C) -> Linear(C->H)        HF/modeling_wav2vec2.py:429-434
-  SUTA_TRY(layernorm_forward(nullptr, feat, e->d_row_utt, prm, (int)e->fp_g, (int)e->fp_b, nullptr, e->y_fp, e->fp_mean,
+  PROF("ln_fwd", layernorm_forward(nullptr, feat, e->d_row_utt, prm, (int)e->fp_g, (int)e->fp_b, nullptr, e->y_fp, e->fp_mean,
                              e->fp_rstd, M, C, c.ln_eps, st));
   {
     GemmProblem p = dense(e->y_fp, M, C, reinterpret_cast<const bf16*>(e->w.proj_w), H);
@@ -651,7 +697,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     SUTA_TRY(gemm(e, p, st));
   }
   // positional conv embedding + GELU + residual               HF/modeling_wav2vec2.py:360-368, :690-691
-  SUTA_TRY(posconv_pack(e->h0, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, st));
+  PROF("posconv_pack", posconv_pack(e->h0, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, st));
   {
     GemmProblem p;
     p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
@@ -661,9 +707,9 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     p.epi.bias = e->w.pos_b; p.epi.out_f32 = e->cpos; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
-  SUTA_TRY(posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->hE, M, H, -(c.pos_k / 2), st));
+  PROF("posconv_combine", posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->hE, M, H, -(c.pos_k / 2), st));
   // encoder.layer_norm                                          HF/modeling_wav2vec2.py:692
-  SUTA_TRY(layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->fa, e->b16, e->enc_mean,
+  PROF("ln_fwd", layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->fa, e->b16, e->enc_mean,
                              e->enc_rstd, M, H, c.ln_eps, st));
   e->launches += 5;
   for (int l = 0; l < c.layers; ++l) {
@@ -674,13 +720,13 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
       p.epi.bias = w.bqkv; p.epi.out_bf16 = x.qkv; p.epi.out_ld = 3 * H;
       SUTA_TRY(gemm(e, p, st));
     }
-    SUTA_TRY(attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+    PROF_F("attn_fwd", 4.0 * H * e->sumT2, attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
     {  // out_proj + residual                                    HF:546, :597
       GemmProblem p = dense(x.attn, M, H, reinterpret_cast<const bf16*>(w.wo), H);
       p.epi.bias = w.bo; p.epi.residual = e->fa; p.epi.res_ld = H; p.epi.out_f32 = x.h1; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    SUTA_TRY(layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], e->fb, e->b16,
+    PROF("ln_fwd", layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], e->fb, e->b16,
                                x.mean1, x.rstd1, M, H, c.ln_eps, st));
     {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
@@ -692,7 +738,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
       p.epi.bias = w.b2; p.epi.residual = e->fb; p.epi.res_ld = H; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    SUTA_TRY(layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], e->fa, e->b16,
+    PROF("ln_fwd", layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], e->fa, e->b16,
                                x.mean2, x.rstd2, M, H, c.ln_eps, st));
     e->launches += 3;
   }
@@ -716,7 +762,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   la.logits = e->logits; la.tok_off = e->d_tok_off; la.T = e->d_T;
   la.dlogits_f32 = e->dlogits; la.dlogits_bf16 = e->dlogits16; la.loss = e->losses; la.n_utts = e->U;
   la.em_coef = h->em_coef; la.temp = h->temp; la.reweight = h->reweight; la.not_blank = h->not_blank;
-  SUTA_TRY(suta_loss_forward_backward(la, st));
+  PROF("loss", suta_loss_forward_backward(la, st));
   // only the LayerNorm segments are accumulated with atomics; every other gradient segment is written whole
   CUDA_TRY(cudaMemset2DAsync(e->G, sizeof(float) * e->n_params, 0, sizeof(float) * e->ln_params, e->U, st));
   e->launches += 2;
@@ -731,7 +777,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   for (int l = c.layers - 1; l >= 0; --l) {
     const suta_layer_weights& w = e->w.layer[l];
     LayerBufs& x = e->lb[l];
-    SUTA_TRY(layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+    PROF("ln_bwd", layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
                                 e->G, db, e->b16, M, H, st));
     {  // output_dense dgrad, times GELU'(pre)
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
@@ -743,14 +789,14 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    SUTA_TRY(layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
+    PROF("ln_bwd", layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
                                 e->G, db, e->b16, M, H, st));
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
       p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    SUTA_TRY(attention_backward(x.qkv, x.attn, e->dO16, x.lse, e->Dbuf, e->dqkv16, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+    PROF_F("attn_bwd", 8.0 * H * e->sumT2, attention_backward(x.qkv, x.attn, e->dO16, x.lse, e->Dbuf, e->dqkv16, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
     {  // q,k,v dgrad + residual path
       GemmProblem p = dense(e->dqkv16, M, 3 * H, reinterpret_cast<const bf16*>(w.wqkv_t), H);
       p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
@@ -759,10 +805,10 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     e->launches += 5;
   }
   // encoder.layer_norm
-  SUTA_TRY(layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
+  PROF("ln_bwd", layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
                               e->G, db, nullptr, M, H, st));
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
-  SUTA_TRY(posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
+  PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
   {
     GemmProblem p;
     p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
@@ -772,7 +818,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     p.epi.out_f32 = e->dcpos; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
-  SUTA_TRY(posconv_combine_grad(db, e->dcpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->train_feature ? da : nullptr,
+  PROF("posconv_combine_grad", posconv_combine_grad(db, e->dcpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->train_feature ? da : nullptr,
                                 e->b16, M, H, -(c.pos_k / 2 - 1), st));
   {  // projection dgrad
     GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.proj_w_t), C);
@@ -793,7 +839,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   // ================= train_feature: projection weight/bias, then the whole CNN (REF/main.py:88-94) =================
   const int last = c.n_conv - 1;
   {  // d W_proj[u] = d h0[u]^T y_fp[u]  (reduction over the utterance's frames; both operands MN-major)
-    SUTA_TRY(gelu_grad_to_padded(da, nullptr, e->dh0_pad, e->d_row_utt, e->d_tok_off, e->d_dpre_off_last, M, H, st));
+    PROF("gelu_grad_pad", gelu_grad_to_padded(da, nullptr, e->dh0_pad, e->d_row_utt, e->d_tok_off, e->d_dpre_off_last, M, H, st));
     GemmProblem p;
     p.a = {e->dh0_pad, e->R64 + 128, H, 1, H};
     p.b = {e->y_fp, M, C, 1, C};
@@ -802,13 +848,13 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     p.epi.out_f32 = e->G + e->proj_w_off; p.epi.out_ld = C; p.out_z_stride = e->n_params;
     p.flops = 2.0 * H * C * (double)M;
     SUTA_TRY(gemm(e, p, st));
-    SUTA_TRY(colsum_per_utt(da, e->d_tok_off, e->d_T, e->G, e->n_params, e->proj_b_off, H, e->U, st));
+    PROF("colsum", colsum_per_utt(da, e->d_tok_off, e->d_T, e->G, e->n_params, e->proj_b_off, H, e->U, st));
   }
   // feature_projection.layer_norm with input gradient
-  SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
+  PROF("ln_bwd", layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
                               (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, st));
   // d(pre-activation) of the last conv layer, in the 64-row-aligned token slab
-  SUTA_TRY(gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
+  PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
                                e->d_dpre_off_last, M, C, st));
   e->launches += 4;
   for (int l = last; l >= 1; --l) {
@@ -840,7 +886,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     ca.off_out = e->d_off[l - 1]; ca.off_in = l == last ? e->d_dpre_off_last : e->d_off[l];
     ca.L_out = e->d_L[l - 1]; ca.L_in = e->d_L[l];
     ca.C = Cin; ca.k = k; ca.s = s; ca.n_utts = e->U; ca.max_L_out = e->max_L[l - 1];
-    SUTA_TRY(conv_col2im_gelu_grad(ca, st));
+    PROF("col2im", conv_col2im_gelu_grad(ca, st));
     e->launches += 1;
   }
   Conv0BwdArgs ba{};
@@ -851,7 +897,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   ba.P = e->P; ba.G = e->G; ba.pstride = e->n_params;
   ba.g_off = e->gn_g; ba.b_off = e->gn_b; ba.w_off = e->conv_w_off[0];
   ba.n_utts = e->U; ba.C = c.conv_dim[0]; ba.k = c.conv_kernel[0]; ba.stride = c.conv_stride[0]; ba.max_L0 = e->max_L0;
-  SUTA_TRY(conv0_groupnorm_backward(ba, st));
+  PROF("conv0_bwd", conv0_groupnorm_backward(ba, st));
   e->launches += 2;
   return SUTA_OK;
 }
@@ -863,7 +909,8 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
   a.n = e->n_params; a.n_utts = e->U; a.step_index = e->opt_steps;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps; a.weight_decay = h->weight_decay;
   a.kind = h->opt_kind; a.shadow = nullptr;
-  SUTA_TRY(optimizer_step(a, S(stream)));
+  cudaStream_t st = S(stream);
+  PROF("adam", optimizer_step(a, st));
   e->opt_steps += 1;
   e->launches += 1;
   return refresh_shadows(e, S(stream));

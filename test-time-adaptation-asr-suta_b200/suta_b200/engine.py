@@ -222,6 +222,14 @@ class SutaEngine:
         check(self.lib.suta_profile(self._h, int(enable), C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def profile_report(self):
+        """Per-kernel-class breakdown of the last profile() read-out: {tag: (ms, flops, launches)}."""
+        out = {}
+        for line in self.lib.suta_profile_report(self._h).decode().splitlines():
+            tag, ms, fl, n = line.split("\t")
+            out[tag] = (float(ms), float(fl), int(n))
+        return out
+
     def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
         off = ptr - self._ws.data_ptr()
         n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
