@@ -125,8 +125,13 @@ int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_laun
 /* per-kernel-class breakdown of the last read-out: lines "tag<TAB>ms<TAB>flops<TAB>launches" */
 const char* suta_profile_report(const suta_engine* e);
 
+/* debug hook for kernel tuning: CTA 0 of every following tcgen05 GEMM launch writes a per-tile clock64 timeline into
+ * dev_buf[cap][8] (device memory; see csrc/gemm_tc.cu); NULL switches it off */
+void suta_debug_set_gemm_trace(long long* dev_buf, int cap);
+
 /* ---- single operators (the kernels behind the calls above, exposed for parity tests) ------------------- */
-/* D[M,N] = A[M,K] B[N,K]^T (+bias)(gelu / gelu')(+residual), tcgen05 GEMM; out_f32 and/or out_bf16 */
+/* D[M,N] = A[M,K] B[N,K]^T (+bias)(act & 3 == 1: GELU, saving GELU' to aux_out; == 2: times aux_in)(+residual), tcgen05
+ * GEMM; out_f32 and/or out_bf16; act & 4: out_f32 += D instead of = D (in-place accumulation, no residual pointer) */
 int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride, const void* b, int64_t b_rows, int64_t b_row_stride,
                  int M, int N, int K, float* out_f32, void* out_bf16, int out_ld, const float* bias,
                  const float* residual, int res_ld, int act, const void* aux_in, void* aux_out, int aux_ld, void* stream);

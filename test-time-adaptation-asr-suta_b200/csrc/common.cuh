@@ -54,24 +54,40 @@ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of erff's
-// branchy polynomial -- the GEMM epilogues evaluate it for every element of the FFN / conv activations.
-__device__ __forceinline__ float erf_fast(float z) {
-  const float a = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = 1.0f - p * t * __expf(-a * a);
-  return copysignf(y, z);
+// erf(|z|) = 1 - 2^p(|z|), p a degree-5 polynomial fitted (weighted minimax, tools/fit_erf.py) to log2(erfc) on [0,4]:
+// |error| <= 6.8e-7 in fp32 over the whole line, p is monotone decreasing so large |z| saturates to 1.  One MUFU.EX2 +
+// 6 FMA-pipe instructions -- the GEMM epilogues evaluate it for every element of the FFN / conv activations, where the
+// instruction budget per element decides whether the tensor pipe or the epilogue warps set the pace.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float erf_abs_fast(float t) {   // t >= 0
+  float p = fmaf(-0.002944157226011157f, t, 0.02959004044532776f);
+  p = fmaf(p, t, -0.1486656218767166f);
+  p = fmaf(p, t, -0.9185093641281128f);
+  p = fmaf(p, t, -1.6278890371322632f);
+  return 1.0f - ex2_approx(p * t);
+}
+__device__ __forceinline__ float erf_fast(float z) { return copysignf(erf_abs_fast(fabsf(z)), z); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_fast(x * 0.70710678118654752f), hx);
+}
 // d/dx [ x * Phi(x) ] = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752f), 0.5f);
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+// both at once (shared erf): the forward epilogues store GELU'(pre) in bf16 so the backward only multiplies
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& dg) {
+  const float e = erf_fast(x * 0.70710678118654752f);
+  const float hx = 0.5f * x;
+  g = fmaf(hx, e, hx);
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);
+  dg = fmaf(x, pdf, fmaf(0.5f, e, 0.5f));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -94,6 +110,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   bf162 v = *reinterpret_cast<bf162*>(&u);
   return __bfloat1622float2(v);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 // ---- mbarrier -------------------------------------------------------------------------------
@@ -140,6 +165,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// TMA stores: shared memory (written through the generic proxy, so fence first) -> global, bulk-group completion
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+// global[box] += shared[box] (fp32 add performed at the L2, no load on the SM side)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

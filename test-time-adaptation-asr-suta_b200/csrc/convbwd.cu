@@ -2,8 +2,8 @@
 // feature_extractor / feature_projection trainable, so autograd reaches the waveform-side layers):
 //   cast_params_bf16        refresh the bf16 GEMM-operand copy of per-utterance trainable weights after an update
 //   conv_col2im_gelu_grad   gather the dgrad GEMM result Z[t,(j,ci)] back to input rows r = s*t + j and multiply by
-//                           GELU'(pre-activation of the layer below)                 (backward of HF:269-272)
-//   gelu_grad_to_padded     dX * GELU'(pre) written into a per-utterance 64-row-aligned slab (zero rows between
+//                           GELU'(pre-activation of the layer below), which the forward saved  (backward of HF:269-272)
+//   gelu_grad_to_padded     dX * GELU' written into a per-utterance 64-row-aligned slab (zero rows between
 //                           utterances) so the weight-gradient GEMM can reduce over time in 64-row steps
 //   conv0_groupnorm_backward  backward of Conv1d(1->C,k,s) + GroupNorm(per channel over time)  (HF:319-323)
 //   colsum_per_utt          bias gradient of the per-utterance projection
@@ -35,8 +35,8 @@ __global__ void gelu_grad_pad_kernel(const float* __restrict__ d, const bf16* __
   if (pre) {
     uint4 p = *reinterpret_cast<const uint4*>(pre + row * C + c);
     float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y), p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
-    a.x *= gelu_erf_grad(p0.x); a.y *= gelu_erf_grad(p0.y); a.z *= gelu_erf_grad(p1.x); a.w *= gelu_erf_grad(p1.y);
-    b.x *= gelu_erf_grad(p2.x); b.y *= gelu_erf_grad(p2.y); b.z *= gelu_erf_grad(p3.x); b.w *= gelu_erf_grad(p3.y);
+    a.x *= p0.x; a.y *= p0.y; a.z *= p1.x; a.w *= p1.y;
+    b.x *= p2.x; b.y *= p2.y; b.z *= p3.x; b.w *= p3.y;
   }
   *reinterpret_cast<uint4*>(out + prow * C + c) =
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
@@ -70,8 +70,8 @@ col2im_kernel(Col2imArgs a) {
     }
     uint4 p = *reinterpret_cast<const uint4*>(a.pre + (oo + r) * a.C + c);
     float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y), p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
-    acc[0] *= gelu_erf_grad(p0.x); acc[1] *= gelu_erf_grad(p0.y); acc[2] *= gelu_erf_grad(p1.x); acc[3] *= gelu_erf_grad(p1.y);
-    acc[4] *= gelu_erf_grad(p2.x); acc[5] *= gelu_erf_grad(p2.y); acc[6] *= gelu_erf_grad(p3.x); acc[7] *= gelu_erf_grad(p3.y);
+    acc[0] *= p0.x; acc[1] *= p0.y; acc[2] *= p1.x; acc[3] *= p1.y;
+    acc[4] *= p2.x; acc[5] *= p2.y; acc[6] *= p3.x; acc[7] *= p3.y;
     *reinterpret_cast<uint4*>(a.out + (oo + r) * a.C + c) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
   }

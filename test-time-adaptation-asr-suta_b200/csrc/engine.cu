@@ -50,7 +50,7 @@ struct LayerBufs {
   float* lse;     // [heads,M]
   float* h1;      // [M,H] pre-LN1
   float *mean1, *rstd1;
-  bf16* pre;      // [M,I] FFN pre-activation
+  bf16* pre;      // [M,I] GELU'(FFN pre-activation)
   float* h2;      // [M,H] pre-LN2
   float *mean2, *rstd2;
 };
@@ -115,7 +115,7 @@ struct suta_engine {
   long long* d_off[SUTA_MAX_CONV] = {};            // [U] row offsets per layer
   long long* d_dpre_off_last = nullptr;            // = off64 on device
   int* d_L[SUTA_MAX_CONV] = {};                    // [U] valid rows per layer
-  bf16* conv_pre[SUTA_MAX_CONV] = {};              // pre-GELU activations (bf16)
+  bf16* conv_pre[SUTA_MAX_CONV] = {};              // GELU'(pre-activation) saved by the forward (bf16)
   bf16* conv_dpre[SUTA_MAX_CONV] = {};             // d(pre-activation), zero outside valid rows
   bf16* w_shadow[SUTA_MAX_CONV] = {};              // bf16 copies of the per-utterance conv weights [U][Cout][k*Cin]
   bf16* proj_shadow = nullptr;                     // [U][H][C]
@@ -973,7 +973,7 @@ extern "C" int suta_op_gemm(const void* a, int64_t a_rows, int64_t a_row_stride,
   p.b = {reinterpret_cast<const bf16*>(b), b_rows, b_row_stride};
   p.M = M; p.N = N; p.K = K;
   p.epi.out_f32 = out_f32; p.epi.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.epi.out_ld = out_ld;
-  p.epi.bias = bias; p.epi.residual = residual; p.epi.res_ld = res_ld; p.epi.act = act;
+  p.epi.bias = bias; p.epi.residual = residual; p.epi.res_ld = res_ld; p.epi.act = act & 3; p.epi.accumulate = (act >> 2) & 1;
   p.epi.aux_in = reinterpret_cast<const bf16*>(aux_in); p.epi.aux_out = reinterpret_cast<bf16*>(aux_out); p.epi.aux_ld = aux_ld;
   return gemm_bf16_tc(p, S(stream));
 }

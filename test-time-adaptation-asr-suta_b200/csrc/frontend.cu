@@ -116,8 +116,11 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
         y0 = (y0 - mean0) * r0 * g0 + b0;
         y1 = (y1 - mean1) * r1 * g1 + b1;
         const long long o = (row0 + t) * a.C + c;
-        if (a.pre_out) *reinterpret_cast<uint32_t*>(a.pre_out + o) = pack_bf16x2(y0, y1);
-        *reinterpret_cast<uint32_t*>(a.out + o) = pack_bf16x2(gelu_erf(y0), gelu_erf(y1));
+        float g0v, g1v, d0v, d1v;
+        gelu_erf_both(y0, g0v, d0v);
+        gelu_erf_both(y1, g1v, d1v);
+        if (a.pre_out) *reinterpret_cast<uint32_t*>(a.pre_out + o) = pack_bf16x2(d0v, d1v);
+        *reinterpret_cast<uint32_t*>(a.out + o) = pack_bf16x2(g0v, g1v);
       }
     }
   }

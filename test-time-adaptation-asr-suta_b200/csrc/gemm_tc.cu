@@ -1,14 +1,25 @@
 // tcgen05 + TMEM + TMA GEMM for sm_100a.  See gemm_tc.cuh for what it computes.
 //
-// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
+// Structure (one persistent CTA per SM, 10 warps, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 boxes, 128B swizzle,
 //               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage into a
 //               double-buffered fp32 accumulator in tensor memory; tcgen05.commit releases the stage
 //   warps 2..9  epilogue: two warps per TMEM lane quarter, each owning half of the tile's columns;
-//               tcgen05.ld the accumulator (one row per thread), apply bias / GELU / GELU' /
-//               residual, store fp32 and/or bf16 straight to global; overlaps the next tile's mainloop
+//               overlaps the next tile's mainloop through the double-buffered accumulator.  Two variants:
+//     EPI_TMA   (dense outputs) tcgen05.ld a 32x32 chunk (one row per thread), bias / GELU (+GELU' saved) / x GELU'
+//               in registers, write the chunk into a swizzled shared-memory patch and hand it to the TMA:
+//               cp.async.bulk.tensor store, or cp.reduce.async.bulk.tensor .add for "out += acc" (the residual
+//               stream is accumulated in place at the L2, the SM never loads it).  Nothing in the warp's dependent
+//               chain waits on a shared- or global-memory LOAD: measured on B200, any such round trip costs
+//               500-3000 cycles while the mainloop saturates the shared-memory and L2 request paths
+//               (profiles/r01c_gemm_timeline.md).
+//     manual    (row-masked outputs: per-utterance M-block tables, z-batched slabs, BN = 48) the chunk is
+//               transposed through a private swizzled patch so lanes run along columns and every global access is
+//               a full 128-byte row segment; all loads of a chunk are issued before the first use.
 #include "gemm_tc.cuh"
+
+#include <string.h>
 
 #include <mutex>
 
@@ -17,6 +28,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
 
 struct GemmKernelParams {
   int M, N, K;
@@ -26,95 +38,75 @@ struct GemmKernelParams {
   const int4* mblk;
   const int4* ztab;
   long long out_z_stride;
+  long long* trace;     // debug: per-tile clock64 timeline of CTA 0 (8 slots per tile iteration), or null
+  int trace_cap;        // tile iterations that fit
   GemmEpilogue epi;
 };
 
-template <int BN>
+long long* g_trace = nullptr;
+int g_trace_cap = 0;
+
+#define TRACE(iter, slot)                                                                              \
+  do {                                                                                                 \
+    if (p.trace && blockIdx.x == 0 && (iter) < p.trace_cap) p.trace[(iter) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+template <int BN, bool EPI_TMA>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int CH = (BN % 32 == 0) ? 32 : 16;       // epilogue column chunk
   static constexpr int EPI_SPLIT = (BN >= 128) ? 2 : 1;      // epilogue warps per TMEM lane quarter
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per epilogue warp: TMA variant = two 4 KB patches (ping-pong) + 512 B of bias; manual = one 4 KB transpose patch
+  static constexpr int PATCH_BYTES = 4096;
+  static constexpr int WARP_EPI_BYTES = EPI_TMA ? 2 * PATCH_BYTES : PATCH_BYTES;
+  static constexpr int BIAS_BYTES = EPI_TMA ? 8 * 512 : 0;
+  static constexpr int EPI_BYTES = 8 * WARP_EPI_BYTES + BIAS_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BUDGET = SMEM_MAX - EPI_BYTES - BAR_BYTES - 1024 /*align slack*/;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+  static_assert(!EPI_TMA || CH == 32, "the TMA epilogue works on 32-column chunks");
+  static_assert(STAGES >= 2, "shared memory budget");
 };
 
-template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[CH], long long row, int oc,
-                                               long long bias_off, long long out_off) {
-  if (e.bias) {
-    const float4* bp = reinterpret_cast<const float4*>(e.bias + bias_off + oc);
-#pragma unroll
-    for (int i = 0; i < CH / 4; ++i) {
-      float4 b = __ldg(bp + i);
-      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  }
+// manual path: one (row, 4 consecutive columns) piece of the output; b4 = bias of these columns (zeros when absent),
+// r4 = residual (zeros when absent), d2 = 4 saved GELU' values (act == 2)
+__device__ __forceinline__ void epilogue4(const GemmEpilogue& e, float4 v, const float4 b4, const float4 r4, const uint2 d2,
+                                          long long row, int oc, long long out_off) {
+  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
   if (e.act == 1) {
-    if (e.aux_out) {
-      uint4* ap = reinterpret_cast<uint4*>(e.aux_out + row * e.aux_ld + oc);
-#pragma unroll
-      for (int i = 0; i < CH / 8; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        ap[i] = u;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+    float4 d;
+    gelu_erf_both(v.x, v.x, d.x); gelu_erf_both(v.y, v.y, d.y); gelu_erf_both(v.z, v.z, d.z); gelu_erf_both(v.w, v.w, d.w);
+    if (e.aux_out)
+      *reinterpret_cast<uint2*>(e.aux_out + row * e.aux_ld + oc) = make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
   } else if (e.act == 2) {
-    const uint4* ap = reinterpret_cast<const uint4*>(e.aux_in + row * e.aux_ld + oc);
-#pragma unroll
-    for (int i = 0; i < CH / 8; ++i) {
-      uint4 u = __ldg(ap + i);
-      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      v[8 * i + 0] *= gelu_erf_grad(f0.x); v[8 * i + 1] *= gelu_erf_grad(f0.y);
-      v[8 * i + 2] *= gelu_erf_grad(f1.x); v[8 * i + 3] *= gelu_erf_grad(f1.y);
-      v[8 * i + 4] *= gelu_erf_grad(f2.x); v[8 * i + 5] *= gelu_erf_grad(f2.y);
-      v[8 * i + 6] *= gelu_erf_grad(f3.x); v[8 * i + 7] *= gelu_erf_grad(f3.y);
-    }
+    const float2 d0 = unpack_bf16x2(d2.x), d1 = unpack_bf16x2(d2.y);
+    v.x *= d0.x; v.y *= d0.y; v.z *= d1.x; v.w *= d1.y;
   }
-  if (e.residual) {
-    const float4* rp = reinterpret_cast<const float4*>(e.residual + row * e.res_ld + oc);
-#pragma unroll
-    for (int i = 0; i < CH / 4; ++i) {
-      float4 r = __ldg(rp + i);
-      v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-    }
-  }
-  if (e.out_f32) {
-    float4* op = reinterpret_cast<float4*>(e.out_f32 + out_off + row * e.out_ld + oc);
-#pragma unroll
-    for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
-  if (e.out_bf16) {
-    uint4* op = reinterpret_cast<uint4*>(e.out_bf16 + out_off + row * e.out_ld + oc);
-#pragma unroll
-    for (int i = 0; i < CH / 8; ++i) {
-      uint4 u;
-      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      op[i] = u;
-    }
-  }
+  v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+  if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + out_off + row * e.out_ld + oc) = v;
+  if (e.out_bf16)
+    *reinterpret_cast<uint2*>(e.out_bf16 + out_off + row * e.out_ld + oc) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
 // A_MN / B_MN: the operand is MN-major in memory ([K rows][M|N contiguous]); its tile is fetched as 64x64 TMA boxes
 // (64 M|N elements = one 128-byte swizzle row, 64 k-rows) laid 8 KB apart, described to the tensor core with
 // leading-dimension byte offset 8192 (next 64 M|N elements) and stride byte offset 1024 (next 8 k-rows).
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool EPI_TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                     const GemmKernelParams p) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, EPI_TMA>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE_BYTES);
+  uint8_t* epi_smem = tiles + C::STAGES * C::STAGE_BYTES;             // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
   uint64_t* acc_full = bars + 2 * C::STAGES;       // [2]
@@ -127,6 +119,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (EPI_TMA) {
+      tma_prefetch_desc(&tma_out);
+      if (p.epi.aux_out) tma_prefetch_desc(&tma_aux);
+    }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -152,7 +148,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        TRACE(iter, 7);
         const int z = tile / tiles_per_z;
         const int r = tile - z * tiles_per_z;
         const int m_blk = r / p.num_nblk;
@@ -201,11 +199,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         int num_kblk = num_kblk_all;
         if (p.ztab) num_kblk = (__ldg(&p.ztab[tile / tiles_per_z]).z + BK - 1) / BK;
+        TRACE(iter, 0);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        TRACE(iter, 1);
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
         for (int kb = 0; kb < num_kblk; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -222,6 +223,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);               // accumulator complete -> epilogue
+        TRACE(iter, 2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -230,45 +232,205 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;              // which column half of the tile this warp owns
     constexpr int COLS_PER_WARP = BN / C::EPI_SPLIT;
+    constexpr int NCH = COLS_PER_WARP / C::CH;     // chunks per warp and tile
+    const uint32_t patch = smem_u32(epi_smem + (warp - 2) * C::WARP_EPI_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x) {
-      const int z = tile / tiles_per_z;
-      const int r = tile - z * tiles_per_z;
-      const int m_blk = r / p.num_nblk;
-      const int n_blk = r - m_blk * p.num_nblk;
-      int out_row0 = m_blk * BM, rows_valid = min(BM, p.M - m_blk * BM), b_off = 0;
-      if (p.mblk) {
-        int4 mi = __ldg(&p.mblk[m_blk]);
-        out_row0 = mi.y;
-        rows_valid = mi.z;
-        b_off = mi.w;
-      }
-      const int row_in_tile = q * 32 + lane;
-      const bool row_ok = row_in_tile < rows_valid;
-      const long long row = (long long)out_row0 + row_in_tile;
+    int iter = 0;
+    const int tslot = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 3 : 5) : -1;
 
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_STRIDE;
-#pragma unroll 1
-      for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += C::CH) {
-        uint32_t raw[C::CH];
-        if constexpr (C::CH == 32) tmem_ld_32x32(t_addr + c0, raw); else tmem_ld_32x16(t_addr + c0, raw);
-        tmem_ld_wait();
-        const int col = n_blk * BN + c0;
-        if (row_ok && col < p.N) {
-          float v[C::CH];
-#pragma unroll
-          for (int i = 0; i < C::CH; ++i) v[i] = __uint_as_float(raw[i]);
-          const long long bias_off = p.epi.bias_utt_stride ? (long long)(b_off / p.N) * p.epi.bias_utt_stride : (long long)b_off;
-          epilogue_chunk<C::CH>(p.epi, v, row, z * p.c_z_cols + col, bias_off, (long long)z * p.out_z_stride);
+    if constexpr (EPI_TMA) {
+      // ---------------------------------------------------------------- TMA-store epilogue
+      const uint32_t bias_s = smem_u32(epi_smem + 8 * C::WARP_EPI_BYTES + (warp - 2) * 512);
+      const bool out_is_f32 = p.epi.out_f32 != nullptr;
+      uint32_t pc = 0;                             // running chunk counter -> patch ping-pong
+      for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int m_blk = tile / p.num_nblk;       // dense problems only: nz == 1, no M-block table
+        const int n_blk = tile - m_blk * p.num_nblk;
+        const int row0 = m_blk * BM + q * 32;      // first output row of this warp
+        const int col0 = n_blk * BN + half * COLS_PER_WARP;
+        if (p.epi.bias) {                          // this warp's COLS_PER_WARP bias values -> shared memory
+          __syncwarp();
+          for (int i = lane * 4; i < COLS_PER_WARP; i += 128) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + i));
+            st_shared_v4(bias_s + i * 4, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+          }
+          __syncwarp();
         }
+        uint4 auxr[NCH][4];                        // act == 2: this thread's row of saved GELU' (32 bf16 per chunk)
+        if (p.epi.act == 2) {
+          const bool ok = row0 + lane < p.M;
+          const uint4* ap = reinterpret_cast<const uint4*>(p.epi.aux_in + (long long)(row0 + (ok ? lane : 0)) * p.epi.aux_ld + col0);
+#pragma unroll
+          for (int kc = 0; kc < NCH; ++kc)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) auxr[kc][j] = ok ? __ldg(ap + kc * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        if (tslot >= 0) TRACE(iter, tslot);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_STRIDE + half * COLS_PER_WARP;
+#pragma unroll
+        for (int kc = 0; kc < NCH; ++kc) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_addr + kc * 32, raw);
+          float v[32];
+          if (p.epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = ld_shared_v4(bias_s + (kc * 32 + 4 * j) * 4);
+              v[4 * j] = b.x; v[4 * j + 1] = b.y; v[4 * j + 2] = b.z; v[4 * j + 3] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          tmem_ld_wait();
+          if (kc == NCH - 1) {                     // accumulator drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(raw[i]);
+
+          if (p.epi.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = auxr[kc][j];
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * j] *= f0.x; v[8 * j + 1] *= f0.y; v[8 * j + 2] *= f1.x; v[8 * j + 3] *= f1.y;
+              v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
+            }
+          }
+          const uint32_t pp = patch + (pc & 1) * C::PATCH_BYTES;
+          ++pc;
+          if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has finished reading this patch
+          __syncwarp();
+          if (out_is_f32) {
+            const uint32_t wrow = pp + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(wrow + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else {
+            const uint32_t wrow = pp + lane * 64;
+            const int swz = (lane >> 1) & 3;
+            if (p.epi.act == 1) {
+              float d[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) gelu_erf_both(v[i], v[i], d[i]);
+              if (p.epi.aux_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(wrow + 2048 + ((j ^ swz) << 4), pack_bf16x2(d[8 * j], d[8 * j + 1]), pack_bf16x2(d[8 * j + 2], d[8 * j + 3]),
+                               pack_bf16x2(d[8 * j + 4], d[8 * j + 5]), pack_bf16x2(d[8 * j + 6], d[8 * j + 7]));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(wrow + ((j ^ swz) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < p.M) {
+              const int cc = col0 + kc * 32;
+              if (p.epi.accumulate) tma_reduce_add_2d(&tma_out, pp, cc, row0);
+              else tma_store_2d(&tma_out, pp, cc, row0);
+              if (p.epi.act == 1 && p.epi.aux_out) tma_store_2d(&tma_aux, pp + 2048, cc, row0);
+            }
+            bulk_commit();
+          }
+        }
+        if (tslot >= 0) TRACE(iter, tslot + 1);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (lane == 0) bulk_wait<0>();               // shared memory must outlive the last store's reads
+    } else {
+      // ---------------------------------------------------------------- manual (row-masked) epilogue
+      constexpr int CGN = C::CH / 4;               // 4-column groups per chunk row (8 or 4)
+      constexpr int RPI = 32 / CGN;                // rows covered by one warp-wide instruction in the column phase
+      const int cg = lane % CGN, r0 = lane / CGN;
+      for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int z = tile / tiles_per_z;
+        const int r = tile - z * tiles_per_z;
+        const int m_blk = r / p.num_nblk;
+        const int n_blk = r - m_blk * p.num_nblk;
+        int out_row0 = m_blk * BM, rows_valid = min(BM, p.M - m_blk * BM), b_off = 0;
+        if (p.mblk) {
+          int4 mi = __ldg(&p.mblk[m_blk]);
+          out_row0 = mi.y;
+          rows_valid = mi.z;
+          b_off = mi.w;
+        }
+        const int rows_here = rows_valid - q * 32;   // valid rows of this warp's 32-row slab
+        const long long row_base = (long long)out_row0 + q * 32;
+        const long long bias_off = p.epi.bias_utt_stride ? (long long)(b_off / p.N) * p.epi.bias_utt_stride : (long long)b_off;
+        const long long out_off = (long long)z * p.out_z_stride;
+        const int oc0 = z * p.c_z_cols + n_blk * BN + half * COLS_PER_WARP + cg * 4;
+        float4 bias4[NCH];                           // loaded before the accumulator is awaited
+#pragma unroll
+        for (int kc = 0; kc < NCH; ++kc) {
+          bias4[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.epi.bias) bias4[kc] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + bias_off + oc0 + kc * C::CH));
+        }
+
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        if (tslot >= 0) TRACE(iter, tslot);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_STRIDE + half * COLS_PER_WARP;
+#pragma unroll
+        for (int kc = 0; kc < NCH; ++kc) {
+          uint32_t raw[C::CH];
+          if constexpr (C::CH == 32) tmem_ld_32x32(t_addr + kc * C::CH, raw); else tmem_ld_32x16(t_addr + kc * C::CH, raw);
+          const int oc = oc0 + kc * C::CH;
+          // side inputs of this chunk, issued before anything waits
+          float4 res4[CGN];
+          uint2 aux2[CGN];
+#pragma unroll
+          for (int i = 0; i < CGN; ++i) {
+            const int rt = r0 + RPI * i;
+            const bool ok = rt < rows_here;
+            res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            aux2[i] = make_uint2(0u, 0u);
+            if (p.epi.residual && ok) res4[i] = __ldg(reinterpret_cast<const float4*>(p.epi.residual + (row_base + rt) * p.epi.res_ld + oc));
+            if (p.epi.act == 2 && ok) aux2[i] = __ldg(reinterpret_cast<const uint2*>(p.epi.aux_in + (row_base + rt) * p.epi.aux_ld + oc));
+          }
+          tmem_ld_wait();
+          if (kc == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          }
+          if (rows_here > 0) {
+            // row-per-thread -> patch (16-byte chunk j of row `lane` at chunk position j ^ swz(lane): conflict-free)
+            const uint32_t wrow = patch + lane * (C::CH * 4);
+            const int wswz = (lane * CGN / 8) & (CGN - 1);
+#pragma unroll
+            for (int j = 0; j < CGN; ++j)
+              st_shared_v4(wrow + ((j ^ wswz) << 4), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+            __syncwarp();
+            float4 vv[CGN];
+#pragma unroll
+            for (int i = 0; i < CGN; ++i) {
+              const int rt = r0 + RPI * i;
+              const int rswz = (rt * CGN / 8) & (CGN - 1);
+              vv[i] = ld_shared_v4(patch + rt * (C::CH * 4) + ((cg ^ rswz) << 4));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < CGN; ++i) {
+              const int rt = r0 + RPI * i;
+              if (rt < rows_here) epilogue4(p.epi, vv[i], bias4[kc], res4[i], aux2[i], row_base + rt, oc, out_off);
+            }
+          }
+        }
+        if (tslot >= 0) TRACE(iter, tslot + 1);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
 
@@ -300,51 +462,65 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap(CUtensorMap* tm, const GemmOperand& op, int K, int box_rows);
-
-// MN-major operand: dims {cols (M|N, contiguous), rows (K)}, 64x64 boxes
-int make_tmap_mn(CUtensorMap* tm, const GemmOperand& op) {
-  GemmOperand t = op;
-  return make_tmap(tm, t, (int)op.cols, 64);
-}
-
-int make_tmap(CUtensorMap* tm, const GemmOperand& op, int K, int box_rows) {
+// generic 2-D map: dims {cols (contiguous), rows}, row pitch in bytes, box {box_cols, box_rows}
+int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, const void* ptr, long long cols, long long rows,
+                long long pitch_bytes, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     suta_set_last_error("cuTensorMapEncodeTiled entry point not available");
     return SUTA_ERR_DRIVER;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)op.rows};
-  cuuint64_t strides[1] = {(cuuint64_t)op.row_stride * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (strides[0] & 15) || op.rows <= 0) {
-    suta_set_last_error("gemm operand not TMA-compatible: ptr=%p row_stride=%lld rows=%lld", (const void*)op.ptr,
-                        op.row_stride, op.rows);
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || rows <= 0 || cols <= 0) {
+    suta_set_last_error("gemm operand not TMA-compatible: ptr=%p pitch=%lld rows=%lld cols=%lld", ptr, pitch_bytes, rows, cols);
     return SUTA_ERR_ARG;
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(op.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    suta_set_last_error("cuTensorMapEncodeTiled failed (%d): K=%d rows=%lld stride=%lld box_rows=%d", (int)r, K,
-                        op.rows, op.row_stride, box_rows);
+    suta_set_last_error("cuTensorMapEncodeTiled failed (%d): cols=%lld rows=%lld pitch=%lld box=%dx%d", (int)r, cols, rows,
+                        pitch_bytes, box_cols, box_rows);
     return SUTA_ERR_DRIVER;
   }
   return SUTA_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// bf16 GEMM operand: K-major (dims {K, rows}) or MN-major (dims {cols, rows = K}), 64-element (128-byte) box rows
+int make_tmap(CUtensorMap* tm, const GemmOperand& op, int K, int box_rows) {
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op.ptr, K, op.rows, op.row_stride * (long long)sizeof(bf16), BK,
+                     box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap_mn(CUtensorMap* tm, const GemmOperand& op) { return make_tmap(tm, op, (int)op.cols, 64); }
+
+template <int BN, bool A_MN, bool B_MN, bool EPI_TMA>
 int launch(const GemmProblem& p, cudaStream_t stream) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, EPI_TMA>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to, tx;
+  memset(&to, 0, sizeof(to));
+  memset(&tx, 0, sizeof(tx));
   if (A_MN) SUTA_TRY(make_tmap_mn(&ta, p.a)); else SUTA_TRY(make_tmap(&ta, p.a, p.K, BM));
   if (B_MN) SUTA_TRY(make_tmap_mn(&tb, p.b)); else SUTA_TRY(make_tmap(&tb, p.b, p.K, BN));
+  if (EPI_TMA) {
+    // 32 x 32 output boxes: fp32 rows are 128 B (128B swizzle), bf16 rows 64 B (64B swizzle); rows >= M are clipped
+    if (p.epi.out_f32)
+      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.epi.out_f32, p.N, p.M, (long long)p.epi.out_ld * 4, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_128B));
+    else
+      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.out_bf16, p.N, p.M, (long long)p.epi.out_ld * 2, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B));
+    if (p.epi.act == 1 && p.epi.aux_out)
+      SUTA_TRY(encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.aux_out, p.N, p.M, (long long)p.epi.aux_ld * 2, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B));
+  }
   GemmKernelParams kp;
   kp.M = p.M; kp.N = p.N; kp.K = p.K;
   kp.num_mblk = p.mblk ? p.num_mblk : ceil_div(p.M, BM);
@@ -354,16 +530,26 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   kp.mblk = p.mblk;
   kp.ztab = p.ztab;
   kp.out_z_stride = p.out_z_stride;
+  kp.trace = g_trace;
+  kp.trace_cap = g_trace_cap;
   kp.epi = p.epi;
   long long total = (long long)kp.num_mblk * kp.num_nblk * kp.nz;
   if (total <= 0) return SUTA_OK;
   int grid = (int)(total < gemm_num_sms() ? total : gemm_num_sms());
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, kp);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tx, kp);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
 
 }  // namespace
+
+// debug hook: CTA 0 of every following GEMM launch writes its per-tile clock64 timeline into dev_buf[cap][8]
+// (0 MMA warp waits for a free accumulator, 1 starts issuing, 2 has issued the tile; 3/4 and 5/6 first epilogue
+// warp of each column half starts/finishes; 7 producer starts the tile).  Pass null to switch off.
+extern "C" void suta_debug_set_gemm_trace(long long* dev_buf, int cap) {
+  g_trace = dev_buf;
+  g_trace_cap = dev_buf ? cap : 0;
+}
 
 int gemm_num_sms() {
   static int n = 0;
@@ -380,22 +566,33 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
   SUTA_CHECK_ARG(p.M > 0 && p.N > 0 && (p.K > 0 || p.ztab) && p.N % 16 == 0 && p.K % 8 == 0);
   SUTA_CHECK_ARG(p.epi.out_f32 || p.epi.out_bf16);
   SUTA_CHECK_ARG(p.epi.out_ld % 8 == 0 && p.epi.res_ld % 4 == 0 && p.epi.aux_ld % 8 == 0);
+  SUTA_CHECK_ARG(!(p.epi.accumulate && (p.epi.residual || !p.epi.out_f32)));
   if (p.a.mn_major || p.b.mn_major) {
-    SUTA_CHECK_ARG(p.N % 64 == 0 && (!p.a.mn_major || p.b.mn_major));
+    SUTA_CHECK_ARG(p.N % 64 == 0 && (!p.a.mn_major || p.b.mn_major) && !p.epi.accumulate);
     if (p.a.mn_major) {
-      if (p.N % 256 == 0) return launch<256, true, true>(p, stream);
-      if (p.N % 128 == 0) return launch<128, true, true>(p, stream);
-      return launch<64, true, true>(p, stream);
+      if (p.N % 256 == 0) return launch<256, true, true, false>(p, stream);
+      if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
+      return launch<64, true, true, false>(p, stream);
     }
-    if (p.N % 256 == 0) return launch<256, false, true>(p, stream);
-    if (p.N % 128 == 0) return launch<128, false, true>(p, stream);
-    return launch<64, false, true>(p, stream);
+    if (p.N % 256 == 0) return launch<256, false, true, false>(p, stream);
+    if (p.N % 128 == 0) return launch<128, false, true, false>(p, stream);
+    return launch<64, false, true, false>(p, stream);
   }
-  if (p.N % 256 == 0) return launch<256, false, false>(p, stream);
-  if (p.N % 128 == 0) return launch<128, false, false>(p, stream);
-  if (p.N % 64 == 0) return launch<64, false, false>(p, stream);
-  if (p.N % 48 == 0) return launch<48, false, false>(p, stream);
-  if (p.N % 32 == 0) return launch<32, false, false>(p, stream);
+  // dense outputs (every row of [0, M) is written, one z slice, shared bias): TMA-store epilogue
+  const bool dense = !p.mblk && !p.ztab && p.nz == 1 && !p.epi.residual && !p.epi.bias_utt_stride && p.N % 32 == 0 &&
+                     ((p.epi.out_f32 != nullptr) != (p.epi.out_bf16 != nullptr)) && (p.epi.act != 1 || p.epi.out_bf16);
+  if (dense) {
+    if (p.N % 256 == 0) return launch<256, false, false, true>(p, stream);
+    if (p.N % 128 == 0) return launch<128, false, false, true>(p, stream);
+    if (p.N % 64 == 0) return launch<64, false, false, true>(p, stream);
+    return launch<32, false, false, true>(p, stream);
+  }
+  SUTA_CHECK_ARG(!p.epi.accumulate);
+  if (p.N % 256 == 0) return launch<256, false, false, false>(p, stream);
+  if (p.N % 128 == 0) return launch<128, false, false, false>(p, stream);
+  if (p.N % 64 == 0) return launch<64, false, false, false>(p, stream);
+  if (p.N % 48 == 0) return launch<48, false, false, false>(p, stream);
+  if (p.N % 32 == 0) return launch<32, false, false, false>(p, stream);
   suta_set_last_error("gemm: N=%d must be a multiple of 32 or 48", p.N);
   return SUTA_ERR_ARG;
 }

@@ -26,11 +26,13 @@ struct GemmEpilogue {
   int out_ld = 0;
   const float* bias = nullptr;     // indexed [b_row_off + out_col], or [(b_row_off / N) * bias_utt_stride + out_col]
   long long bias_utt_stride = 0;   //   when bias_utt_stride != 0 (per-utterance bias inside the trainable vector)
-  const float* residual = nullptr; // fp32 [rows, res_ld], added last
+  const float* residual = nullptr; // fp32 [rows, res_ld], added last (row-masked epilogue only)
   int res_ld = 0;
-  int act = 0;                     // 0 none, 1 GELU(erf), 2 multiply by GELU'(aux_in)
-  const bf16* aux_in = nullptr;    // pre-activation saved by the forward (act == 2)
-  bf16* aux_out = nullptr;         // where to save the pre-activation (act == 1), may be null
+  int accumulate = 0;              // out_f32 += result instead of = (TMA reduce-add at the L2; dense outputs only):
+                                   // how the encoder's residual stream is updated in place
+  int act = 0;                     // 0 none, 1 GELU(erf), 2 multiply by aux_in
+  const bf16* aux_in = nullptr;    // GELU'(pre-activation) saved by the forward (act == 2)
+  bf16* aux_out = nullptr;         // where to save GELU'(pre-activation) (act == 1), may be null
   int aux_ld = 0;
 };
 

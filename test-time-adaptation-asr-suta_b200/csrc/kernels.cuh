@@ -42,7 +42,7 @@ struct Conv0Args {
   int g_off, b_off;
   double* stats;               // [U][C][2] sum, sumsq scratch (zeroed by the launcher)
   bf16* out;                   // [rows, C]
-  bf16* pre_out;               // optional: pre-GELU normalised value (train_feature backward)
+  bf16* pre_out;               // optional: GELU'(normalised value) for the train_feature backward
   int n_utts, C, k, stride, max_L0;
 };
 int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
@@ -50,12 +50,12 @@ int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
 // ---- convbwd.cu (train_feature backward of the CNN front end) ---------------------------------
 int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,
                      cudaStream_t stream);
-// out[pad_off[u] + t] = d[row] * GELU'(pre[row]) (pre may be null: plain cast) into a 64-row-aligned, zero-gapped slab
+// out[pad_off[u] + t] = d[row] * pre[row] (pre = GELU' saved by the forward; may be null: plain cast) into a 64-row-aligned, zero-gapped slab
 int gelu_grad_to_padded(const float* d, const bf16* pre, bf16* out, const int* row_utt, const long long* tok_off,
                         const long long* pad_off, long long M, int C, cudaStream_t stream);
 struct Col2imArgs {
   const bf16* Z;               // [rows_in, k*C] dgrad GEMM output of the layer above, (tap, cin) column order
-  const bf16* pre;             // [rows_out, C] pre-activation of this layer's output
+  const bf16* pre;             // [rows_out, C] GELU'(pre-activation) of this layer's output, saved by the forward
   bf16* out;                   // [rows_out, C] d(pre-activation)
   const long long *off_out, *off_in;   // [U] first row of each utterance in this / the upper layer
   const int *L_out, *L_in;     // [U] valid rows

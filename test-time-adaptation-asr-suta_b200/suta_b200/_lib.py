@@ -83,6 +83,7 @@ SIGNATURES = {
     "suta_launch_count": (c_int64, [c_void_p]),
     "suta_profile": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
     "suta_profile_report": (C.c_char_p, [c_void_p]),
+    "suta_debug_set_gemm_trace": (None, [c_void_p, c_int]),
     "suta_op_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
                              c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "suta_op_gemm_mn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,

@@ -63,19 +63,31 @@ def check_gemm_epilogue(M=517, N=384, K=256, seed=1):
     aux = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
     gemm(a, b, M, N, K, out_bf16=o16, bias=bias, act=1, aux_out=aux)
     out["gelu_rel"] = relerr(o16.float(), torch.nn.functional.gelu(pre_ref))
-    out["aux_rel"] = relerr(aux.float(), pre_ref)
+    xr = pre_ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xr).sum().backward()
+    out["aux_rel"] = relerr(aux.float(), xr.grad)            # the forward epilogue saves GELU'(pre-activation)
     # bias + residual, fp32 + bf16 out
     o32 = torch.zeros(M, N, device=DEV)
     o16b = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
     gemm(a, b, M, N, K, out_f32=o32, out_bf16=o16b, bias=bias, residual=res)
     out["res_rel"] = relerr(o32, pre_ref + res)
     out["res16_rel"] = relerr(o16b.float(), pre_ref + res)
-    # gelu backward: acc * gelu'(aux_in)
-    x = aux.float().requires_grad_(True)
-    torch.nn.functional.gelu(x).sum().backward()
+    # gelu backward: acc * aux_in (the saved derivative)
     o32c = torch.zeros(M, N, device=DEV)
     gemm(a, b, M, N, K, out_f32=o32c, act=2, aux_in=aux)
-    out["gelu_bwd_rel"] = relerr(o32c, (a.float() @ b.float().t()) * x.grad)
+    out["gelu_bwd_rel"] = relerr(o32c, (a.float() @ b.float().t()) * aux.float())
+    out["gelu_bwd_vs_exact_rel"] = relerr(o32c, (a.float() @ b.float().t()) * xr.grad)
+    # in-place accumulation (how the residual stream is updated): out = res; out += a b^T + bias
+    o32d = res.clone()
+    gemm(a, b, M, N, K, out_f32=o32d, bias=bias, act=4)
+    out["acc_rel"] = relerr(o32d, pre_ref + res)
+    # bf16 output alone through the dense path, ragged M
+    o16c = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    gemm(a, b, M, N, K, out_bf16=o16c, bias=bias)
+    out["bf16_rel"] = relerr(o16c.float(), pre_ref)
+    o16d = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    gemm(a, b, M, N, K, out_bf16=o16d, act=2, aux_in=aux)
+    out["gelu_bwd16_rel"] = relerr(o16d.float(), (a.float() @ b.float().t()) * aux.float())
     return out
 
 

@@ -24,8 +24,9 @@ def test_gemm_plain(K):
 
 def test_gemm_epilogues(K):
     r = K.check_gemm_epilogue()
-    assert r["res_rel"] < F32 and r["gelu_bwd_rel"] < F32
-    assert r["gelu_rel"] < BF16 and r["aux_rel"] < BF16 and r["res16_rel"] < BF16
+    assert r["res_rel"] < F32 and r["gelu_bwd_rel"] < F32 and r["acc_rel"] < F32
+    assert r["bf16_rel"] < BF16 and r["gelu_bwd16_rel"] < BF16
+    assert r["gelu_rel"] < BF16 and r["aux_rel"] < BF16 and r["res16_rel"] < BF16 and r["gelu_bwd_vs_exact_rel"] < BF16
 
 
 def test_gemm_shapes_of_the_path(K):
