@@ -106,7 +106,7 @@ struct suta_engine {
   int4* d_mblk[SUTA_MAX_CONV] = {};
   int4* d_attn_tab = nullptr;
   // train_feature only
-  std::vector<long long> off64;                    // [u] first row of utterance u in the 64-row-aligned token slabs
+  std::vector<long long> off64;                    // [u] first row of utterance u in the 128-row-aligned token slabs
   long long R64 = 0;
   int n_tok_mblk = 0;
   int4* d_tok_mblk = nullptr;                      // per-utterance M-blocks over packed tokens (per-utterance projection)
@@ -233,8 +233,9 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
     for (int u = 0; u < U; ++u) {
       e->off[l][u] = r;
       // rows of the next layer's implicit-GEMM view start at off/stride: keep offsets multiples of 8; under
-      // train_feature the weight-gradient GEMMs reduce over time in 64-row steps, so utterances are 64-row aligned
-      const int al = e->train_feature ? 63 : 7;
+      // train_feature every utterance starts on a 128-row boundary, so (a) the weight-gradient GEMMs can reduce over
+      // time in 64-row steps and (b) every 128-row GEMM tile owns its output rows outright (TMA-store epilogue)
+      const int al = e->train_feature ? 127 : 7;
       r += last ? e->L[l][u] : ((e->L[l][u] + al) & ~al);
       if (l >= 1) e->n_mblk[l] += ceil_div(e->L[l][u], 128);
       e->max_L[l] = u == 0 ? e->L[l][u] : (e->L[l][u] > e->max_L[l] ? e->L[l][u] : e->max_L[l]);
@@ -260,7 +261,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
   long long r64 = 0;
   for (int u = 0; u < U; ++u) {
     e->off64[u] = r64;
-    r64 += (e->T[u] + 63) & ~63;
+    r64 += (e->T[u] + 127) & ~127;
     e->n_tok_mblk += ceil_div(e->T[u], 128);
   }
   e->R64 = r64;
@@ -384,7 +385,7 @@ int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   char tag[96];
   snprintf(tag, sizeof(tag), "gemm N%d K%d%s%s%s%s%s%s", p.N, p.K, p.nz > 1 ? " batched" : "", p.a.mn_major ? " wgrad" : "",
            (!p.a.mn_major && p.b.mn_major) ? " Bmn" : "", p.epi.act == 1 ? " gelu" : (p.epi.act == 2 ? " gelu'" : ""),
-           p.epi.residual ? " +res" : "", p.epi.bias ? " +bias" : "");
+           (p.epi.residual || p.epi.accumulate) ? " +res" : "", p.epi.bias ? " +bias" : "");
   ProfScope ps(e, st, tag, flops, true);
   return gemm_bf16_tc(p, st);
 }
@@ -666,6 +667,10 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     if (e->train_feature) {
       p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin};
       p.epi.aux_out = e->conv_pre[l]; p.epi.aux_ld = Cout;
+      if (l < c.n_conv - 1) {    // 128-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
+        p.tiles_own_rows = 1;
+        p.out_rows = e->rows_total[l] + 128;
+      }
     }
     SUTA_TRY(gemm(e, p, st));
   }
@@ -709,7 +714,10 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   }
   PROF("posconv_combine", posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->hE, M, H, -(c.pos_k / 2), st));
   // encoder.layer_norm                                          HF/modeling_wav2vec2.py:692
-  PROF("ln_fwd", layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->fa, e->b16, e->enc_mean,
+  // The residual stream is updated IN PLACE: every LayerNorm writes its fp32 output straight into the buffer that holds
+  // the next pre-LayerNorm sum (lb[l].h1 / h2, kept per layer for the backward), and the following GEMM accumulates
+  // "+= x W^T + b" into it with a TMA reduce-add -- the GEMM epilogue never loads the residual.
+  PROF("ln_fwd", layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, e->b16, e->enc_mean,
                              e->enc_rstd, M, H, c.ln_eps, st));
   e->launches += 5;
   for (int l = 0; l < c.layers; ++l) {
@@ -723,10 +731,10 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     PROF_F("attn_fwd", 4.0 * H * e->sumT2, attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
     {  // out_proj + residual                                    HF:546, :597
       GemmProblem p = dense(x.attn, M, H, reinterpret_cast<const bf16*>(w.wo), H);
-      p.epi.bias = w.bo; p.epi.residual = e->fa; p.epi.res_ld = H; p.epi.out_f32 = x.h1; p.epi.out_ld = H;
+      p.epi.bias = w.bo; p.epi.accumulate = 1; p.epi.out_f32 = x.h1; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_fwd", layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], e->fb, e->b16,
+    PROF("ln_fwd", layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
                                x.mean1, x.rstd1, M, H, c.ln_eps, st));
     {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
@@ -735,11 +743,11 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     }
     {  // output_dense + residual                                HF:569, :600
       GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
-      p.epi.bias = w.b2; p.epi.residual = e->fb; p.epi.res_ld = H; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
+      p.epi.bias = w.b2; p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_fwd", layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], e->fa, e->b16,
-                               x.mean2, x.rstd2, M, H, c.ln_eps, st));
+    PROF("ln_fwd", layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+                               l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, e->b16, x.mean2, x.rstd2, M, H, c.ln_eps, st));
     e->launches += 3;
   }
   {  // lm_head                                                   HF:1708
@@ -767,6 +775,8 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   CUDA_TRY(cudaMemset2DAsync(e->G, sizeof(float) * e->n_params, 0, sizeof(float) * e->ln_params, e->U, st));
   e->launches += 2;
 
+  // two fp32 gradient streams, updated in place like the forward's residual stream: LayerNorm backward writes d(input)
+  // into the other buffer and the following dgrad GEMM accumulates its product onto it (TMA reduce-add)
   float* da = e->fa;   // gradient w.r.t. the current LayerNorm output
   float* db = e->fb;   // gradient w.r.t. the pre-LayerNorm sum
   {  // lm_head dgrad
@@ -786,11 +796,11 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     }
     {  // intermediate_dense dgrad + residual path
       GemmProblem p = dense(e->dpre16, M, I, reinterpret_cast<const bf16*>(w.w1_t), H);
-      p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
+      p.epi.accumulate = 1; p.epi.out_f32 = db; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_bwd", layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
-                                e->G, db, e->b16, M, H, st));
+    PROF("ln_bwd", layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
+                                e->G, da, e->b16, M, H, st));
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
       p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
@@ -799,7 +809,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     PROF_F("attn_bwd", 8.0 * H * e->sumT2, attention_backward(x.qkv, x.attn, e->dO16, x.lse, e->Dbuf, e->dqkv16, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
     {  // q,k,v dgrad + residual path
       GemmProblem p = dense(e->dqkv16, M, 3 * H, reinterpret_cast<const bf16*>(w.wqkv_t), H);
-      p.epi.residual = db; p.epi.res_ld = H; p.epi.out_f32 = da; p.epi.out_ld = H;
+      p.epi.accumulate = 1; p.epi.out_f32 = da; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
     e->launches += 5;
@@ -878,6 +888,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin, 1, (long long)k * Cin};
       p.M = (int)rows_valid; p.N = k * Cin; p.K = Cout;
       p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_mblk[l];
+      p.tiles_own_rows = 1; p.out_rows = dpre_rows;
       p.epi.out_bf16 = e->zbuf; p.epi.out_ld = k * Cin;
       SUTA_TRY(gemm(e, p, st));
     }
@@ -909,11 +920,17 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
   a.n = e->n_params; a.n_utts = e->U; a.step_index = e->opt_steps;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps; a.weight_decay = h->weight_decay;
   a.kind = h->opt_kind; a.shadow = nullptr;
+  if (e->train_feature) {        // the update also refreshes the bf16 GEMM-operand copies of the trainable matrices
+    const suta_model_cfg& c = e->cfg;
+    for (int l = 1; l < c.n_conv; ++l) a.seg[a.n_seg++] = {e->conv_w_off[l], e->conv_w_size[l], e->w_shadow[l]};
+    a.seg[a.n_seg++] = {e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->proj_shadow};
+    e->frontend_done = false;    // the CNN output depends on the updated weights
+  }
   cudaStream_t st = S(stream);
   PROF("adam", optimizer_step(a, st));
   e->opt_steps += 1;
   e->launches += 1;
-  return refresh_shadows(e, S(stream));
+  return SUTA_OK;
 }
 
 extern "C" int suta_adapt_step(suta_engine* e, const suta_hyper* h, void* stream) {

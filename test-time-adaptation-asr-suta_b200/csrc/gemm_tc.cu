@@ -32,6 +32,7 @@ constexpr int SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
 
 struct GemmKernelParams {
   int M, N, K;
+  int out_rows;         // addressable rows of the output (TMA epilogue)
   int num_mblk, num_nblk, nz;
   long long a_z_rows, b_z_rows;
   int c_z_cols;
@@ -245,9 +246,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const bool out_is_f32 = p.epi.out_f32 != nullptr;
       uint32_t pc = 0;                             // running chunk counter -> patch ping-pong
       for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int m_blk = tile / p.num_nblk;       // dense problems only: nz == 1, no M-block table
+        const int m_blk = tile / p.num_nblk;       // nz == 1; with an M-block table every tile OWNS its 128 output rows
         const int n_blk = tile - m_blk * p.num_nblk;
-        const int row0 = m_blk * BM + q * 32;      // first output row of this warp
+        const int row0 = (p.mblk ? __ldg(&p.mblk[m_blk]).y : m_blk * BM) + q * 32;      // first output row of this warp
         const int col0 = n_blk * BN + half * COLS_PER_WARP;
         if (p.epi.bias) {                          // this warp's COLS_PER_WARP bias values -> shared memory
           __syncwarp();
@@ -259,7 +260,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         uint4 auxr[NCH][4];                        // act == 2: this thread's row of saved GELU' (32 bf16 per chunk)
         if (p.epi.act == 2) {
-          const bool ok = row0 + lane < p.M;
+          const bool ok = row0 + lane < p.out_rows;
           const uint4* ap = reinterpret_cast<const uint4*>(p.epi.aux_in + (long long)(row0 + (ok ? lane : 0)) * p.epi.aux_ld + col0);
 #pragma unroll
           for (int kc = 0; kc < NCH; ++kc)
@@ -336,7 +337,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (row0 < p.M) {
+            if (row0 < p.out_rows) {
               const int cc = col0 + kc * 32;
               if (p.epi.accumulate) tma_reduce_add_2d(&tma_out, pp, cc, row0);
               else tma_store_2d(&tma_out, pp, cc, row0);
@@ -510,19 +511,21 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   if (A_MN) SUTA_TRY(make_tmap_mn(&ta, p.a)); else SUTA_TRY(make_tmap(&ta, p.a, p.K, BM));
   if (B_MN) SUTA_TRY(make_tmap_mn(&tb, p.b)); else SUTA_TRY(make_tmap(&tb, p.b, p.K, BN));
   if (EPI_TMA) {
-    // 32 x 32 output boxes: fp32 rows are 128 B (128B swizzle), bf16 rows 64 B (64B swizzle); rows >= M are clipped
+    // 32 x 32 output boxes: fp32 rows are 128 B (128B swizzle), bf16 rows 64 B (64B swizzle); rows >= out_rows are clipped
+    const long long orows = p.out_rows > 0 ? p.out_rows : p.M;
     if (p.epi.out_f32)
-      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.epi.out_f32, p.N, p.M, (long long)p.epi.out_ld * 4, 32, 32,
+      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.epi.out_f32, p.N, orows, (long long)p.epi.out_ld * 4, 32, 32,
                            CU_TENSOR_MAP_SWIZZLE_128B));
     else
-      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.out_bf16, p.N, p.M, (long long)p.epi.out_ld * 2, 32, 32,
+      SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.out_bf16, p.N, orows, (long long)p.epi.out_ld * 2, 32, 32,
                            CU_TENSOR_MAP_SWIZZLE_64B));
     if (p.epi.act == 1 && p.epi.aux_out)
-      SUTA_TRY(encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.aux_out, p.N, p.M, (long long)p.epi.aux_ld * 2, 32, 32,
+      SUTA_TRY(encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.aux_out, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32,
                            CU_TENSOR_MAP_SWIZZLE_64B));
   }
   GemmKernelParams kp;
   kp.M = p.M; kp.N = p.N; kp.K = p.K;
+  kp.out_rows = p.out_rows > 0 ? (int)p.out_rows : p.M;
   kp.num_mblk = p.mblk ? p.num_mblk : ceil_div(p.M, BM);
   kp.num_nblk = ceil_div(p.N, BN);
   kp.nz = p.nz;
@@ -567,6 +570,11 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
   SUTA_CHECK_ARG(p.epi.out_f32 || p.epi.out_bf16);
   SUTA_CHECK_ARG(p.epi.out_ld % 8 == 0 && p.epi.res_ld % 4 == 0 && p.epi.aux_ld % 8 == 0);
   SUTA_CHECK_ARG(!(p.epi.accumulate && (p.epi.residual || !p.epi.out_f32)));
+  // dense outputs: every tile owns all 128 of its output rows (plain row blocks, or an M-block table whose owner says so
+  // with tiles_own_rows), one z slice, shared bias -> TMA-store epilogue
+  const bool dense = (!p.mblk || p.tiles_own_rows) && !p.ztab && p.nz == 1 && !p.epi.residual && !p.epi.bias_utt_stride &&
+                     p.N % 32 == 0 && ((p.epi.out_f32 != nullptr) != (p.epi.out_bf16 != nullptr)) &&
+                     (p.epi.act != 1 || p.epi.out_bf16);
   if (p.a.mn_major || p.b.mn_major) {
     SUTA_CHECK_ARG(p.N % 64 == 0 && (!p.a.mn_major || p.b.mn_major) && !p.epi.accumulate);
     if (p.a.mn_major) {
@@ -574,13 +582,15 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
       if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
       return launch<64, true, true, false>(p, stream);
     }
+    if (dense) {
+      if (p.N % 256 == 0) return launch<256, false, true, true>(p, stream);
+      if (p.N % 128 == 0) return launch<128, false, true, true>(p, stream);
+      return launch<64, false, true, true>(p, stream);
+    }
     if (p.N % 256 == 0) return launch<256, false, true, false>(p, stream);
     if (p.N % 128 == 0) return launch<128, false, true, false>(p, stream);
     return launch<64, false, true, false>(p, stream);
   }
-  // dense outputs (every row of [0, M) is written, one z slice, shared bias): TMA-store epilogue
-  const bool dense = !p.mblk && !p.ztab && p.nz == 1 && !p.epi.residual && !p.epi.bias_utt_stride && p.N % 32 == 0 &&
-                     ((p.epi.out_f32 != nullptr) != (p.epi.out_bf16 != nullptr)) && (p.epi.act != 1 || p.epi.out_bf16);
   if (dense) {
     if (p.N % 256 == 0) return launch<256, false, false, true>(p, stream);
     if (p.N % 128 == 0) return launch<128, false, false, true>(p, stream);

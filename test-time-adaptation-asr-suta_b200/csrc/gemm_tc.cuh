@@ -44,6 +44,9 @@ struct GemmProblem {
   int c_z_cols = 0;
   const int4* mblk = nullptr;      // optional per-M-block table {a_row0, out_row0, rows_valid, b_row_off}
   int num_mblk = 0;                // = ceil(M/128) when mblk == nullptr
+  int tiles_own_rows = 0;          // with mblk: every tile may write all 128 rows from its out_row0 (the rows past
+                                   // rows_valid are padding nobody else owns) -> eligible for the TMA-store epilogue
+  long long out_rows = 0;          // addressable rows of the output buffers (default M)
   const int4* ztab = nullptr;      // optional per-z table {a_k_row0, b_k_row0, k_len, 0} (MN-major operands: the
                                    // reduction runs over rows [k_row0, k_row0 + k_len) of each operand)
   long long out_z_stride = 0;      // elements added to the output pointers per z (per-utterance gradient slabs)

@@ -129,6 +129,11 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay;
   int kind;                    // 0 Adam/AdamW, 1 SGD
   bf16* shadow;                // optional bf16 copy of P (GEMM operands of trainable weights), same layout
+  // optional bf16 copies of selected segments, each stored [U][size] contiguously (the stacked per-utterance B operands
+  // of the conv / projection GEMMs): written by the same pass that updates P
+  struct Seg { long long off, size; bf16* dst; };
+  Seg seg[8];
+  int n_seg;
 };
 int optimizer_step(const AdamArgs& a, cudaStream_t stream);
 int params_reset(float* P, const float* P0, float* Mom, float* Var, bf16* shadow, long long n, int n_utts,

@@ -44,6 +44,52 @@ __global__ void adam_kernel(AdamArgs a, AdamConsts c) {
   }
 }
 
+// float4 version: one utterance per blockIdx.y, 4 consecutive parameters per thread (all segment offsets are multiples
+// of 4).  28 B/param of state traffic + 2 B for the bf16 operand copy, independent of the multiplicity k.
+__global__ void __launch_bounds__(256)
+adam_vec4_kernel(AdamArgs a, AdamConsts c) {
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e >= a.n) return;
+  const long long i = (long long)blockIdx.y * a.n + e;
+  float4 p = *reinterpret_cast<const float4*>(a.P + i);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(a.G + i));
+  uchar4 k4 = make_uchar4(1, 1, 1, 1);
+  if (a.mult) k4 = __ldg(reinterpret_cast<const uchar4*>(a.mult + e));
+  float pv[4] = {p.x, p.y, p.z, p.w};
+  const float gv[4] = {g.x, g.y, g.z, g.w};
+  const int kv[4] = {k4.x, k4.y, k4.z, k4.w};
+  if (a.kind == 1) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      for (int j = 0; j < kv[t]; ++j) pv[t] -= a.lr * gv[t];
+  } else {
+    float4 m4 = *reinterpret_cast<const float4*>(a.Mom + i), v4 = *reinterpret_cast<const float4*>(a.Var + i);
+    float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = kv[t];
+      for (int j = 0; j < k; ++j) {
+        if (a.weight_decay != 0.f) pv[t] *= 1.0f - a.lr * a.weight_decay;
+        mv[t] = mv[t] + (gv[t] - mv[t]) * (1.0f - a.beta1);
+        vv[t] = vv[t] * a.beta2 + (1.0f - a.beta2) * gv[t] * gv[t];
+        const float denom = sqrtf(vv[t]) / c.bc2_sqrt[k][j] + a.eps;
+        pv[t] = pv[t] - c.step_size[k][j] * (mv[t] / denom);
+      }
+    }
+    if (kv[0] | kv[1] | kv[2] | kv[3]) {
+      *reinterpret_cast<float4*>(a.Mom + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(a.Var + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  }
+  if (kv[0] | kv[1] | kv[2] | kv[3]) *reinterpret_cast<float4*>(a.P + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+  const uint2 packed = make_uint2(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]));
+  if (a.shadow) *reinterpret_cast<uint2*>(a.shadow + i) = packed;
+  for (int s = 0; s < a.n_seg; ++s) {
+    const long long o = e - a.seg[s].off;
+    if (o >= 0 && o < a.seg[s].size) *reinterpret_cast<uint2*>(a.seg[s].dst + (long long)blockIdx.y * a.seg[s].size + o) = packed;
+  }
+}
+
 __global__ void reset_kernel(float* __restrict__ P, const float* __restrict__ P0, float* __restrict__ Mom,
                              float* __restrict__ Var, bf16* __restrict__ shadow, long long n, int n_utts) {
   const long long total = n * n_utts;
@@ -75,7 +121,15 @@ int optimizer_step(const AdamArgs& a, cudaStream_t stream) {
       c.step_size[k][j] = (float)((double)a.lr / bc1);
       c.bc2_sqrt[k][j] = (float)sqrt(bc2);
     }
-  adam_kernel<<<grid_for(a.n * a.n_utts), 256, 0, stream>>>(a, c);
+  bool vec = a.n % 4 == 0 && a.n_seg <= 8;
+  for (int s = 0; s < a.n_seg; ++s) vec = vec && a.seg[s].off % 4 == 0 && a.seg[s].size % 4 == 0 && a.seg[s].dst;
+  if (vec) {
+    dim3 grid((unsigned)((a.n / 4 + 255) / 256), (unsigned)a.n_utts);
+    adam_vec4_kernel<<<grid, 256, 0, stream>>>(a, c);
+  } else {
+    SUTA_CHECK_ARG(a.n_seg == 0);
+    adam_kernel<<<grid_for(a.n * a.n_utts), 256, 0, stream>>>(a, c);
+  }
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
