@@ -82,9 +82,11 @@ col2im_kernel(Col2imArgs a) {
 //   dbeta = S1 = sum_t dy,  dgamma = S2 = sum_t dy zhat,
 //   dz[t] = rstd*gamma*(dy[t] - S1/L - zhat[t]*S2/L),  dw[j] = sum_t dz[t] x[s t + j]
 //         = rstd*gamma*(A_j - (S1/L) B_j - (S2/L) C_j),  A_j = sum dy x, B_j = sum x, C_j = sum zhat x.
-constexpr int C0B_TT = 512;
+// Only S1 and A_j need a pass over dy (a [C x (k+1)] = dy^T [X | 1] reduction over time, HBM-bound on reading dy);
+// the rest follows from the audio moments Sx, R (frontend.cu):  B_j = Sx[j],
+//   sum_t z x_j = sum_j' w_j' R[j'][j]  =>  C_j = rstd (sum_j' w_j' R[j'][j] - mu Sx[j]),   S2 = rstd (sum_j w_j A_j - mu S1).
+constexpr int C0B_TT = 1024;
 constexpr int C0B_MAXK = 16;
-constexpr int C0B_ACC = 2 + 2 * C0B_MAXK;   // S1, S2, A[16], C[16] per channel (B_j is channel independent)
 
 __global__ void __launch_bounds__(256)
 conv0_bwd_accum_kernel(Conv0BwdArgs a) {
@@ -98,44 +100,29 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
   const int nx = (nt - 1) * a.stride + a.k;
   for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = x[i];
   __syncthreads();
-  if (threadIdx.x < a.k) {     // B_j = sum_t x[s t + j]
-    float b = 0.f;
-    for (int t = 0; t < nt; ++t) b += sx[t * a.stride + threadIdx.x];
-    atomicAdd(a.acc_x + (long long)u * C0B_MAXK + threadIdx.x, (double)b);
-  }
-  const float* w = a.w + (long long)u * a.w_stride;
   const long long row0 = a.out_off[u] + t0;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    float wj[C0B_MAXK];
+  const int k = a.k;
+  for (int cp = threadIdx.x; 2 * cp < a.C; cp += blockDim.x) {
+    const int c = 2 * cp;
+    float s1a = 0.f, s1b = 0.f, Aa[C0B_MAXK], Ab[C0B_MAXK];
 #pragma unroll
-    for (int j = 0; j < C0B_MAXK; ++j) wj[j] = j < a.k ? w[(long long)c * a.k + j] : 0.f;
-    const double* st = a.stats + ((long long)u * a.C + c) * 2;
-    const double m = st[0] / L0;
-    const float mean = (float)m, rstd = (float)(1.0 / sqrt(st[1] / L0 - m * m + 1e-5));
-    float s1 = 0.f, s2 = 0.f, A[C0B_MAXK], Cc[C0B_MAXK];
-#pragma unroll
-    for (int j = 0; j < C0B_MAXK; ++j) A[j] = Cc[j] = 0.f;
+    for (int j = 0; j < C0B_MAXK; ++j) Aa[j] = Ab[j] = 0.f;
+    const bf16* dyp = a.dy + row0 * a.C + c;
+#pragma unroll 2
     for (int t = 0; t < nt; ++t) {
+      const float2 dy = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)t * a.C)));
       const float* xs = sx + t * a.stride;
-      float z = 0.f;
+      s1a += dy.x;
+      s1b += dy.y;
 #pragma unroll
       for (int j = 0; j < C0B_MAXK; ++j)
-        if (j < a.k) z += wj[j] * xs[j];
-      const float zh = (z - mean) * rstd;
-      const float dy = __bfloat162float(a.dy[(row0 + t) * a.C + c]);
-      s1 += dy;
-      s2 += dy * zh;
-#pragma unroll
-      for (int j = 0; j < C0B_MAXK; ++j)
-        if (j < a.k) { A[j] += dy * xs[j]; Cc[j] += zh * xs[j]; }
+        if (j < k) { const float xv = xs[j]; Aa[j] = fmaf(dy.x, xv, Aa[j]); Ab[j] = fmaf(dy.y, xv, Ab[j]); }
     }
-    double* acc = a.acc + ((long long)u * a.C + c) * C0B_ACC;
-    atomicAdd(acc + 0, (double)s1);
-    atomicAdd(acc + 1, (double)s2);
-    for (int j = 0; j < a.k; ++j) {
-      atomicAdd(acc + 2 + j, (double)A[j]);
-      atomicAdd(acc + 2 + C0B_MAXK + j, (double)Cc[j]);
-    }
+    float* pa = a.part + (((long long)u * a.n_chunk + blockIdx.x) * a.C + c) * (k + 1);
+    float* pb = pa + (k + 1);
+    pa[0] = s1a;
+    pb[0] = s1b;
+    for (int j = 0; j < k; ++j) { pa[1 + j] = Aa[j]; pb[1 + j] = Ab[j]; }
   }
 }
 
@@ -143,19 +130,39 @@ __global__ void conv0_bwd_finalize_kernel(Conv0BwdArgs a) {
   const int u = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
+  const int k = a.k;
   const int L0 = a.L0[u];
+  const int nchunk = (L0 + C0B_TT - 1) / C0B_TT;
+  double S1 = 0.0, A[C0B_MAXK];
+  for (int j = 0; j < C0B_MAXK; ++j) A[j] = 0.0;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const float* pp = a.part + (((long long)u * a.n_chunk + ch) * a.C + c) * (k + 1);
+    S1 += (double)pp[0];
+    for (int j = 0; j < k; ++j) A[j] += (double)pp[1 + j];
+  }
   const double* st = a.stats + ((long long)u * a.C + c) * 2;
-  const double m = st[0] / L0;
-  const double rstd = 1.0 / sqrt(st[1] / L0 - m * m + 1e-5);
-  const double* acc = a.acc + ((long long)u * a.C + c) * C0B_ACC;
-  const double s1 = acc[0], s2 = acc[1];
+  const double mu = st[0] / L0;
+  const double rstd = 1.0 / sqrt(st[1] / L0 - mu * mu + 1e-5);
+  const int npair = k + k * (k + 1) / 2;
+  const double* mom = a.mom + (long long)u * npair;
+  const float* w = a.w + (long long)u * a.w_stride + (long long)c * k;
+  double wj[C0B_MAXK];
+  for (int j = 0; j < C0B_MAXK; ++j) wj[j] = j < k ? (double)w[j] : 0.0;
+  double wa = 0.0;
+  for (int j = 0; j < k; ++j) wa += wj[j] * A[j];
+  const double S2 = rstd * (wa - mu * S1);
   const double gamma = a.P[(long long)u * a.pstride + a.g_off + c];
   float* G = a.G + (long long)u * a.pstride;
-  G[a.b_off + c] = (float)s1;
-  G[a.g_off + c] = (float)s2;
-  for (int j = 0; j < a.k; ++j) {
-    const double bj = a.acc_x[(long long)u * C0B_MAXK + j];
-    G[a.w_off + (long long)c * a.k + j] = (float)(rstd * gamma * (acc[2 + j] - s1 / L0 * bj - s2 / L0 * acc[2 + C0B_MAXK + j]));
+  G[a.b_off + c] = (float)S1;
+  G[a.g_off + c] = (float)S2;
+  for (int j = 0; j < k; ++j) {
+    double wr = 0.0;                                   // sum_j' w_j' R[j'][j]
+    for (int j2 = 0; j2 < k; ++j2) {
+      const int lo = j2 < j ? j2 : j, hi = j2 < j ? j : j2;
+      wr += wj[j2] * mom[k + lo * k - lo * (lo - 1) / 2 + (hi - lo)];
+    }
+    const double Cj = rstd * (wr - mu * mom[j]);
+    G[a.w_off + (long long)c * k + j] = (float)(rstd * gamma * (A[j] - S1 / L0 * mom[j] - S2 / L0 * Cj));
   }
 }
 
@@ -204,9 +211,8 @@ int conv_col2im_gelu_grad(const Col2imArgs& a, cudaStream_t stream) {
 }
 
 int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream) {
-  SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0);
-  CUDA_TRY(cudaMemsetAsync(a.acc, 0, sizeof(double) * (size_t)a.n_utts * a.C * C0B_ACC, stream));
-  CUDA_TRY(cudaMemsetAsync(a.acc_x, 0, sizeof(double) * (size_t)a.n_utts * C0B_MAXK, stream));
+  SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0 && a.C % 2 == 0 && a.mom && a.part);
+  SUTA_CHECK_ARG(a.n_chunk >= ceil_div(a.max_L0, C0B_TT));
   dim3 grid(ceil_div(a.max_L0, C0B_TT), a.n_utts);
   size_t smem = sizeof(float) * (C0B_TT * a.stride + a.k);
   conv0_bwd_accum_kernel<<<grid, 256, smem, stream>>>(a);
@@ -222,4 +228,7 @@ int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float
   return SUTA_OK;
 }
 
-long long conv0_bwd_scratch_doubles(int n_utts, int C) { return (long long)n_utts * C * C0B_ACC + (long long)n_utts * C0B_MAXK; }
+long long conv0_bwd_scratch_floats(int n_utts, int C, int k, int max_L0) {
+  return (long long)n_utts * ceil_div(max_L0, C0B_TT) * C * (k + 1);
+}
+int conv0_bwd_chunks(int max_L0) { return ceil_div(max_L0, C0B_TT); }

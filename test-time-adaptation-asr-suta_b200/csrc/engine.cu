@@ -122,7 +122,9 @@ struct suta_engine {
   bf16* zbuf = nullptr;                            // dgrad GEMM output [rows_l, k*Cin]
   bf16* dh0_pad = nullptr;                         // [R64, H]
   float* d_feat = nullptr;                         // [M, C]
-  double* c0_scratch = nullptr;
+  float* c0_scratch = nullptr;
+  double* mom = nullptr;                           // [U][k + k(k+1)/2] audio moments (conv0 GroupNorm statistics / backward)
+  bool moments_done = false;
   int max_L[SUTA_MAX_CONV] = {};
   // device buffers
   float *wav = nullptr, *wav_norm = nullptr;
@@ -283,6 +285,7 @@ void carve(suta_engine* e, Bump& b) {
   e->d_attn_tab = b.take<int4>(e->n_attn_blk);
   e->wav = b.take<float>(e->S); e->wav_norm = b.take<float>(e->S + 64);
   e->stats = b.take<double>((size_t)2 * U * (c.conv_dim[0] > 1 ? c.conv_dim[0] : 1) + 2 * U);
+  e->mom = b.take<double>((size_t)U * (c.conv_kernel[0] + c.conv_kernel[0] * (c.conv_kernel[0] + 1) / 2));
   for (int l = 0; l < c.n_conv; ++l) e->conv_out[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
   e->fp_mean = b.take<float>(M); e->fp_rstd = b.take<float>(M);
   e->y_fp = b.take<bf16>((size_t)M * C);
@@ -342,7 +345,7 @@ void carve(suta_engine* e, Bump& b) {
     e->proj_shadow = b.take<bf16>((size_t)U * H * C);
     e->dh0_pad = b.take<bf16>((size_t)(e->R64 + 128) * H);
     e->d_feat = b.take<float>((size_t)M * C);
-    e->c0_scratch = b.take<double>((size_t)conv0_bwd_scratch_doubles(U, c.conv_dim[0]));
+    e->c0_scratch = b.take<float>((size_t)conv0_bwd_scratch_floats(U, c.conv_dim[0], c.conv_kernel[0], e->max_L0));
   }
   b.off = align_up(b.off, 256);
 }
@@ -544,6 +547,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
   for (int l = 0; l < c.n_conv; ++l)
     CUDA_TRY(cudaMemsetAsync(e->conv_out[l] + (size_t)e->rows_total[l] * c.conv_dim[l], 0, sizeof(bf16) * 128 * c.conv_dim[l], st));
   e->frontend_done = false;
+  e->moments_done = false;
   e->opt_steps = 0;
   return SUTA_OK;
 }
@@ -568,6 +572,7 @@ extern "C" int suta_batch_set_audio(suta_engine* e, const float* wav, int flags,
   CUDA_TRY(cudaMemcpyAsync(e->audio_normalized ? e->wav_norm : e->wav, wav, sizeof(float) * e->S,
                            is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, S(stream)));
   e->frontend_done = false;
+  e->moments_done = false;
   return SUTA_OK;
 }
 
@@ -636,9 +641,16 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   const suta_model_cfg& c = e->cfg;
   cudaStream_t st = S(stream);
-  if (!e->audio_normalized)
+  if (!e->audio_normalized && !e->moments_done)     // once per set_audio
     PROF("normalize", normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
+  if (!e->moments_done) {      // second moments of the conv0 input windows: depend on the audio only, once per batch
+    PROF("conv0_moments", audio_conv0_moments(e->wav_norm, e->d_samp_off, e->d_L0, e->mom, c.conv_kernel[0], c.conv_stride[0], e->U,
+                                              e->max_L0, st));
+    e->moments_done = true;
+    e->launches += 2;
+  }
   Conv0Args a{};
+  a.mom = e->mom;
   a.x = e->wav_norm; a.samp_off = e->d_samp_off; a.L0 = e->d_L0; a.out_off = e->d_off0;
   a.w = e->w.conv0_w; a.w_stride = 0;
   a.gn_shared_g = e->w.gn_g; a.gn_shared_b = e->w.gn_b;
@@ -651,7 +663,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   }
   a.n_utts = e->U; a.C = c.conv_dim[0]; a.k = c.conv_kernel[0]; a.stride = c.conv_stride[0]; a.max_L0 = e->max_L0;
   PROF("conv0_fwd", conv0_groupnorm_gelu(a, st));
-  e->launches += 4;
+  e->launches += 2;
   for (int l = 1; l < c.n_conv; ++l) {
     const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l], s = c.conv_stride[l];
     GemmProblem p;
@@ -904,7 +916,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   ba.x = e->wav_norm; ba.samp_off = e->d_samp_off; ba.L0 = e->d_L0; ba.out_off = e->d_off0;
   ba.w = e->P + e->conv_w_off[0]; ba.w_stride = e->n_params;
   ba.dy = e->conv_dpre[0]; ba.stats = e->stats + 2 * e->U;
-  ba.acc = e->c0_scratch; ba.acc_x = e->c0_scratch + (size_t)e->U * c.conv_dim[0] * 34;
+  ba.mom = e->mom; ba.part = e->c0_scratch; ba.n_chunk = conv0_bwd_chunks(e->max_L0);
   ba.P = e->P; ba.G = e->G; ba.pstride = e->n_params;
   ba.g_off = e->gn_g; ba.b_off = e->gn_b; ba.w_off = e->conv_w_off[0];
   ba.n_utts = e->U; ba.C = c.conv_dim[0]; ba.k = c.conv_kernel[0]; ba.stride = c.conv_stride[0]; ba.max_L0 = e->max_L0;

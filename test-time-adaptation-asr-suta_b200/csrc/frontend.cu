@@ -5,6 +5,11 @@
 // Cin = 1, so this layer is HBM-bound (writes L0*C bf16, reads 4 B per sample): direct convolution on CUDA cores,
 // channels-last bf16 output so the next layer's implicit GEMM can read overlapping rows straight through TMA.
 // In a batch, GroupNorm statistics are taken over each utterance's own valid frames only.
+//
+// The statistics never touch the conv output: with Sx[j] = sum_t x[s t + j] and R[j][j'] = sum_t x[s t + j] x[s t + j']
+// (k + k(k+1)/2 numbers per utterance, computed ONCE per batch from the audio by audio_conv0_moments),
+//   sum_t y[t,c] = w_c . Sx        sum_t y[t,c]^2 = w_c^T R w_c
+// so a weight update (train_feature) only costs a 512 x 100-MAC kernel, not a pass over the waveform.
 #include "kernels.cuh"
 
 namespace {
@@ -126,6 +131,64 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
   }
 }
 
+// ---- audio moments: Sx[j] and R[j][j'] (j <= j') per utterance, double precision ---------------------------------
+constexpr int MOM_TT = 2048;    // frames per CTA
+
+__global__ void __launch_bounds__(160)
+moments_kernel(const float* __restrict__ xin, const long long* __restrict__ samp_off, const int* __restrict__ L0p,
+               double* __restrict__ mom, int k, int stride) {
+  extern __shared__ float sx[];
+  const int u = blockIdx.y;
+  const int L0 = L0p[u];
+  const int t0 = blockIdx.x * MOM_TT;
+  if (t0 >= L0) return;
+  const int nt = min(MOM_TT, L0 - t0);
+  const float* x = xin + samp_off[u] + (long long)t0 * stride;
+  const int nx = (nt - 1) * stride + k;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = x[i];
+  __syncthreads();
+  const int npair = k + k * (k + 1) / 2;
+  for (int p = threadIdx.x; p < npair; p += blockDim.x) {
+    int j = p, j2 = -1;                        // p < k: Sx[j];  else the (j, j2) entry of R
+    if (p >= k) {
+      int q = p - k;
+      j = 0;
+      while (q >= k - j) { q -= k - j; ++j; }
+      j2 = j + q;
+    }
+    double acc = 0.0;
+    if (j2 < 0) {
+      for (int t = 0; t < nt; ++t) acc += (double)sx[t * stride + j];
+    } else {
+      for (int t = 0; t < nt; ++t) acc += (double)sx[t * stride + j] * (double)sx[t * stride + j2];
+    }
+    atomicAdd(mom + (long long)u * npair + p, acc);
+  }
+}
+
+// per (utterance, channel): sum and sum of squares of the conv0 output from the audio moments and the current weights
+__global__ void conv0_stats_kernel(Conv0Args a) {
+  const int u = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const int k = a.k;
+  const int npair = k + k * (k + 1) / 2;
+  const double* mom = a.mom + (long long)u * npair;
+  const float* w = a.w + (a.w_stride ? (long long)u * a.w_stride : 0) + (long long)c * k;
+  double wj[C0_MAXK];
+#pragma unroll
+  for (int j = 0; j < C0_MAXK; ++j) wj[j] = j < k ? (double)w[j] : 0.0;
+  double s = 0.0, q = 0.0;
+  int p = k;
+  for (int j = 0; j < k; ++j) {
+    s += wj[j] * mom[j];
+    for (int j2 = j; j2 < k; ++j2, ++p) q += (j2 == j ? 1.0 : 2.0) * wj[j] * wj[j2] * mom[p];
+  }
+  double* st = a.stats + ((long long)u * a.C + c) * 2;
+  st[0] = s;
+  st[1] = q;
+}
+
 }  // namespace
 
 int normalize_audio(const float* wav, float* out, const long long* samp_off, const int* n_samples, int n_utts,
@@ -139,14 +202,24 @@ int normalize_audio(const float* wav, float* out, const long long* samp_off, con
   return SUTA_OK;
 }
 
+int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0, double* mom, int k, int stride, int n_utts,
+                        int max_L0, cudaStream_t stream) {
+  SUTA_CHECK_ARG(k <= C0_MAXK && n_utts > 0 && max_L0 > 0);
+  const int npair = k + k * (k + 1) / 2;
+  CUDA_TRY(cudaMemsetAsync(mom, 0, sizeof(double) * (size_t)npair * n_utts, stream));
+  dim3 grid(ceil_div(max_L0, MOM_TT), n_utts);
+  size_t smem = sizeof(float) * (MOM_TT * stride + k);
+  moments_kernel<<<grid, 160, smem, stream>>>(x, samp_off, L0, mom, k, stride);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
 int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream) {
-  SUTA_CHECK_ARG(a.k <= C0_MAXK && a.C % 2 == 0 && a.n_utts > 0);
-  double* stats = a.stats;
-  CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * a.C * a.n_utts, stream));
+  SUTA_CHECK_ARG(a.k <= C0_MAXK && a.C % 2 == 0 && a.n_utts > 0 && a.mom);
+  conv0_stats_kernel<<<dim3(ceil_div(a.C, 128), a.n_utts), 128, 0, stream>>>(a);
   dim3 grid(ceil_div(a.max_L0, C0_TT), a.n_utts);
   size_t smem = sizeof(float) * (C0_TT * a.stride + a.k);
-  conv0_kernel<0><<<grid, 256, smem, stream>>>(a, stats);
-  conv0_kernel<1><<<grid, 256, smem, stream>>>(a, stats);
+  conv0_kernel<1><<<grid, 256, smem, stream>>>(a, a.stats);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

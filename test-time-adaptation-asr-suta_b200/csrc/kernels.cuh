@@ -40,12 +40,16 @@ struct Conv0Args {
   const float* gn_shared_g;    // used when gn.P == nullptr
   const float* gn_shared_b;
   int g_off, b_off;
-  double* stats;               // [U][C][2] sum, sumsq scratch (zeroed by the launcher)
+  double* stats;               // [U][C][2] sum, sumsq of the conv output per (utterance, channel) (written by the launcher)
+  const double* mom;           // [U][k + k(k+1)/2] audio moments from audio_conv0_moments
   bf16* out;                   // [rows, C]
   bf16* pre_out;               // optional: GELU'(normalised value) for the train_feature backward
   int n_utts, C, k, stride, max_L0;
 };
 int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
+// Sx[j] = sum_t x[s t + j] (k values) then R[j][j'] = sum_t x[s t + j] x[s t + j'] for j <= j', per utterance, in double
+int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0, double* mom, int k, int stride, int n_utts,
+                        int max_L0, cudaStream_t stream);
 
 // ---- convbwd.cu (train_feature backward of the CNN front end) ---------------------------------
 int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,
@@ -71,8 +75,9 @@ struct Conv0BwdArgs {
   long long w_stride;
   const bf16* dy;              // [rows0, C] d(GroupNorm output) (already multiplied by GELU')
   const double* stats;         // [U][C][2] forward sum / sumsq
-  double* acc;                 // scratch [U][C][34]
-  double* acc_x;               // scratch [U][16]
+  const double* mom;           // [U][k + k(k+1)/2] audio moments
+  float* part;                 // scratch [U][n_chunk][C][k+1] per-chunk partial sums
+  int n_chunk;
   const float* P;              // trainable vectors (for gamma)
   float* G;                    // gradient vectors (same layout)
   long long pstride;
@@ -80,7 +85,8 @@ struct Conv0BwdArgs {
   int n_utts, C, k, stride, max_L0;
 };
 int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream);
-long long conv0_bwd_scratch_doubles(int n_utts, int C);
+long long conv0_bwd_scratch_floats(int n_utts, int C, int k, int max_L0);
+int conv0_bwd_chunks(int max_L0);
 int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
                    int C, int n_utts, cudaStream_t stream);
 
