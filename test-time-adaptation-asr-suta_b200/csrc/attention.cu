@@ -8,7 +8,10 @@
 // (DESIGN.md "what comes next"); attention is 5-10 % of the path's FLOPs at LibriSpeech lengths.
 //
 // Layout: qkv bf16 [M, 3H] (q | k | v, head h at columns h*64), O bf16 [M, H], LSE fp32 [heads, M] in
-// base-2 units, block table int4 {utt_row0, T_u, block_start_in_utt, 0}.
+// base-2 units, block table int4 {utt_row0, T_u, block_start_in_utt, 0} with one entry per 128 rows (these kernels
+// work on 64-row blocks: two CTAs per entry).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -91,10 +94,11 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ O, float* __res
                 int H, long long M, float scale_log2) {
   __shared__ __align__(1024) uint8_t smem[5 * TILE_BYTES];
   const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
-  const int4 t = tab[blockIdx.x];
+  const int4 t = tab[blockIdx.x >> 1];
   const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long urow0 = t.x;
-  const int T = t.y, m0 = t.z;
+  const int T = t.y, m0 = t.z + 64 * (blockIdx.x & 1);
+  if (m0 >= T) return;
   const int ld = 3 * H;
   const int nkv = (T + BLK - 1) / BLK;
 
@@ -219,10 +223,11 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, co
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   const uint32_t sQ = smem_u32(smem), sdO = sQ + TILE_BYTES, sK = sdO + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
-  const int4 t = tab[blockIdx.x];
+  const int4 t = tab[blockIdx.x >> 1];
   const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long urow0 = t.x;
-  const int T = t.y, m0 = t.z;
+  const int T = t.y, m0 = t.z + 64 * (blockIdx.x & 1);
+  if (m0 >= T) return;
   const int ld = 3 * H;
   const int nkv = (T + BLK - 1) / BLK;
   const int g = lane >> 2, c = lane & 3;
@@ -303,10 +308,11 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, c
   const uint32_t sK = smem_u32(smem), sV = sK + TILE_BYTES, sQ = sV + TILE_BYTES, sdO = sQ + 2 * TILE_BYTES;
   float* sLSE = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);     // [2][64]
   float* sD = sLSE + 2 * BLK;                                        // [2][64]
-  const int4 t = tab[blockIdx.x];
+  const int4 t = tab[blockIdx.x >> 1];
   const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long urow0 = t.x;
-  const int T = t.y, n0 = t.z;            // n0 = first key of this block
+  const int T = t.y, n0 = t.z + 64 * (blockIdx.x & 1);            // n0 = first key of this block
+  if (n0 >= T) return;
   const int ld = 3 * H;
   const int nq = (T + BLK - 1) / BLK;
   const int g = lane >> 2, c = lane & 3;
@@ -391,8 +397,10 @@ int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab,
                       cudaStream_t stream) {
   SUTA_CHECK_ARG(H == heads * HD);
   if (n_blk <= 0) return SUTA_OK;
+  static const bool legacy = getenv("SUTA_ATTN_LEGACY") != nullptr;    // A/B switch while the tcgen05 kernels are tuned
+  if (!legacy) return attention_forward_tc(qkv, O, LSE, blk_tab, n_blk, H, heads, M, stream);
   const float scale = 0.125f;   // 64^-0.5
-  attn_fwd_kernel<<<dim3(n_blk, heads), 128, 0, stream>>>(qkv, O, LSE, blk_tab, H, M, scale * 1.4426950408889634f);
+  attn_fwd_kernel<<<dim3(2 * n_blk, heads), 128, 0, stream>>>(qkv, O, LSE, blk_tab, H, M, scale * 1.4426950408889634f);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
@@ -411,9 +419,9 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
   long long n = M * heads;
   attn_bwd_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(O, dO, D, H, heads, M);
   CUDA_TRY(cudaGetLastError());
-  attn_bwd_dq_kernel<<<dim3(n_blk, heads), 128, DQ_SMEM, stream>>>(qkv, dO, LSE, D, dqkv, blk_tab, H, M, scale, scale_log2);
+  attn_bwd_dq_kernel<<<dim3(2 * n_blk, heads), 128, DQ_SMEM, stream>>>(qkv, dO, LSE, D, dqkv, blk_tab, H, M, scale, scale_log2);
   CUDA_TRY(cudaGetLastError());
-  attn_bwd_dkv_kernel<<<dim3(n_blk, heads), 128, DKV_SMEM, stream>>>(qkv, dO, LSE, D, dqkv, blk_tab, H, M, scale, scale_log2);
+  attn_bwd_dkv_kernel<<<dim3(2 * n_blk, heads), 128, DKV_SMEM, stream>>>(qkv, dO, LSE, D, dqkv, blk_tab, H, M, scale, scale_log2);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

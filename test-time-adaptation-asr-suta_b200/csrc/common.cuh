@@ -143,15 +143,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.  No printf here: a call
+// in the slow path makes ptxas spill every register that is live across the wait (measured: 64 spilled registers in the
+// attention softmax loop).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("suta_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

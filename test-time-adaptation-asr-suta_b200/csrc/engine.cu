@@ -253,7 +253,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
     e->pad_off[u] = p;
     m += e->T[u];
     p += e->T[u] + c.pos_k / 2;
-    nblk += ceil_div(e->T[u], 64);
+    nblk += ceil_div(e->T[u], 128);
   }
   e->sumT2 = 0.0;
   for (int u = 0; u < U; ++u) e->sumT2 += (double)e->T[u] * e->T[u];
@@ -477,7 +477,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
   std::vector<int4> attn_tab;
   attn_tab.reserve(e->n_attn_blk);
   for (int u = 0; u < U; ++u)
-    for (int m0 = 0; m0 < e->T[u]; m0 += 64) attn_tab.push_back(make_int4((int)e->tok_off[u], e->T[u], m0, 0));
+    for (int m0 = 0; m0 < e->T[u]; m0 += 128) attn_tab.push_back(make_int4((int)e->tok_off[u], e->T[u], m0, 0));
   auto up = [&](void* dst, const void* src, size_t n) { return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st); };
   CUDA_TRY(up(e->d_samp_off, e->samp_off.data(), sizeof(long long) * U));
   CUDA_TRY(up(e->d_tok_off, e->tok_off.data(), sizeof(long long) * U));

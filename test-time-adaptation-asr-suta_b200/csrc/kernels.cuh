@@ -14,6 +14,10 @@ int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab,
 int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const float* LSE, float* D, bf16* dqkv,
                        const int4* blk_tab, int n_blk, int H, int heads, long long M, cudaStream_t stream);
 
+// ---- attention_tc.cu (tcgen05 / TMEM) --------------------------------------------------------
+int attention_forward_tc(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
+                         cudaStream_t stream);
+
 // ---- norm.cu --------------------------------------------------------------------------------
 // y = LayerNorm(x) * gamma[u] + beta[u]; x is fp32 (x_f32) or bf16 (x_bf16), exactly one non-null.
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,

@@ -182,7 +182,7 @@ def check_layernorm(N=768, Ts=(70, 3, 129), seed=5, bf16_in=False):
 def attn_table(Ts):
     tab, off = [], 0
     for T in Ts:
-        for m0 in range(0, T, 64):
+        for m0 in range(0, T, 128):
             tab.append((off, T, m0, 0))
         off += T
     return torch.tensor(tab, dtype=torch.int32, device=DEV)
