@@ -243,14 +243,14 @@ def run_b200(args):
     out["rtf_p50"] = rtfs[len(rtfs) // 2]
     out["rtf_throughput"] = (ms_e2e / 1e3) / (audio_all / world)      # GPU-seconds per audio-second
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.model)
+        out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.model, train_feature=tf)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(seconds, model="base", threads=None):
+def cpu_baseline(seconds, model="base", threads=None, train_feature=False):
     """The oracle (CPU restatement of the reference loop, pinned to the reference by tests/golden) on the host cores."""
     import torch
     from oracle import suta_oracle as O
@@ -261,10 +261,11 @@ def cpu_baseline(seconds, model="base", threads=None):
     n = int(seconds * 16000)
     x = O.normalize_audio(O.synth_audio(n, 1234))
     t0 = time.time()
-    O.adapt_utterance(cfg, sd, x, steps=SUTA_STEPS)
+    O.adapt_utterance(cfg, sd, x, steps=SUTA_STEPS, train_feature=train_feature)
     dt = time.time() - t0
+    mode = "train_feature" if train_feature else "LayerNorm-only"
     return {"value": seconds / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"one {seconds:g} s utterance, {SUTA_STEPS}-step LayerNorm-only SUTA, fp32 torch CPU oracle "
+            "sample": f"one {seconds:g} s utterance, {SUTA_STEPS}-step {mode} SUTA, fp32 torch CPU oracle "
                       f"(reset + vanilla forward + 10 x (forward, backward, AdamW, forward)), {dt:.1f} s wall"}
 
 
@@ -282,20 +283,23 @@ def run_reference(args):
     seconds = args.cpu_seconds
     n = int(seconds * 16000)
     xs = [O.normalize_audio(O.synth_audio(n, 100 + i)) for i in range(args.warmup + args.steps)]
+    tf = args.mode == "feature"
+    mode = "train_feature (LayerNorm + CNN front end + projection)" if tf else "LayerNorm-only"
     for i in range(args.warmup):
-        O.adapt_utterance(cfg, sd, xs[i], steps=SUTA_STEPS)
+        O.adapt_utterance(cfg, sd, xs[i], steps=SUTA_STEPS, train_feature=tf)
     t0 = time.time()
     for i in range(args.steps):
-        O.adapt_utterance(cfg, sd, xs[args.warmup + i], steps=SUTA_STEPS)
+        O.adapt_utterance(cfg, sd, xs[args.warmup + i], steps=SUTA_STEPS, train_feature=tf)
     dt = time.time() - t0
     val = seconds * args.steps / dt
     sample = (f"each step = ONE {seconds:g} s utterance of the same synthetic generator (bounded sample of the batch the "
-              f"CUDA arm adapts per step), {SUTA_STEPS}-step LayerNorm-only SUTA, fp32 torch on {threads} host threads")
+              f"CUDA arm adapts per step), {SUTA_STEPS}-step {mode} SUTA, fp32 torch on {threads} host threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (0.1*randn audio, random-init wav2vec2 weights)",
-        "config": {"workload": f"wav2vec2-{args.model} CTC, {SUTA_STEPS}-step EM+MCC SUTA, LayerNorm-only, CPU", "sample": sample},
+        "config": {"workload": f"wav2vec2-{args.model} CTC, LibriSpeech-test-other-shaped synthetic set, {SUTA_STEPS}-step EM+MCC SUTA, "
+                               f"{mode}, reference algorithm on the host CPU", "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
