@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--mode", default="feature", choices=["feature", "ln"],
                     help="feature = BASELINE.json configs[1] (--train_feature preset of REF/scripts/LS.sh); ln = LayerNorm-only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-utts", type=int, default=MAX_UTTS, help="utterances per adaptation batch")
+    ap.add_argument("--max-frames", type=int, default=MAX_FRAMES, help="frames per adaptation batch")
     ap.add_argument("--cpu-seconds", type=float, default=5.0, help="duration of the CPU-baseline utterance")
     return ap.parse_args()
 
@@ -107,10 +109,10 @@ def utt_flops(cfg, n_samples, steps, train_feature=False):
     return f_conv + (steps + 1) * enc_f + steps * enc_b
 
 
-def select_batches(utts, cfg, n_batches, offset=0):
+def select_batches(utts, cfg, n_batches, offset=0, max_utts=MAX_UTTS, max_frames=MAX_FRAMES):
     from suta_b200.shard import bucket_batches
     frames = [cfg.frames(u.n_samples) for u in utts]
-    batches = bucket_batches(frames, list(range(len(utts))), MAX_UTTS, MAX_FRAMES)
+    batches = bucket_batches(frames, list(range(len(utts))), max_utts, max_frames)
     nb = len(batches)
     pick = [int(round(offset + (i + 0.5) * nb / n_batches)) % nb for i in range(n_batches)]
     return [[utts[i] for i in batches[j]] for j in pick]
@@ -142,8 +144,8 @@ def run_b200(args):
     hp, vocab = AdaptHyper(), CTCVocab()
     utts = librispeech_shaped(2939, seed=rank)           # weak scaling: every rank adapts its own draw of the set
     K, W = args.steps, max(args.warmup, 0)
-    timed = select_batches(utts, cfg, K)
-    warm = select_batches(utts, cfg, max(W, 1), offset=0.25)[:W]
+    timed = select_batches(utts, cfg, K, max_utts=args.max_utts, max_frames=args.max_frames)
+    warm = select_batches(utts, cfg, max(W, 1), offset=0.25, max_utts=args.max_utts, max_frames=args.max_frames)[:W]
 
     def stage(batch):                                     # synthetic-data generation is outside the timed region
         lens = np.asarray([u.n_samples for u in batch], dtype=np.int32)
@@ -218,7 +220,7 @@ def run_b200(args):
         "config": {"workload": f"wav2vec2-{args.model} CTC, LibriSpeech-test-other-shaped synthetic set (2939 utts, 2-35 s), "
                                f"{SUTA_STEPS}-step EM+MCC SUTA, " + ("train_feature (LayerNorm + CNN front end + projection adapted per utterance)"
                                                                 if tf else "LayerNorm-only") + ", "
-                               f"<= {MAX_UTTS} utts / {MAX_FRAMES} frames per adaptation batch, length-bucketed",
+                               f"<= {args.max_utts} utts / {args.max_frames} frames per adaptation batch, length-bucketed",
                    "utts_per_step": utts_all / K / world, "audio_s_per_step": audio_all / K / world,
                    "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2",
                    "suta": {"steps": SUTA_STEPS, "em_coef": hp.em_coef, "temp": hp.temp, "reweight": hp.reweight,

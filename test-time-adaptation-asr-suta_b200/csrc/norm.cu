@@ -1,8 +1,7 @@
 // Fused LayerNorm forward / backward with PER-UTTERANCE affine parameters.
 // Restates torch native_layer_norm(+backward) as used by HF/modeling_wav2vec2.py:429-434,692,599-602 for a
 // token-packed batch in which every utterance carries its own adapted gamma/beta (REF/main.py:81-87).
-// One warp per row; row statistics by warp shuffle; dgamma/dbeta accumulated per utterance:
-// registers -> shared memory -> one atomicAdd per column per CTA.  HBM-bound.
+// Forward: one warp per row, row statistics by warp shuffle.  Backward: see ln_bwd_kernel.  HBM-bound.
 #include "kernels.cuh"
 
 namespace {
@@ -83,108 +82,114 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
     }
 }
 
-constexpr int BWD_ROWS_PER_WARP = 8;
-constexpr int BWD_WARPS = 8;
+// Backward.  One thread owns 4 fixed columns for all rows of its CTA (N/4 threads per CTA), so dgamma/dbeta live in 8
+// registers and are flushed with one atomicAdd per column per (CTA, utterance); the two row reductions are batched
+// over R = 4 rows: every thread first issues the 8 independent 16-byte loads of the tile, then 8 warp reductions, one
+// exchange through shared memory, one __syncthreads.  (The first version kept whole rows per warp: 150 registers, one
+// CTA per SM, 3 TB/s.)
+constexpr int BWD_R = 4;          // rows per tile
+constexpr int BWD_ROWS = 64;      // rows per CTA
 
 template <int N, typename TIn>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__((N / 4 + 31) / 32 * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const int* __restrict__ row_utt, const float* __restrict__ P,
               long long pstride, int g_off, int b_off, float* __restrict__ G, float* __restrict__ dx32,
               bf16* __restrict__ dx16, long long M) {
-  constexpr int NV = Cols<N>::NV;
-  __shared__ float s_dg[N];
-  __shared__ float s_db[N];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    s_dg[i] = 0.f;
-    s_db[i] = 0.f;
-  }
-  __syncthreads();
-  const long long cta_row0 = (long long)blockIdx.x * (BWD_WARPS * BWD_ROWS_PER_WARP);
-  const int u_cta = row_utt[cta_row0 < M ? cta_row0 : M - 1];
-  const long long r0 = cta_row0 + warp * BWD_ROWS_PER_WARP;
+  constexpr int NT = N / 4;                       // active threads
+  constexpr int NW = (NT + 31) / 32;              // warps
+  __shared__ float red[2][2][NW][BWD_R];          // [tile parity][c1 | c2][warp][row]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool act = tid < NT;
+  const int col = 4 * tid;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, g = ag;
+  int u_acc = -1;                                 // utterance the accumulators (and g) belong to
 
-  float4 ag[NV], ab[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int u_cur = -1;
-
-  auto flush = [&](int u) {
-    if (u < 0) return;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (Cols<N>::active(lane, i)) {
-        const int col = 4 * lane + 128 * i;
-        if (u == u_cta) {
-          atomicAdd(&s_dg[col + 0], ag[i].x); atomicAdd(&s_dg[col + 1], ag[i].y);
-          atomicAdd(&s_dg[col + 2], ag[i].z); atomicAdd(&s_dg[col + 3], ag[i].w);
-          atomicAdd(&s_db[col + 0], ab[i].x); atomicAdd(&s_db[col + 1], ab[i].y);
-          atomicAdd(&s_db[col + 2], ab[i].z); atomicAdd(&s_db[col + 3], ab[i].w);
-        } else if (G) {
-          float* gg = G + (long long)u * pstride + g_off + col;
-          float* gb = G + (long long)u * pstride + b_off + col;
-          atomicAdd(gg + 0, ag[i].x); atomicAdd(gg + 1, ag[i].y); atomicAdd(gg + 2, ag[i].z); atomicAdd(gg + 3, ag[i].w);
-          atomicAdd(gb + 0, ab[i].x); atomicAdd(gb + 1, ab[i].y); atomicAdd(gb + 2, ab[i].z); atomicAdd(gb + 3, ab[i].w);
-        }
-        ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  auto flush = [&]() {
+    if (u_acc < 0 || !G || !act) return;
+    float* gg = G + (long long)u_acc * pstride + g_off + col;
+    float* gb = G + (long long)u_acc * pstride + b_off + col;
+    atomicAdd(gg + 0, ag.x); atomicAdd(gg + 1, ag.y); atomicAdd(gg + 2, ag.z); atomicAdd(gg + 3, ag.w);
+    atomicAdd(gb + 0, ab.x); atomicAdd(gb + 1, ab.y); atomicAdd(gb + 2, ab.z); atomicAdd(gb + 3, ab.w);
+    ag = ab = make_float4(0.f, 0.f, 0.f, 0.f);
   };
 
-  for (int rr = 0; rr < BWD_ROWS_PER_WARP; ++rr) {
-    const long long row = r0 + rr;
-    if (row >= M) break;
-    const int u = row_utt[row];
-    if (u != u_cur) {
-      flush(u_cur);
-      u_cur = u;
-    }
-    const float mu = mean[row], rs = rstd[row];
-    const float* gam = P + (long long)u * pstride + g_off;
-    float4 xh[NV], dxh[NV];
-    float c1 = 0.f, c2 = 0.f;
+  const long long cta_row0 = (long long)blockIdx.x * BWD_ROWS;
+#pragma unroll 1
+  for (int it = 0; it < BWD_ROWS / BWD_R; ++it) {
+    const long long row0 = cta_row0 + it * BWD_R;
+    if (row0 >= M) break;
+    float4 xv[BWD_R], dv[BWD_R];
+    float mu[BWD_R], rs[BWD_R];
+    int uu[BWD_R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (Cols<N>::active(lane, i)) {
-        const int col = 4 * lane + 128 * i;
-        float4 xv = Loader<TIn>::ld4(x + row * N + col);
-        float4 d = *reinterpret_cast<const float4*>(dy + row * N + col);
-        float4 g = *reinterpret_cast<const float4*>(gam + col);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-        dxh[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        c1 += dxh[i].x + dxh[i].y + dxh[i].z + dxh[i].w;
-        c2 += dxh[i].x * xh[i].x + dxh[i].y * xh[i].y + dxh[i].z * xh[i].z + dxh[i].w * xh[i].w;
+    for (int r = 0; r < BWD_R; ++r) {
+      const long long row = row0 + r;
+      const bool ok = row < M;
+      uu[r] = ok ? __ldg(row_utt + row) : -1;
+      mu[r] = ok ? __ldg(mean + row) : 0.f;
+      rs[r] = ok ? __ldg(rstd + row) : 0.f;
+      xv[r] = dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && act) {
+        xv[r] = Loader<TIn>::ld4(x + row * N + col);
+        dv[r] = *reinterpret_cast<const float4*>(dy + row * N + col);
       }
-    if (dx32 || dx16) {
-      c1 = warp_sum(c1) * (1.0f / N);
-      c2 = warp_sum(c2) * (1.0f / N);
+    }
+    float p1[BWD_R], p2[BWD_R];
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (Cols<N>::active(lane, i)) {
-          const int col = 4 * lane + 128 * i;
-          float4 o;
-          o.x = rs * (dxh[i].x - c1 - xh[i].x * c2);
-          o.y = rs * (dxh[i].y - c1 - xh[i].y * c2);
-          o.z = rs * (dxh[i].z - c1 - xh[i].z * c2);
-          o.w = rs * (dxh[i].w - c1 - xh[i].w * c2);
-          if (dx32) *reinterpret_cast<float4*>(dx32 + row * N + col) = o;
-          if (dx16) *reinterpret_cast<uint2*>(dx16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    for (int r = 0; r < BWD_R; ++r) {
+      if (uu[r] != u_acc && uu[r] >= 0) {         // utterance boundary (uniform over the CTA): new gamma, new accumulators
+        flush();
+        u_acc = uu[r];
+        if (act) g = __ldg(reinterpret_cast<const float4*>(P + (long long)u_acc * pstride + g_off + col));
+      }
+      const float4 d = dv[r];
+      float4 xh = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);
+      ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+      const float4 dxh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      p1[r] = (dxh.x + dxh.y) + (dxh.z + dxh.w);
+      p2[r] = (dxh.x * xh.x + dxh.y * xh.y) + (dxh.z * xh.z + dxh.w * xh.w);
+      xv[r] = xh;
+      dv[r] = dxh;
+    }
+    if (dx32 || dx16) {
+#pragma unroll
+      for (int r = 0; r < BWD_R; ++r) {
+        p1[r] = warp_sum(p1[r]);
+        p2[r] = warp_sum(p2[r]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < BWD_R; ++r) {
+          red[it & 1][0][warp][r] = p1[r];
+          red[it & 1][1][warp][r] = p2[r];
         }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < BWD_R; ++r) {
+        const long long row = row0 + r;
+        if (row >= M || !act) continue;
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          c1 += red[it & 1][0][w][r];
+          c2 += red[it & 1][1][w][r];
+        }
+        c1 *= 1.0f / N;
+        c2 *= 1.0f / N;
+        float4 o;
+        o.x = rs[r] * (dv[r].x - c1 - xv[r].x * c2);
+        o.y = rs[r] * (dv[r].y - c1 - xv[r].y * c2);
+        o.z = rs[r] * (dv[r].z - c1 - xv[r].z * c2);
+        o.w = rs[r] * (dv[r].w - c1 - xv[r].w * c2);
+        if (dx32) *reinterpret_cast<float4*>(dx32 + row * N + col) = o;
+        if (dx16) *reinterpret_cast<uint2*>(dx16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
     }
   }
-  flush(u_cur);
-  __syncthreads();
-  if (G) {
-    float* gg = G + (long long)u_cta * pstride + g_off;
-    float* gb = G + (long long)u_cta * pstride + b_off;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      float a = s_dg[i], b = s_db[i];
-      if (a != 0.f) atomicAdd(gg + i, a);
-      if (b != 0.f) atomicAdd(gb + i, b);
-    }
-  }
+  flush();
 }
 
 template <int N, typename TIn>
@@ -199,8 +204,8 @@ int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b
 template <int N, typename TIn>
 int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
                int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, cudaStream_t stream) {
-  const int rows = BWD_WARPS * BWD_ROWS_PER_WARP;
-  ln_bwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), BWD_WARPS * 32, 0, stream>>>(
+  constexpr int threads = (N / 4 + 31) / 32 * 32;
+  ln_bwd_kernel<N, TIn><<<(unsigned)((M + BWD_ROWS - 1) / BWD_ROWS), threads, 0, stream>>>(
       dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, b_off, G, dx32, dx16, M);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;

@@ -52,7 +52,7 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
   if (e >= a.n) return;
   const long long i = (long long)blockIdx.y * a.n + e;
   float4 p = *reinterpret_cast<const float4*>(a.P + i);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(a.G + i));
+  const float4 g = __ldcs(reinterpret_cast<const float4*>(a.G + i));       // streamed once: evict-first
   uchar4 k4 = make_uchar4(1, 1, 1, 1);
   if (a.mult) k4 = __ldg(reinterpret_cast<const uchar4*>(a.mult + e));
   float pv[4] = {p.x, p.y, p.z, p.w};
@@ -63,7 +63,7 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
     for (int t = 0; t < 4; ++t)
       for (int j = 0; j < kv[t]; ++j) pv[t] -= a.lr * gv[t];
   } else {
-    float4 m4 = *reinterpret_cast<const float4*>(a.Mom + i), v4 = *reinterpret_cast<const float4*>(a.Var + i);
+    float4 m4 = __ldcs(reinterpret_cast<const float4*>(a.Mom + i)), v4 = __ldcs(reinterpret_cast<const float4*>(a.Var + i));
     float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -77,8 +77,8 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
       }
     }
     if (kv[0] | kv[1] | kv[2] | kv[3]) {
-      *reinterpret_cast<float4*>(a.Mom + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
-      *reinterpret_cast<float4*>(a.Var + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      __stcs(reinterpret_cast<float4*>(a.Mom + i), make_float4(mv[0], mv[1], mv[2], mv[3]));
+      __stcs(reinterpret_cast<float4*>(a.Var + i), make_float4(vv[0], vv[1], vv[2], vv[3]));
     }
   }
   if (kv[0] | kv[1] | kv[2] | kv[3]) *reinterpret_cast<float4*>(a.P + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
