@@ -1,0 +1,369 @@
+// Attention backward on tcgen05 / TMEM (head_dim 64, per-utterance, non-causal).  See attention_tc.cu for the layouts.
+//
+//   S = Q K^T,  P = exp2(S * scale * log2e - LSE),  dP = dO V^T,  dS = P o (dP - D),  D = rowsum(dO o O)
+//   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K
+//
+// One templated persistent kernel (one CTA per SM: tensor-memory kernels do not share an SM) serves both halves:
+//   DKV = true   item = (128 keys, head).  The 128 rows of X1 = K_j, X2 = V_j stay in shared memory; the queries stream
+//                by in blocks of 64 (Y1 = Q_i, Y2 = dO_i).  Score MMAs give the TRANSPOSED tiles S^T = K Q^T and
+//                dP^T = V dO^T (M = 128 keys on the TMEM lanes, N = 64 queries), so each thread owns one key row and
+//                the accumulators dV += P^T dO_i, dK += dS^T Q_i need no cross-CTA reduction.  LSE and D belong to the
+//                columns here: staged in shared memory, +inf / 0 for queries past the utterance end (their P is 0).
+//   DKV = false  item = (128 queries, head): X1 = Q_i, X2 = dO_i resident, keys stream by (Y1 = K_j, Y2 = V_j);
+//                S = Q K^T, dP = dO V^T, one thread per query row (LSE, D in registers), dQ += dS K_j.
+// Warp roles as in the forward: warp 0 TMA producer (X double buffered across items, Y through a 4-stage ring that
+// runs across item boundaries), warp 1 MMA issuer, warps 2..5 / 6..9 two groups that take the even / odd streamed
+// blocks (each with its own score tiles in TMEM and its own A-operand buffers in shared memory) and ping-pong on the
+// MUFU.  Unlike the forward there is no running maximum: LSE is known, both groups add into the SAME accumulators.
+// The streamed tiles are used twice with two descriptors: K-major as the B operand of the score MMAs and MN-major
+// as the B operand of the output MMAs.
+#include "attention_tc.cuh"
+
+namespace {
+
+using namespace attn_tc;
+
+constexpr int HD = 64;
+constexpr int BX = 128;                      // resident rows per item (= TMEM lanes)
+constexpr int BY = 64;                       // streamed rows per block
+constexpr int XTILE = BX * HD * 2;           // 16 KB
+constexpr int YTILE = BY * HD * 2;           // 8 KB
+constexpr int NS = 4;                        // Y ring depth
+constexpr int BWD_THREADS = 320;
+
+// shared-memory map (offsets from a 1024-byte aligned base)
+constexpr int B_X = 0;                       // [2 item buffers][X1 | X2]
+constexpr int B_Y = B_X + 4 * XTILE;         // [NS][Y1 | Y2]
+constexpr int B_A = B_Y + NS * 2 * YTILE;    // [2 groups][dS | P] bf16 [128 rows][64], K-major, 128B swizzle
+constexpr int B_C = B_A + 4 * XTILE;         // [2 groups][lse[64] | D[64]] fp32 (DKV only)
+constexpr int B_BAR = B_C + 2 * 512;
+constexpr int B_SMEM = B_BAR + 256;
+
+template <bool DKV>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_constant__ CUtensorMap tm_qkv_y,
+                   const __grid_constant__ CUtensorMap tm_do_x, const __grid_constant__ CUtensorMap tm_do_y,
+                   const float* __restrict__ LSE, const float* __restrict__ Dv, bf16* __restrict__ dqkv,
+                   const int4* __restrict__ tab, int n_blk, int heads, int H, long long M, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = n_blk * heads;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BAR);
+  uint64_t* x_full = bars;               // [2]  TMA: resident tiles of item parity landed
+  uint64_t* x_empty = bars + 2;          // [2]  MMA: every MMA of that item that reads X has retired
+  uint64_t* y_full = bars + 4;           // [NS] TMA: streamed tiles landed
+  uint64_t* y_empty = bars + 4 + NS;     // [NS] MMA: output MMAs of that block retired
+  uint64_t* sc_full = bars + 4 + 2 * NS; // [2]  MMA: both score tiles of group g complete
+  uint64_t* a_full = sc_full + 2;        // [2]  group g (128 arrivals): A operands written, score tiles consumed
+  uint64_t* a_empty = a_full + 2;        // [2]  MMA: output MMAs that read group g's A operands retired
+  uint64_t* acc_full = a_empty + 2;      //      MMA: accumulators of the item are final
+  uint64_t* acc_empty = acc_full + 1;    //      groups (256 arrivals): accumulators read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_qkv_x);
+    tma_prefetch_desc(&tm_qkv_y);
+    tma_prefetch_desc(&tm_do_x);
+    tma_prefetch_desc(&tm_do_y);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&sc_full[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // TMEM columns: group g score tiles Sc1 at 128 g, Sc2 at 128 g + 64; accumulators at 256 (dV | dQ) and 320 (dK)
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sX = smem_u32(smem + B_X), sY = smem_u32(smem + B_Y), sA = smem_u32(smem + B_A);
+  // column offsets of the four operand tiles inside qkv / dO
+  const int colQ = 0, colK = H, colV = 2 * H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t yc = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int item = n_items - 1 - w;
+        const int4 t = __ldg(&tab[item / heads]);
+        const int head = item - (item / heads) * heads;
+        const int urow0 = t.x, T = t.y, m0 = t.z;
+        const int ny = (T + BY - 1) / BY;
+        const int xb = it & 1;
+        mbar_wait(&x_empty[xb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&x_full[xb], 2 * XTILE);
+        uint8_t* xs = smem + B_X + xb * 2 * XTILE;
+        if (DKV) {
+          tma_load_2d(xs, &tm_qkv_x, &x_full[xb], colK + head * HD, urow0 + m0);
+          tma_load_2d(xs + XTILE, &tm_qkv_x, &x_full[xb], colV + head * HD, urow0 + m0);
+        } else {
+          tma_load_2d(xs, &tm_qkv_x, &x_full[xb], colQ + head * HD, urow0 + m0);
+          tma_load_2d(xs + XTILE, &tm_do_x, &x_full[xb], head * HD, urow0 + m0);
+        }
+        for (int j = 0; j < ny; ++j, ++yc) {
+          const int s = yc % NS;
+          mbar_wait(&y_empty[s], ((yc / NS) & 1) ^ 1);
+          mbar_expect_tx(&y_full[s], 2 * YTILE);
+          uint8_t* ys = smem + B_Y + s * 2 * YTILE;
+          if (DKV) {
+            tma_load_2d(ys, &tm_qkv_y, &y_full[s], colQ + head * HD, urow0 + j * BY);
+            tma_load_2d(ys + YTILE, &tm_do_y, &y_full[s], head * HD, urow0 + j * BY);
+          } else {
+            tma_load_2d(ys, &tm_qkv_y, &y_full[s], colK + head * HD, urow0 + j * BY);
+            tma_load_2d(ys + YTILE, &tm_qkv_y, &y_full[s], colV + head * HD, urow0 + j * BY);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_sc = idesc_bf16(128, BY, false, false);     // X Y^T: both K-major
+      constexpr uint32_t idesc_out = idesc_bf16(128, HD, false, true);     // A (K-major) x Y (MN-major)
+      uint32_t yc = 0;                         // ring position of block 0 of the current item
+      uint32_t ac0 = 0, ac1 = 0;               // A-operand hand-overs from group 0 / 1 so far
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int item = n_items - 1 - w;
+        const int T = __ldg(&tab[item / heads]).y;
+        const int ny = (T + BY - 1) / BY;
+        const int xb = it & 1;
+        const uint32_t x1 = sX + xb * 2 * XTILE, x2 = x1 + XTILE;
+        auto issue_scores = [&](int j) {       // Sc1 = X1 Y1_j^T, Sc2 = X2 Y2_j^T into group (j & 1)'s tiles
+          const uint32_t c = yc + j;
+          const int s = c % NS;
+          const int g = j & 1;
+          mbar_wait(&y_full[s], (c / NS) & 1);
+          tc_fence_after();
+          const uint32_t y1 = sY + s * 2 * YTILE, y2 = y1 + YTILE;
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base + g * 128, umma_desc_sw128(x1 + k * 32), umma_desc_sw128(y1 + k * 32), idesc_sc, k != 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base + g * 128 + 64, umma_desc_sw128(x2 + k * 32), umma_desc_sw128(y2 + k * 32), idesc_sc, k != 0);
+          umma_commit(&sc_full[g]);
+        };
+        mbar_wait(&x_full[xb], (it >> 1) & 1);
+        issue_scores(0);
+        if (ny > 1) issue_scores(1);
+        for (int j = 0; j < ny; ++j) {
+          const int g = j & 1;
+          const uint32_t c = yc + j;
+          const int s = c % NS;
+          const int nvalid = min(BY, T - j * BY);
+          const int ksteps = (nvalid + 15) >> 4;           // reduction over the streamed rows that exist
+          const uint32_t n = g ? ac1 : ac0;
+          if (g) ++ac1; else ++ac0;
+          mbar_wait(&a_full[g], n & 1);
+          if (j == 0 && it > 0) mbar_wait(acc_empty, (it - 1) & 1);   // previous item's accumulators have been read
+          tc_fence_after();
+          const uint32_t y1 = sY + s * 2 * YTILE, y2 = y1 + YTILE;
+          const uint32_t a_ds = sA + g * 2 * XTILE, a_p = a_ds + XTILE;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+            if (DKV) {
+              umma_bf16_ss(tmem_base + 256, umma_desc_sw128(a_p + ks * 32), umma_desc_sw128_mn(y2 + ks * 2048), idesc_out, acc);   // dV += P^T dO
+              umma_bf16_ss(tmem_base + 320, umma_desc_sw128(a_ds + ks * 32), umma_desc_sw128_mn(y1 + ks * 2048), idesc_out, acc);  // dK += dS^T Q
+            } else {
+              umma_bf16_ss(tmem_base + 256, umma_desc_sw128(a_ds + ks * 32), umma_desc_sw128_mn(y1 + ks * 2048), idesc_out, acc);  // dQ += dS K
+            }
+          }
+          umma_commit(&y_empty[s]);
+          umma_commit(&a_empty[g]);
+          if (j + 2 < ny) issue_scores(j + 2);
+          if (j + 1 == ny) umma_commit(&x_empty[xb]);       // every score MMA of the item has been issued before this
+        }
+        umma_commit(acc_full);
+        yc += ny;
+      }
+    }
+  } else {
+    // ===================== elementwise groups: one resident row per thread =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                       // resident row = TMEM lane
+    const int gi = (warp - 2 - 4 * g) * 32 + lane;     // thread index inside the group
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t t1 = tmem_base + lane_off + g * 128, t2 = t1 + 64;
+    const uint32_t a_ds = sA + g * 2 * XTILE + r * 128, a_p = a_ds + XTILE;
+    float* cst = reinterpret_cast<float*>(smem + B_C + g * 512);     // lse[64] | D[64] of the streamed block (DKV)
+    const uint32_t cst_u = smem_u32(cst);
+    float sc = scale_log2;
+    asm volatile("" : "+f"(sc));
+    uint32_t cnt = 0;                                  // blocks this group has processed (sc_full / a_empty phase)
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int item = n_items - 1 - w;
+      const int4 t = __ldg(&tab[item / heads]);
+      const int head = item - (item / heads) * heads;
+      const int urow0 = t.x, T = t.y, m0 = t.z;
+      const int ny = (T + BY - 1) / BY;
+      const bool row_ok = m0 + r < T;
+      const long long row = (long long)urow0 + m0 + r;
+      float lse_r = INFINITY, d_r = 0.f;               // DQ: this thread's query row (+inf: rows past the end give P = 0)
+      if (!DKV && row_ok) {
+        lse_r = __ldg(LSE + (long long)head * M + row);
+        d_r = __ldg(Dv + (long long)head * M + row);
+      }
+      for (int j = g; j < ny; j += 2, ++cnt) {
+        const int nvalid = min(BY, T - j * BY);
+        if (DKV) {                                     // column constants of this query block -> shared memory
+          const int c = gi & 63;
+          const bool ok = j * BY + c < T;
+          const long long qrow = (long long)head * M + urow0 + j * BY + c;
+          // past the utterance end: LSE = +inf makes P = 0, so those (foreign) query rows contribute nothing
+          const float v = gi < 64 ? (ok ? __ldg(LSE + qrow) : INFINITY) : (ok ? __ldg(Dv + qrow) : 0.f);
+          named_bar_sync(2 + g, 128);                  // everyone is done with the previous block's constants
+          cst[gi] = v;
+          named_bar_sync(2 + g, 128);
+        }
+        mbar_wait(&sc_full[g], cnt & 1);
+        tc_fence_after();
+        mbar_wait(&a_empty[g], (cnt & 1) ^ 1);          // the MMAs that read this group's previous operands have retired
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                  // two halves of 32 streamed rows (columns of the score tiles)
+          uint32_t s1[32], s2[32];
+          tmem_ld_32x32(t1 + 32 * h, s1);
+          tmem_ld_32x32(t2 + 32 * h, s2);
+          tmem_ld_wait();
+          uint32_t pds[16], pp[16];                    // packed bf16 pairs: dS (and P for DKV)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float l0, l1, d0, d1;
+            if (DKV) {
+              const float2 lv = ld_shared_v2(cst_u + (32 * h + 2 * i) * 4);
+              const float2 dv = ld_shared_v2(cst_u + 256 + (32 * h + 2 * i) * 4);
+              l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
+            } else {
+              l0 = l1 = lse_r; d0 = d1 = d_r;
+            }
+            float p0 = ex2_approx(fmaf(__uint_as_float(s1[2 * i]), sc, -l0));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s1[2 * i + 1]), sc, -l1));
+            if (!DKV && nvalid < BY) {                 // keys past the utterance end
+              p0 = 32 * h + 2 * i < nvalid ? p0 : 0.f;
+              p1 = 32 * h + 2 * i + 1 < nvalid ? p1 : 0.f;
+            }
+            const float e0 = p0 * (__uint_as_float(s2[2 * i]) - d0), e1 = p1 * (__uint_as_float(s2[2 * i + 1]) - d1);
+            pds[i] = pack_bf16x2(e0, e1);
+            if (DKV) pp[i] = pack_bf16x2(p0, p1);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            st_shared_v4(a_ds + (((4 * h + i) ^ (r & 7)) << 4), pds[4 * i], pds[4 * i + 1], pds[4 * i + 2], pds[4 * i + 3]);
+            if (DKV) st_shared_v4(a_p + (((4 * h + i) ^ (r & 7)) << 4), pp[4 * i], pp[4 * i + 1], pp[4 * i + 2], pp[4 * i + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&a_full[g]);
+      }
+      // ---- end of item: accumulators -> bf16 -> dqkv ----
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+      uint32_t o[32], o2[32];
+      if (DKV) {                                       // group 0 stores dV, group 1 stores dK (* scale)
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64, o);
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64 + 32, o2);
+      } else {                                         // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 32, o);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      if (row_ok) {
+        if (DKV) {
+          const float f = g ? scale : 1.0f;
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + (g ? colK : colV) + head * HD);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            op[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * f, __uint_as_float(o[8 * i + 1]) * f),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 2]) * f, __uint_as_float(o[8 * i + 3]) * f),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 4]) * f, __uint_as_float(o[8 * i + 5]) * f),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 6]) * f, __uint_as_float(o[8 * i + 7]) * f));
+            op[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o2[8 * i]) * f, __uint_as_float(o2[8 * i + 1]) * f),
+                                   pack_bf16x2(__uint_as_float(o2[8 * i + 2]) * f, __uint_as_float(o2[8 * i + 3]) * f),
+                                   pack_bf16x2(__uint_as_float(o2[8 * i + 4]) * f, __uint_as_float(o2[8 * i + 5]) * f),
+                                   pack_bf16x2(__uint_as_float(o2[8 * i + 6]) * f, __uint_as_float(o2[8 * i + 7]) * f));
+          }
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + colQ + head * HD + g * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            op[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * scale, __uint_as_float(o[8 * i + 1]) * scale),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale),
+                               pack_bf16x2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// D[h][row] = sum_d dO[row, h, d] * O[row, h, d]
+__global__ void attn_bwd_prep_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int H,
+                                        int heads, long long M) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, head)
+  if (i >= M * heads) return;
+  long long row = i / heads;
+  int h = (int)(i - row * heads);
+  const uint4* o = reinterpret_cast<const uint4*>(O + row * H + h * HD);
+  const uint4* d = reinterpret_cast<const uint4*>(dO + row * H + h * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint4 a = __ldg(o + k), b = __ldg(d + k);
+    float2 x, y;
+    x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); acc += x.x * y.x + x.y * y.y;
+  }
+  D[(long long)h * M + row] = acc;
+}
+
+}  // namespace
+
+int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const float* LSE, float* D, bf16* dqkv,
+                          const int4* blk_tab, int n_blk, int H, int heads, long long M, cudaStream_t stream) {
+  SUTA_CHECK_ARG(H == heads * HD);
+  if (n_blk <= 0) return SUTA_OK;
+  static bool attr = false;
+  static int n_sm = 148;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  CUtensorMap qx, qy, dx, dy;
+  SUTA_TRY(make_map(&qx, qkv, M, 3LL * H, 3LL * H, BX));
+  SUTA_TRY(make_map(&qy, qkv, M, 3LL * H, 3LL * H, BY));
+  SUTA_TRY(make_map(&dx, dO, M, H, H, BX));
+  SUTA_TRY(make_map(&dy, dO, M, H, H, BY));
+  const float scale = 0.125f, scale_log2 = scale * 1.4426950408889634f;
+  const long long n = M * heads;
+  attn_bwd_prep_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(O, dO, D, H, heads, M);
+  const long long n_items = (long long)n_blk * heads;
+  const int grid = (int)(n_items < n_sm ? n_items : n_sm);
+  attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
+  attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}

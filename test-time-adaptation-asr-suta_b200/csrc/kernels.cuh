@@ -8,15 +8,12 @@ struct UttParams {
   long long stride = 0;
 };
 
-// ---- attention.cu ---------------------------------------------------------------------------
+// ---- attention_tc.cu / attention_bwd_tc.cu (tcgen05 / TMEM) -----------------------------------
+// qkv bf16 [M,3H], O bf16 [M,H], LSE fp32 [heads,M] (base 2), block table: one int4 {utt_row0, T_u, m0, 0} per 128 rows
 int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
                       cudaStream_t stream);
 int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const float* LSE, float* D, bf16* dqkv,
                        const int4* blk_tab, int n_blk, int H, int heads, long long M, cudaStream_t stream);
-
-// ---- attention_tc.cu (tcgen05 / TMEM) --------------------------------------------------------
-int attention_forward_tc(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
-                         cudaStream_t stream);
 
 // ---- norm.cu --------------------------------------------------------------------------------
 // y = LayerNorm(x) * gamma[u] + beta[u]; x is fp32 (x_f32) or bf16 (x_bf16), exactly one non-null.
