@@ -19,6 +19,7 @@
 //               a full 128-byte row segment; all loads of a chunk are issued before the first use.
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -545,6 +546,13 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// tensor-map encoder shared with gemm_tc2.cu: dtype 0 = fp32, 1 = bf16; swizzle 128 / 64 bytes
+int gemm_encode_tmap(CUtensorMap* tm, int dtype, const void* ptr, long long cols, long long rows, long long pitch_bytes,
+                     int box_cols, int box_rows, int swizzle) {
+  return encode_tmap(tm, dtype ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ptr, cols, rows, pitch_bytes,
+                     box_cols, box_rows, swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
 
 // debug hook: CTA 0 of every following GEMM launch writes its per-tile clock64 timeline into dev_buf[cap][8]
 // (0 MMA warp waits for a free accumulator, 1 starts issuing, 2 has issued the tile; 3/4 and 5/6 first epilogue

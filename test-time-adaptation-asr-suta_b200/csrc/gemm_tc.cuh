@@ -55,4 +55,8 @@ struct GemmProblem {
 };
 
 int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream);
+// experimental/gemm_tc2.cu (not built): the cta_group::2 kernel for dense K-major problems with N % 128 == 0
+int gemm_bf16_tc_2cta(const GemmProblem& p, cudaStream_t stream);
+int gemm_encode_tmap(CUtensorMap* tm, int dtype, const void* ptr, long long cols, long long rows, long long pitch_bytes,
+                     int box_cols, int box_rows, int swizzle);
 int gemm_num_sms();
