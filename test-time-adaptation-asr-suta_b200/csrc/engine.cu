@@ -729,8 +729,9 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   // The residual stream is updated IN PLACE: every LayerNorm writes its fp32 output straight into the buffer that holds
   // the next pre-LayerNorm sum (lb[l].h1 / h2, kept per layer for the backward), and the following GEMM accumulates
   // "+= x W^T + b" into it with a TMA reduce-add -- the GEMM epilogue never loads the residual.
+  // (the bias of that GEMM is added by the LayerNorm too, so its fp32 epilogue needs no bias and keeps 4 stages)
   PROF("ln_fwd", layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, e->b16, e->enc_mean,
-                             e->enc_rstd, M, H, c.ln_eps, st));
+                             e->enc_rstd, M, H, c.ln_eps, st, e->w.layer[0].bo));
   e->launches += 5;
   for (int l = 0; l < c.layers; ++l) {
     const suta_layer_weights& w = e->w.layer[l];
@@ -743,11 +744,11 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     PROF_F("attn_fwd", 4.0 * H * e->sumT2, attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
     {  // out_proj + residual                                    HF:546, :597
       GemmProblem p = dense(x.attn, M, H, reinterpret_cast<const bf16*>(w.wo), H);
-      p.epi.bias = w.bo; p.epi.accumulate = 1; p.epi.out_f32 = x.h1; p.epi.out_ld = H;
+      p.epi.accumulate = 1; p.epi.out_f32 = x.h1; p.epi.out_ld = H;      // + bo: already in h1 (added by the LayerNorm)
       SUTA_TRY(gemm(e, p, st));
     }
     PROF("ln_fwd", layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
-                               x.mean1, x.rstd1, M, H, c.ln_eps, st));
+                               x.mean1, x.rstd1, M, H, c.ln_eps, st, w.b2));
     {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
       p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->gelu16; p.epi.out_ld = I;
@@ -755,11 +756,12 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     }
     {  // output_dense + residual                                HF:569, :600
       GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
-      p.epi.bias = w.b2; p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
+      p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;      // + b2: already in h2
       SUTA_TRY(gemm(e, p, st));
     }
     PROF("ln_fwd", layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
-                               l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, e->b16, x.mean2, x.rstd2, M, H, c.ln_eps, st));
+                               l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, e->b16, x.mean2, x.rstd2, M, H, c.ln_eps, st,
+                               l + 1 < c.layers ? e->w.layer[l + 1].bo : nullptr));
     e->launches += 3;
   }
   {  // lm_head                                                   HF:1708

@@ -53,7 +53,9 @@ int g_trace_cap = 0;
     if (p.trace && blockIdx.x == 0 && (iter) < p.trace_cap) p.trace[(iter) * 8 + (slot)] = clock64(); \
   } while (0)
 
-template <int BN, bool EPI_TMA>
+// LEAN (TMA epilogue only): one 4 KB region per epilogue warp -- an fp32 patch (then no bias) or a 2 KB bf16 patch plus the
+// warp's bias values -- which leaves room for a 4th 48 KB stage at BN = 256 (the kernel is mainloop-bound with 3)
+template <int BN, bool EPI_TMA, bool LEAN = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
@@ -64,14 +66,15 @@ struct GemmCfg {
   static constexpr int EPI_SPLIT = (BN >= 128) ? 2 : 1;      // epilogue warps per TMEM lane quarter
   // per epilogue warp: TMA variant = two 4 KB patches (ping-pong) + 512 B of bias; manual = one 4 KB transpose patch
   static constexpr int PATCH_BYTES = 4096;
-  static constexpr int WARP_EPI_BYTES = EPI_TMA ? 2 * PATCH_BYTES : PATCH_BYTES;
-  static constexpr int BIAS_BYTES = EPI_TMA ? 8 * 512 : 0;
+  static constexpr int WARP_EPI_BYTES = (EPI_TMA && !LEAN) ? 2 * PATCH_BYTES : PATCH_BYTES;
+  static constexpr int BIAS_BYTES = (EPI_TMA && !LEAN) ? 8 * 512 : 0;
   static constexpr int EPI_BYTES = 8 * WARP_EPI_BYTES + BIAS_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BUDGET = SMEM_MAX - EPI_BYTES - BAR_BYTES - 1024 /*align slack*/;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static_assert(!EPI_TMA || CH == 32, "the TMA epilogue works on 32-column chunks");
+  static_assert(!LEAN || EPI_TMA, "LEAN is a variant of the TMA epilogue");
   static_assert(STAGES >= 2, "shared memory budget");
 };
 
@@ -98,12 +101,12 @@ __device__ __forceinline__ void epilogue4(const GemmEpilogue& e, float4 v, const
 // A_MN / B_MN: the operand is MN-major in memory ([K rows][M|N contiguous]); its tile is fetched as 64x64 TMA boxes
 // (64 M|N elements = one 128-byte swizzle row, 64 k-rows) laid 8 KB apart, described to the tensor core with
 // leading-dimension byte offset 8192 (next 64 M|N elements) and stride byte offset 1024 (next 8 k-rows).
-template <int BN, bool A_MN, bool B_MN, bool EPI_TMA>
+template <int BN, bool A_MN, bool B_MN, bool EPI_TMA, bool LEAN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                     const GemmKernelParams p) {
-  using C = GemmCfg<BN, EPI_TMA>;
+  using C = GemmCfg<BN, EPI_TMA, LEAN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles must start on 1024-byte boundaries
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -243,7 +246,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     if constexpr (EPI_TMA) {
       // ---------------------------------------------------------------- TMA-store epilogue
-      const uint32_t bias_s = smem_u32(epi_smem + 8 * C::WARP_EPI_BYTES + (warp - 2) * 512);
+      const uint32_t bias_s = LEAN ? patch + 2048 : smem_u32(epi_smem + 8 * C::WARP_EPI_BYTES + (warp - 2) * 512);
       const bool out_is_f32 = p.epi.out_f32 != nullptr;
       uint32_t pc = 0;                             // running chunk counter -> patch ping-pong
       for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -306,9 +309,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
             }
           }
-          const uint32_t pp = patch + (pc & 1) * C::PATCH_BYTES;
+          const uint32_t pp = LEAN ? patch : patch + (pc & 1) * C::PATCH_BYTES;
           ++pc;
-          if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has finished reading this patch
+          if (lane == 0) {                         // the store that last read this patch has finished reading it
+            if (LEAN) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          }
           __syncwarp();
           if (out_is_f32) {
             const uint32_t wrow = pp + lane * 128;
@@ -497,12 +502,12 @@ int make_tmap(CUtensorMap* tm, const GemmOperand& op, int K, int box_rows) {
 }
 int make_tmap_mn(CUtensorMap* tm, const GemmOperand& op) { return make_tmap(tm, op, (int)op.cols, 64); }
 
-template <int BN, bool A_MN, bool B_MN, bool EPI_TMA>
+template <int BN, bool A_MN, bool B_MN, bool EPI_TMA, bool LEAN = false>
 int launch(const GemmProblem& p, cudaStream_t stream) {
-  using C = GemmCfg<BN, EPI_TMA>;
+  using C = GemmCfg<BN, EPI_TMA, LEAN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
     attr_set = true;
   }
@@ -540,7 +545,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   long long total = (long long)kp.num_mblk * kp.num_nblk * kp.nz;
   if (total <= 0) return SUTA_OK;
   int grid = (int)(total < gemm_num_sms() ? total : gemm_num_sms());
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tx, kp);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA, LEAN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tx, kp);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
@@ -590,7 +595,9 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
       if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
       return launch<64, true, true, false>(p, stream);
     }
+    const bool lean = dense && !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias);
     if (dense) {
+      if (p.N % 256 == 0 && lean) return launch<256, false, true, true, true>(p, stream);
       if (p.N % 256 == 0) return launch<256, false, true, true>(p, stream);
       if (p.N % 128 == 0) return launch<128, false, true, true>(p, stream);
       return launch<64, false, true, true>(p, stream);
@@ -600,6 +607,9 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
     return launch<64, false, true, false>(p, stream);
   }
   if (dense) {
+    // 4-stage variant when the epilogue needs neither the second patch (GELU' side output) nor an fp32 patch AND a bias
+    const bool lean = !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias);
+    if (p.N % 256 == 0 && lean) return launch<256, false, false, true, true>(p, stream);
     if (p.N % 256 == 0) return launch<256, false, false, true>(p, stream);
     if (p.N % 128 == 0) return launch<128, false, false, true>(p, stream);
     if (p.N % 64 == 0) return launch<64, false, false, true>(p, stream);

@@ -17,9 +17,11 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
 
 // ---- norm.cu --------------------------------------------------------------------------------
 // y = LayerNorm(x) * gamma[u] + beta[u]; x is fp32 (x_f32) or bf16 (x_bf16), exactly one non-null.
+// y32_bias (optional, fp32 [N]) is added to the fp32 output only: that copy seeds the residual sum the next GEMM accumulates
+// into, so the GEMM's bias is folded in here.
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const float* y32_bias = nullptr);
 // dgamma/dbeta are accumulated (atomicAdd) into G (same layout as the parameter vector); dx outputs optional.
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,

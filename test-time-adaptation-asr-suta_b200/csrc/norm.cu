@@ -35,7 +35,7 @@ template <int N, typename TIn>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const float* __restrict__ P, long long pstride,
               int g_off, int b_off, float* __restrict__ y32, bf16* __restrict__ y16, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long long M, float eps) {
+              float* __restrict__ rstd_out, long long M, float eps, const float* __restrict__ y32_bias) {
   constexpr int NV = Cols<N>::NV;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -77,8 +77,14 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (y32) *reinterpret_cast<float4*>(y32 + row * N + col) = o;
       if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      if (y32) {
+        if (y32_bias) {     // the fp32 copy seeds the next residual sum: the bias of the GEMM that accumulates into it rides along
+          const float4 nb = __ldg(reinterpret_cast<const float4*>(y32_bias + col));
+          o.x += nb.x; o.y += nb.y; o.z += nb.z; o.w += nb.w;
+        }
+        *reinterpret_cast<float4*>(y32 + row * N + col) = o;
+      }
     }
 }
 
@@ -194,10 +200,10 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
 
 template <int N, typename TIn>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
-               float* rstd, long long M, float eps, cudaStream_t stream) {
+               float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
   const int warps = 8;
   ln_fwd_kernel<N, TIn><<<(unsigned)((M + warps - 1) / warps), warps * 32, 0, stream>>>(
-      x, row_utt, prm.P, prm.stride, g_off, b_off, y32, y16, mean, rstd, M, eps);
+      x, row_utt, prm.P, prm.stride, g_off, b_off, y32, y16, mean, rstd, M, eps, y32_bias);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
@@ -228,14 +234,14 @@ int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rs
 
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const float* y32_bias) {
   SUTA_CHECK_ARG((x_f32 != nullptr) != (x_bf16 != nullptr));
   SUTA_CHECK_ARG(g_off % 4 == 0 && b_off % 4 == 0 && prm.stride % 4 == 0);
   if (M <= 0) return SUTA_OK;
   if (x_f32) {
-    LN_DISPATCH(N, return (launch_fwd<NN, float>(x_f32, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, stream)));
+    LN_DISPATCH(N, return (launch_fwd<NN, float>(x_f32, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
   } else {
-    LN_DISPATCH(N, return (launch_fwd<NN, bf16>(x_bf16, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, stream)));
+    LN_DISPATCH(N, return (launch_fwd<NN, bf16>(x_bf16, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
   }
   return SUTA_OK;
 }
