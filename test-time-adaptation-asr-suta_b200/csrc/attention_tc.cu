@@ -11,8 +11,8 @@
 // items are dealt round-robin to the CTAs and the next item's tiles are prefetched while the current one finishes.
 //   warp 0      TMA producer: Q (double buffered across items), then the K_j / V_j tiles (64 keys x 64) through a
 //               4-stage ring that runs straight across item boundaries
-//   warp 1      MMA issuer:  S_g = Q K_j^T  (M=128, N=64, K=64)  into TMEM S[g], g = j & 1
-//                            O_g += P_j V_j (M=128, N=64, K=64; A = P[g] from shared memory, B = V_j MN-major)
+//   warp 1      score issuer:  S[g][b] = Q K_j^T  (M=128, N=64, K=64) into TMEM, g = j & 1, four key blocks ahead
+//   warp 10     output issuer: O_g += P[g][b] V_j (M=128, N=64, K=64; A = P from shared memory, B = V_j MN-major)
 //   warps 2..5  softmax group 0 (even key blocks), warps 6..9 softmax group 1 (odd key blocks): one query row per
 //               thread (TMEM lane = row).  The groups ping-pong: while one exponentiates its block the tensor core
 //               produces the other's scores, and every SM sub-partition always has two softmax warps to interleave.
@@ -35,7 +35,7 @@ constexpr int BKV = 64;                      // keys per block
 constexpr int QTILE = BQ * HD * 2;           // 16 KB: 128 rows x 128 B
 constexpr int KTILE = BKV * HD * 2;          // 8 KB
 constexpr int NS = 6;                        // K/V ring depth (S runs four key blocks ahead of P V)
-constexpr int FWD_THREADS = 320;
+constexpr int FWD_THREADS = 352;            // TMA, score MMA, 8 softmax warps, output MMA
 
 // shared-memory map of the forward kernel (offsets from a 1024-byte aligned base)
 constexpr int F_Q = 0;                       // 2 buffers (item parity)
@@ -43,7 +43,7 @@ constexpr int F_KV = F_Q + 2 * QTILE;        // NS stages of {K_j, V_j}
 constexpr int F_P = F_KV + NS * 2 * KTILE;   // P[g][b]: 4 x [128 rows][64 keys] bf16, K-major, 128B swizzle (b = 0 also merge buffers)
 constexpr int F_X = F_P + 4 * QTILE;         // merge scalars: m[2][128], l[2][128] fp32
 constexpr int F_BAR = F_X + 4 * 128 * 4;
-constexpr int F_SMEM = F_BAR + 256;
+constexpr int F_SMEM = F_BAR + 512;
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ O,
@@ -72,7 +72,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* p_empty = p_full + 4;      // [g][b] MMA: P[g][b] V retired (O_g includes it; the buffer may be rewritten)
   uint64_t* o_full = p_empty + 4;      //      MMA: both accumulators of the item are final
   uint64_t* o_empty = o_full + 1;      //      softmax (256 arrivals): accumulators read, next item may overwrite them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* tok = o_empty + 1;         // [2][4] MUFU token of each sub-partition's warp pair: [0][q] "group 1 done", [1][q] "group 0 done"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();      // the swizzled tiles need a 1024-byte aligned base
@@ -83,6 +84,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 256);
+    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -118,37 +120,51 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
+      // ===================== score issuer: S[g][b] = Q K_j^T, four key blocks ahead of the softmax =====================
+      // (Issuing one tcgen05.mma costs this thread ~130 cycles of dependent uniform-datapath work, so the two kinds of
+      // MMA have an issuing thread each; descriptors advance by plain adds: +2 per 32 bytes in the address field.)
       constexpr uint32_t idesc_qk = idesc_bf16(128, BKV, false, false);
-      constexpr uint32_t idesc_pv = idesc_bf16(128, HD, false, true);
       uint32_t kvc = 0;                        // ring position of block 0 of the current item
       uint32_t sc0 = 0, sc1 = 0;               // S tiles issued for group 0 / 1 so far  (buffer = count & 1)
-      uint32_t pc0 = 0, pc1 = 0;               // P tiles consumed from group 0 / 1 so far
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int item = n_items - 1 - w;
         const int T = __ldg(&tab[item / heads]).y;
         const int nkv = (T + BKV - 1) / BKV;
         const int qb = it & 1;
-        const uint32_t q_addr = sQ + qb * QTILE;
-        auto issue_qk = [&](int j) {           // S[g][b] = Q K_j^T, g = j & 1
+        const uint64_t q_desc = umma_desc_sw128(sQ + qb * QTILE);
+        mbar_wait(&q_full[qb], (it >> 1) & 1);
+        for (int j = 0; j < nkv; ++j) {
           const uint32_t c = kvc + j;
           const int s = c % NS;
           const int g = j & 1;
           const uint32_t n = g ? sc1 : sc0;
           const int sb = g * 2 + (n & 1);
           if (g) ++sc1; else ++sc0;
+          // S[g][b] is free once the softmax of this group's block two (local) blocks earlier has consumed it
+          if (n >= 2) mbar_wait(&p_full[sb], ((n >> 1) & 1) ^ 1);
           mbar_wait(&kv_full[s], (c / NS) & 1);
           tc_fence_after();
-          const uint32_t k_addr = sKV + s * 2 * KTILE;
+          const uint64_t k_desc = umma_desc_sw128(sKV + s * 2 * KTILE);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base + sb * BKV, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + sb * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
           umma_commit(&s_full[sb]);
-          if (j == nkv - 1) umma_commit(&q_empty[qb]);
-        };
-        mbar_wait(&q_full[qb], (it >> 1) & 1);
-        for (int j = 0; j < 4 && j < nkv; ++j) issue_qk(j);      // scores run four key blocks (two per group) ahead
+        }
+        umma_commit(&q_empty[qb]);
+        kvc += nkv;
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ===================== output issuer: O_g += P[g][b] V_j =====================
+      constexpr uint32_t idesc_pv = idesc_bf16(128, HD, false, true);
+      uint32_t kvc = 0;
+      uint32_t pc0 = 0, pc1 = 0;               // P tiles consumed from group 0 / 1 so far
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int item = n_items - 1 - w;
+        const int T = __ldg(&tab[item / heads]).y;
+        const int nkv = (T + BKV - 1) / BKV;
         for (int j = 0; j < nkv; ++j) {
           const int g = j & 1;
           const uint32_t c = kvc + j;
@@ -161,13 +177,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           mbar_wait(&p_full[pb], (n >> 1) & 1);
           if (j < 2 && it > 0) mbar_wait(o_empty, (it - 1) & 1);       // previous item's accumulators have been read
           tc_fence_after();
-          const uint32_t v_addr = sKV + s * 2 * KTILE + KTILE;
+          const uint64_t p_desc = umma_desc_sw128(sP + pb * QTILE);
+          const uint64_t v_desc = umma_desc_sw128_mn(sKV + s * 2 * KTILE + KTILE);
           for (int ks = 0; ks < ksteps; ++ks)
-            umma_bf16_ss(tmem_base + 256 + g * HD, umma_desc_sw128(sP + pb * QTILE + ks * 32), umma_desc_sw128_mn(v_addr + ks * 2048),
-                         idesc_pv, (j >= 2 || ks > 0) ? 1u : 0u);
-          umma_commit(&kv_empty[s]);
+            umma_bf16_ss(tmem_base + 256 + g * HD, p_desc + 2 * ks, v_desc + 128 * ks, idesc_pv, (j >= 2 || ks > 0) ? 1u : 0u);
+          umma_commit(&kv_empty[s]);           // K_j was consumed by S_j long ago (its softmax has finished), V_j by these MMAs
           umma_commit(&p_empty[pb]);
-          if (j + 4 < nkv) issue_qk(j + 4);
         }
         umma_commit(o_full);
         kvc += nkv;
@@ -175,13 +190,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else {
     // ===================== softmax groups: one query row per thread =====================
-    const int g = (warp - 2) >> 2;                   // group 0: even key blocks, group 1: odd key blocks
+    const int g = (warp - 2) >> 2;                   // group 0: even key blocks, group 1: odd key blocks (warps 2..9)
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row inside the 128-query block = TMEM lane
     const uint32_t tO = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + g * HD;
     float* xm = reinterpret_cast<float*>(smem + F_X);   // [2][128] running max of each group
     float* xl = xm + 256;                               // [2][128] running sum
-    uint32_t cnt = 0;                                   // blocks this group has processed so far (s_full / pv_done phase)
+    uint32_t cnt = 0;                                   // blocks this group has processed so far (s_full / p_empty phase)
+    uint32_t rnd = 0;                                   // rounds so far (token phase)
     float sc = scale_log2;
     asm volatile("" : "+f"(sc));                        // keep the scale in a register (not re-read from the constant bank per element)
     int it = 0;
@@ -192,7 +208,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int urow0 = t.x, T = t.y, m0 = t.z;
       const int nkv = (T + BKV - 1) / BKV;
       float m_run = -INFINITY, l_run = 0.f;
-      for (int j = g; j < nkv; j += 2, ++cnt) {
+      // Rounds: in round rr group g owns key block 2 rr + g.  The two warps that share an SM sub-partition (same q, one per
+      // group) pass a token around the exp2 section so that they never compete for the MUFU (8 cycles per warp
+      // instruction): while one exponentiates, the other loads scores, reduces the row maximum, packs and stores P.
+      // Both groups run every round (an odd block count gives group 1 an empty last round) so the token keeps alternating.
+      const int rounds = (nkv + 1) >> 1;
+      for (int rr = 0; rr < rounds; ++rr, ++rnd) {
+        const int j = 2 * rr + g;
+        if (j >= nkv) {                                // empty round: pass the token on
+          mbar_wait(&tok[4 + q], rnd & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tok[q]);
+          continue;
+        }
         const int nvalid = min(BKV, T - j * BKV);
         const int sb2 = g * 2 + (cnt & 1);               // S / P buffer of this block
         const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + sb2 * BKV;
@@ -242,8 +270,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tmem_st_wait();
           }
         }
-        const float nm = -m_run;
+        float nm = -m_run;
         STAMP();
+        // ---- MUFU token: group 0 goes first in every round, then group 1 ----
+        mbar_wait(&tok[(g ? 4 : 0) + q], g ? (rnd & 1) : ((rnd & 1) ^ 1));
+        asm volatile("" : "+f"(nm));                   // nothing of the exp2 section may be scheduled above the wait
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[32];
         if (full) {
@@ -269,16 +300,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             pk[16 + i] = pack_bf16x2(e2, e3);
           }
         }
+        float lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        asm volatile("" : "+f"(lsum));                 // every exp2 has been issued and consumed before the token moves on
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tok[(g ? 0 : 4) + q]);
         STAMP();
         mbar_wait(&p_empty[sb2], ((cnt >> 1) & 1) ^ 1);  // the P V that read this buffer two blocks ago has retired
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_v4(prow + ((i ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        l_run += lsum;
         STAMP();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&p_full[sb2]);
+        ++cnt;
       }
       STAMP();
       // ---- end of item: merge the two groups' partial results (split-KV merge), normalise, store ----
