@@ -12,7 +12,7 @@
 //   DKV = false  item = (128 queries, head): X1 = Q_i, X2 = dO_i resident, keys stream by (Y1 = K_j, Y2 = V_j);
 //                S = Q K^T, dP = dO V^T, one thread per query row (LSE, D in registers), dQ += dS K_j.
 // Warp roles as in the forward: warp 0 TMA producer (X double buffered across items, Y through a 4-stage ring that
-// runs across item boundaries), warp 1 MMA issuer, warps 2..5 / 6..9 two groups that take the even / odd streamed
+// runs across item boundaries), warp 1 score-MMA issuer, warps 10 / 11 output-MMA issuers, warps 2..5 / 6..9 two groups that take the even / odd streamed
 // blocks (each with its own score tiles in TMEM and its own A-operand buffers in shared memory) and ping-pong on the
 // MUFU.  Unlike the forward there is no running maximum: LSE is known, both groups add into the SAME accumulators.
 // The streamed tiles are used twice with two descriptors: K-major as the B operand of the score MMAs and MN-major
@@ -29,7 +29,7 @@ constexpr int BY = 64;                       // streamed rows per block
 constexpr int XTILE = BX * HD * 2;           // 16 KB
 constexpr int YTILE = BY * HD * 2;           // 8 KB
 constexpr int NS = 4;                        // Y ring depth
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 384;          // TMA, score MMA, 8 elementwise warps, 2 output-MMA warps
 
 // shared-memory map (offsets from a 1024-byte aligned base)
 constexpr int B_X = 0;                       // [2 item buffers][X1 | X2]
@@ -67,11 +67,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     tma_prefetch_desc(&tm_qkv_y);
     tma_prefetch_desc(&tm_do_x);
     tma_prefetch_desc(&tm_do_y);
+    constexpr int NOUT = DKV ? 2 : 1;          // output issuers: each commits its own arrival
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&sc_full[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&sc_full[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NOUT);
     }
-    for (int i = 0; i < NS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], NOUT); }
+    mbar_init(acc_full, NOUT);
     mbar_init(acc_empty, 256);
     mbar_fence_init();
   }
@@ -124,36 +125,54 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
+      // ===================== score issuer: Sc1 = X1 Y1_j^T, Sc2 = X2 Y2_j^T into group (j & 1)'s tiles =================
+      // (one tcgen05.mma issue costs the issuing thread ~130 cycles of dependent uniform-datapath work, so scores and the
+      // two output products each have their own issuing warp; descriptors advance by adds in the address field.  A fourth
+      // issuing warp would push the CTA to 13 warps and the register cap to 128: measured slower.)
       constexpr uint32_t idesc_sc = idesc_bf16(128, BY, false, false);     // X Y^T: both K-major
-      constexpr uint32_t idesc_out = idesc_bf16(128, HD, false, true);     // A (K-major) x Y (MN-major)
       uint32_t yc = 0;                         // ring position of block 0 of the current item
-      uint32_t ac0 = 0, ac1 = 0;               // A-operand hand-overs from group 0 / 1 so far
+      uint32_t sn0 = 0, sn1 = 0;               // score tiles issued for group 0 / 1 so far
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int item = n_items - 1 - w;
         const int T = __ldg(&tab[item / heads]).y;
         const int ny = (T + BY - 1) / BY;
         const int xb = it & 1;
-        const uint32_t x1 = sX + xb * 2 * XTILE, x2 = x1 + XTILE;
-        auto issue_scores = [&](int j) {       // Sc1 = X1 Y1_j^T, Sc2 = X2 Y2_j^T into group (j & 1)'s tiles
+        const uint64_t x1 = umma_desc_sw128(sX + xb * 2 * XTILE), x2 = umma_desc_sw128(sX + xb * 2 * XTILE + XTILE);
+        mbar_wait(&x_full[xb], (it >> 1) & 1);
+        for (int j = 0; j < ny; ++j) {
           const uint32_t c = yc + j;
           const int s = c % NS;
           const int g = j & 1;
+          const uint32_t n = g ? sn1 : sn0;
+          if (g) ++sn1; else ++sn0;
+          if (n >= 1) mbar_wait(&a_full[g], (n - 1) & 1);      // the group has consumed its previous score tiles
           mbar_wait(&y_full[s], (c / NS) & 1);
           tc_fence_after();
-          const uint32_t y1 = sY + s * 2 * YTILE, y2 = y1 + YTILE;
+          const uint64_t y1 = umma_desc_sw128(sY + s * 2 * YTILE), y2 = umma_desc_sw128(sY + s * 2 * YTILE + YTILE);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base + g * 128, umma_desc_sw128(x1 + k * 32), umma_desc_sw128(y1 + k * 32), idesc_sc, k != 0);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base + g * 128 + 64, umma_desc_sw128(x2 + k * 32), umma_desc_sw128(y2 + k * 32), idesc_sc, k != 0);
+          for (int k = 0; k < HD / 16; ++k) {                  // two independent accumulation chains, interleaved
+            umma_bf16_ss(tmem_base + g * 128, x1 + 2 * k, y1 + 2 * k, idesc_sc, k != 0);
+            umma_bf16_ss(tmem_base + g * 128 + 64, x2 + 2 * k, y2 + 2 * k, idesc_sc, k != 0);
+          }
           umma_commit(&sc_full[g]);
-        };
-        mbar_wait(&x_full[xb], (it >> 1) & 1);
-        issue_scores(0);
-        if (ny > 1) issue_scores(1);
+        }
+        umma_commit(&x_empty[xb]);
+        yc += ny;
+      }
+    }
+  } else if (warp == 10 || warp == 11) {
+    // ===================== output issuers: warp 10 -> accumulator 0 (dV | dQ), warp 11 -> accumulator 1 (dK, DKV only) ====
+    const int which = warp - 10;
+    if (lane == 0 && (DKV || which == 0)) {
+      constexpr uint32_t idesc_out = idesc_bf16(128, HD, false, true);     // A (K-major) x Y (MN-major)
+      uint32_t yc = 0;
+      uint32_t ac0 = 0, ac1 = 0;               // A-operand hand-overs from group 0 / 1 so far
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int item = n_items - 1 - w;
+        const int T = __ldg(&tab[item / heads]).y;
+        const int ny = (T + BY - 1) / BY;
         for (int j = 0; j < ny; ++j) {
           const int g = j & 1;
           const uint32_t c = yc + j;
@@ -165,21 +184,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           mbar_wait(&a_full[g], n & 1);
           if (j == 0 && it > 0) mbar_wait(acc_empty, (it - 1) & 1);   // previous item's accumulators have been read
           tc_fence_after();
-          const uint32_t y1 = sY + s * 2 * YTILE, y2 = y1 + YTILE;
-          const uint32_t a_ds = sA + g * 2 * XTILE, a_p = a_ds + XTILE;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-            if (DKV) {
-              umma_bf16_ss(tmem_base + 256, umma_desc_sw128(a_p + ks * 32), umma_desc_sw128_mn(y2 + ks * 2048), idesc_out, acc);   // dV += P^T dO
-              umma_bf16_ss(tmem_base + 320, umma_desc_sw128(a_ds + ks * 32), umma_desc_sw128_mn(y1 + ks * 2048), idesc_out, acc);  // dK += dS^T Q
-            } else {
-              umma_bf16_ss(tmem_base + 256, umma_desc_sw128(a_ds + ks * 32), umma_desc_sw128_mn(y1 + ks * 2048), idesc_out, acc);  // dQ += dS K
-            }
-          }
+          // DKV: dV += P^T dO (A = P, B = Y2) on warp 10, dK += dS^T Q (A = dS, B = Y1) on warp 11;  DQ: dQ += dS K (A = dS, B = Y1)
+          const bool use_p = DKV && which == 0;
+          const uint64_t a_desc = umma_desc_sw128(sA + g * 2 * XTILE + (use_p ? XTILE : 0));
+          const uint64_t y_desc = umma_desc_sw128_mn(sY + s * 2 * YTILE + (use_p ? YTILE : 0));
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_bf16_ss(tmem_base + 256 + which * 64, a_desc + 2 * ks, y_desc + 128 * ks, idesc_out, (j > 0 || ks > 0) ? 1u : 0u);
           umma_commit(&y_empty[s]);
           umma_commit(&a_empty[g]);
-          if (j + 2 < ny) issue_scores(j + 2);
-          if (j + 1 == ny) umma_commit(&x_empty[xb]);       // every score MMA of the item has been issued before this
         }
         umma_commit(acc_full);
         yc += ny;
