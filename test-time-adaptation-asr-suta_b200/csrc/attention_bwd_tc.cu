@@ -124,8 +124,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== score issuer: Sc1 = X1 Y1_j^T, Sc2 = X2 Y2_j^T into group (j & 1)'s tiles =================
+    {
+      // ===================== score issuer (whole warp runs the loop, one elected lane issues, see elect_one()): Sc1 = X1 Y1_j^T, Sc2 = X2 Y2_j^T into group (j & 1)'s tiles =================
       // (one tcgen05.mma issue costs the issuing thread ~130 cycles of dependent uniform-datapath work, so scores and the
       // two output products each have their own issuing warp; descriptors advance by adds in the address field.  A fourth
       // issuing warp would push the CTA to 13 warps and the register cap to 128: measured slower.)
@@ -150,21 +150,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           mbar_wait(&y_full[s], (c / NS) & 1);
           tc_fence_after();
           const uint64_t y1 = umma_desc_sw128(sY + s * 2 * YTILE), y2 = umma_desc_sw128(sY + s * 2 * YTILE + YTILE);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {                  // two independent accumulation chains, interleaved
-            umma_bf16_ss(tmem_base + g * 128, x1 + 2 * k, y1 + 2 * k, idesc_sc, k != 0);
-            umma_bf16_ss(tmem_base + g * 128 + 64, x2 + 2 * k, y2 + 2 * k, idesc_sc, k != 0);
+            for (int k = 0; k < HD / 16; ++k) {                // two independent accumulation chains, interleaved
+              umma_bf16_ss(tmem_base + g * 128, x1 + 2 * k, y1 + 2 * k, idesc_sc, k != 0);
+              umma_bf16_ss(tmem_base + g * 128 + 64, x2 + 2 * k, y2 + 2 * k, idesc_sc, k != 0);
+            }
+            umma_commit(&sc_full[g]);
           }
-          umma_commit(&sc_full[g]);
+          __syncwarp();
         }
-        umma_commit(&x_empty[xb]);
+        if (elect_one()) umma_commit(&x_empty[xb]);
+        __syncwarp();
         yc += ny;
       }
     }
   } else if (warp == 10 || warp == 11) {
     // ===================== output issuers: warp 10 -> accumulator 0 (dV | dQ), warp 11 -> accumulator 1 (dK, DKV only) ====
     const int which = warp - 10;
-    if (lane == 0 && (DKV || which == 0)) {
+    if (DKV || which == 0) {
       constexpr uint32_t idesc_out = idesc_bf16(128, HD, false, true);     // A (K-major) x Y (MN-major)
       uint32_t yc = 0;
       uint32_t ac0 = 0, ac1 = 0;               // A-operand hand-overs from group 0 / 1 so far
@@ -188,12 +192,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           const bool use_p = DKV && which == 0;
           const uint64_t a_desc = umma_desc_sw128(sA + g * 2 * XTILE + (use_p ? XTILE : 0));
           const uint64_t y_desc = umma_desc_sw128_mn(sY + s * 2 * YTILE + (use_p ? YTILE : 0));
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_bf16_ss(tmem_base + 256 + which * 64, a_desc + 2 * ks, y_desc + 128 * ks, idesc_out, (j > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(&y_empty[s]);
-          umma_commit(&a_empty[g]);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) umma_bf16_ss(tmem_base + 256 + which * 64, a_desc + 2 * ks, y_desc + 128 * ks, idesc_out, (j > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&y_empty[s]);
+            umma_commit(&a_empty[g]);
+          }
+          __syncwarp();
         }
-        umma_commit(acc_full);
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
         yc += ny;
       }
     }

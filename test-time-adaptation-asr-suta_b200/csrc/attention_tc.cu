@@ -119,10 +119,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== score issuer: S[g][b] = Q K_j^T, four key blocks ahead of the softmax =====================
-      // (Issuing one tcgen05.mma costs this thread ~130 cycles of dependent uniform-datapath work, so the two kinds of
-      // MMA have an issuing thread each; descriptors advance by plain adds: +2 per 32 bytes in the address field.)
+      // (The whole warp runs the loop and one elected lane issues, see elect_one(); the two kinds of MMA have an issuing
+      // warp each; descriptors advance by plain adds: +2 per 32 bytes in the address field.)
       constexpr uint32_t idesc_qk = idesc_bf16(128, BKV, false, false);
       uint32_t kvc = 0;                        // ring position of block 0 of the current item
       uint32_t sc0 = 0, sc1 = 0;               // S tiles issued for group 0 / 1 so far  (buffer = count & 1)
@@ -146,16 +146,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           mbar_wait(&kv_full[s], (c / NS) & 1);
           tc_fence_after();
           const uint64_t k_desc = umma_desc_sw128(sKV + s * 2 * KTILE);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + sb * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
-          umma_commit(&s_full[sb]);
+            for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + sb * BKV, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
+            umma_commit(&s_full[sb]);
+          }
+          __syncwarp();
         }
-        umma_commit(&q_empty[qb]);
+        if (elect_one()) umma_commit(&q_empty[qb]);
+        __syncwarp();
         kvc += nkv;
       }
     }
   } else if (warp == 10) {
-    if (lane == 0) {
+    {
       // ===================== output issuer: O_g += P[g][b] V_j =====================
       constexpr uint32_t idesc_pv = idesc_bf16(128, HD, false, true);
       uint32_t kvc = 0;
@@ -179,12 +183,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tc_fence_after();
           const uint64_t p_desc = umma_desc_sw128(sP + pb * QTILE);
           const uint64_t v_desc = umma_desc_sw128_mn(sKV + s * 2 * KTILE + KTILE);
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_bf16_ss(tmem_base + 256 + g * HD, p_desc + 2 * ks, v_desc + 128 * ks, idesc_pv, (j >= 2 || ks > 0) ? 1u : 0u);
-          umma_commit(&kv_empty[s]);           // K_j was consumed by S_j long ago (its softmax has finished), V_j by these MMAs
-          umma_commit(&p_empty[pb]);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) umma_bf16_ss(tmem_base + 256 + g * HD, p_desc + 2 * ks, v_desc + 128 * ks, idesc_pv, (j >= 2 || ks > 0) ? 1u : 0u);
+            umma_commit(&kv_empty[s]);         // K_j was consumed by S_j long ago (its softmax has finished), V_j by these MMAs
+            umma_commit(&p_empty[pb]);
+          }
+          __syncwarp();
         }
-        umma_commit(o_full);
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
         kvc += nkv;
       }
     }

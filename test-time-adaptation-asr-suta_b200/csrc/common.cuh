@@ -207,6 +207,17 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// One lane of a CONVERGED warp (the lowest one).  tcgen05.mma / commit are single-thread instructions that execute on the
+// uniform datapath: issued from a region the compiler sees as divergent (if (lane == 0) {...}) every one of them is wrapped
+// in an ELECT / BRA.U.ANY loop with its descriptors rebuilt through a dependent chain of uniform ops -- ~130 cycles per
+// MMA, as long as a 128x256x16 MMA takes to execute.  With the whole warp running the role loop and only the issue under
+// elect_one(), ptxas emits the UTCHMMAs back to back with UIADD3.64 descriptor updates.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -197,8 +197,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
@@ -208,27 +208,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         int num_kblk = num_kblk_all;
         if (p.ztab) num_kblk = (__ldg(&p.ztab[tile / tiles_per_z]).z + BK - 1) / BK;
-        TRACE(iter, 0);
+        if (lane == 0) TRACE(iter, 0);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        TRACE(iter, 1);
+        if (lane == 0) TRACE(iter, 1);
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
         for (int kb = 0; kb < num_kblk; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+          // descriptors advance through the stage by adds in the 16-byte-unit address field: 32 B (K-major) or 2048 B (MN-major) per k16
+          const uint64_t da = A_MN ? umma_desc_sw128_mn(a_addr) : umma_desc_sw128(a_addr);
+          const uint64_t db = B_MN ? umma_desc_sw128_mn(a_addr + C::A_BYTES) : umma_desc_sw128(a_addr + C::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_desc_sw128_mn(a_addr + k * 2048) : umma_desc_sw128(a_addr + k * 32);
-            const uint64_t db = B_MN ? umma_desc_sw128_mn(b_addr + k * 2048) : umma_desc_sw128(b_addr + k * 32);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);        // frees the smem stage once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);               // accumulator complete -> epilogue
-        TRACE(iter, 2);
+        if (elect_one()) umma_commit(&acc_full[acc]);   // accumulator complete -> epilogue
+        __syncwarp();
+        if (lane == 0) TRACE(iter, 2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
