@@ -42,37 +42,60 @@ __global__ void gelu_grad_pad_kernel(const float* __restrict__ d, const bf16* __
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
-constexpr int C2I_ROWS = 16;
+constexpr int C2I_ROWS = 16;      // rows per CTA: 4 per thread, all loads of the 4 rows issued before the first use
+constexpr int C2I_MAXTAPS = 2;    // a row receives ceil(k / s) <= 2 taps for the wav2vec2 feature extractor (k <= 2 s)
 
 __global__ void __launch_bounds__(256)
 col2im_kernel(Col2imArgs a) {
   const int u = blockIdx.y;
   const int Lo = a.L_out[u], Li = a.L_in[u];
-  const int c8n = a.C >> 3;
+  if (blockIdx.x * C2I_ROWS >= Lo) return;
+  const int c8n = a.C >> 3;                       // 16-byte channel groups per row (64 for C = 512)
   const long long oo = a.off_out[u], oi = a.off_in[u];
   const int ldz = a.k * a.C;
-  for (int idx = threadIdx.x; idx < C2I_ROWS * c8n; idx += blockDim.x) {
-    const int r = blockIdx.x * C2I_ROWS + idx / c8n;
-    if (r >= Lo) continue;
-    const int c = (idx % c8n) * 8;
+  const bf16* __restrict__ Z = a.Z;
+  const bf16* __restrict__ pre = a.pre;
+  bf16* __restrict__ out = a.out;
+  const int rows_per_pass = 256 / c8n;            // 4 for C = 512
+  const int c = (threadIdx.x % c8n) * 8;
+  const int rsub = threadIdx.x / c8n;
+  constexpr int NR = 4;
+  uint4 z[NR][C2I_MAXTAPS], pv[NR];
+  bool zok[NR][C2I_MAXTAPS], rok[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int r = blockIdx.x * C2I_ROWS + rsub + rows_per_pass * i;
+    rok[i] = r < Lo && rsub + rows_per_pass * i < C2I_ROWS;
+    // taps j = (r mod s), (r mod s) + s, ... < k  read Z row t = (r - j) / s
+    const int j0 = r % a.s;
+#pragma unroll
+    for (int q = 0; q < C2I_MAXTAPS; ++q) {
+      const int j = j0 + q * a.s;
+      const int t = (r - j) / a.s;
+      zok[i][q] = rok[i] && j < a.k && r - j >= 0 && t < Li;
+      z[i][q] = make_uint4(0u, 0u, 0u, 0u);
+      if (zok[i][q]) z[i][q] = __ldg(reinterpret_cast<const uint4*>(Z + (oi + t) * ldz + j * a.C + c));
+    }
+    pv[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (rok[i]) pv[i] = __ldg(reinterpret_cast<const uint4*>(pre + (oo + r) * a.C + c));
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (!rok[i]) continue;
+    const int r = blockIdx.x * C2I_ROWS + rsub + rows_per_pass * i;
     float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int j = 0; j < a.k; ++j) {
-      const int rj = r - j;
-      if (rj < 0 || rj % a.s != 0) continue;
-      const int t = rj / a.s;
-      if (t >= Li) continue;
-      uint4 z = *reinterpret_cast<const uint4*>(a.Z + (oi + t) * ldz + j * a.C + c);
-      float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y), z2 = unpack_bf16x2(z.z), z3 = unpack_bf16x2(z.w);
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < C2I_MAXTAPS; ++q) {
+      const float2 z0 = unpack_bf16x2(z[i][q].x), z1 = unpack_bf16x2(z[i][q].y), z2 = unpack_bf16x2(z[i][q].z), z3 = unpack_bf16x2(z[i][q].w);
       acc[0] += z0.x; acc[1] += z0.y; acc[2] += z1.x; acc[3] += z1.y;
       acc[4] += z2.x; acc[5] += z2.y; acc[6] += z3.x; acc[7] += z3.y;
     }
-    uint4 p = *reinterpret_cast<const uint4*>(a.pre + (oo + r) * a.C + c);
-    float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y), p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
+    const float2 p0 = unpack_bf16x2(pv[i].x), p1 = unpack_bf16x2(pv[i].y), p2 = unpack_bf16x2(pv[i].z), p3 = unpack_bf16x2(pv[i].w);
     acc[0] *= p0.x; acc[1] *= p0.y; acc[2] *= p1.x; acc[3] *= p1.y;
     acc[4] *= p2.x; acc[5] *= p2.y; acc[6] *= p3.x; acc[7] *= p3.y;
-    *reinterpret_cast<uint4*>(a.out + (oo + r) * a.C + c) =
+    *reinterpret_cast<uint4*>(out + (oo + r) * a.C + c) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
   }
 }
@@ -108,8 +131,32 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
 #pragma unroll
     for (int j = 0; j < C0B_MAXK; ++j) Aa[j] = Ab[j] = 0.f;
     const bf16* dyp = a.dy + row0 * a.C + c;
-#pragma unroll 2
-    for (int t = 0; t < nt; ++t) {
+    int t = 0;
+    const bool vec_ok = a.stride == 5 && k <= 10;    // the wav2vec2 front end: 4 frames = 20 samples = five 16-byte words
+    for (; vec_ok && t + 4 <= nt; t += 4) {      // four independent loads in flight per thread (the kernel is latency-bound)
+      const unsigned int r0 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 0) * a.C));
+      const unsigned int r1 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 1) * a.C));
+      const unsigned int r2 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 2) * a.C));
+      const unsigned int r3 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 3) * a.C));
+      const unsigned int rr[4] = {r0, r1, r2, r3};
+      // the 4 windows cover samples [5 t, 5 t + 25): seven 16-byte broadcast loads instead of 40 scalar ones
+      float xw[28];
+#pragma unroll
+      for (int v = 0; v < 7; ++v) {
+        const float4 f = *reinterpret_cast<const float4*>(sx + 5 * t + 4 * v);
+        xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 dy = unpack_bf16x2(rr[q]);
+        s1a += dy.x;
+        s1b += dy.y;
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          if (j < k) { const float xv = xw[5 * q + j]; Aa[j] = fmaf(dy.x, xv, Aa[j]); Ab[j] = fmaf(dy.y, xv, Ab[j]); }
+      }
+    }
+    for (; t < nt; ++t) {
       const float2 dy = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)t * a.C)));
       const float* xs = sx + t * a.stride;
       s1a += dy.x;
@@ -118,11 +165,12 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
       for (int j = 0; j < C0B_MAXK; ++j)
         if (j < k) { const float xv = xs[j]; Aa[j] = fmaf(dy.x, xv, Aa[j]); Ab[j] = fmaf(dy.y, xv, Ab[j]); }
     }
-    float* pa = a.part + (((long long)u * a.n_chunk + blockIdx.x) * a.C + c) * (k + 1);
-    float* pb = pa + (k + 1);
-    pa[0] = s1a;
-    pb[0] = s1b;
-    for (int j = 0; j < k; ++j) { pa[1 + j] = Aa[j]; pb[1 + j] = Ab[j]; }
+    // partial sums, layout [U][chunk][k + 1][C]: channel-contiguous, so this store and the finalize kernel's loads coalesce
+    float* pa = a.part + ((long long)u * a.n_chunk + blockIdx.x) * (k + 1) * a.C + c;
+    *reinterpret_cast<float2*>(pa) = make_float2(s1a, s1b);
+#pragma unroll
+    for (int j = 0; j < C0B_MAXK; ++j)           // static indices: a runtime-indexed copy would put Aa/Ab in local memory
+      if (j < k) *reinterpret_cast<float2*>(pa + (long long)(1 + j) * a.C) = make_float2(Aa[j], Ab[j]);
   }
 }
 
@@ -136,9 +184,11 @@ __global__ void conv0_bwd_finalize_kernel(Conv0BwdArgs a) {
   double S1 = 0.0, A[C0B_MAXK];
   for (int j = 0; j < C0B_MAXK; ++j) A[j] = 0.0;
   for (int ch = 0; ch < nchunk; ++ch) {
-    const float* pp = a.part + (((long long)u * a.n_chunk + ch) * a.C + c) * (k + 1);
+    const float* pp = a.part + ((long long)u * a.n_chunk + ch) * (k + 1) * a.C + c;
     S1 += (double)pp[0];
-    for (int j = 0; j < k; ++j) A[j] += (double)pp[1 + j];
+#pragma unroll
+    for (int j = 0; j < C0B_MAXK; ++j)
+      if (j < k) A[j] += (double)pp[(long long)(1 + j) * a.C];
   }
   const double* st = a.stats + ((long long)u * a.C + c) * 2;
   const double mu = st[0] / L0;
@@ -204,6 +254,7 @@ int gelu_grad_to_padded(const float* d, const bf16* pre, bf16* out, const int* r
 
 int conv_col2im_gelu_grad(const Col2imArgs& a, cudaStream_t stream) {
   SUTA_CHECK_ARG(a.C % 8 == 0 && a.n_utts > 0 && a.max_L_out > 0);
+  SUTA_CHECK_ARG(256 % (a.C >> 3) == 0 && (256 / (a.C >> 3)) * 4 >= C2I_ROWS && a.k <= C2I_MAXTAPS * a.s);
   dim3 grid(ceil_div(a.max_L_out, C2I_ROWS), a.n_utts);
   col2im_kernel<<<grid, 256, 0, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
@@ -214,7 +265,7 @@ int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream) {
   SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0 && a.C % 2 == 0 && a.mom && a.part);
   SUTA_CHECK_ARG(a.n_chunk >= ceil_div(a.max_L0, C0B_TT));
   dim3 grid(ceil_div(a.max_L0, C0B_TT), a.n_utts);
-  size_t smem = sizeof(float) * (C0B_TT * a.stride + a.k);
+  size_t smem = sizeof(float) * (C0B_TT * a.stride + a.k + 32);      // slack for the 16-byte window loads
   conv0_bwd_accum_kernel<<<grid, 256, smem, stream>>>(a);
   conv0_bwd_finalize_kernel<<<dim3(ceil_div(a.C, 128), a.n_utts), 128, 0, stream>>>(a);
   CUDA_TRY(cudaGetLastError());

@@ -112,12 +112,7 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
         g0 = a.gn_shared_g[c]; g1 = a.gn_shared_g[c + 1]; b0 = a.gn_shared_b[c]; b1 = a.gn_shared_b[c + 1];
       }
       const long long row0 = a.out_off[u] + t0;
-      for (int t = 0; t < nt; ++t) {
-        const float* xs = sx + t * a.stride;
-        float y0 = 0.f, y1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < C0_MAXK; ++j)
-          if (j < a.k) { y0 += w0[j] * xs[j]; y1 += w1[j] * xs[j]; }
+      auto emit = [&](int t, float y0, float y1) {
         y0 = (y0 - mean0) * r0 * g0 + b0;
         y1 = (y1 - mean1) * r1 * g1 + b1;
         const long long o = (row0 + t) * a.C + c;
@@ -126,6 +121,33 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
         gelu_erf_both(y1, g1v, d1v);
         if (a.pre_out) *reinterpret_cast<uint32_t*>(a.pre_out + o) = pack_bf16x2(d0v, d1v);
         *reinterpret_cast<uint32_t*>(a.out + o) = pack_bf16x2(g0v, g1v);
+      };
+      int t = 0;
+      if (a.stride == 5 && a.k <= 10) {          // wav2vec2: 4 frames = 20 samples = five 16-byte words; 7 vector loads per 4 frames
+        for (; t + 4 <= nt; t += 4) {
+          float xw[28];
+#pragma unroll
+          for (int v = 0; v < 7; ++v) {
+            const float4 f = *reinterpret_cast<const float4*>(sx + 5 * t + 4 * v);
+            xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+              if (j < a.k) { y0 = fmaf(w0[j], xw[5 * q + j], y0); y1 = fmaf(w1[j], xw[5 * q + j], y1); }
+            emit(t + q, y0, y1);
+          }
+        }
+      }
+      for (; t < nt; ++t) {
+        const float* xs = sx + t * a.stride;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < C0_MAXK; ++j)
+          if (j < a.k) { y0 += w0[j] * xs[j]; y1 += w1[j] * xs[j]; }
+        emit(t, y0, y1);
       }
     }
   }
@@ -218,7 +240,7 @@ int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream) {
   SUTA_CHECK_ARG(a.k <= C0_MAXK && a.C % 2 == 0 && a.n_utts > 0 && a.mom);
   conv0_stats_kernel<<<dim3(ceil_div(a.C, 128), a.n_utts), 128, 0, stream>>>(a);
   dim3 grid(ceil_div(a.max_L0, C0_TT), a.n_utts);
-  size_t smem = sizeof(float) * (C0_TT * a.stride + a.k);
+  size_t smem = sizeof(float) * (C0_TT * a.stride + a.k + 32);       // slack for the 16-byte window loads
   conv0_kernel<1><<<grid, 256, smem, stream>>>(a, a.stats);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
