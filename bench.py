@@ -231,7 +231,8 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05, all dense contractions)",
                      "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peaks["tflops"]) if gemm_ms else None,
-                     "traffic": None, "peak_source": peaks["source"], "launches": gemm_n,
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,
+                     "peak_source": peaks["source"], "launches": gemm_n,
                      "avg_launch_us": gemm_ms * 1e3 / gemm_n if gemm_n else None,
                      "gemm_share_of_step": gemm_ms / ms_dev if ms_dev else None},
         "path": {"algorithmic_tflop_per_step": flops_all / K / 1e12,
@@ -250,6 +251,16 @@ def run_b200(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per tcgen05 GEMM launch, from the committed `ncu --set full` capture
+# (profiles/r01d_ncu_full_gemm_attention.md: 9 GEMM launches of tools/profile_step.py --utts 32 --seconds 6 --mode feature,
+# 9.8 k frames per batch, i.e. about 1/5 of a bench batch; read 62.0 MB + written 6.8 MB on average.  Reads equal the
+# operand bytes -- e.g. the FFN dgrad launch reads 80.3 MB for 15 MB dY + 60 MB GELU' + 4.7 MB W, the accumulate launch
+# 95.3 MB for 60 MB dH + 4.7 MB W + 30 MB fp32 reduce target -- so no re-reads; results are mostly still in L2 at kernel end).
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 68.9e6
+NCU_GEMM_TRAFFIC_NOTE = ("ncu capture of the 9.8k-frame profile batch (profiles/r01d_ncu_full_gemm_attention.md), not of this run; "
+                         "tensor-bound kernel, traffic ~= algorithmic bytes")
 
 
 def cpu_baseline(seconds, model="base", threads=None, train_feature=False):
