@@ -90,6 +90,51 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& g, float& dg) {
   dg = fmaf(x, pdf, fmaf(0.5f, e, 0.5f));
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: two fp32 lanes per instruction) ------------------------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t dup2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf_both on two values: identical arithmetic (every step is the same rounded fp32 operation), half the
+// FMA-pipe instructions -- the GELU epilogues and conv0 are bound by instruction issue, not by memory
+__device__ __forceinline__ void gelu_erf_both2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t z = mul2(x, dup2(0.70710678118654752f));
+  float z0, z1;
+  upk2(z, z0, z1);
+  const uint64_t t = pk2(fabsf(z0), fabsf(z1));
+  uint64_t p = fma2(dup2(-0.002944157226011157f), t, dup2(0.02959004044532776f));
+  p = fma2(p, t, dup2(-0.1486656218767166f));
+  p = fma2(p, t, dup2(-0.9185093641281128f));
+  p = fma2(p, t, dup2(-1.6278890371322632f));
+  p = mul2(p, t);
+  const uint64_t q = mul2(mul2(x, x), dup2(-0.72134752044448170f));
+  float p0, p1, q0, q1;
+  upk2(p, p0, p1);
+  upk2(q, q0, q1);
+  const uint64_t e = pk2(copysignf(1.0f - ex2_approx(p0), z0), copysignf(1.0f - ex2_approx(p1), z1));
+  const uint64_t hx = mul2(x, dup2(0.5f));
+  const uint64_t g = fma2(hx, e, hx);
+  const uint64_t cdf = fma2(e, dup2(0.5f), dup2(0.5f));
+  const uint64_t pdf = mul2(pk2(ex2_approx(q0), ex2_approx(q1)), dup2(0.39894228040143268f));
+  const uint64_t dg = fma2(x, pdf, cdf);
+  upk2(g, g0, g1);
+  upk2(dg, d0, d1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -182,6 +227,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// pull one box of the tensor into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(

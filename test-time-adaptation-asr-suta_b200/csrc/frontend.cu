@@ -111,43 +111,48 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
       } else {
         g0 = a.gn_shared_g[c]; g1 = a.gn_shared_g[c + 1]; b0 = a.gn_shared_b[c]; b1 = a.gn_shared_b[c + 1];
       }
+      // GroupNorm affine folded into the taps: y = sum_j (w_j r g) x_j + (b - mean r g); channel pairs ride in packed
+      // fp32 registers (FFMA2), so a frame costs 10 packed FMAs + one packed GELU/GELU' for two channels
+      const float s0 = r0 * g0, s1 = r1 * g1;
+      const float c0 = b0 - mean0 * s0, c1 = b1 - mean1 * s1;
+      const uint64_t bias2 = pk2(c0, c1);
+      uint64_t w2[C0_MAXK];
+#pragma unroll
+      for (int j = 0; j < C0_MAXK; ++j) w2[j] = pk2(w0[j] * s0, w1[j] * s1);
       const long long row0 = a.out_off[u] + t0;
-      auto emit = [&](int t, float y0, float y1) {
-        y0 = (y0 - mean0) * r0 * g0 + b0;
-        y1 = (y1 - mean1) * r1 * g1 + b1;
+      auto emit = [&](int t, uint64_t y) {
         const long long o = (row0 + t) * a.C + c;
-        float g0v, g1v, d0v, d1v;
-        gelu_erf_both(y0, g0v, d0v);
-        gelu_erf_both(y1, g1v, d1v);
+        float y0, y1, g0v, g1v, d0v, d1v;
+        upk2(y, y0, y1);
+        gelu_erf_both2(y0, y1, g0v, g1v, d0v, d1v);
         if (a.pre_out) *reinterpret_cast<uint32_t*>(a.pre_out + o) = pack_bf16x2(d0v, d1v);
         *reinterpret_cast<uint32_t*>(a.out + o) = pack_bf16x2(g0v, g1v);
       };
       int t = 0;
-      if (a.stride == 5 && a.k <= 10) {          // wav2vec2: 4 frames = 20 samples = five 16-byte words; 7 vector loads per 4 frames
+      if (a.stride == 5 && a.k == 10) {          // wav2vec2: 4 frames = 20 samples = five 16-byte words; 7 vector loads per 4 frames
         for (; t + 4 <= nt; t += 4) {
-          float xw[28];
+          uint64_t xw[28];
 #pragma unroll
           for (int v = 0; v < 7; ++v) {
             const float4 f = *reinterpret_cast<const float4*>(sx + 5 * t + 4 * v);
-            xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+            xw[4 * v] = dup2(f.x); xw[4 * v + 1] = dup2(f.y); xw[4 * v + 2] = dup2(f.z); xw[4 * v + 3] = dup2(f.w);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float y0 = 0.f, y1 = 0.f;
+            uint64_t y = bias2;
 #pragma unroll
-            for (int j = 0; j < 10; ++j)
-              if (j < a.k) { y0 = fmaf(w0[j], xw[5 * q + j], y0); y1 = fmaf(w1[j], xw[5 * q + j], y1); }
-            emit(t + q, y0, y1);
+            for (int j = 0; j < 10; ++j) y = fma2(w2[j], xw[5 * q + j], y);
+            emit(t + q, y);
           }
         }
       }
       for (; t < nt; ++t) {
         const float* xs = sx + t * a.stride;
-        float y0 = 0.f, y1 = 0.f;
+        uint64_t y = bias2;
 #pragma unroll
         for (int j = 0; j < C0_MAXK; ++j)
-          if (j < a.k) { y0 += w0[j] * xs[j]; y1 += w1[j] * xs[j]; }
-        emit(t, y0, y1);
+          if (j < a.k) y = fma2(w2[j], dup2(xs[j]), y);
+        emit(t, y);
       }
     }
   }

@@ -15,7 +15,14 @@ constexpr int MAXK = 4;
 struct AdamConsts {
   float step_size[MAXK + 1][MAXK];   // [k][j]: lr / (1 - beta1^s), s = k*step_index + j + 1
   float bc2_sqrt[MAXK + 1][MAXK];    // sqrt(1 - beta2^s)
+  float inv_bc2_sqrt[MAXK + 1][MAXK];
 };
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void adam_kernel(AdamArgs a, AdamConsts c) {
   const long long total = a.n * a.n_utts;
@@ -65,15 +72,38 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
   } else {
     float4 m4 = __ldcs(reinterpret_cast<const float4*>(a.Mom + i)), v4 = __ldcs(reinterpret_cast<const float4*>(a.Var + i));
     float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float omb1 = 1.0f - a.beta1, omb2 = 1.0f - a.beta2;
+    const float decay = 1.0f - a.lr * a.weight_decay;
+    if (kv[0] == kv[1] && kv[1] == kv[2] && kv[2] == kv[3]) {
+      // the usual case (segment sizes are multiples of 4): the four elements advance through the k sub-steps
+      // together.  With k = 4 on every conv weight (REF/main.py:88-94) the update is instruction-bound unless the
+      // square root and the two divisions are single MUFU operations.
+      const int k = kv[0];
+      float gg[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int k = kv[t];
+      for (int t = 0; t < 4; ++t) gg[t] = omb2 * gv[t] * gv[t];
       for (int j = 0; j < k; ++j) {
-        if (a.weight_decay != 0.f) pv[t] *= 1.0f - a.lr * a.weight_decay;
-        mv[t] = mv[t] + (gv[t] - mv[t]) * (1.0f - a.beta1);
-        vv[t] = vv[t] * a.beta2 + (1.0f - a.beta2) * gv[t] * gv[t];
-        const float denom = sqrtf(vv[t]) / c.bc2_sqrt[k][j] + a.eps;
-        pv[t] = pv[t] - c.step_size[k][j] * (mv[t] / denom);
+        const float ss = c.step_size[k][j], ib = c.inv_bc2_sqrt[k][j];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (a.weight_decay != 0.f) pv[t] *= decay;
+          mv[t] = fmaf(gv[t] - mv[t], omb1, mv[t]);
+          vv[t] = fmaf(vv[t], a.beta2, gg[t]);
+          const float denom = fmaf(sqrt_approx(vv[t]), ib, a.eps);
+          pv[t] = fmaf(-ss, __fdividef(mv[t], denom), pv[t]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = kv[t];
+        for (int j = 0; j < k; ++j) {
+          if (a.weight_decay != 0.f) pv[t] *= decay;
+          mv[t] = fmaf(gv[t] - mv[t], omb1, mv[t]);
+          vv[t] = fmaf(vv[t], a.beta2, omb2 * gv[t] * gv[t]);
+          const float denom = fmaf(sqrt_approx(vv[t]), c.inv_bc2_sqrt[k][j], a.eps);
+          pv[t] = fmaf(-c.step_size[k][j], __fdividef(mv[t], denom), pv[t]);
+        }
       }
     }
     if (kv[0] | kv[1] | kv[2] | kv[3]) {
@@ -120,6 +150,7 @@ int optimizer_step(const AdamArgs& a, cudaStream_t stream) {
       double bc1 = 1.0 - pow((double)a.beta1, s), bc2 = 1.0 - pow((double)a.beta2, s);
       c.step_size[k][j] = (float)((double)a.lr / bc1);
       c.bc2_sqrt[k][j] = (float)sqrt(bc2);
+      c.inv_bc2_sqrt[k][j] = (float)(1.0 / sqrt(bc2));
     }
   bool vec = a.n % 4 == 0 && a.n_seg <= 8;
   for (int s = 0; s < a.n_seg; ++s) vec = vec && a.seg[s].off % 4 == 0 && a.seg[s].size % 4 == 0 && a.seg[s].dst;

@@ -22,7 +22,12 @@ def P(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def run(name, N, K, bias=False, res=False, act=0, f32=False, bf16=True, acc=False, reps=20, nset=4):
+FILTER = os.environ.get("GEMM_FILTER")
+
+
+def run(name, N, K, bias=False, res=False, act=0, f32=False, bf16=True, acc=False, reps=20, nset=4, noaux=False):
+    if FILTER and FILTER not in name:
+        return
     sets = []
     for _ in range(nset):
         a = torch.randn(M, K, device="cuda").bfloat16()
@@ -38,7 +43,7 @@ def run(name, N, K, bias=False, res=False, act=0, f32=False, bf16=True, acc=Fals
 
     def ours(d):
         check(lib.suta_op_gemm(P(d["a"]), M, K, P(d["b"]), N, K, M, N, K, P(d["o32"]), P(d["o16"]), N, P(d["bias"]),
-                               P(d["res"]), N, act | (4 if acc else 0), P(d["aux"]) if act == 2 else None, P(d["aux"]) if act == 1 else None, N, st))
+                               P(d["res"]), N, act | (4 if acc else 0), P(d["aux"]) if act == 2 else None, P(d["aux"]) if act == 1 and not noaux else None, N, st))
 
     def cublas(d):
         torch.matmul(d["a"], d["b"].t())
@@ -80,6 +85,9 @@ run("qkv  (+bias, bf16)", 3 * H, H, bias=True)
 run("oproj(+bias+res, f32)", H, H, bias=True, res=True, f32=True, bf16=False)
 run("oproj(+bias, f32 +=)", H, H, bias=True, acc=True, f32=True, bf16=False)
 run("ffn1 (+bias, gelu, aux)", I, H, bias=True, act=1)
+run("ffn1 (+bias, gelu, no aux)", I, H, bias=True, act=1, noaux=True)
+run("ffn1 (+bias only)", I, H, bias=True)
+run("ffn1 (gelu, aux, no bias)", I, H, act=1)
 run("ffn2 (+bias, f32 +=)", H, I, bias=True, acc=True, f32=True, bf16=False)
 run("ffn2 dgrad (x aux)", I, H, act=2)
 run("ffn1 dgrad (f32 +=)", H, I, acc=True, f32=True, bf16=False)
