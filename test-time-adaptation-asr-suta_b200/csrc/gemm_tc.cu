@@ -652,6 +652,10 @@ extern "C" void suta_debug_set_gemm_trace(long long* dev_buf, int cap) {
   g_trace = dev_buf;
   g_trace_cap = dev_buf ? cap : 0;
 }
+long long* gemm_trace_buffer(int* cap) {
+  *cap = g_trace_cap;
+  return g_trace;
+}
 
 int gemm_num_sms() {
   static int n = 0;
@@ -695,6 +699,9 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
   if (dense) {
     // 4-stage variant when the epilogue needs neither the second patch (GELU' side output) nor an fp32 patch AND a bias
     const bool lean = !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias);
+    // plain row blocks with N % 256 == 0: CTA pairs on 256 x 256 tiles (gemm_tc2.cu) -- one SM cannot ingest 48 KB per k-block
+    static const bool use_pairs = getenv("SUTA_NO_GEMM2") == nullptr;
+    if (use_pairs && !p.mblk && p.N % 256 == 0 && p.M > 128 && !(p.epi.out_f32 && p.epi.bias)) return gemm_bf16_tc_2cta(p, stream);
     if (p.N % 256 == 0 && lean) return launch<256, false, false, true, true>(p, stream);
     if (p.N % 256 == 0) return launch<256, false, false, true>(p, stream);
     if (p.N % 128 == 0) return launch<128, false, false, true>(p, stream);

@@ -55,8 +55,9 @@ struct GemmProblem {
 };
 
 int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream);
-// experimental/gemm_tc2.cu (not built): the cta_group::2 kernel for dense K-major problems with N % 128 == 0
+// gemm_tc2.cu: the cta_group::2 (CTA pair, 256 x 256 tiles) kernel for dense K-major problems with N % 256 == 0
 int gemm_bf16_tc_2cta(const GemmProblem& p, cudaStream_t stream);
 int gemm_encode_tmap(CUtensorMap* tm, int dtype, const void* ptr, long long cols, long long rows, long long pitch_bytes,
                      int box_cols, int box_rows, int swizzle);
 int gemm_num_sms();
+long long* gemm_trace_buffer(int* cap);   // debug timeline buffer set by suta_debug_set_gemm_trace (null = off)

@@ -22,8 +22,11 @@ def test_gemm_plain(K):
     assert r["nan"] == 0 and r["rel"] < F32
 
 
-def test_gemm_epilogues(K):
-    r = K.check_gemm_epilogue()
+# N = 384 runs the one-SM kernel; N = 768 (N % 256 == 0) the CTA-pair kernel: 5 / 11 row blocks = an odd number of pairs' halves,
+# ragged last block, K not a multiple of the ring depth
+@pytest.mark.parametrize("M,N,Kd", [(517, 384, 256), (517, 768, 256), (1300, 512, 832), (129, 256, 64)])
+def test_gemm_epilogues(K, M, N, Kd):
+    r = K.check_gemm_epilogue(M, N, Kd, seed=M + N)
     assert r["res_rel"] < F32 and r["gelu_bwd_rel"] < F32 and r["acc_rel"] < F32
     assert r["bf16_rel"] < BF16 and r["gelu_bwd16_rel"] < BF16
     assert r["gelu_rel"] < BF16 and r["aux_rel"] < BF16 and r["res16_rel"] < BF16 and r["gelu_bwd_vs_exact_rel"] < BF16
