@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--max-utts", type=int, default=MAX_UTTS, help="utterances per adaptation batch")
     ap.add_argument("--max-frames", type=int, default=MAX_FRAMES, help="frames per adaptation batch")
     ap.add_argument("--cpu-seconds", type=float, default=5.0, help="duration of the CPU-baseline utterance")
+    ap.add_argument("--suta-steps", type=int, default=10, help="adaptation steps per utterance (configs[4]: 20)")
+    ap.add_argument("--extra-noise", type=float, default=0.0, help="REF/data.py:23 noise added before normalisation (configs[4]: 0.01)")
     return ap.parse_args()
 
 
@@ -142,7 +144,7 @@ def run_b200(args):
         mult = reference_multiplicities(cfg, train_feature=True)
     eng = SutaEngine(cfg, random_state_dict(cfg, seed=0, blank_bias=1.75), train_feature=tf, trainable_mult=mult)
     hp, vocab = AdaptHyper(), CTCVocab()
-    utts = librispeech_shaped(2939, seed=rank)           # weak scaling: every rank adapts its own draw of the set
+    utts = librispeech_shaped(2939, seed=rank, extra_noise=args.extra_noise)           # weak scaling: every rank adapts its own draw of the set
     K, W = args.steps, max(args.warmup, 0)
     timed = select_batches(utts, cfg, K, max_utts=args.max_utts, max_frames=args.max_frames)
     warm = select_batches(utts, cfg, max(W, 1), offset=0.25, max_utts=args.max_utts, max_frames=args.max_frames)[:W]
@@ -212,7 +214,8 @@ def run_b200(args):
     audio_all, utts_all, flops_all = (float(x) for x in tot.tolist())
     peaks = measured_peaks()
     h2d = sum(h.numel() * 4 for _, h in staged) / K
-    d2h = sum(sum(cfg.frames(u.n_samples) for u in b) * 4 * 5 + len(b) * 4 * 5 for b in timed) / K    # collapsed ids + lengths, 5 decodes
+    n_dec = 1 + sum(1 for c in (1, 3, 5, 10, 20, 40) if c <= SUTA_STEPS)      # REF/main.py:331-398 decode points
+    d2h = sum(sum(cfg.frames(u.n_samples) for u in b) * 4 * n_dec + len(b) * 4 * n_dec for b in timed) / K    # collapsed ids + lengths
     out = {
         "metric": METRIC, "value": audio_all / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -320,6 +323,7 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    SUTA_STEPS = a.suta_steps
     if a.impl == "reference":
         run_reference(a)
     else:
