@@ -1,10 +1,23 @@
 // Fused LayerNorm forward / backward with PER-UTTERANCE affine parameters.
 // Restates torch native_layer_norm(+backward) as used by HF/modeling_wav2vec2.py:429-434,692,599-602 for a
 // token-packed batch in which every utterance carries its own adapted gamma/beta (REF/main.py:81-87).
-// Forward: one warp per row, row statistics by warp shuffle.  Backward: see ln_bwd_kernel.  HBM-bound.
+// Forward: one warp per row, row statistics by warp shuffle, rows streamed through a bulk-async shared-memory ring.
+// Backward: see ln_bwd_kernel.  HBM-bound.
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace {
+
+int n_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 template <typename T>
 struct Loader;
@@ -31,61 +44,121 @@ struct Cols {
   static __device__ __forceinline__ bool active(int lane, int i) { return 4 * lane + 128 * i < N; }
 };
 
+constexpr int FWD_W = 8;          // warps per CTA = rows per tile
+constexpr int FWD_STAGES = 3;     // tiles in flight per CTA
+
 template <int N, typename TIn>
-__global__ void __launch_bounds__(256)
+struct FwdSmem {
+  static constexpr int TILE_BYTES = FWD_W * N * (int)sizeof(TIn);
+  static constexpr int BYTES = FWD_STAGES * TILE_BYTES + 64;
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// One warp per row, 8 rows per tile; the tiles of a CTA's row range stream through a 3-deep shared-memory ring filled by
+// 1-D bulk copies issued two tiles ahead (the register-only version was latency-bound at 41 % of the HBM rate: its loads
+// could not start before the previous row's dependent chain -- statistics, per-utterance gamma/beta, stores -- had drained).
+template <int N, typename TIn>
+__global__ void __launch_bounds__(FWD_W * 32)
 ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const float* __restrict__ P, long long pstride,
               int g_off, int b_off, float* __restrict__ y32, bf16* __restrict__ y16, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long long M, float eps, const float* __restrict__ y32_bias) {
+              float* __restrict__ rstd_out, long long M, float eps, const float* __restrict__ y32_bias, int rows_per_cta) {
   constexpr int NV = Cols<N>::NV;
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const TIn* xr = x + row * N;
-  float4 v[NV];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (Cols<N>::active(lane, i)) {
-      v[i] = Loader<TIn>::ld4(xr + 4 * lane + 128 * i);
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
-    } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  using S = FwdSmem<N, TIn>;
+  extern __shared__ __align__(128) uint8_t ring[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + FWD_STAGES * S::TILE_BYTES);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long cta_row0 = (long long)blockIdx.x * rows_per_cta;
+  const int n_tiles = (int)min((long long)(rows_per_cta / FWD_W), (M - cta_row0 + FWD_W - 1) / FWD_W);
+  auto issue = [&](int t) {                        // thread 0: fetch tile t into stage t % FWD_STAGES
+    const long long r0 = cta_row0 + (long long)t * FWD_W;
+    const int nr = (int)min((long long)FWD_W, M - r0);
+    uint64_t* bar = &full[t % FWD_STAGES];
+    mbar_expect_tx(bar, (uint32_t)(nr * N * sizeof(TIn)));
+    bulk_load_1d(smem_u32(ring + (t % FWD_STAGES) * S::TILE_BYTES), x + r0 * N, (uint32_t)(nr * N * sizeof(TIn)), bar);
+  };
+  if (threadIdx.x == 0) {
+    for (int s2 = 0; s2 < FWD_STAGES; ++s2) mbar_init(&full[s2], 1);
+    mbar_fence_init();
+    for (int t = 0; t < FWD_STAGES - 1 && t < n_tiles; ++t) issue(t);
   }
-  const float mean = warp_sum(s) * (1.0f / N);
-  float ss = 0.f;
+  __syncthreads();
+  int u_next = cta_row0 + warp < M ? __ldg(row_utt + cta_row0 + warp) : 0;
+  int u_cur = -1;
+  float4 gv[NV], bv[NV], nbv[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (Cols<N>::active(lane, i)) {
-      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      ss += a * a + b * b + c * c + d * d;
-    }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / N) + eps);
-  if (lane == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
-  }
-  const float* gam = P + (long long)row_utt[row] * pstride + g_off;
-  const float* bet = P + (long long)row_utt[row] * pstride + b_off;
+  for (int i = 0; i < NV; ++i) gv[i] = bv[i] = nbv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int it = 0; it < n_tiles; ++it) {
+    // every warp passed the __syncthreads of tile it - 1, i.e. finished reading the stage tile it + 2 goes into
+    if (threadIdx.x == 0 && it + FWD_STAGES - 1 < n_tiles) issue(it + FWD_STAGES - 1);
+    const long long row = cta_row0 + (long long)it * FWD_W + warp;
+    const int u = u_next;
+    u_next = row + FWD_W < M ? __ldg(row_utt + row + FWD_W) : 0;
+    if (u != u_cur && row < M) {                   // per-utterance gamma/beta stay in registers until the utterance changes
+      u_cur = u;
+      const float* gam = P + (long long)u * pstride + g_off;
+      const float* bet = P + (long long)u * pstride + b_off;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (Cols<N>::active(lane, i)) {
-      const int col = 4 * lane + 128 * i;
-      float4 g = *reinterpret_cast<const float4*>(gam + col), b = *reinterpret_cast<const float4*>(bet + col);
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + b.x;
-      o.y = (v[i].y - mean) * rstd * g.y + b.y;
-      o.z = (v[i].z - mean) * rstd * g.z + b.z;
-      o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      if (y32) {
-        if (y32_bias) {     // the fp32 copy seeds the next residual sum: the bias of the GEMM that accumulates into it rides along
-          const float4 nb = __ldg(reinterpret_cast<const float4*>(y32_bias + col));
-          o.x += nb.x; o.y += nb.y; o.z += nb.z; o.w += nb.w;
+      for (int i = 0; i < NV; ++i)
+        if (Cols<N>::active(lane, i)) {
+          gv[i] = __ldg(reinterpret_cast<const float4*>(gam + 4 * lane + 128 * i));
+          bv[i] = __ldg(reinterpret_cast<const float4*>(bet + 4 * lane + 128 * i));
+          if (y32_bias) nbv[i] = __ldg(reinterpret_cast<const float4*>(y32_bias + 4 * lane + 128 * i));
         }
-        *reinterpret_cast<float4*>(y32 + row * N + col) = o;
-      }
     }
+    mbar_wait(&full[it % FWD_STAGES], (uint32_t)((it / FWD_STAGES) & 1));
+    if (row < M) {
+      const TIn* xr = reinterpret_cast<const TIn*>(ring + (it % FWD_STAGES) * S::TILE_BYTES) + warp * N;
+      float4 v[NV];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (Cols<N>::active(lane, i)) {
+          v[i] = Loader<TIn>::ld4(xr + 4 * lane + 128 * i);
+          s += v[i].x + v[i].y + v[i].z + v[i].w;
+        } else {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      const float mean = warp_sum(s) * (1.0f / N);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (Cols<N>::active(lane, i)) {
+          float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          ss += a * a + b * b + c * c + d * d;
+        }
+      const float rstd = rsqrtf(warp_sum(ss) * (1.0f / N) + eps);
+      if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (Cols<N>::active(lane, i)) {
+          const int col = 4 * lane + 128 * i;
+          const float4 g = gv[i], b = bv[i];
+          float4 o;
+          o.x = (v[i].x - mean) * rstd * g.x + b.x;
+          o.y = (v[i].y - mean) * rstd * g.y + b.y;
+          o.z = (v[i].z - mean) * rstd * g.z + b.z;
+          o.w = (v[i].w - mean) * rstd * g.w + b.w;
+          if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+          if (y32) {
+            if (y32_bias) {   // the fp32 copy seeds the next residual sum: the bias of the GEMM that accumulates into it rides along
+              const float4 nb = nbv[i];
+              o.x += nb.x; o.y += nb.y; o.z += nb.z; o.w += nb.w;
+            }
+            *reinterpret_cast<float4*>(y32 + row * N + col) = o;
+          }
+        }
+    }
+    __syncthreads();
+  }
 }
 
 // Backward.  One thread owns 4 fixed columns for all rows of its CTA (N/4 threads per CTA), so dgamma/dbeta live in 8
@@ -94,16 +167,30 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
 // exchange through shared memory, one __syncthreads.  (The first version kept whole rows per warp: 150 registers, one
 // CTA per SM, 3 TB/s.)
 constexpr int BWD_R = 4;          // rows per tile
-constexpr int BWD_ROWS = 64;      // rows per CTA
+constexpr int BWD_STAGES = 3;     // tiles in flight per CTA (bulk-async copies into shared memory)
 
+template <int N, typename TIn>
+struct BwdSmem {
+  static constexpr int X_BYTES = BWD_R * N * (int)sizeof(TIn);
+  static constexpr int D_BYTES = BWD_R * N * 4;
+  static constexpr int STAGE_BYTES = X_BYTES + D_BYTES;
+  static constexpr int BYTES = BWD_STAGES * STAGE_BYTES + 64;
+};
+
+// The tiles (4 rows of x and of dy: 24 KB at N = 768) stream through a 3-deep shared-memory ring filled by 1-D bulk
+// copies that one thread issues two tiles ahead -- with register-only loads the kernel had ~45 KB in flight per SM and
+// reached 34 % of the HBM rate (profiles/r01e); the __syncthreads of the row reduction doubles as the "stage is free" signal.
 template <int N, typename TIn>
 __global__ void __launch_bounds__((N / 4 + 31) / 32 * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const int* __restrict__ row_utt, const float* __restrict__ P,
               long long pstride, int g_off, int b_off, float* __restrict__ G, float* __restrict__ dx32,
-              bf16* __restrict__ dx16, long long M) {
+              bf16* __restrict__ dx16, long long M, int rows_per_cta) {
   constexpr int NT = N / 4;                       // active threads
   constexpr int NW = (NT + 31) / 32;              // warps
+  using S = BwdSmem<N, TIn>;
+  extern __shared__ __align__(128) uint8_t ring[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + BWD_STAGES * S::STAGE_BYTES);
   __shared__ float red[2][2][NW][BWD_R];          // [tile parity][c1 | c2][warp][row]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool act = tid < NT;
@@ -120,25 +207,54 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
     ag = ab = make_float4(0.f, 0.f, 0.f, 0.f);
   };
 
-  const long long cta_row0 = (long long)blockIdx.x * BWD_ROWS;
+  const long long cta_row0 = (long long)blockIdx.x * rows_per_cta;
+  const int n_tiles = (int)min((long long)(rows_per_cta / BWD_R), (M - cta_row0 + BWD_R - 1) / BWD_R);
+  auto issue = [&](int t) {                        // thread 0: fetch tile t into stage t % BWD_STAGES
+    const long long r0 = cta_row0 + (long long)t * BWD_R;
+    const int nr = (int)min((long long)BWD_R, M - r0);
+    uint64_t* bar = &full[t % BWD_STAGES];
+    const uint32_t dst = smem_u32(ring + (t % BWD_STAGES) * S::STAGE_BYTES);
+    mbar_expect_tx(bar, (uint32_t)(nr * N * (sizeof(TIn) + 4)));
+    bulk_load_1d(dst, x + r0 * N, (uint32_t)(nr * N * sizeof(TIn)), bar);
+    bulk_load_1d(dst + S::X_BYTES, dy + r0 * N, (uint32_t)(nr * N * 4), bar);
+  };
+  if (tid == 0) {
+    for (int s2 = 0; s2 < BWD_STAGES; ++s2) mbar_init(&full[s2], 1);
+    mbar_fence_init();
+    for (int t = 0; t < BWD_STAGES - 1 && t < n_tiles; ++t) issue(t);
+  }
+  __syncthreads();
+  float mu_n[BWD_R], rs_n[BWD_R];
+  int uu_n[BWD_R];
+  auto load_scalars = [&](long long r0) {
+#pragma unroll
+    for (int r = 0; r < BWD_R; ++r) {
+      const bool ok = r0 + r < M;
+      uu_n[r] = ok ? __ldg(row_utt + r0 + r) : -1;
+      mu_n[r] = ok ? __ldg(mean + r0 + r) : 0.f;
+      rs_n[r] = ok ? __ldg(rstd + r0 + r) : 0.f;
+    }
+  };
+  load_scalars(cta_row0);
 #pragma unroll 1
-  for (int it = 0; it < BWD_ROWS / BWD_R; ++it) {
+  for (int it = 0; it < n_tiles; ++it) {
     const long long row0 = cta_row0 + it * BWD_R;
-    if (row0 >= M) break;
+    // every thread passed the __syncthreads of tile it - 1, i.e. finished reading the stage tile it + 2 goes into
+    if (tid == 0 && it + BWD_STAGES - 1 < n_tiles) issue(it + BWD_STAGES - 1);
     float4 xv[BWD_R], dv[BWD_R];
     float mu[BWD_R], rs[BWD_R];
     int uu[BWD_R];
 #pragma unroll
+    for (int r = 0; r < BWD_R; ++r) { uu[r] = uu_n[r]; mu[r] = mu_n[r]; rs[r] = rs_n[r]; }
+    load_scalars(row0 + BWD_R);                    // next tile's row constants: their L2 latency hides behind this tile
+    mbar_wait(&full[it % BWD_STAGES], (uint32_t)((it / BWD_STAGES) & 1));
+    const uint8_t* st = ring + (it % BWD_STAGES) * S::STAGE_BYTES;
+#pragma unroll
     for (int r = 0; r < BWD_R; ++r) {
-      const long long row = row0 + r;
-      const bool ok = row < M;
-      uu[r] = ok ? __ldg(row_utt + row) : -1;
-      mu[r] = ok ? __ldg(mean + row) : 0.f;
-      rs[r] = ok ? __ldg(rstd + row) : 0.f;
       xv[r] = dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && act) {
-        xv[r] = Loader<TIn>::ld4(x + row * N + col);
-        dv[r] = *reinterpret_cast<const float4*>(dy + row * N + col);
+      if (row0 + r < M && act) {
+        xv[r] = Loader<TIn>::ld4(reinterpret_cast<const TIn*>(st) + r * N + col);
+        dv[r] = *reinterpret_cast<const float4*>(st + S::X_BYTES + (r * N + col) * 4);
       }
     }
     float p1[BWD_R], p2[BWD_R];
@@ -193,6 +309,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
         if (dx32) *reinterpret_cast<float4*>(dx32 + row * N + col) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
+    } else {
+      __syncthreads();                            // the ring hand-over needs one CTA-wide sync per tile either way
     }
   }
   flush();
@@ -201,9 +319,18 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
 template <int N, typename TIn>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
                float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
-  const int warps = 8;
-  ln_fwd_kernel<N, TIn><<<(unsigned)((M + warps - 1) / warps), warps * 32, 0, stream>>>(
-      x, row_utt, prm.P, prm.stride, g_off, b_off, y32, y16, mean, rstd, M, eps, y32_bias);
+  using S = FwdSmem<N, TIn>;
+  static int resident = 0;                         // CTAs of this instantiation that fit on one SM
+  if (!resident) {
+    CUDA_TRY(cudaFuncSetAttribute(ln_fwd_kernel<N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_fwd_kernel<N, TIn>, FWD_W * 32, S::BYTES));
+    resident = std::max(1, std::min(8, resident));
+  }
+  // one wave: at most (resident CTAs per SM) x (SMs) CTAs, rows per CTA a multiple of the tile height
+  long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
+  rows = std::max<long long>(FWD_W, (rows + FWD_W - 1) / FWD_W * FWD_W);
+  ln_fwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), FWD_W * 32, S::BYTES, stream>>>(
+      x, row_utt, prm.P, prm.stride, g_off, b_off, y32, y16, mean, rstd, M, eps, y32_bias, (int)rows);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
@@ -211,8 +338,18 @@ template <int N, typename TIn>
 int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
                int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, cudaStream_t stream) {
   constexpr int threads = (N / 4 + 31) / 32 * 32;
-  ln_bwd_kernel<N, TIn><<<(unsigned)((M + BWD_ROWS - 1) / BWD_ROWS), threads, 0, stream>>>(
-      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, b_off, G, dx32, dx16, M);
+  using S = BwdSmem<N, TIn>;
+  static int resident = 0;                         // CTAs of this instantiation that fit on one SM
+  if (!resident) {
+    CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_bwd_kernel<N, TIn>, threads, S::BYTES));
+    resident = std::max(1, std::min(8, resident));
+  }
+  // one wave: at most (resident CTAs per SM) x (SMs) CTAs, rows per CTA a multiple of the tile height
+  long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
+  rows = std::max<long long>(16, (rows + BWD_R - 1) / BWD_R * BWD_R);
+  ln_bwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
+      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, b_off, G, dx32, dx16, M, (int)rows);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
