@@ -10,6 +10,7 @@
 // Work per adaptation step = 1 backward + 1 forward (the reference's "repeat_inference" forward of step i IS the
 // training forward of step i+1, REF/main.py:181 vs :212-214); LayerNorm-only mode runs the CNN once per utterance.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -96,6 +97,7 @@ struct suta_engine {
   std::vector<long long> samp_off, tok_off, pad_off;
   std::vector<int> T;
   std::vector<int> n_mblk;                         // [layer]
+  std::vector<int> n_dg_mblk;                      // [layer] M-blocks of the conv dgrad GEMM(s)
   int n_attn_blk = 0;
   bool frontend_done = false;
   int opt_steps = 0;
@@ -199,6 +201,15 @@ int check_cfg(const suta_model_cfg& c) {
   return SUTA_OK;
 }
 
+// Transposed-conv dgrad of layer l as GEMMs that write d(input) directly (no [rows, k*Cin] intermediate, no col2im):
+// stride 2 with k = 2 (rows 2j, 2j+1 are the two halves of one N = 2*Cin output row) or k = 3 (even rows 2j =
+// dY[j] W_0 + dY[j-1] W_2, odd rows 2j+1 = dY[j] W_1).
+static bool dgrad_fused(const suta_engine* e, int l) {
+  const suta_model_cfg& c = e->cfg;
+  return e->train_feature && l >= 1 && c.conv_stride[l] == 2 && (c.conv_kernel[l] == 2 || c.conv_kernel[l] == 3) &&
+         c.conv_dim[l] % 64 == 0 && c.conv_dim[l - 1] % 64 == 0 && getenv("SUTA_NO_FUSED_DGRAD") == nullptr;
+}
+
 // geometry of a batch; fills host vectors, returns workspace size through the bump allocator
 int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
   const suta_model_cfg& c = e->cfg;
@@ -210,6 +221,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
   e->rows_total.assign(c.n_conv, 0);
   e->samp_off.resize(U); e->tok_off.resize(U); e->pad_off.resize(U); e->T.resize(U);
   e->n_mblk.assign(c.n_conv, 0);
+  e->n_dg_mblk.assign(c.n_conv, 0);
   long long s = 0;
   e->max_samples = 0; e->max_L0 = 0;
   for (int u = 0; u < U; ++u) {
@@ -237,9 +249,13 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
       // rows of the next layer's implicit-GEMM view start at off/stride: keep offsets multiples of 8; under
       // train_feature every utterance starts on a 128-row boundary, so (a) the weight-gradient GEMMs can reduce over
       // time in 64-row steps and (b) every 128-row GEMM tile owns its output rows outright (TMA-store epilogue)
-      const int al = e->train_feature ? 127 : 7;
-      r += last ? e->L[l][u] : ((e->L[l][u] + al) & ~al);
-      if (l >= 1) e->n_mblk[l] += ceil_div(e->L[l][u], 128);
+      // (c) the parity-split conv dgrad (conv_backward) writes 256 rows of layer l per 128-row tile of layer l + 1 and
+      // reads one zero row past the utterance's last gradient row: 256-row alignment with at least one spare row
+      r += last ? e->L[l][u] : (e->train_feature ? ((e->L[l][u] + 1 + 255) & ~255) : ((e->L[l][u] + 7) & ~7));
+      if (l >= 1) {
+        e->n_mblk[l] += ceil_div(e->L[l][u], 128);
+        e->n_dg_mblk[l] += ceil_div(e->L[l][u] + (dgrad_fused(e, l) && !last ? 1 : 0), 128);
+      }
       e->max_L[l] = u == 0 ? e->L[l][u] : (e->L[l][u] > e->max_L[l] ? e->L[l][u] : e->max_L[l]);
     }
     e->rows_total[l] = r;
@@ -332,12 +348,13 @@ void carve(suta_engine* e, Bump& b) {
       e->d_off[l] = b.take<long long>(U);
       e->d_L[l] = b.take<int>(U);
       e->conv_pre[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
-      e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 128) * c.conv_dim[l]);
+      // 128 leading rows (zero): the even-row dgrad GEMM reads row -1 of the first utterance
+      e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
       if (l >= 1) {
-        e->d_dgrad_mblk[l] = b.take<int4>(e->n_mblk[l]);
+        e->d_dgrad_mblk[l] = b.take<int4>(e->n_dg_mblk[l]);
         e->d_ztab[l] = b.take<int4>(U);
         e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
-        size_t z = (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
+        size_t z = dgrad_fused(e, l) ? 0 : (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
         zmax = z > zmax ? z : zmax;
       }
     }
@@ -520,9 +537,13 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
         std::vector<int4> dg, zt;
         for (int u = 0; u < U; ++u) {
           const long long dro = l == last ? e->off64[u] : e->off[l][u];
-          for (int m0 = 0; m0 < e->L[l][u]; m0 += 128)
-            dg.push_back(make_int4((int)(dro + m0), (int)(dro + m0), e->L[l][u] - m0 < 128 ? e->L[l][u] - m0 : 128,
-                                   u * c.conv_dim[l]));
+          const bool fused = dgrad_fused(e, l);
+          // fused: one extra (zero) gradient row j = L so that the last input rows get their zeros written; the
+          // output row index counts PAIRS of layer l-1 rows
+          const int Lx = e->L[l][u] + (fused && l != last ? 1 : 0);
+          for (int m0 = 0; m0 < Lx; m0 += 128)
+            dg.push_back(make_int4((int)(dro + m0), fused ? (int)(e->off[l - 1][u] / 2 + m0) : (int)(dro + m0),
+                                   Lx - m0 < 128 ? Lx - m0 : 128, u * c.conv_dim[l]));
           zt.push_back(make_int4((int)dro, (int)(e->off[l - 1][u] / c.conv_stride[l]), e->L[l][u], 0));
         }
         CUDA_TRY(up(e->d_dgrad_mblk[l], dg.data(), sizeof(int4) * dg.size()));
@@ -532,7 +553,9 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
       // gap rows between utterances must be exact zeros: they are reduced over by the weight-gradient GEMMs
       const long long rows = l == last ? e->R64 : e->rows_total[l];
       CUDA_TRY(cudaMemsetAsync(e->conv_out[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
-      CUDA_TRY(cudaMemsetAsync(e->conv_dpre[l], 0, sizeof(bf16) * (size_t)(rows + 128) * c.conv_dim[l], st));
+      CUDA_TRY(cudaMemsetAsync(e->conv_dpre[l] - (size_t)128 * c.conv_dim[l], 0, sizeof(bf16) * (size_t)(rows + 256) * c.conv_dim[l], st));
+      // GELU' of rows no forward tile covers is multiplied with zero gradients by the fused dgrad: must be finite
+      CUDA_TRY(cudaMemsetAsync(e->conv_pre[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
     }
     std::vector<int4> zt;
     for (int u = 0; u < U; ++u) zt.push_back(make_int4((int)e->off64[u], (int)e->tok_off[u], e->T[u], 0));
@@ -896,12 +919,41 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.flops = 2.0 * Cout * k * Cin * (double)rows_valid;
       SUTA_TRY(gemm(e, p, st));
     }
+    if (dgrad_fused(e, l)) {
+      // d pre_{l-1} = GELU'(pre_{l-1}) * (transposed conv of d pre_l), written in place by the GEMM epilogue.  The output
+      // (and the saved GELU') is addressed as [pairs of rows][2*Cin]: row j of that view = input rows 2j, 2j+1.
+      GemmProblem p;
+      p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin, 1, (long long)k * Cin};
+      p.M = (int)rows_valid; p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_dg_mblk[l];
+      p.tiles_own_rows = 1; p.out_rows = (e->rows_total[l - 1] + 128) / 2;
+      p.epi.out_ld = 2 * Cin; p.epi.act = 2; p.epi.aux_ld = 2 * Cin;
+      if (k == 2) {
+        p.a = {e->conv_dpre[l], dpre_rows, Cout};
+        p.N = 2 * Cin; p.K = Cout;
+        p.epi.out_bf16 = e->conv_dpre[l - 1]; p.epi.aux_in = e->conv_pre[l - 1];
+        SUTA_TRY(gemm(e, p, st));
+      } else {
+        // even rows: k runs over (dY[j-1], dY[j]) = one 2*Cout-long overlapping row starting one row early; taps (2, 0)
+        p.a = {e->conv_dpre[l] - Cout, dpre_rows + 1, Cout};
+        p.N = Cin; p.K = 2 * Cout; p.b_kwrap = Cout; p.b_tap_col[0] = 2 * Cin; p.b_tap_col[1] = 0;
+        p.epi.out_bf16 = e->conv_dpre[l - 1]; p.epi.aux_in = e->conv_pre[l - 1];
+        p.flops = 2.0 * (2 * Cout) * Cin * (double)rows_valid;
+        SUTA_TRY(gemm(e, p, st));
+        // odd rows: tap 1
+        p.a = {e->conv_dpre[l], dpre_rows, Cout};
+        p.K = Cout; p.b_tap_col[0] = Cin; p.b_tap_col[1] = Cin;
+        p.epi.out_bf16 = e->conv_dpre[l - 1] + Cin; p.epi.aux_in = e->conv_pre[l - 1] + Cin;
+        p.flops = 2.0 * Cout * Cin * (double)rows_valid;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      continue;
+    }
     {  // Z = d pre_l * W_l[u]  -> [rows_l, (tap, Cin)]
       GemmProblem p;
       p.a = {e->conv_dpre[l], dpre_rows, Cout};
       p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin, 1, (long long)k * Cin};
       p.M = (int)rows_valid; p.N = k * Cin; p.K = Cout;
-      p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_mblk[l];
+      p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_dg_mblk[l];
       p.tiles_own_rows = 1; p.out_rows = dpre_rows;
       p.epi.out_bf16 = e->zbuf; p.epi.out_ld = k * Cin;
       SUTA_TRY(gemm(e, p, st));

@@ -44,6 +44,7 @@ struct GemmKernelParams {
   long long* trace;     // debug: per-tile clock64 timeline of CTA 0 (8 slots per tile iteration), or null
   int trace_cap;        // tile iterations that fit
   int dbg_skip_loads;   // experiment switch (SUTA_GEMM_SKIP_LOADS): wrong results, isolates the MMA side of the mainloop
+  int b_kwrap, b_tap_col0, b_tap_col1;   // tap-split MN-major B (GemmProblem::b_kwrap)
   int l2_prefetch;      // producer prefetches A boxes into L2 ahead of the stage ring
   int streamk;          // accumulate-epilogue GEMMs: CTAs split the (tile, k-block) space evenly instead of whole tiles
   GemmEpilogue epi;
@@ -252,10 +253,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             tma_load_2d(sa, &tma_a, &full_bar[stage], a_k0 + kb * BK, a_row);
           }
           if constexpr (B_MN) {
+            int bk = b_k0 + kb * BK, bc = n_blk * BN + (int)(z * p.b_z_rows);
+            if (p.b_kwrap) {
+              const int t = bk / p.b_kwrap;
+              bk -= t * p.b_kwrap;
+              bc += t ? p.b_tap_col1 : p.b_tap_col0;
+            }
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sa + C::A_BYTES + i * 8192, &tma_b, &full_bar[stage], n_blk * BN + (int)(z * p.b_z_rows) + i * 64,
-                          b_off + b_k0 + kb * BK);
+              tma_load_2d(sa + C::A_BYTES + i * 8192, &tma_b, &full_bar[stage], bc + i * 64, b_off + bk);
           } else {
             tma_load_2d(sa + C::A_BYTES, &tma_b, &full_bar[stage], b_k0 + kb * BK, b_row);
           }
@@ -611,6 +617,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   kp.mblk = p.mblk;
   kp.ztab = p.ztab;
   kp.out_z_stride = p.out_z_stride;
+  kp.b_kwrap = p.b_kwrap; kp.b_tap_col0 = p.b_tap_col[0]; kp.b_tap_col1 = p.b_tap_col[1];
   kp.trace = g_trace;
   kp.trace_cap = g_trace_cap;
   kp.epi = p.epi;

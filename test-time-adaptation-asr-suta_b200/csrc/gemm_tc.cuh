@@ -50,6 +50,10 @@ struct GemmProblem {
   const int4* ztab = nullptr;      // optional per-z table {a_k_row0, b_k_row0, k_len, 0} (MN-major operands: the
                                    // reduction runs over rows [k_row0, k_row0 + k_len) of each operand)
   long long out_z_stride = 0;      // elements added to the output pointers per z (per-utterance gradient slabs)
+  // MN-major B whose reduction index runs over TAPS of a conv weight [Cout][tap][Cin] (transposed-conv dgrad split by
+  // output-row parity): k in [t * b_kwrap, (t+1) * b_kwrap) reads B rows k - t * b_kwrap at columns b_tap_col[t] + n
+  int b_kwrap = 0;
+  int b_tap_col[2] = {0, 0};
   double flops = 0.0;              // algorithmic FLOPs of this launch when it cannot be derived from M,N,K,nz
   GemmEpilogue epi;
 };
