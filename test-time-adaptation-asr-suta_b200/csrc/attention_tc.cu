@@ -321,8 +321,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         l_run += lsum;
         STAMP();
         fence_proxy_async_smem();
+        STAMP();
         tc_fence_before();
         mbar_arrive(&p_full[sb2]);
+        STAMP();
         ++cnt;
       }
       STAMP();

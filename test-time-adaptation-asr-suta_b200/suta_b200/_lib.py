@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsuta_b200.so")
+LIB_PATH = os.environ.get("SUTA_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsuta_b200.so")   # override: instrumented builds
 
 MAX_LAYERS = 48
 MAX_CONV = 8
