@@ -201,6 +201,12 @@ int check_cfg(const suta_model_cfg& c) {
   return SUTA_OK;
 }
 
+static bool use_posconv_tc(const suta_engine* e) {
+  const suta_model_cfg& c = e->cfg;
+  static const bool on = getenv("SUTA_NO_POSCONV_TC") == nullptr;
+  return on && posconv_tc_supported(c.hidden / c.pos_groups, c.pos_k);
+}
+
 // Transposed-conv dgrad of layer l as GEMMs that write d(input) directly (no [rows, k*Cin] intermediate, no col2im):
 // stride 2 with k = 2 (rows 2j, 2j+1 are the two halves of one N = 2*Cin output row) or k = 3 (even rows 2j =
 // dY[j] W_0 + dY[j-1] W_2, odd rows 2j+1 = dY[j] W_1).
@@ -738,7 +744,10 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   }
   // positional conv embedding + GELU + residual               HF/modeling_wav2vec2.py:360-368, :690-691
   PROF("posconv_pack", posconv_pack(e->h0, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, st));
-  {
+  if (use_posconv_tc(e)) {
+    PROF("posconv_tc", posconv_tc(e->xg, reinterpret_cast<const bf16*>(e->w.pos_w), e->w.pos_b, e->cpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
+    e->launches += 1;
+  } else {
     GemmProblem p;
     p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
     p.b = {reinterpret_cast<const bf16*>(e->w.pos_w), H, (long long)c.pos_k * CG};
@@ -856,7 +865,10 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
                               e->G, db, nullptr, M, H, st));
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
   PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
-  {
+  if (use_posconv_tc(e)) {
+    PROF("posconv_tc", posconv_tc(e->xg, reinterpret_cast<const bf16*>(e->w.pos_w_t), nullptr, e->dcpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
+    e->launches += 1;
+  } else {
     GemmProblem p;
     p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
     p.b = {reinterpret_cast<const bf16*>(e->w.pos_w_t), H, (long long)c.pos_k * CG};

@@ -652,6 +652,29 @@ int gemm_encode_tmap(CUtensorMap* tm, int dtype, const void* ptr, long long cols
                      box_cols, box_rows, swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// plain (un-swizzled) bf16 tensor map of rank 2 or 3 for kernels that lay operands out themselves (posconv_tc.cu):
+// dims / box innermost first, strides in bytes for dims 1..rank-1
+int gemm_encode_tmap_nd(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_bytes,
+                        const int* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    suta_set_last_error("cuTensorMapEncodeTiled entry point not available");
+    return SUTA_ERR_DRIVER;
+  }
+  SUTA_CHECK_ARG(rank >= 2 && rank <= 3 && !(reinterpret_cast<uintptr_t>(ptr) & 15));
+  cuuint64_t d[3], s[2];
+  cuuint32_t b[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) { s[i] = (cuuint64_t)strides_bytes[i]; SUTA_CHECK_ARG((s[i] & 15) == 0); }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    suta_set_last_error("cuTensorMapEncodeTiled (rank %d, plain) failed (%d)", rank, (int)r);
+    return SUTA_ERR_DRIVER;
+  }
+  return SUTA_OK;
+}
+
 // debug hook: CTA 0 of every following GEMM launch writes its per-tile clock64 timeline into dev_buf[cap][8]
 // (0 MMA warp waits for a free accumulator, 1 starts issuing, 2 has issued the tile; 3/4 and 5/6 first epilogue
 // warp of each column half starts/finishes; 7 producer starts the tile).  Pass null to switch off.

@@ -63,5 +63,7 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream);
 int gemm_bf16_tc_2cta(const GemmProblem& p, cudaStream_t stream);
 int gemm_encode_tmap(CUtensorMap* tm, int dtype, const void* ptr, long long cols, long long rows, long long pitch_bytes,
                      int box_cols, int box_rows, int swizzle);
+int gemm_encode_tmap_nd(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_bytes,
+                        const int* box);
 int gemm_num_sms();
 long long* gemm_trace_buffer(int* cap);   // debug timeline buffer set by suta_debug_set_gemm_trace (null = off)

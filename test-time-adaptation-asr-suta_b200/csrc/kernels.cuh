@@ -93,6 +93,12 @@ int conv0_bwd_chunks(int max_L0);
 int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
                    int C, int n_utts, cudaStream_t stream);
 
+// ---- posconv_tc.cu --------------------------------------------------------------------------
+// grouped positional conv on tcgen05 with a shared-memory-resident input window (CG = H/G in {48, 64})
+bool posconv_tc_supported(int CG, int pos_k);
+int posconv_tc(const bf16* xg, const bf16* w, const float* bias, float* out, int out_ld, int G, int CG, long long R, long long Rm,
+               int pos_k, cudaStream_t stream);
+
 // ---- posconv.cu -----------------------------------------------------------------------------
 // scatter fp32 [M,H] tokens into the zero-padded per-group bf16 layout [G][R][CGP] used as the implicit-GEMM A operand
 int posconv_pack(const float* h, const int* row_utt, const long long* tok_off, const long long* pad_off, bf16* xg,
