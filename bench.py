@@ -231,7 +231,7 @@ def run_b200(args):
         "e2e": {"value": audio_all / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05, all dense contractions)",
+        "roofline": {"bound": "tensor", "kernel": "gemm2_kernel (cta_group::2 pairs) + gemm_bf16_tc_kernel (tcgen05, all dense contractions)",
                      "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peaks["tflops"]) if gemm_ms else None,
                      "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,
