@@ -98,6 +98,8 @@ struct suta_engine {
   std::vector<int> T;
   std::vector<int> n_mblk;                         // [layer]
   std::vector<int> n_dg_mblk;                      // [layer] M-blocks of the conv dgrad GEMM(s)
+  std::vector<int> n_mpair;                        // [layer] 256-row pair tiles of the forward conv GEMM (train_feature)
+  int4* d_mpair[SUTA_MAX_CONV] = {};
   int n_attn_blk = 0;
   bool frontend_done = false;
   int opt_steps = 0;
@@ -228,6 +230,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
   e->samp_off.resize(U); e->tok_off.resize(U); e->pad_off.resize(U); e->T.resize(U);
   e->n_mblk.assign(c.n_conv, 0);
   e->n_dg_mblk.assign(c.n_conv, 0);
+  e->n_mpair.assign(c.n_conv, 0);
   long long s = 0;
   e->max_samples = 0; e->max_L0 = 0;
   for (int u = 0; u < U; ++u) {
@@ -260,6 +263,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
       r += last ? e->L[l][u] : (e->train_feature ? ((e->L[l][u] + 1 + 255) & ~255) : ((e->L[l][u] + 7) & ~7));
       if (l >= 1) {
         e->n_mblk[l] += ceil_div(e->L[l][u], 128);
+        e->n_mpair[l] += ceil_div(e->L[l][u], 256);
         e->n_dg_mblk[l] += ceil_div(e->L[l][u] + (dgrad_fused(e, l) && !last ? 1 : 0), 128);
       }
       e->max_L[l] = u == 0 ? e->L[l][u] : (e->L[l][u] > e->max_L[l] ? e->L[l][u] : e->max_L[l]);
@@ -357,6 +361,7 @@ void carve(suta_engine* e, Bump& b) {
       // 128 leading rows (zero): the even-row dgrad GEMM reads row -1 of the first utterance
       e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
       if (l >= 1) {
+        e->d_mpair[l] = b.take<int4>(e->n_mpair[l]);
         e->d_dgrad_mblk[l] = b.take<int4>(e->n_dg_mblk[l]);
         e->d_ztab[l] = b.take<int4>(U);
         e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
@@ -523,6 +528,14 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
                                 e->train_feature ? u * c.conv_dim[l] : 0));
       }
     CUDA_TRY(up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size()));
+    std::vector<int4> ptab;                // 256-row tiles for the CTA-pair kernel: utterance regions are 256-row aligned
+    if (e->train_feature) {
+      for (int u = 0; u < U; ++u)
+        for (int m0 = 0; m0 < e->L[l][u]; m0 += 256)
+          ptab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0),
+                                   e->L[l][u] - m0 < 256 ? e->L[l][u] - m0 : 256, u * c.conv_dim[l]));
+      CUDA_TRY(up(e->d_mpair[l], ptab.data(), sizeof(int4) * ptab.size()));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));   // `tab` is pageable stack-owned memory
   }
   if (e->train_feature) {
@@ -711,6 +724,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
       if (l < c.n_conv - 1) {    // 128-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
         p.tiles_own_rows = 1;
         p.out_rows = e->rows_total[l] + 128;
+        p.mpair = e->d_mpair[l]; p.num_mpair = e->n_mpair[l];
       }
     }
     SUTA_TRY(gemm(e, p, st));

@@ -731,7 +731,7 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
     const bool lean = !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias);
     // plain row blocks with N % 256 == 0: CTA pairs on 256 x 256 tiles (gemm_tc2.cu) -- one SM cannot ingest 48 KB per k-block
     static const bool use_pairs = getenv("SUTA_NO_GEMM2") == nullptr;
-    if (use_pairs && !p.mblk && p.N % 256 == 0 && p.M > 128 && !(p.epi.out_f32 && p.epi.bias)) return gemm_bf16_tc_2cta(p, stream);
+    if (use_pairs && (!p.mblk || p.mpair) && p.N % 256 == 0 && p.M > 128 && !(p.epi.out_f32 && p.epi.bias)) return gemm_bf16_tc_2cta(p, stream);
     if (p.N % 256 == 0 && lean) return launch<256, false, false, true, true>(p, stream);
     if (p.N % 256 == 0) return launch<256, false, false, true>(p, stream);
     if (p.N % 128 == 0) return launch<128, false, false, true>(p, stream);

@@ -44,6 +44,8 @@ struct GemmProblem {
   int c_z_cols = 0;
   const int4* mblk = nullptr;      // optional per-M-block table {a_row0, out_row0, rows_valid, b_row_off}
   int num_mblk = 0;                // = ceil(M/128) when mblk == nullptr
+  const int4* mpair = nullptr;     // optional per-256-row table {a_row0, out_row0, rows_valid, b_row_off} for the CTA-pair kernel:
+  int num_mpair = 0;               //   both 128-row halves of an entry share b_row_off (256-row-aligned utterances)
   int tiles_own_rows = 0;          // with mblk: every tile may write all 128 rows from its out_row0 (the rows past
                                    // rows_valid are padding nobody else owns) -> eligible for the TMA-store epilogue
   long long out_rows = 0;          // addressable rows of the output buffers (default M)

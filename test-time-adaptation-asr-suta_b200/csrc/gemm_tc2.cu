@@ -35,6 +35,7 @@ struct Params2 {
   int M, N, K;
   int num_mpair, num_nblk;
   int out_rows;
+  const int4* mpair;    // optional per-pair-tile table {a_row0, out_row0, rows_valid, b_row_off}
   long long* trace;     // debug: clock64 timeline of the leader CTA of pair 0 (same 8 slots per tile as gemm_tc.cu)
   int trace_cap;
   GemmEpilogue epi;
@@ -172,8 +173,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         TRACE2(iter, 7);
         const int m_pair = tile / p.num_nblk;
         const int n_blk = tile - m_pair * p.num_nblk;
-        const int a_row = (2 * m_pair + (int)rank) * BM;
-        const int b_row = n_blk * BN + (int)rank * (BN / 2);
+        int a_row = (2 * m_pair + (int)rank) * BM;
+        int b_row = n_blk * BN + (int)rank * (BN / 2);
+        if (p.mpair) {
+          const int4 mi = __ldg(&p.mpair[m_pair]);
+          a_row = mi.x + (int)rank * BM;
+          b_row += mi.w;
+        }
         for (int kb = 0; kb < num_kblk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
@@ -235,7 +241,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     for (int tile = cid; tile < total_tiles; tile += ncl, ++iter) {
       const int m_pair = tile / p.num_nblk;
       const int n_blk = tile - m_pair * p.num_nblk;
-      const int row0 = (2 * m_pair + (int)rank) * BM + q * 32;
+      const int row0 = (p.mpair ? __ldg(&p.mpair[m_pair]).y : 2 * m_pair * BM) + (int)rank * BM + q * 32;
       const int col0 = n_blk * BN + half * C::COLS_PER_WARP;
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 of the half's 128 bias values (bf16 outputs only)
       if (p.epi.bias) breg = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + lane * 4));
@@ -367,7 +373,8 @@ int launch2(const GemmProblem& p, cudaStream_t stream) {
   if (AUX) SUTA_TRY(gemm_encode_tmap(&tx, 1, p.epi.aux_out, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32, 64));
   Params2 kp;
   kp.M = p.M; kp.N = p.N; kp.K = p.K;
-  kp.num_mpair = ceil_div(ceil_div(p.M, BM), 2);
+  kp.num_mpair = p.mpair ? p.num_mpair : ceil_div(ceil_div(p.M, BM), 2);
+  kp.mpair = p.mpair;
   kp.num_nblk = p.N / BN;
   kp.out_rows = (int)orows;
   kp.trace = gemm_trace_buffer(&kp.trace_cap);
@@ -382,7 +389,7 @@ int launch2(const GemmProblem& p, cudaStream_t stream) {
 
 }  // namespace
 
-// Eligibility (checked by gemm_bf16_tc): dense, K-major, un-batched, no M-block table, N % 256 == 0, exactly one output,
+// Eligibility (checked by gemm_bf16_tc): dense, K-major, un-batched, plain row blocks or an M-PAIR table, N % 256 == 0, exactly one output,
 // no residual operand, a bias only with a bf16 output.
 int gemm_bf16_tc_2cta(const GemmProblem& p, cudaStream_t stream) {
   if (p.epi.act == 1 && p.epi.aux_out) return launch2<true>(p, stream);
