@@ -27,6 +27,9 @@
 
 namespace {
 
+constexpr int TOKEN_EARLY = 11;      // exp2 iteration (of 16) after which a softmax warp releases the MUFU token
+
+
 using namespace attn_tc;
 
 constexpr int HD = 64;
@@ -286,6 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         asm volatile("" : "+f"(nm));                   // nothing of the exp2 section may be scheduled above the wait
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[32];
+        bool token_passed = false;
         if (full) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -294,7 +298,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             l4[i & 3] += (e0 + e1) + (e2 + e3);
             pk[i] = pack_bf16x2(e0, e1);
             pk[16 + i] = pack_bf16x2(e2, e3);
+            if (i == TOKEN_EARLY) {                      // hand the MUFU token on early: the partner needs ~200 cycles to wake
+              asm volatile("" : "+f"(l4[i & 3]));
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tok[(g ? 0 : 4) + q]);
+            }
           }
+          token_passed = true;
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -312,7 +322,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         float lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         asm volatile("" : "+f"(lsum));                 // every exp2 has been issued and consumed before the token moves on
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tok[(g ? 0 : 4) + q]);
+        if (!token_passed && lane == 0) mbar_arrive(&tok[(g ? 0 : 4) + q]);
         STAMP();
         mbar_wait(&p_empty[sb2], ((cnt >> 1) & 1) ^ 1);  // the P V that read this buffer two blocks ago has retired
 #pragma unroll
