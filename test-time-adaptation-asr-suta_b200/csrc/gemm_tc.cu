@@ -43,48 +43,10 @@ struct GemmKernelParams {
   long long out_z_stride;
   long long* trace;     // debug: per-tile clock64 timeline of CTA 0 (8 slots per tile iteration), or null
   int trace_cap;        // tile iterations that fit
-  int dbg_skip_loads;   // experiment switch (SUTA_GEMM_SKIP_LOADS): wrong results, isolates the MMA side of the mainloop
   int b_kwrap, b_tap_col0, b_tap_col1;   // tap-split MN-major B (GemmProblem::b_kwrap)
-  int l2_prefetch;      // producer prefetches A boxes into L2 ahead of the stage ring
-  int streamk;          // accumulate-epilogue GEMMs: CTAs split the (tile, k-block) space evenly instead of whole tiles
   GemmEpilogue epi;
 };
 
-// Work distribution of the persistent kernel.  Default: whole output tiles, strided over the CTAs.  Stream-K (only with
-// the reduce-add epilogue, where a partial sum needs no fix-up pass): every CTA owns the same number of k-blocks of the
-// flattened (tile, k-block) space, so a 471-tile problem does not cost four waves on 148 SMs.
-struct WorkIter {
-  int tile, kb0, kb1;
-  long long cur, end;
-  int KB, stride;
-  bool sk;
-  __device__ __forceinline__ WorkIter(bool sk_, int total_tiles, int KB_) : tile(0), kb0(0), kb1(KB_), KB(KB_), stride(gridDim.x), sk(sk_) {
-    if (sk) {
-      const long long tot = (long long)total_tiles * KB;
-      cur = tot * blockIdx.x / gridDim.x;
-      end = tot * (blockIdx.x + 1) / gridDim.x;
-    } else {
-      cur = blockIdx.x;
-      end = total_tiles;
-    }
-  }
-  __device__ __forceinline__ bool next() {
-    if (cur >= end) return false;
-    if (sk) {
-      tile = (int)(cur / KB);
-      kb0 = (int)(cur - (long long)tile * KB);
-      kb1 = (int)min((long long)KB, kb0 + (end - cur));
-      cur += kb1 - kb0;
-    } else {
-      tile = (int)cur;
-      cur += stride;
-    }
-    return true;
-  }
-};
-
-bool g_streamk = getenv("SUTA_STREAMK") != nullptr;        // experiment switch, off: measured neutral to -10 % (the mainloop, not wave quantisation, limits the N = 768 GEMMs)
-bool g_l2_prefetch = getenv("SUTA_L2PF") != nullptr;       // experiment switch, off: +4 % on N = 768, -5 % where A tiles are shared by many CTAs
 long long* g_trace = nullptr;
 int g_trace_cap = 0;
 
@@ -188,7 +150,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_kblk_all = (p.K + BK - 1) / BK;
   const int tiles_per_z = p.num_mblk * p.num_nblk;
   const int total_tiles = tiles_per_z * p.nz;
-  const bool sk = EPI_TMA && LEAN && p.streamk;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -196,29 +157,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      // L2 prefetch cursor (K-major A, no z batching): runs PF_DIST k-blocks ahead of the shared-memory loads, across
-      // tile boundaries.  With few column blocks (N = 768: three CTAs share an A tile) nearly every A box is a DRAM
-      // miss, and four 512-cycle stages do not cover DRAM latency under load; L2 hits they do cover.
-      constexpr int PF_DIST = 8;
-      const bool pf_on = !A_MN && !p.ztab && p.nz == 1 && p.l2_prefetch;
-      WorkIter wpf(sk, total_tiles, num_kblk_all);
-      bool pf_live = pf_on && wpf.next();
-      int pf_kb = wpf.kb0, pf_row = 0;
-      auto pf_tile_row = [&]() { const int mb = wpf.tile / p.num_nblk; pf_row = p.mblk ? __ldg(&p.mblk[mb]).x : mb * BM; };
-      if (pf_live) pf_tile_row();
-      auto pf_step = [&]() {
-        if (!pf_live) return;
-        tma_prefetch_l2_2d(&tma_a, pf_kb * BK, pf_row);
-        if (++pf_kb >= wpf.kb1) {
-          pf_live = wpf.next();
-          pf_kb = wpf.kb0;
-          if (pf_live) pf_tile_row();
-        }
-      };
-      for (int i = 0; i < PF_DIST; ++i) pf_step();
-      for (WorkIter w(sk, total_tiles, num_kblk_all); w.next(); ++iter) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         TRACE(iter, 7);
-        const int tile = w.tile;
         const int z = tile / tiles_per_z;
         const int r = tile - z * tiles_per_z;
         const int m_blk = r / p.num_nblk;
@@ -231,19 +171,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         const int a_row = a_row0 + (int)(z * p.a_z_rows);
         const int b_row = b_off + (int)(z * p.b_z_rows) + n_blk * BN;
-        int a_k0 = 0, b_k0 = 0, num_kblk = w.kb1;
+        int a_k0 = 0, b_k0 = 0, num_kblk = num_kblk_all;
         if (p.ztab) {
           int4 zi = __ldg(&p.ztab[z]);
           a_k0 = zi.x; b_k0 = zi.y; num_kblk = (zi.z + BK - 1) / BK;
         }
-        for (int kb = w.kb0; kb < num_kblk; ++kb) {
+        for (int kb = 0; kb < num_kblk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
-          if (p.dbg_skip_loads && (iter > 0 || kb >= C::STAGES)) {   // experiment: MMAs on stale operands, no TMA traffic
-            mbar_arrive(&full_bar[stage]);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           if constexpr (A_MN) {
 #pragma unroll
@@ -265,7 +200,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
             tma_load_2d(sa + C::A_BYTES, &tma_b, &full_bar[stage], b_k0 + kb * BK, b_row);
           }
-          pf_step();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -279,15 +213,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       int iter = 0;
-      for (WorkIter w(sk, total_tiles, num_kblk_all); w.next(); ++iter) {
-        int num_kblk = w.kb1;
-        if (p.ztab) num_kblk = (__ldg(&p.ztab[w.tile / tiles_per_z]).z + BK - 1) / BK;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        int num_kblk = num_kblk_all;
+        if (p.ztab) num_kblk = (__ldg(&p.ztab[tile / tiles_per_z]).z + BK - 1) / BK;
         if (lane == 0) TRACE(iter, 0);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (lane == 0) TRACE(iter, 1);
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
-        for (int kb = w.kb0; kb < num_kblk; ++kb) {
+        for (int kb = 0; kb < num_kblk; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
@@ -297,7 +231,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+              umma_bf16_ss(d_tmem, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit(&empty_bar[stage]);        // frees the smem stage once these MMAs retire
           }
           __syncwarp();
@@ -326,8 +260,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t bias_s = LEAN ? patch + 2048 : smem_u32(epi_smem + 8 * C::WARP_EPI_BYTES + (warp - 2) * 512);
       const bool out_is_f32 = p.epi.out_f32 != nullptr;
       uint32_t pc = 0;                             // running chunk counter -> patch ping-pong
-      for (WorkIter w(sk, total_tiles, num_kblk_all); half < C::EPI_SPLIT && w.next(); ++iter) {
-        const int tile = w.tile;
+      for (int tile = blockIdx.x; half < C::EPI_SPLIT && tile < total_tiles; tile += gridDim.x, ++iter) {
         const int m_blk = tile / p.num_nblk;       // nz == 1; with an M-block table every tile OWNS its 128 output rows
         const int n_blk = tile - m_blk * p.num_nblk;
         const int row0 = (p.mblk ? __ldg(&p.mblk[m_blk]).y : m_blk * BM) + q * 32;      // first output row of this warp
@@ -624,20 +557,6 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   long long total = (long long)kp.num_mblk * kp.num_nblk * kp.nz;
   if (total <= 0) return SUTA_OK;
   int grid = (int)(total < gemm_num_sms() ? total : gemm_num_sms());
-  if (const char* e = getenv("SUTA_GEMM_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;   // experiment: fewer CTAs
-  kp.dbg_skip_loads = getenv("SUTA_GEMM_SKIP_LOADS") ? 1 : 0;
-  kp.streamk = 0;
-  kp.l2_prefetch = g_l2_prefetch ? 1 : 0;
-  if (EPI_TMA && LEAN && p.epi.accumulate && p.epi.out_f32 && !p.ztab && p.nz == 1 && g_streamk) {
-    // even k-block shares pay when whole tiles leave part of the last wave idle; keep >= 4 k-blocks per CTA
-    const long long units = total * ceil_div(p.K, BK);
-    const long long waves = ceil_div((int)total, gemm_num_sms());
-    const bool ragged = total % gemm_num_sms() != 0 && (double)total / (waves * gemm_num_sms()) < 0.93;
-    if (ragged && units >= 4LL * gemm_num_sms()) {
-      kp.streamk = 1;
-      if (!getenv("SUTA_GEMM_GRID")) grid = gemm_num_sms();
-    }
-  }
   gemm_bf16_tc_kernel<BN, A_MN, B_MN, EPI_TMA, LEAN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tx, kp);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
