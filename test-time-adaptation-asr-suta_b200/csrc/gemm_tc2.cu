@@ -35,6 +35,7 @@ struct Params2 {
   int M, N, K;
   int num_mpair, num_nblk;
   int out_rows;
+  int tail_tiles, tail_split;   // reduce-add epilogue only: the last (partial) wave's tiles are split tail_split ways along K
   const int4* mpair;    // optional per-pair-tile table {a_row0, out_row0, rows_valid, b_row_off}
   long long* trace;     // debug: clock64 timeline of the leader CTA of pair 0 (same 8 slots per tile as gemm_tc.cu)
   int trace_cap;
@@ -45,6 +46,35 @@ struct Params2 {
   do {                                                                                                              \
     if (p.trace && blockIdx.x == 0 && (iter) < p.trace_cap) p.trace[(iter) * 8 + (slot)] = clock64();               \
   } while (0)
+
+// Work of one CTA pair: whole 256 x 256 tiles strided over the pairs; with the reduce-add epilogue (partial sums need no
+// fix-up pass) the tiles of the last, partial wave are split along K so that wave costs 1/tail_split of a tile time
+// instead of a whole one (255 tiles on 74 pairs: 3.5 tile times instead of 4).  Splitting EVERY tile (stream-K) was
+// slower: pairs sharing an A tile stop walking k in step and lose each other's L2 hits.
+struct WorkIter2 {
+  int tile, kb0, kb1;
+  int next_tile, stride, full_tiles, KB, tail_split, tail_units, cid;
+  bool tail_done;
+  __device__ __forceinline__ WorkIter2(const int total_tiles, int KB_, int cid_, int ncl, int tail_tiles, int tail_split_)
+      : tile(0), kb0(0), kb1(KB_), next_tile(cid_), stride(ncl), full_tiles(total_tiles - tail_tiles), KB(KB_),
+        tail_split(tail_split_), tail_units(tail_tiles * tail_split_), cid(cid_), tail_done(false) {}
+  __device__ __forceinline__ bool next() {
+    if (next_tile < full_tiles) {
+      tile = next_tile;
+      next_tile += stride;
+      kb0 = 0;
+      kb1 = KB;
+      return true;
+    }
+    if (tail_done || cid >= tail_units) return false;
+    tail_done = true;
+    tile = full_tiles + cid / tail_split;
+    const int part = cid - (cid / tail_split) * tail_split;
+    kb0 = (int)((long long)KB * part / tail_split);
+    kb1 = (int)((long long)KB * (part + 1) / tail_split);
+    return kb1 > kb0;
+  }
+};
 
 // Shared memory: 5 stages of 32 KB (tools/ubench/mma2.cu: 5 and 6 stages run the mainloop equally fast, 4 do not), two
 // 4 KB epilogue patches per epilogue warp (ping-pong: chunk c+1 is converted while the TMA store of chunk c still reads its
@@ -169,8 +199,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       uint32_t phase = 0;
       const uint32_t leader_full0 = mapa_rank0(smem_u32(&full_bar[0]));
       int iter = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl, ++iter) {
+      for (WorkIter2 w(total_tiles, num_kblk, cid, ncl, p.tail_tiles, p.tail_split); w.next(); ++iter) {
         TRACE2(iter, 7);
+        const int tile = w.tile;
         const int m_pair = tile / p.num_nblk;
         const int n_blk = tile - m_pair * p.num_nblk;
         int a_row = (2 * m_pair + (int)rank) * BM;
@@ -180,7 +211,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           a_row = mi.x + (int)rank * BM;
           b_row += mi.w;
         }
-        for (int kb = 0; kb < num_kblk; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
@@ -200,20 +231,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       int iter = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl, ++iter) {
+      for (WorkIter2 w(total_tiles, num_kblk, cid, ncl, p.tail_tiles, p.tail_split); w.next(); ++iter) {
         if (lane == 0) TRACE2(iter, 0);
         mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (lane == 0) TRACE2(iter, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kblk; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * C::STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + C::A_BYTES);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma2_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
             umma2_commit_both(&empty_bar[stage]);  // the stage is free in both CTAs once these MMAs retire
           }
           __syncwarp();
@@ -238,7 +269,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint32_t acc_phase = 0;
     int iter = 0;
     const int tslot = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 3 : 5) : -1;
-    for (int tile = cid; tile < total_tiles; tile += ncl, ++iter) {
+    for (WorkIter2 w(total_tiles, num_kblk, cid, ncl, p.tail_tiles, p.tail_split); w.next(); ++iter) {
+      const int tile = w.tile;
       const int m_pair = tile / p.num_nblk;
       const int n_blk = tile - m_pair * p.num_nblk;
       const int row0 = (p.mpair ? __ldg(&p.mpair[m_pair]).y : 2 * m_pair * BM) + (int)rank * BM + q * 32;
@@ -382,6 +414,15 @@ int launch2(const GemmProblem& p, cudaStream_t stream) {
   const long long total = (long long)kp.num_mpair * kp.num_nblk;
   const int pairs = gemm_num_sms() / 2;
   const int grid = 2 * (int)(total < pairs ? total : pairs);
+  kp.tail_tiles = 0;
+  kp.tail_split = 1;
+  static const bool tail_on = getenv("SUTA_NO_TAIL_SPLIT") == nullptr;
+  const int tail = (int)(total % pairs), kblocks = ceil_div(p.K, BK);
+  if (tail_on && p.epi.accumulate && p.epi.out_f32 && !p.epi.bias && total > pairs && tail > 0 && 2 * tail <= pairs) {
+    int split = pairs / tail;
+    while (split > 1 && kblocks / split < 4) --split;     // keep at least 4 k-blocks per part
+    if (split > 1) { kp.tail_tiles = tail; kp.tail_split = split; }
+  }
   gemm2_kernel<AUX><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tx, kp);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
