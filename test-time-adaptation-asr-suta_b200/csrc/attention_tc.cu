@@ -288,23 +288,33 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(&tok[(g ? 4 : 0) + q], g ? (rnd & 1) : ((rnd & 1) ^ 1));
         asm volatile("" : "+f"(nm));                   // nothing of the exp2 section may be scheduled above the wait
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t lacc[2] = {0ull, 0ull};               // two packed pairs of partial row sums
+        const uint64_t sc2 = dup2(sc), nm2 = dup2(nm);
         uint32_t pk[32];
         bool token_passed = false;
         if (full) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(sa[2 * i]), sc, nm)), e1 = ex2_approx(fmaf(__uint_as_float(sa[2 * i + 1]), sc, nm));
-            const float e2 = ex2_approx(fmaf(__uint_as_float(sb[2 * i]), sc, nm)), e3 = ex2_approx(fmaf(__uint_as_float(sb[2 * i + 1]), sc, nm));
-            l4[i & 3] += (e0 + e1) + (e2 + e3);
+            // packed fp32 (FFMA2 / FADD2): the section shares its scheduler with the partner warp's score loads, row
+            // maximum and P stores, and 64 scalar FFMAs + 63 FADDs on top of the 64 MUFUs made it issue-bound
+            float x0, x1, x2, x3;
+            upk2(fma2(pk2(__uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1])), sc2, nm2), x0, x1);
+            upk2(fma2(pk2(__uint_as_float(sb[2 * i]), __uint_as_float(sb[2 * i + 1])), sc2, nm2), x2, x3);
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+            lacc[i & 1] = add2(lacc[i & 1], add2(pk2(e0, e1), pk2(e2, e3)));
             pk[i] = pack_bf16x2(e0, e1);
             pk[16 + i] = pack_bf16x2(e2, e3);
             if (i == TOKEN_EARLY) {                      // hand the MUFU token on early: the partner needs ~200 cycles to wake
-              asm volatile("" : "+f"(l4[i & 3]));
+              asm volatile("" : "+l"(lacc[i & 1]));
               __syncwarp();
               if (lane == 0) mbar_arrive(&tok[(g ? 0 : 4) + q]);
             }
           }
           token_passed = true;
+          float a0, a1, a2, a3;
+          upk2(lacc[0], a0, a1);
+          upk2(lacc[1], a2, a3);
+          l4[0] = a0; l4[1] = a1; l4[2] = a2; l4[3] = a3;
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

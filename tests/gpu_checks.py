@@ -91,6 +91,20 @@ def check_gemm_epilogue(M=517, N=384, K=256, seed=1):
     return out
 
 
+def check_gemm_pair_tail(M=7700, N=768, K=1024, seed=21):
+    """> 74 pair tiles with a small last wave: the CTA-pair kernel splits those tiles along K and reduce-adds the parts."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    res = torch.randn(M, N, device=DEV, generator=g)
+    out = res.clone()
+    gemm(a, b, M, N, K, out_f32=out, act=4)
+    ref = a.float() @ b.float().t() + res
+    o16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    gemm(a, b, M, N, K, out_bf16=o16)
+    return dict(acc_rel=relerr(out, ref), bf16_rel=relerr(o16.float(), a.float() @ b.float().t()))
+
+
 def check_gemm_shapes():
     out = {}
     for (M, N, K) in [(249, 32, 768), (249, 768, 32), (1000, 768, 3072), (64, 2304, 768), (130, 64, 64), (5, 128, 128),

@@ -32,6 +32,13 @@ def test_gemm_epilogues(K, M, N, Kd):
     assert r["gelu_rel"] < BF16 and r["aux_rel"] < BF16 and r["res16_rel"] < BF16 and r["gelu_bwd_vs_exact_rel"] < BF16
 
 
+def test_gemm_pair_kernel_tail_split(K):
+    r = K.check_gemm_pair_tail()                     # 31 row pairs x 3 column blocks = 93 tiles = 74 + 19 -> 3-way K split
+    assert r["acc_rel"] < F32 and r["bf16_rel"] < BF16
+    r = K.check_gemm_pair_tail(M=20000, N=768, K=3072, seed=22)
+    assert r["acc_rel"] < F32 and r["bf16_rel"] < BF16
+
+
 def test_gemm_shapes_of_the_path(K):
     for name, rel in K.check_gemm_shapes().items():
         assert rel < 2e-5, name
