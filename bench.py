@@ -257,12 +257,12 @@ def run_b200(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per tcgen05 GEMM launch, from the committed `ncu --set full` capture
-# (profiles/r01d_ncu_full_gemm_attention.md: 9 GEMM launches of tools/profile_step.py --utts 32 --seconds 6 --mode feature,
-# 9.8 k frames per batch, i.e. about 1/5 of a bench batch; read 62.0 MB + written 6.8 MB on average.  Reads equal the
+# (profiles/r01g_ncu_full_pair_gemm_posconv.md: 10 launches of the CTA-pair kernel in tools/profile_step.py --utts 32
+# --seconds 6 --mode feature, 9.8 k frames per batch, i.e. about 1/2 of a bench batch; 72.6 MB on average).  Reads equal the
 # operand bytes -- e.g. the FFN dgrad launch reads 80.3 MB for 15 MB dY + 60 MB GELU' + 4.7 MB W, the accumulate launch
-# 95.3 MB for 60 MB dH + 4.7 MB W + 30 MB fp32 reduce target -- so no re-reads; results are mostly still in L2 at kernel end).
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 68.9e6
-NCU_GEMM_TRAFFIC_NOTE = ("ncu capture of the 9.8k-frame profile batch (profiles/r01d_ncu_full_gemm_attention.md), not of this run; "
+# 95.3 MB for 60 MB dH + 4.7 MB W + 30 MB fp32 reduce target -- so no re-reads; results are mostly still in L2 at kernel end.
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 72.6e6
+NCU_GEMM_TRAFFIC_NOTE = ("ncu capture of the 9.8k-frame profile batch (profiles/r01g_ncu_full_pair_gemm_posconv.md), not of this run; "
                          "tensor-bound kernel, traffic ~= algorithmic bytes")
 
 
