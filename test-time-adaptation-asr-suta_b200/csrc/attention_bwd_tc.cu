@@ -35,8 +35,8 @@ constexpr int BWD_THREADS = 384;          // TMA, score MMA, 8 elementwise warps
 constexpr int B_X = 0;                       // [2 item buffers][X1 | X2]
 constexpr int B_Y = B_X + 4 * XTILE;         // [NS][Y1 | Y2]
 constexpr int B_A = B_Y + NS * 2 * YTILE;    // [2 groups][dS | P] bf16 [128 rows][64], K-major, 128B swizzle
-constexpr int B_C = B_A + 4 * XTILE;         // [2 groups][lse[64] | D[64]] fp32 (DKV only)
-constexpr int B_BAR = B_C + 2 * 512;
+constexpr int B_C = B_A + 4 * XTILE;         // [2 groups][2 buffers][lse[64] | D[64]] fp32 (DKV only)
+constexpr int B_BAR = B_C + 4 * 512;
 constexpr int B_SMEM = B_BAR + 256;
 
 template <bool DKV>
@@ -215,8 +215,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t t1 = tmem_base + lane_off + g * 128, t2 = t1 + 64;
     const uint32_t a_ds = sA + g * 2 * XTILE + r * 128, a_p = a_ds + XTILE;
-    float* cst = reinterpret_cast<float*>(smem + B_C + g * 512);     // lse[64] | D[64] of the streamed block (DKV)
-    const uint32_t cst_u = smem_u32(cst);
+    float* cst0 = reinterpret_cast<float*>(smem + B_C + g * 1024);   // 2 x (lse[64] | D[64]) of the streamed blocks (DKV)
     float sc = scale_log2;
     asm volatile("" : "+f"(sc));
     uint32_t cnt = 0;                                  // blocks this group has processed (sc_full / a_empty phase)
@@ -234,16 +233,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         lse_r = __ldg(LSE + (long long)head * M + row);
         d_r = __ldg(Dv + (long long)head * M + row);
       }
+      // column constants (LSE, D of the streamed query block) of block jj for this thread's slot; past the utterance
+      // end LSE = +inf makes P = 0, so those (foreign) query rows contribute nothing
+      auto load_cst = [&](int jj) -> float {
+        const int c = gi & 63;
+        const bool ok = jj < ny && jj * BY + c < T;
+        const long long qrow = (long long)head * M + urow0 + jj * BY + c;
+        return gi < 64 ? (ok ? __ldg(LSE + qrow) : INFINITY) : (ok ? __ldg(Dv + qrow) : 0.f);
+      };
+      float cst_next = 0.f;
+      if (DKV) cst_next = load_cst(g);
       for (int j = g; j < ny; j += 2, ++cnt) {
         const int nvalid = min(BY, T - j * BY);
-        if (DKV) {                                     // column constants of this query block -> shared memory
-          const int c = gi & 63;
-          const bool ok = j * BY + c < T;
-          const long long qrow = (long long)head * M + urow0 + j * BY + c;
-          // past the utterance end: LSE = +inf makes P = 0, so those (foreign) query rows contribute nothing
-          const float v = gi < 64 ? (ok ? __ldg(LSE + qrow) : INFINITY) : (ok ? __ldg(Dv + qrow) : 0.f);
-          named_bar_sync(2 + g, 128);                  // everyone is done with the previous block's constants
-          cst[gi] = v;
+        float* cst = cst0 + (cnt & 1) * 128;
+        const uint32_t cst_u = smem_u32(cst);
+        if (DKV) {
+          // double-buffered: the value was fetched one block ahead, so its global latency is off the chain, and one
+          // barrier per block suffices (whoever passes it has finished reading the buffer written two blocks ago)
+          cst[gi] = cst_next;
+          cst_next = load_cst(j + 2);
           named_bar_sync(2 + g, 128);
         }
         mbar_wait(&sc_full[g], cnt & 1);
