@@ -110,3 +110,23 @@ def test_drop_in_api_single_utterance(E, capsys):
 def test_smoke_entry_point():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+@pytest.mark.parametrize("switches", ["SUTA_NO_GEMM2 SUTA_NO_TAIL_SPLIT", "SUTA_NO_POSCONV_TC SUTA_NO_FUSED_DGRAD"])
+def test_alternative_cuda_paths_keep_parity(switches):
+    """The debug switches of INTEGRATION.md select other CUDA kernels for the same operators (one-SM GEMM instead of CTA
+    pairs, generic-GEMM positional conv, col2im conv dgrad): the golden-vector parity must hold on those paths too.
+    The switches are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    env = dict(os.environ)
+    for s in switches.split():
+        env[s] = "1"
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_e2e.py"), "-k",
+                        "golden_vectors and (base_ln_5s_noblank or base_feat_2s or tiny_feat)"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(here), timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
