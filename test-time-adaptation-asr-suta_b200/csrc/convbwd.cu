@@ -3,7 +3,7 @@
 //   cast_params_bf16        refresh the bf16 GEMM-operand copy of per-utterance trainable weights after an update
 //   conv_col2im_gelu_grad   gather the dgrad GEMM result Z[t,(j,ci)] back to input rows r = s*t + j and multiply by
 //                           GELU'(pre-activation of the layer below), which the forward saved  (backward of HF:269-272)
-//   gelu_grad_to_padded     dX * GELU' written into a per-utterance 64-row-aligned slab (zero rows between
+//   gelu_grad_to_padded     dX * GELU' written into a per-utterance 128-row-aligned slab (zero rows between
 //                           utterances) so the weight-gradient GEMM can reduce over time in 64-row steps
 //   conv0_groupnorm_backward  backward of Conv1d(1->C,k,s) + GroupNorm(per channel over time)  (HF:319-323)
 //   colsum_per_utt          bias gradient of the per-utterance projection

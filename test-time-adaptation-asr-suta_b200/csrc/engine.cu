@@ -552,7 +552,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
       CUDA_TRY(up(e->d_off[l], e->off[l].data(), sizeof(long long) * U));
       CUDA_TRY(up(e->d_L[l], e->L[l].data(), sizeof(int) * U));
       if (l >= 1) {
-        // rows of d(pre-activation) of layer l: own 64-aligned layout, except the last layer (token slab off64)
+        // rows of d(pre-activation) of layer l: the layer's own (256-row-aligned) layout, except the last layer (token slab off64)
         std::vector<int4> dg, zt;
         for (int u = 0; u < U; ++u) {
           const long long dro = l == last ? e->off64[u] : e->off[l][u];
@@ -721,7 +721,7 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     if (e->train_feature) {
       p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin};
       p.epi.aux_out = e->conv_pre[l]; p.epi.aux_ld = Cout;
-      if (l < c.n_conv - 1) {    // 128-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
+      if (l < c.n_conv - 1) {    // 256-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
         p.tiles_own_rows = 1;
         p.out_rows = e->rows_total[l] + 128;
         p.mpair = e->d_mpair[l]; p.num_mpair = e->n_mpair[l];
@@ -926,7 +926,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   // feature_projection.layer_norm with input gradient
   PROF("ln_bwd", layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
                               (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, st));
-  // d(pre-activation) of the last conv layer, in the 64-row-aligned token slab
+  // d(pre-activation) of the last conv layer, in the 128-row-aligned token slab
   PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
                                e->d_dpre_off_last, M, C, st));
   e->launches += 4;

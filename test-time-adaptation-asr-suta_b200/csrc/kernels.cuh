@@ -57,7 +57,7 @@ int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0
 // ---- convbwd.cu (train_feature backward of the CNN front end) ---------------------------------
 int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,
                      cudaStream_t stream);
-// out[pad_off[u] + t] = d[row] * pre[row] (pre = GELU' saved by the forward; may be null: plain cast) into a 64-row-aligned, zero-gapped slab
+// out[pad_off[u] + t] = d[row] * pre[row] (pre = GELU' saved by the forward; may be null: plain cast) into a 128-row-aligned, zero-gapped slab
 int gelu_grad_to_padded(const float* d, const bf16* pre, bf16* out, const int* row_utt, const long long* tok_off,
                         const long long* pad_off, long long M, int C, cudaStream_t stream);
 struct Col2imArgs {
