@@ -424,6 +424,8 @@ int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab,
                          cudaStream_t stream) {
   SUTA_CHECK_ARG(H == heads * HD);
   if (n_blk <= 0) return SUTA_OK;
+  static const bool shared_items = getenv("SUTA_ATTN_FWD_V1") != nullptr;    // debug switch: this file's kernel
+  if (!shared_items) return attention_forward_v2(qkv, O, LSE, blk_tab, n_blk, H, heads, M, stream);
   static bool attr = false;
   static int n_sm = 148;
   if (!attr) {

@@ -4,6 +4,11 @@
 
 #include "kernels.cuh"
 
+// attention_fwd2_tc.cu: two independent item pipelines per CTA (the default forward); attention_tc.cu keeps the kernel in
+// which both softmax groups share one item
+int attention_forward_v2(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
+                         cudaStream_t stream);
+
 namespace attn_tc {
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool a_mn, bool b_mn) {
