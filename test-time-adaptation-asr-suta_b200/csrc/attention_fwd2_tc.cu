@@ -179,6 +179,15 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     float sc = scale_log2;
     asm volatile("" : "+f"(sc));                       // keep the scale in a register
     int it = 0;
+#ifdef ATTN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // s_full wait | S load | max | exp | p_empty wait + P store | fence + arrive | o_full wait | epilogue
+    long long tprev = clock64();
+    const long long tstart = tprev;
+    int nblocks = 0;
+#define LAP(k) do { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; } while (0)
+#else
+#define LAP(k) do {} while (0)
+#endif
     for (int w = w0; w < n_items; w += wstep, ++it) {
       const int item = n_items - 1 - w;
       const int4 t = __ldg(&tab[item / heads]);
@@ -191,8 +200,10 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int sb = cnt & 1;
         const uint32_t tS = tmem_g + lane_off + sb * BKV;
         const uint32_t prow = sP + sb * QTILE + r * 128;
+        LAP(7);
         mbar_wait(&s_full[sb], (cnt >> 1) & 1);
         tc_fence_after();
+        LAP(0);
         // One step of the online softmax over the block's 64 keys.  P = exp2(S * scale - m), row sum, bf16 A operand of
         // the second MMA (K-major, 128B swizzle).  Scores of masked keys (another utterance's rows) are exponentiated
         // too and then discarded by a select, never multiplied.
@@ -200,6 +211,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tmem_ld_32x32(tS, sa);
         tmem_ld_32x32(tS + 32, sb2);
         tmem_ld_wait();
+        LAP(1);
         const bool full = nvalid == BKV;               // only an utterance's last block is partial
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (full) {
@@ -235,6 +247,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         const float nm = -m_run;
+        LAP(2);
         float lsum;
         uint32_t pk[32];
         if (full) {
@@ -269,18 +282,26 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         }
+        asm volatile("" : "+f"(lsum));
+        LAP(3);
         mbar_wait(&p_empty[sb], ((cnt >> 1) & 1) ^ 1);   // the P V that read this buffer two blocks ago has retired
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_v4(prow + ((i ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         l_run += lsum;
+        LAP(4);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&p_full[sb]);
+        LAP(5);
+#ifdef ATTN_TIMING
+        ++nblocks;
+#endif
       }
       // ---- end of item: normalise this group's accumulator and store (nothing to merge, nobody else to wait for) ----
       mbar_wait(o_full, it & 1);
       tc_fence_after();
+      LAP(6);
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(tO, o0);
       tmem_ld_32x32(tO + 32, o1);
@@ -305,6 +326,12 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         LSE[(long long)head * M + row] = m_run + log2f(l_run);
       }
     }
+#ifdef ATTN_TIMING
+    LAP(7);
+    if ((threadIdx.x == 64 || threadIdx.x == 192) && (blockIdx.x == 3 || blockIdx.x == 100))
+      printf("attn fwd2 cta %d thread %d: items %d blocks %d total %lld | s_wait %lld ld %lld max %lld exp %lld pstore %lld fence %lld o_wait %lld epi %lld\n",
+             blockIdx.x, threadIdx.x, it, nblocks, clock64() - tstart, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
   }
 
   tc_fence_before();
