@@ -188,9 +188,11 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #else
 #define LAP(k) do {} while (0)
 #endif
+    int4 t_next = w0 < n_items ? __ldg(&tab[(n_items - 1 - w0) / heads]) : make_int4(0, 0, 0, 0);
     for (int w = w0; w < n_items; w += wstep, ++it) {
       const int item = n_items - 1 - w;
-      const int4 t = __ldg(&tab[item / heads]);
+      const int4 t = t_next;                           // fetched one item ahead: a dependent global load per item start is
+      if (w + wstep < n_items) t_next = __ldg(&tab[(n_items - 1 - w - wstep) / heads]);   // ~700 exposed cycles otherwise
       const int head = item - (item / heads) * heads;
       const int urow0 = t.x, T = t.y, m0 = t.z;
       const int nkv = (T + BKV - 1) / BKV;
