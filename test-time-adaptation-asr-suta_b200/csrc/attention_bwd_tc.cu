@@ -220,6 +220,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     asm volatile("" : "+f"(sc));
     uint32_t cnt = 0;                                  // blocks this group has processed (sc_full / a_empty phase)
     int it = 0;
+#ifdef ATTN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // constants + barrier | sc_full wait | a_empty wait | elementwise | fence + arrive | acc_full wait | epilogue + set-up
+    long long tprev = clock64();
+    const long long tstart = tprev;
+    int nblocks = 0;
+#define LAP(k) do { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; } while (0)
+#else
+#define LAP(k) do {} while (0)
+#endif
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int item = n_items - 1 - w;
       const int4 t = __ldg(&tab[item / heads]);
@@ -247,6 +256,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         const int nvalid = min(BY, T - j * BY);
         float* cst = cst0 + (cnt & 1) * 128;
         const uint32_t cst_u = smem_u32(cst);
+        LAP(6);
         if (DKV) {
           // double-buffered: the value was fetched one block ahead, so its global latency is off the chain, and one
           // barrier per block suffices (whoever passes it has finished reading the buffer written two blocks ago)
@@ -254,9 +264,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           cst_next = load_cst(j + 2);
           named_bar_sync(2 + g, 128);
         }
+        LAP(0);
         mbar_wait(&sc_full[g], cnt & 1);
         tc_fence_after();
+        LAP(1);
         mbar_wait(&a_empty[g], (cnt & 1) ^ 1);          // the MMAs that read this group's previous operands have retired
+        LAP(2);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                  // two halves of 32 streamed rows (columns of the score tiles)
           uint32_t s1[32], s2[32];
@@ -290,13 +303,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
             if (DKV) st_shared_v4(a_p + (((4 * h + i) ^ (r & 7)) << 4), pp[4 * i], pp[4 * i + 1], pp[4 * i + 2], pp[4 * i + 3]);
           }
         }
+        LAP(3);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&a_full[g]);
+        LAP(4);
+#ifdef ATTN_TIMING
+        ++nblocks;
+#endif
       }
       // ---- end of item: accumulators -> bf16 -> dqkv ----
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
+      LAP(5);
       uint32_t o[32], o2[32];
       if (DKV) {                                       // group 0 stores dV, group 1 stores dK (* scale)
         tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64, o);
@@ -333,6 +352,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         }
       }
     }
+#ifdef ATTN_TIMING
+    LAP(6);
+    if ((threadIdx.x == 64 || threadIdx.x == 192) && blockIdx.x == 3)
+      printf("attn bwd dkv=%d cta %d thread %d: items %d blocks %d total %lld | cst %lld sc_wait %lld a_wait %lld elementwise %lld fence %lld acc_wait %lld epi %lld\n",
+             (int)DKV, blockIdx.x, threadIdx.x, it, nblocks, clock64() - tstart, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6]);
+#endif
   }
 
   tc_fence_before();

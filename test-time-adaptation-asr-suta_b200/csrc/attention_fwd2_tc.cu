@@ -40,7 +40,8 @@ constexpr int F_SMEM = F_BAR + 512;
 constexpr int NBAR = 2 + 2 + NSG + NSG + 2 + 2 + 2 + 1 + 1;   // barriers per group
 
 __global__ void __launch_bounds__(THREADS, 1)
-attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ O,
+attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    const __grid_constant__ CUtensorMap tm_o, bf16* __restrict__ O,
                     float* __restrict__ LSE, const int4* __restrict__ tab, int n_blk, int heads, int H, long long M,
                     float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -66,6 +67,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (smem_u32(smem) & 1023u) __trap();      // the swizzled tiles need a 1024-byte aligned base
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_o);
     for (int gg = 0; gg < 2; ++gg) {
       uint64_t* b = reinterpret_cast<uint64_t*>(smem + F_BAR) + gg * NBAR;
       for (int i = 0; i < 4; ++i) mbar_init(&b[i], 1);                        // q_full, q_empty
@@ -287,6 +289,10 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         asm volatile("" : "+f"(lsum));
         LAP(3);
         mbar_wait(&p_empty[sb], ((cnt >> 1) & 1) ^ 1);   // the P V that read this buffer two blocks ago has retired
+        if (j < 2) {                                   // ... and so has the previous item's output store staged in it
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_v4(prow + ((i ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -310,24 +316,42 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(o_empty);
-      if (m0 + r < T) {
-        const long long row = (long long)urow0 + m0 + r;
-        const float inv = 1.0f / l_run;
+      const bool row_ok = m0 + r < T;
+      const long long row = (long long)urow0 + m0 + r;
+      const float inv = 1.0f / l_run;
+      uint4 ov[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv));
+        ov[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv));
+      }
+      // A thread's 128 output bytes lie 2 H bytes from its neighbour's: 8 scattered 16-byte stores per thread cost ~2 k
+      // cycles per item.  When the warp's 32 rows all exist they go through the warp's own 32 rows of the P buffer that is
+      // written LAST (free: every P V of the item has retired) and out with one TMA store.
+      if (m0 + q * 32 + 32 <= T) {
+        const uint32_t stage = sP + ((cnt & 1) ^ 1) * QTILE + r * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_shared_v4(stage + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_o, sP + ((cnt & 1) ^ 1) * QTILE + q * 32 * 128, head * HD, (int)(urow0 + m0 + q * 32));
+          bulk_commit();
+        }
+      } else if (row_ok) {
         uint4* op = reinterpret_cast<uint4*>(O + row * H + head * HD);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          op[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv),
-                             pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv),
-                             pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv),
-                             pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv));
-          op[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv));
-        }
-        LSE[(long long)head * M + row] = m_run + log2f(l_run);
+        for (int i = 0; i < 8; ++i) op[i] = ov[i];
       }
+      if (row_ok) LSE[(long long)head * M + row] = m_run + log2f(l_run);
     }
+    if (lane == 0) bulk_wait<0>();                     // shared memory must outlive the last store's reads
 #ifdef ATTN_TIMING
     LAP(7);
     if ((threadIdx.x == 64 || threadIdx.x == 192) && (blockIdx.x == 3 || blockIdx.x == 100))
@@ -359,14 +383,15 @@ int attention_forward_v2(const bf16* qkv, bf16* O, float* LSE, const int4* blk_t
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     attr = true;
   }
-  CUtensorMap tmq, tmkv;
+  CUtensorMap tmq, tmkv, tmo;
   SUTA_TRY(make_map(&tmq, qkv, M, 3LL * H, 3LL * H, BQ));
   SUTA_TRY(make_map(&tmkv, qkv, M, 3LL * H, 3LL * H, BKV));
+  SUTA_TRY(make_map(&tmo, O, M, H, H, 32));                  // output: 32-row boxes, one per softmax warp
   const float scale_log2 = 0.125f * 1.4426950408889634f;   // 64^-0.5 * log2(e)
   const long long n_items = (long long)n_blk * heads;
   const long long want = (n_items + 1) / 2;                 // two item streams per CTA
   const int grid = (int)(want < n_sm ? want : n_sm);
-  attn_fwd2_tc_kernel<<<grid, THREADS, F_SMEM, stream>>>(tmq, tmkv, O, LSE, blk_tab, n_blk, heads, H, M, scale_log2);
+  attn_fwd2_tc_kernel<<<grid, THREADS, F_SMEM, stream>>>(tmq, tmkv, tmo, O, LSE, blk_tab, n_blk, heads, H, M, scale_log2);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
