@@ -43,7 +43,7 @@ template <bool DKV>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_constant__ CUtensorMap tm_qkv_y,
                    const __grid_constant__ CUtensorMap tm_do_x, const __grid_constant__ CUtensorMap tm_do_y,
-                   const float* __restrict__ LSE, const float* __restrict__ Dv, bf16* __restrict__ dqkv,
+                   const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ LSE, const float* __restrict__ Dv, bf16* __restrict__ dqkv,
                    const int4* __restrict__ tab, int n_blk, int heads, int H, long long M, float scale, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,6 +67,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     tma_prefetch_desc(&tm_qkv_y);
     tma_prefetch_desc(&tm_do_x);
     tma_prefetch_desc(&tm_do_y);
+    tma_prefetch_desc(&tm_out);
     constexpr int NOUT = DKV ? 2 : 1;          // output issuers: each commits its own arrival
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&sc_full[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NOUT);
@@ -269,6 +270,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         tc_fence_after();
         LAP(1);
         mbar_wait(&a_empty[g], (cnt & 1) ^ 1);          // the MMAs that read this group's previous operands have retired
+        if (j < 2) {                                   // ... and so has the previous item's result store staged in the dS buffer
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
         LAP(2);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                  // two halves of 32 streamed rows (columns of the score tiles)
@@ -326,32 +331,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty);
-      if (row_ok) {
-        if (DKV) {
-          const float f = g ? scale : 1.0f;
-          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + (g ? colK : colV) + head * HD);
+      // Results leave through the warp's own 32 rows of the group's (now idle) dS buffer and one TMA store per warp when
+      // all 32 rows exist; scattered 16-byte stores (rows are 6 H bytes apart) cost ~2 k cycles per item.
+      const bool warp_full = m0 + q * 32 + 32 <= T;
+      const uint32_t stage_w = sA + g * 2 * XTILE + q * 32 * 128;
+      if (DKV) {
+        const float f = g ? scale : 1.0f;              // group 0 stores dV, group 1 stores dK (* scale)
+        uint4 ov[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            op[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * f, __uint_as_float(o[8 * i + 1]) * f),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 2]) * f, __uint_as_float(o[8 * i + 3]) * f),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 4]) * f, __uint_as_float(o[8 * i + 5]) * f),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 6]) * f, __uint_as_float(o[8 * i + 7]) * f));
-            op[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o2[8 * i]) * f, __uint_as_float(o2[8 * i + 1]) * f),
-                                   pack_bf16x2(__uint_as_float(o2[8 * i + 2]) * f, __uint_as_float(o2[8 * i + 3]) * f),
-                                   pack_bf16x2(__uint_as_float(o2[8 * i + 4]) * f, __uint_as_float(o2[8 * i + 5]) * f),
-                                   pack_bf16x2(__uint_as_float(o2[8 * i + 6]) * f, __uint_as_float(o2[8 * i + 7]) * f));
+        for (int i = 0; i < 4; ++i) {
+          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * f, __uint_as_float(o[8 * i + 1]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * f, __uint_as_float(o[8 * i + 3]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * f, __uint_as_float(o[8 * i + 5]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * f, __uint_as_float(o[8 * i + 7]) * f));
+          ov[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o2[8 * i]) * f, __uint_as_float(o2[8 * i + 1]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 2]) * f, __uint_as_float(o2[8 * i + 3]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 4]) * f, __uint_as_float(o2[8 * i + 5]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 6]) * f, __uint_as_float(o2[8 * i + 7]) * f));
+        }
+        const int col = (g ? colK : colV) + head * HD;
+        if (warp_full) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_shared_v4(a_ds + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
+            bulk_commit();
           }
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + colQ + head * HD + g * 32);
+        } else if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            op[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * scale, __uint_as_float(o[8 * i + 1]) * scale),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale),
-                               pack_bf16x2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale));
+          for (int i = 0; i < 8; ++i) op[i] = ov[i];
+        }
+      } else {
+        uint4 ov[4];                                   // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * scale, __uint_as_float(o[8 * i + 1]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale));
+        const int col = colQ + head * HD + g * 32;
+        if (warp_full) {                               // 32 rows x 64 bytes, 64-byte swizzle
+          const uint32_t wrow = stage_w + lane * 64;
+          const int swz = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) st_shared_v4(wrow + ((i ^ swz) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
+            bulk_commit();
+          }
+        } else if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = ov[i];
         }
       }
     }
+    if (lane == 0) bulk_wait<0>();                     // shared memory must outlive the last store's reads
 #ifdef ATTN_TIMING
     LAP(6);
     if ((threadIdx.x == 64 || threadIdx.x == 192) && blockIdx.x == 3)
@@ -411,13 +451,16 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
   SUTA_TRY(make_map(&qy, qkv, M, 3LL * H, 3LL * H, BY));
   SUTA_TRY(make_map(&dx, dO, M, H, H, BX));
   SUTA_TRY(make_map(&dy, dO, M, H, H, BY));
+  CUtensorMap out128, out64;                                 // result stores: 32-row boxes of 64 (dK, dV) / 32 (dQ halves) columns
+  SUTA_TRY(make_map(&out128, dqkv, M, 3LL * H, 3LL * H, 32, 64));
+  SUTA_TRY(make_map(&out64, dqkv, M, 3LL * H, 3LL * H, 32, 32));
   const float scale = 0.125f, scale_log2 = scale * 1.4426950408889634f;
   const long long n = M * heads;
   attn_bwd_prep_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(O, dO, D, H, heads, M);
   const long long n_items = (long long)n_blk * heads;
   const int grid = (int)(n_items < n_sm ? n_items : n_sm);
-  attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
-  attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
+  attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, out128, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
+  attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, out64, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

@@ -56,8 +56,9 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 row-major matrix [rows, cols] with `ld` elements per row; boxes of 64 columns (128 B) x box_rows rows, 128B swizzle
-inline int make_map(CUtensorMap* tm, const bf16* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// bf16 row-major matrix [rows, cols] with `ld` elements per row; boxes of box_cols columns x box_rows rows; box_cols = 64
+// (128 B rows, 128B swizzle) or 32 (64 B rows, 64B swizzle)
+inline int make_map(CUtensorMap* tm, const bf16* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols = 64) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     suta_set_last_error("cuTensorMapEncodeTiled entry point not available");
@@ -65,14 +66,15 @@ inline int make_map(CUtensorMap* tm, const bf16* ptr, long long rows, long long 
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15)) {
     suta_set_last_error("attention operand not TMA-compatible: ptr=%p ld=%lld", (const void*)ptr, ld);
     return SUTA_ERR_ARG;
   }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     suta_set_last_error("cuTensorMapEncodeTiled (attention) failed (%d)", (int)r);
