@@ -54,8 +54,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
   uint64_t* x_empty = bars + 2;          // [2]  MMA: every MMA of that item that reads X has retired
   uint64_t* y_full = bars + 4;           // [NS] TMA: streamed tiles landed
   uint64_t* y_empty = bars + 4 + NS;     // [NS] MMA: output MMAs of that block retired
-  uint64_t* sc_full = bars + 4 + 2 * NS; // [2]  MMA: both score tiles of group g complete
-  uint64_t* a_full = sc_full + 2;        // [2]  group g (128 arrivals): A operands written, score tiles consumed
+  uint64_t* sc_full = bars + 4 + 2 * NS; // [3]  MMA: both score tiles of set (block % 3) complete
+  uint64_t* sc_free = sc_full + 3;       // [3]  consuming group (128 arrivals): the set's scores are in registers
+  uint64_t* a_full = sc_free + 3;        // [2]  group g (128 arrivals): A operands written
   uint64_t* a_empty = a_full + 2;        // [2]  MMA: output MMAs that read group g's A operands retired
   uint64_t* acc_full = a_empty + 2;      //      MMA: accumulators of the item are final
   uint64_t* acc_empty = acc_full + 1;    //      groups (256 arrivals): accumulators read
@@ -70,8 +71,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     tma_prefetch_desc(&tm_out);
     constexpr int NOUT = DKV ? 2 : 1;          // output issuers: each commits its own arrival
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&sc_full[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NOUT);
+      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NOUT);
     }
+    for (int i = 0; i < 3; ++i) { mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], 128); }
     for (int i = 0; i < NS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], NOUT); }
     mbar_init(acc_full, NOUT);
     mbar_init(acc_empty, 256);
@@ -81,7 +83,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // TMEM columns: group g score tiles Sc1 at 128 g, Sc2 at 128 g + 64; accumulators at 256 (dV | dQ) and 320 (dK)
+  // TMEM columns: three sets of score tiles (Sc1 | Sc2, 128 columns) at 0, 128 and 384, used by the streamed blocks in
+  // rotation (block c -> set c % 3) so that the scores of a group's NEXT block are produced while it works on the current
+  // one; accumulators at 256 (dV | dQ) and 320 (dK)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sX = smem_u32(smem + B_X), sY = smem_u32(smem + B_Y), sA = smem_u32(smem + B_A);
   // column offsets of the four operand tiles inside qkv / dO
@@ -132,7 +136,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
       // issuing warp would push the CTA to 13 warps and the register cap to 128: measured slower.)
       constexpr uint32_t idesc_sc = idesc_bf16(128, BY, false, false);     // X Y^T: both K-major
       uint32_t yc = 0;                         // ring position of block 0 of the current item
-      uint32_t sn0 = 0, sn1 = 0;               // score tiles issued for group 0 / 1 so far
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int item = n_items - 1 - w;
@@ -144,20 +147,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         for (int j = 0; j < ny; ++j) {
           const uint32_t c = yc + j;
           const int s = c % NS;
-          const int g = j & 1;
-          const uint32_t n = g ? sn1 : sn0;
-          if (g) ++sn1; else ++sn0;
-          if (n >= 1) mbar_wait(&a_full[g], (n - 1) & 1);      // the group has consumed its previous score tiles
+          const int set = c % 3;
+          const uint32_t use = c / 3;
+          const uint32_t sc_col = set == 2 ? 384u : (uint32_t)set * 128u;
+          if (use >= 1) mbar_wait(&sc_free[set], (use - 1) & 1);   // the block that used this set last is in registers
           mbar_wait(&y_full[s], (c / NS) & 1);
           tc_fence_after();
           const uint64_t y1 = umma_desc_sw128(sY + s * 2 * YTILE), y2 = umma_desc_sw128(sY + s * 2 * YTILE + YTILE);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {                // two independent accumulation chains, interleaved
-              umma_bf16_ss(tmem_base + g * 128, x1 + 2 * k, y1 + 2 * k, idesc_sc, k != 0);
-              umma_bf16_ss(tmem_base + g * 128 + 64, x2 + 2 * k, y2 + 2 * k, idesc_sc, k != 0);
+              umma_bf16_ss(tmem_base + sc_col, x1 + 2 * k, y1 + 2 * k, idesc_sc, k != 0);
+              umma_bf16_ss(tmem_base + sc_col + 64, x2 + 2 * k, y2 + 2 * k, idesc_sc, k != 0);
             }
-            umma_commit(&sc_full[g]);
+            umma_commit(&sc_full[set]);
           }
           __syncwarp();
         }
@@ -214,12 +217,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     const int r = q * 32 + lane;                       // resident row = TMEM lane
     const int gi = (warp - 2 - 4 * g) * 32 + lane;     // thread index inside the group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t t1 = tmem_base + lane_off + g * 128, t2 = t1 + 64;
     const uint32_t a_ds = sA + g * 2 * XTILE + r * 128, a_p = a_ds + XTILE;
     float* cst0 = reinterpret_cast<float*>(smem + B_C + g * 1024);   // 2 x (lse[64] | D[64]) of the streamed blocks (DKV)
     float sc = scale_log2;
     asm volatile("" : "+f"(sc));
-    uint32_t cnt = 0;                                  // blocks this group has processed (sc_full / a_empty phase)
+    uint32_t cnt = 0;                                  // blocks this group has processed (a_full / a_empty phase)
+    uint32_t blk0 = 0;                                 // streamed blocks of this CTA before the current item (score-set rotation)
     int it = 0;
 #ifdef ATTN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // constants + barrier | sc_full wait | a_empty wait | elementwise | fence + arrive | acc_full wait | epilogue + set-up
@@ -266,7 +269,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           named_bar_sync(2 + g, 128);
         }
         LAP(0);
-        mbar_wait(&sc_full[g], cnt & 1);
+        const uint32_t c = blk0 + j;
+        const int set = c % 3;
+        const uint32_t t1 = tmem_base + lane_off + (set == 2 ? 384u : (uint32_t)set * 128u), t2 = t1 + 64;
+        mbar_wait(&sc_full[set], (c / 3) & 1);
         tc_fence_after();
         LAP(1);
         mbar_wait(&a_empty[g], (cnt & 1) ^ 1);          // the MMAs that read this group's previous operands have retired
@@ -281,6 +287,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           tmem_ld_32x32(t1 + 32 * h, s1);
           tmem_ld_32x32(t2 + 32 * h, s2);
           tmem_ld_wait();
+          if (h == 1) {                                // the whole set is in registers: the score issuer may reuse it
+            tc_fence_before();
+            mbar_arrive(&sc_free[set]);
+          }
           uint32_t pds[16], pp[16];                    // packed bf16 pairs: dS (and P for DKV)
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -317,6 +327,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         ++nblocks;
 #endif
       }
+      blk0 += ny;
       // ---- end of item: accumulators -> bf16 -> dqkv ----
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
