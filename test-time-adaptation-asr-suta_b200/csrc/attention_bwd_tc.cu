@@ -57,8 +57,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
   uint64_t* sc_full = bars + 4 + 2 * NS; // [3]  MMA: both score tiles of set (block % 3) complete
   uint64_t* sc_free = sc_full + 3;       // [3]  consuming group (128 arrivals): the set's scores are in registers
   uint64_t* a_full = sc_free + 3;        // [2]  group g (128 arrivals): A operands written
-  uint64_t* a_empty = a_full + 2;        // [2]  MMA: output MMAs that read group g's A operands retired
-  uint64_t* acc_full = a_empty + 2;      //      MMA: accumulators of the item are final
+  uint64_t* a_empty = a_full + 2;        // [g][b] MMA: output MMAs that read group g's A operands (buffer b) retired
+  uint64_t* acc_full = a_empty + 4;      //      MMA: accumulators of the item are final
   uint64_t* acc_empty = acc_full + 1;    //      groups (256 arrivals): accumulators read
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
@@ -71,8 +71,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     tma_prefetch_desc(&tm_out);
     constexpr int NOUT = DKV ? 2 : 1;          // output issuers: each commits its own arrival
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NOUT);
+      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&a_full[i], 128);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_empty[i], NOUT);
     for (int i = 0; i < 3; ++i) { mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], 128); }
     for (int i = 0; i < NS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], NOUT); }
     mbar_init(acc_full, NOUT);
@@ -194,14 +195,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
           tc_fence_after();
           // DKV: dV += P^T dO (A = P, B = Y2) on warp 10, dK += dS^T Q (A = dS, B = Y1) on warp 11;  DQ: dQ += dS K (A = dS, B = Y1)
           const bool use_p = DKV && which == 0;
-          const uint64_t a_desc = umma_desc_sw128(sA + g * 2 * XTILE + (use_p ? XTILE : 0));
+          // DKV: [dS | P] single-buffered; DQ needs no P, so its dS operand is double-buffered in the same space
+          const int ab = DKV ? 0 : (int)(n & 1);
+          const uint64_t a_desc = umma_desc_sw128(sA + g * 2 * XTILE + (DKV ? (use_p ? XTILE : 0) : ab * XTILE));
           const uint64_t y_desc = umma_desc_sw128_mn(sY + s * 2 * YTILE + (use_p ? YTILE : 0));
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < ksteps) umma_bf16_ss(tmem_base + 256 + which * 64, a_desc + 2 * ks, y_desc + 128 * ks, idesc_out, (j > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&y_empty[s]);
-            umma_commit(&a_empty[g]);
+            umma_commit(&a_empty[g * 2 + ab]);
           }
           __syncwarp();
         }
@@ -217,7 +220,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
     const int r = q * 32 + lane;                       // resident row = TMEM lane
     const int gi = (warp - 2 - 4 * g) * 32 + lane;     // thread index inside the group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t a_ds = sA + g * 2 * XTILE + r * 128, a_p = a_ds + XTILE;
+    const uint32_t a_ds0 = sA + g * 2 * XTILE + r * 128, a_p = a_ds0 + XTILE;
     float* cst0 = reinterpret_cast<float*>(smem + B_C + g * 1024);   // 2 x (lse[64] | D[64]) of the streamed blocks (DKV)
     float sc = scale_log2;
     asm volatile("" : "+f"(sc));
@@ -275,8 +278,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         mbar_wait(&sc_full[set], (c / 3) & 1);
         tc_fence_after();
         LAP(1);
-        mbar_wait(&a_empty[g], (cnt & 1) ^ 1);          // the MMAs that read this group's previous operands have retired
-        if (j < 2) {                                   // ... and so has the previous item's result store staged in the dS buffer
+        // the MMAs that read the operand buffer about to be rewritten have retired (DKV: the previous block's; DQ: the
+        // dS buffer alternates, so the block before the previous one's)
+        const int ab = DKV ? 0 : (int)(cnt & 1);
+        const uint32_t a_ds = a_ds0 + ab * XTILE;
+        mbar_wait(&a_empty[g * 2 + ab], (DKV ? (cnt & 1) : ((cnt >> 1) & 1)) ^ 1);
+        if (j < 4) {                                   // ... and so has the previous item's result store staged in dS buffer 0
+                                                       // (the group's first two blocks of an item cover both buffers)
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
         }
@@ -363,7 +371,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         const int col = (g ? colK : colV) + head * HD;
         if (warp_full) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) st_shared_v4(a_ds + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+          for (int i = 0; i < 8; ++i) st_shared_v4(a_ds0 + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
