@@ -428,25 +428,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
 }
 
 // D[h][row] = sum_d dO[row, h, d] * O[row, h, d]
-__global__ void attn_bwd_prep_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int H,
-                                        int heads, long long M) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, head)
-  if (i >= M * heads) return;
-  long long row = i / heads;
-  int h = (int)(i - row * heads);
-  const uint4* o = reinterpret_cast<const uint4*>(O + row * H + h * HD);
-  const uint4* d = reinterpret_cast<const uint4*>(dO + row * H + h * HD);
+// 8 threads per (row, head): one 16-byte piece of O and dO each, 3-step shuffle reduction.  A block covers 32 consecutive
+// rows of one head, so the reads are 128-byte segments and the 32 results are one contiguous 128-byte store (one thread
+// per (row, head) wrote D with a stride of M floats between neighbouring threads).
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D, int H, long long M) {
+  const int h = blockIdx.y, sub = threadIdx.x & 7;
+  const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
   float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint4 a = __ldg(o + k), b = __ldg(d + k);
+  if (row < M) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + row * H + h * HD) + sub);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(dO + row * H + h * HD) + sub);
     float2 x, y;
     x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); acc += x.x * y.x + x.y * y.y;
     x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); acc += x.x * y.x + x.y * y.y;
     x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); acc += x.x * y.x + x.y * y.y;
     x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); acc += x.x * y.x + x.y * y.y;
   }
-  D[(long long)h * M + row] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0 && row < M) D[(long long)h * M + row] = acc;
 }
 
 }  // namespace
@@ -474,8 +476,7 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
   SUTA_TRY(make_map(&out128, dqkv, M, 3LL * H, 3LL * H, 32, 64));
   SUTA_TRY(make_map(&out64, dqkv, M, 3LL * H, 3LL * H, 32, 32));
   const float scale = 0.125f, scale_log2 = scale * 1.4426950408889634f;
-  const long long n = M * heads;
-  attn_bwd_prep_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(O, dO, D, H, heads, M);
+  attn_bwd_prep_tc_kernel<<<dim3((unsigned)((M + 31) / 32), (unsigned)heads), 256, 0, stream>>>(O, dO, D, H, M);
   const long long n_items = (long long)n_blk * heads;
   const int grid = (int)(n_items < n_sm ? n_items : n_sm);
   attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, B_SMEM, stream>>>(qx, qy, dx, dy, out128, LSE, D, dqkv, blk_tab, n_blk, heads, H, M, scale, scale_log2);
