@@ -44,6 +44,7 @@ struct GemmKernelParams {
   long long* trace;     // debug: per-tile clock64 timeline of CTA 0 (8 slots per tile iteration), or null
   int trace_cap;        // tile iterations that fit
   int b_kwrap, b_tap_col0, b_tap_col1;   // tap-split MN-major B (GemmProblem::b_kwrap)
+  int aux_tma;          // TMA epilogue, act == 2, bf16 output: the saved GELU' tile of a chunk arrives by TMA in the patch's idle half
   GemmEpilogue epi;
 };
 
@@ -71,7 +72,7 @@ struct GemmCfg {
   static constexpr int WARP_EPI_BYTES = (EPI_TMA && !LEAN) ? 2 * PATCH_BYTES : PATCH_BYTES;
   static constexpr int BIAS_BYTES = (EPI_TMA && !LEAN) ? 8 * 512 : 0;
   static constexpr int EPI_BYTES = 8 * WARP_EPI_BYTES + BIAS_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 384;   // up to 8 stages x 2 + 4 accumulator barriers + 16 aux-tile barriers + TMEM slot
   static constexpr int SMEM_BUDGET = SMEM_MAX - EPI_BYTES - BAR_BYTES - 1024 /*align slack*/;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
@@ -119,7 +120,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
   uint64_t* acc_full = bars + 2 * C::STAGES;       // [2]
   uint64_t* acc_empty = bars + 2 * C::STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* aux_bar = bars + 2 * C::STAGES + 4;    // [8 epilogue warps][2]: the chunk's saved GELU' tile has landed (act == 2, TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,7 +131,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_b);
     if (EPI_TMA) {
       tma_prefetch_desc(&tma_out);
-      if (p.epi.aux_out) tma_prefetch_desc(&tma_aux);
+      if (p.epi.aux_out || p.aux_tma) tma_prefetch_desc(&tma_aux);
     }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -139,6 +141,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 4 * C::EPI_SPLIT);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&aux_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -273,8 +276,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           __syncwarp();
         }
-        uint4 auxr[NCH][4];                        // act == 2: this thread's row of saved GELU' (32 bf16 per chunk)
-        if (p.epi.act == 2) {
+        // act == 2 (multiply by the saved GELU').  bf16 output without a LEAN bias: the 32 x 32 tile of a chunk comes by TMA
+        // into the idle second half of the chunk's patch (row-per-thread global loads, 16 x 16 B per thread at a multi-KB
+        // row pitch, kept the LSU busy for thousands of cycles per tile); otherwise: register prefetch.
+        uint64_t* my_aux = aux_bar + (warp - 2) * 2;
+        uint8_t* my_patch = epi_smem + (warp - 2) * C::WARP_EPI_BYTES;
+        auto aux_issue = [&](uint32_t chunk_no, int kc) {      // lane 0: fetch chunk kc's tile for running chunk number chunk_no
+          const int slot = LEAN ? 0 : (int)(chunk_no & 1);
+          mbar_expect_tx(&my_aux[slot], 2048);
+          tma_load_2d(my_patch + slot * C::PATCH_BYTES + 2048, &tma_aux, &my_aux[slot], col0 + kc * 32, row0);
+        };
+        if (p.aux_tma && lane == 0) aux_issue(pc, 0);
+        uint4 auxr[NCH][4];                        // act == 2 fallback: this thread's row of saved GELU' (32 bf16 per chunk)
+        if (p.epi.act == 2 && !p.aux_tma) {
           const bool ok = row0 + lane < p.out_rows;
           const uint4* ap = reinterpret_cast<const uint4*>(p.epi.aux_in + (long long)(row0 + (ok ? lane : 0)) * p.epi.aux_ld + col0);
 #pragma unroll
@@ -311,7 +325,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(raw[i]);
 
-          if (p.epi.act == 2) {
+          if (p.aux_tma) {
+            const int slot = LEAN ? 0 : (int)(pc & 1);
+            if (!LEAN) {                           // two patches: the next chunk's tile goes into the other one
+              __syncwarp();
+              if (lane == 0 && kc + 1 < NCH) aux_issue(pc + 1, kc + 1);
+            }
+            mbar_wait(&my_aux[slot], LEAN ? (pc & 1) : ((pc >> 1) & 1));
+            const uint32_t arow = patch + slot * C::PATCH_BYTES + 2048 + lane * 64;
+            const int aswz = (lane >> 1) & 3;
+            float4 uf[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uf[j] = ld_shared_v4(arow + ((j ^ aswz) << 4));
+            if (LEAN) {                            // one patch: refill it as soon as everyone holds this chunk's tile
+              __syncwarp();
+              if (lane == 0 && kc + 1 < NCH) aux_issue(pc + 1, kc + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = make_uint4(__float_as_uint(uf[j].x), __float_as_uint(uf[j].y), __float_as_uint(uf[j].z), __float_as_uint(uf[j].w));
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * j] *= f0.x; v[8 * j + 1] *= f0.y; v[8 * j + 2] *= f1.x; v[8 * j + 3] *= f1.y;
+              v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
+            }
+          } else if (p.epi.act == 2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = auxr[kc][j];
@@ -536,6 +573,9 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     else
       SUTA_TRY(encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.out_bf16, p.N, orows, (long long)p.epi.out_ld * 2, 32, 32,
                            CU_TENSOR_MAP_SWIZZLE_64B));
+    if (p.epi.act == 2 && p.epi.out_bf16 && !(LEAN && p.epi.bias) && p.epi.aux_ld % 8 == 0)
+      SUTA_TRY(encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.aux_in, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B));
     if (p.epi.act == 1 && p.epi.aux_out)
       SUTA_TRY(encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.epi.aux_out, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32,
                            CU_TENSOR_MAP_SWIZZLE_64B));
@@ -551,6 +591,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   kp.ztab = p.ztab;
   kp.out_z_stride = p.out_z_stride;
   kp.b_kwrap = p.b_kwrap; kp.b_tap_col0 = p.b_tap_col[0]; kp.b_tap_col1 = p.b_tap_col[1];
+  kp.aux_tma = (EPI_TMA && p.epi.act == 2 && p.epi.out_bf16 && !(LEAN && p.epi.bias) && p.epi.aux_ld % 8 == 0) ? 1 : 0;
   kp.trace = g_trace;
   kp.trace_cap = g_trace_cap;
   kp.epi = p.epi;

@@ -35,6 +35,7 @@ struct Params2 {
   int M, N, K;
   int num_mpair, num_nblk;
   int out_rows;
+  int aux_tma;          // act == 2 with a bf16 output: the saved GELU' tile of a chunk arrives by TMA in the patch's idle half
   int tail_tiles, tail_split;   // reduce-add epilogue only: the last (partial) wave's tiles are split tail_split ways along K
   const int4* mpair;    // optional per-pair-tile table {a_row0, out_row0, rows_valid, b_row_off}
   long long* trace;     // debug: clock64 timeline of the leader CTA of pair 0 (same 8 slots per tile as gemm_tc.cu)
@@ -161,7 +162,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   uint64_t* empty_bar = bars + C::STAGES;          // [STAGES] per CTA, released by the multicast commit
   uint64_t* acc_full = bars + 2 * C::STAGES;       // [2] per CTA (multicast commit)
   uint64_t* acc_empty = bars + 2 * C::STAGES + 2;  // [2] used in the leader CTA (16 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* aux_bar = bars + 2 * C::STAGES + 4;    // [8 epilogue warps][2] per CTA: the chunk's saved GELU' tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -171,7 +173,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
-    if (AUX) tma_prefetch_desc(&tma_aux);
+    if (AUX || p.aux_tma) tma_prefetch_desc(&tma_aux);
+    for (int i = 0; i < 16; ++i) mbar_init(&aux_bar[i], 1);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -277,8 +280,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const int col0 = n_blk * BN + half * C::COLS_PER_WARP;
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 of the half's 128 bias values (bf16 outputs only)
       if (p.epi.bias) breg = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + lane * 4));
+      // act == 2 (multiply by the saved GELU').  bf16 output: the 32 x 32 tile of a chunk is fetched by TMA into the idle
+      // half of the chunk's patch, one chunk ahead (row-per-thread global loads -- 16 x 16 B per thread at a 6 KB row
+      // pitch -- kept the LSU busy for ~4 k cycles per tile); fp32 output (patch fully used): register prefetch as before.
+      uint64_t* my_aux = aux_bar + (warp - 2) * 2;
+      uint8_t* my_patch = epi_smem + (warp - 2) * C::WARP_EPI_BYTES;
+      if (p.aux_tma) {
+        if (lane == 0) {
+          mbar_expect_tx(&my_aux[pc & 1], 2048);
+          tma_load_2d(my_patch + (pc & 1) * C::PATCH_BYTES + 2048, &tma_aux, &my_aux[pc & 1], col0, row0);
+        }
+      }
       uint4 auxr[C::NCH][4];
-      if (p.epi.act == 2) {
+      if (p.epi.act == 2 && !p.aux_tma) {
         const bool ok = row0 + lane < p.out_rows;
         const uint4* ap = reinterpret_cast<const uint4*>(p.epi.aux_in + (long long)(row0 + (ok ? lane : 0)) * p.epi.aux_ld + col0);
 #pragma unroll
@@ -320,7 +334,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(raw[i]);
-        if (p.epi.act == 2) {
+        if (p.aux_tma) {
+          __syncwarp();                            // everyone has read the other patch's tile (the previous chunk's)
+          if (lane == 0 && kc + 1 < C::NCH) {
+            mbar_expect_tx(&my_aux[(pc + 1) & 1], 2048);
+            tma_load_2d(my_patch + ((pc + 1) & 1) * C::PATCH_BYTES + 2048, &tma_aux, &my_aux[(pc + 1) & 1], col0 + (kc + 1) * 32, row0);
+          }
+          mbar_wait(&my_aux[pc & 1], (pc >> 1) & 1);
+          const uint32_t arow = patch + (pc & 1) * C::PATCH_BYTES + 2048 + lane * 64;
+          const int aswz = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 uf = ld_shared_v4(arow + ((j ^ aswz) << 4));
+            const uint4 u = make_uint4(__float_as_uint(uf.x), __float_as_uint(uf.y), __float_as_uint(uf.z), __float_as_uint(uf.w));
+            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+            v[8 * j] *= f0.x; v[8 * j + 1] *= f0.y; v[8 * j + 2] *= f1.x; v[8 * j + 3] *= f1.y;
+            v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
+          }
+        } else if (p.epi.act == 2) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 u = auxr[kc][j];
@@ -403,10 +434,13 @@ int launch2(const GemmProblem& p, cudaStream_t stream) {
   else
     SUTA_TRY(gemm_encode_tmap(&to, 1, p.epi.out_bf16, p.N, orows, (long long)p.epi.out_ld * 2, 32, 32, 64));
   if (AUX) SUTA_TRY(gemm_encode_tmap(&tx, 1, p.epi.aux_out, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32, 64));
+  const bool aux_tma = !AUX && p.epi.act == 2 && p.epi.out_bf16 && p.epi.aux_ld % 8 == 0;
+  if (aux_tma) SUTA_TRY(gemm_encode_tmap(&tx, 1, p.epi.aux_in, p.N, orows, (long long)p.epi.aux_ld * 2, 32, 32, 64));
   Params2 kp;
   kp.M = p.M; kp.N = p.N; kp.K = p.K;
   kp.num_mpair = p.mpair ? p.num_mpair : ceil_div(ceil_div(p.M, BM), 2);
   kp.mpair = p.mpair;
+  kp.aux_tma = aux_tma ? 1 : 0;
   kp.num_nblk = p.N / BN;
   kp.out_rows = (int)orows;
   kp.trace = gemm_trace_buffer(&kp.trace_cap);
