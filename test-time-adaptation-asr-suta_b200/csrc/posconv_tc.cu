@@ -141,15 +141,18 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
         tc_fence_after();
         const uint64_t b_base = umma_desc_plain(smem_u32(wst + ws * C::WSTAGE_BYTES), CG * 16, 128);
         if (elect_one()) {
-#pragma unroll 1
+          // fully unrolled: every descriptor is (per-stage base) + (compile-time constant); a 128 x 48 x 16 MMA takes
+          // ~24 cycles, so the issue loop itself must stay at a handful of uniform-datapath instructions per MMA
+          const uint64_t a_stage = a_base + (uint64_t)(s * C::TPS);
+          const uint32_t acc0 = s != 0 ? 1u : 0u;
+#pragma unroll
           for (int t = 0; t < C::TPS; ++t) {
-            const int tap = s * C::TPS + t;
 #pragma unroll
             for (int kk = 0; kk < CG / 16; ++kk) {
               // descriptor start addresses are in 16-byte units: one row = 1, 128 rows = 128, two octet planes
-              const uint64_t da = a_base + (uint64_t)(tap + kk * 2 * (C::PLANE_BYTES >> 4));
+              const uint64_t da = a_stage + (uint64_t)(t + kk * 2 * (C::PLANE_BYTES >> 4));
               const uint64_t db = b_base + (uint64_t)((t * C::TAP_BYTES + kk * 2 * CG * 16) >> 4);
-              const uint32_t acc = (tap | kk) != 0 ? 1u : 0u;
+              const uint32_t acc = (t | kk) != 0 ? 1u : acc0;
               umma_bf16_ss(d0, da, db, idesc, acc);
               umma_bf16_ss(d0 + 64, da + 128, db, idesc, acc);
             }
