@@ -36,7 +36,8 @@ constexpr int B_X = 0;                       // [2 item buffers][X1 | X2]
 constexpr int B_Y = B_X + 4 * XTILE;         // [NS][Y1 | Y2]
 constexpr int B_A = B_Y + NS * 2 * YTILE;    // [2 groups][dS | P] bf16 [128 rows][64], K-major, 128B swizzle
 constexpr int B_C = B_A + 4 * XTILE;         // [2 groups][2 buffers][lse[64] | D[64]] fp32 (DKV only)
-constexpr int B_BAR = B_C + 4 * 512;
+constexpr int B_S = B_C + 4 * 512;           // [2 groups] result staging [128 rows][128 B] for the TMA stores
+constexpr int B_BAR = B_S + 2 * XTILE;
 constexpr int B_SMEM = B_BAR + 256;
 
 template <bool DKV>
@@ -88,7 +89,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
   // rotation (block c -> set c % 3) so that the scores of a group's NEXT block are produced while it works on the current
   // one; accumulators at 256 (dV | dQ) and 320 (dK)
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t sX = smem_u32(smem + B_X), sY = smem_u32(smem + B_Y), sA = smem_u32(smem + B_A);
+  const uint32_t sX = smem_u32(smem + B_X), sY = smem_u32(smem + B_Y), sA = smem_u32(smem + B_A), sS = smem_u32(smem + B_S);
   // column offsets of the four operand tiles inside qkv / dO
   const int colQ = 0, colK = H, colV = 2 * H;
 
@@ -236,6 +237,90 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
 #else
 #define LAP(k) do {} while (0)
 #endif
+    // ---- accumulators -> bf16 -> dqkv for a finished item.  DEFERRED: an item is drained after the group's first block of
+    // the NEXT item, when the last output MMAs have long retired (waiting for them right away cost ~1.2 k cycles per item);
+    // the next item's output MMAs wait for acc_empty meanwhile.  Results go through a staging tile of their own. ----
+    struct Pending { int valid, it, head, urow0, m0, T; };
+    Pending pend = {0, 0, 0, 0, 0, 0};
+    auto drain = [&](const Pending& pd) {
+      mbar_wait(acc_full, pd.it & 1);
+      tc_fence_after();
+      LAP(5);
+      uint32_t o[32], o2[32];
+      if (DKV) {                                       // group 0 stores dV, group 1 stores dK (* scale)
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64, o);
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64 + 32, o2);
+      } else {                                         // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
+        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 32, o);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      // Results leave through the warp's own 32 rows of the group's staging tile and one TMA store per warp when all 32
+      // rows exist; scattered 16-byte stores (rows are 6 H bytes apart) cost ~2 k cycles per item.
+      const bool warp_full = pd.m0 + q * 32 + 32 <= pd.T;
+      const bool row_ok = pd.m0 + r < pd.T;
+      const long long row = (long long)pd.urow0 + pd.m0 + r;
+      const int head = pd.head, urow0 = pd.urow0, m0 = pd.m0;
+      const uint32_t stage_w = sS + g * XTILE + q * 32 * 128, stage_r = sS + g * XTILE + r * 128;
+      if (lane == 0) bulk_wait_read<0>();               // the previous item's store has finished reading the staging rows
+      __syncwarp();
+      if (DKV) {
+        const float f = g ? scale : 1.0f;              // group 0 stores dV, group 1 stores dK (* scale)
+        uint4 ov[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * f, __uint_as_float(o[8 * i + 1]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * f, __uint_as_float(o[8 * i + 3]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * f, __uint_as_float(o[8 * i + 5]) * f),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * f, __uint_as_float(o[8 * i + 7]) * f));
+          ov[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o2[8 * i]) * f, __uint_as_float(o2[8 * i + 1]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 2]) * f, __uint_as_float(o2[8 * i + 3]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 4]) * f, __uint_as_float(o2[8 * i + 5]) * f),
+                                 pack_bf16x2(__uint_as_float(o2[8 * i + 6]) * f, __uint_as_float(o2[8 * i + 7]) * f));
+        }
+        const int col = (g ? colK : colV) + head * HD;
+        if (warp_full) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_shared_v4(stage_r + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
+            bulk_commit();
+          }
+        } else if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) op[i] = ov[i];
+        }
+      } else {
+        uint4 ov[4];                                   // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * scale, __uint_as_float(o[8 * i + 1]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale),
+                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale));
+        const int col = colQ + head * HD + g * 32;
+        if (warp_full) {                               // 32 rows x 64 bytes, 64-byte swizzle
+          const uint32_t wrow = stage_w + lane * 64;
+          const int swz = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) st_shared_v4(wrow + ((i ^ swz) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
+            bulk_commit();
+          }
+        } else if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = ov[i];
+        }
+      }
+    };
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int item = n_items - 1 - w;
       const int4 t = __ldg(&tab[item / heads]);
@@ -259,6 +344,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
       };
       float cst_next = 0.f;
       if (DKV) cst_next = load_cst(g);
+      bool drained = false;
       for (int j = g; j < ny; j += 2, ++cnt) {
         const int nvalid = min(BY, T - j * BY);
         float* cst = cst0 + (cnt & 1) * 128;
@@ -283,11 +369,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         const int ab = DKV ? 0 : (int)(cnt & 1);
         const uint32_t a_ds = a_ds0 + ab * XTILE;
         mbar_wait(&a_empty[g * 2 + ab], (DKV ? (cnt & 1) : ((cnt >> 1) & 1)) ^ 1);
-        if (j < 4) {                                   // ... and so has the previous item's result store staged in dS buffer 0
-                                                       // (the group's first two blocks of an item cover both buffers)
-          if (lane == 0) bulk_wait_read<0>();
-          __syncwarp();
-        }
         LAP(2);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                  // two halves of 32 streamed rows (columns of the score tiles)
@@ -330,86 +411,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_x, const __grid_co
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&a_full[g]);
+        if (!drained) {                                // first block of the item done: now drain the previous item
+          if (pend.valid) drain(pend);
+          drained = true;
+        }
         LAP(4);
 #ifdef ATTN_TIMING
         ++nblocks;
 #endif
       }
       blk0 += ny;
-      // ---- end of item: accumulators -> bf16 -> dqkv ----
-      mbar_wait(acc_full, it & 1);
-      tc_fence_after();
-      LAP(5);
-      uint32_t o[32], o2[32];
-      if (DKV) {                                       // group 0 stores dV, group 1 stores dK (* scale)
-        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64, o);
-        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64 + 32, o2);
-      } else {                                         // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
-        tmem_ld_32x32(tmem_base + lane_off + 256 + g * 32, o);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(acc_empty);
-      // Results leave through the warp's own 32 rows of the group's (now idle) dS buffer and one TMA store per warp when
-      // all 32 rows exist; scattered 16-byte stores (rows are 6 H bytes apart) cost ~2 k cycles per item.
-      const bool warp_full = m0 + q * 32 + 32 <= T;
-      const uint32_t stage_w = sA + g * 2 * XTILE + q * 32 * 128;
-      if (DKV) {
-        const float f = g ? scale : 1.0f;              // group 0 stores dV, group 1 stores dK (* scale)
-        uint4 ov[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * f, __uint_as_float(o[8 * i + 1]) * f),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * f, __uint_as_float(o[8 * i + 3]) * f),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * f, __uint_as_float(o[8 * i + 5]) * f),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * f, __uint_as_float(o[8 * i + 7]) * f));
-          ov[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o2[8 * i]) * f, __uint_as_float(o2[8 * i + 1]) * f),
-                                 pack_bf16x2(__uint_as_float(o2[8 * i + 2]) * f, __uint_as_float(o2[8 * i + 3]) * f),
-                                 pack_bf16x2(__uint_as_float(o2[8 * i + 4]) * f, __uint_as_float(o2[8 * i + 5]) * f),
-                                 pack_bf16x2(__uint_as_float(o2[8 * i + 6]) * f, __uint_as_float(o2[8 * i + 7]) * f));
-        }
-        const int col = (g ? colK : colV) + head * HD;
-        if (warp_full) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) st_shared_v4(a_ds0 + ((i ^ (r & 7)) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
-            bulk_commit();
-          }
-        } else if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) op[i] = ov[i];
-        }
-      } else {
-        uint4 ov[4];                                   // group g stores columns [32 g, 32 g + 32) of dQ (* scale)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          ov[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * scale, __uint_as_float(o[8 * i + 1]) * scale),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 2]) * scale, __uint_as_float(o[8 * i + 3]) * scale),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * scale, __uint_as_float(o[8 * i + 5]) * scale),
-                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * scale, __uint_as_float(o[8 * i + 7]) * scale));
-        const int col = colQ + head * HD + g * 32;
-        if (warp_full) {                               // 32 rows x 64 bytes, 64-byte swizzle
-          const uint32_t wrow = stage_w + lane * 64;
-          const int swz = (lane >> 1) & 3;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) st_shared_v4(wrow + ((i ^ swz) << 4), ov[i].x, ov[i].y, ov[i].z, ov[i].w);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tm_out, stage_w, col, (int)(urow0 + m0 + q * 32));
-            bulk_commit();
-          }
-        } else if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(dqkv + row * (3LL * H) + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = ov[i];
-        }
-      }
+      if (!drained && pend.valid) drain(pend);         // this group had no block in the item
+      pend = Pending{1, it, head, urow0, m0, T};
     }
+    if (pend.valid) drain(pend);
     if (lane == 0) bulk_wait<0>();                     // shared memory must outlive the last store's reads
 #ifdef ATTN_TIMING
     LAP(6);
