@@ -285,14 +285,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       // pitch -- kept the LSU busy for ~4 k cycles per tile); fp32 output (patch fully used): register prefetch as before.
       uint64_t* my_aux = aux_bar + (warp - 2) * 2;
       uint8_t* my_patch = epi_smem + (warp - 2) * C::WARP_EPI_BYTES;
-      if (p.aux_tma) {
+      const bool aux_tma = !AUX && p.aux_tma;        // compile-time off in the GELU'-writing variant (it spilled otherwise)
+      if (aux_tma) {
         if (lane == 0) {
           mbar_expect_tx(&my_aux[pc & 1], 2048);
           tma_load_2d(my_patch + (pc & 1) * C::PATCH_BYTES + 2048, &tma_aux, &my_aux[pc & 1], col0, row0);
         }
       }
       uint4 auxr[C::NCH][4];
-      if (p.epi.act == 2 && !p.aux_tma) {
+      if (!AUX && p.epi.act == 2 && !aux_tma) {
         const bool ok = row0 + lane < p.out_rows;
         const uint4* ap = reinterpret_cast<const uint4*>(p.epi.aux_in + (long long)(row0 + (ok ? lane : 0)) * p.epi.aux_ld + col0);
 #pragma unroll
@@ -334,7 +335,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(raw[i]);
-        if (p.aux_tma) {
+        if (aux_tma) {
           __syncwarp();                            // everyone has read the other patch's tile (the previous chunk's)
           if (lane == 0 && kc + 1 < C::NCH) {
             mbar_expect_tx(&my_aux[(pc + 1) & 1], 2048);
@@ -351,7 +352,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             v[8 * j] *= f0.x; v[8 * j + 1] *= f0.y; v[8 * j + 2] *= f1.x; v[8 * j + 3] *= f1.y;
             v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
           }
-        } else if (p.epi.act == 2) {
+        } else if (!AUX && p.epi.act == 2) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 u = auxr[kc][j];
