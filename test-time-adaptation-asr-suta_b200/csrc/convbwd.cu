@@ -127,12 +127,14 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
   const int k = a.k;
   for (int cp = threadIdx.x; 2 * cp < a.C; cp += blockDim.x) {
     const int c = 2 * cp;
-    float s1a = 0.f, s1b = 0.f, Aa[C0B_MAXK], Ab[C0B_MAXK];
+    // the two channels of the pair ride in packed fp32 registers (FFMA2 with the window sample as the broadcast operand):
+    // the kernel is bound by FMA-pipe instructions, not by memory
+    uint64_t s1 = 0ull, A2[C0B_MAXK];
 #pragma unroll
-    for (int j = 0; j < C0B_MAXK; ++j) Aa[j] = Ab[j] = 0.f;
+    for (int j = 0; j < C0B_MAXK; ++j) A2[j] = 0ull;
     const bf16* dyp = a.dy + row0 * a.C + c;
     int t = 0;
-    const bool vec_ok = a.stride == 5 && k <= 10;    // the wav2vec2 front end: 4 frames = 20 samples = five 16-byte words
+    const bool vec_ok = a.stride == 5 && k == 10;    // the wav2vec2 front end: 4 frames = 20 samples = five 16-byte words
     for (; vec_ok && t + 4 <= nt; t += 4) {      // four independent loads in flight per thread (the kernel is latency-bound)
       const unsigned int r0 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 0) * a.C));
       const unsigned int r1 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 1) * a.C));
@@ -149,28 +151,32 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 dy = unpack_bf16x2(rr[q]);
-        s1a += dy.x;
-        s1b += dy.y;
+        const uint64_t dy2 = pk2(dy.x, dy.y);
+        s1 = add2(s1, dy2);
 #pragma unroll
-        for (int j = 0; j < 10; ++j)
-          if (j < k) { const float xv = xw[5 * q + j]; Aa[j] = fmaf(dy.x, xv, Aa[j]); Ab[j] = fmaf(dy.y, xv, Ab[j]); }
+        for (int j = 0; j < 10; ++j) A2[j] = fma2(dy2, dup2(xw[5 * q + j]), A2[j]);
       }
     }
     for (; t < nt; ++t) {
       const float2 dy = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)t * a.C)));
       const float* xs = sx + t * a.stride;
-      s1a += dy.x;
-      s1b += dy.y;
+      const uint64_t dy2 = pk2(dy.x, dy.y);
+      s1 = add2(s1, dy2);
 #pragma unroll
       for (int j = 0; j < C0B_MAXK; ++j)
-        if (j < k) { const float xv = xs[j]; Aa[j] = fmaf(dy.x, xv, Aa[j]); Ab[j] = fmaf(dy.y, xv, Ab[j]); }
+        if (j < k) A2[j] = fma2(dy2, dup2(xs[j]), A2[j]);
     }
     // partial sums, layout [U][chunk][k + 1][C]: channel-contiguous, so this store and the finalize kernel's loads coalesce
     float* pa = a.part + ((long long)u * a.n_chunk + blockIdx.x) * (k + 1) * a.C + c;
-    *reinterpret_cast<float2*>(pa) = make_float2(s1a, s1b);
+    float lo, hi;
+    upk2(s1, lo, hi);
+    *reinterpret_cast<float2*>(pa) = make_float2(lo, hi);
 #pragma unroll
-    for (int j = 0; j < C0B_MAXK; ++j)           // static indices: a runtime-indexed copy would put Aa/Ab in local memory
-      if (j < k) *reinterpret_cast<float2*>(pa + (long long)(1 + j) * a.C) = make_float2(Aa[j], Ab[j]);
+    for (int j = 0; j < C0B_MAXK; ++j)           // static indices: a runtime-indexed copy would put the accumulators in local memory
+      if (j < k) {
+        upk2(A2[j], lo, hi);
+        *reinterpret_cast<float2*>(pa + (long long)(1 + j) * a.C) = make_float2(lo, hi);
+      }
   }
 }
 
