@@ -131,17 +131,17 @@ conv0_kernel(Conv0Args a, double* __restrict__ stats) {
       int t = 0;
       if (a.stride == 5 && a.k == 10) {          // wav2vec2: 4 frames = 20 samples = five 16-byte words; 7 vector loads per 4 frames
         for (; t + 4 <= nt; t += 4) {
-          uint64_t xw[28];
+          float xw[28];
 #pragma unroll
           for (int v = 0; v < 7; ++v) {
             const float4 f = *reinterpret_cast<const float4*>(sx + 5 * t + 4 * v);
-            xw[4 * v] = dup2(f.x); xw[4 * v + 1] = dup2(f.y); xw[4 * v + 2] = dup2(f.z); xw[4 * v + 3] = dup2(f.w);
+            xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint64_t y = bias2;
 #pragma unroll
-            for (int j = 0; j < 10; ++j) y = fma2(w2[j], xw[5 * q + j], y);
+            for (int j = 0; j < 10; ++j) y = fma2(w2[j], dup2(xw[5 * q + j]), y);   // FFMA2 takes the sample as a broadcast operand
             emit(t + q, y);
           }
         }
