@@ -19,7 +19,7 @@ extern "C" {
 
 #define SUTA_MAX_LAYERS 48
 #define SUTA_MAX_CONV 8
-#define SUTA_ABI_VERSION 1
+#define SUTA_ABI_VERSION 2
 
 typedef struct suta_engine suta_engine;
 
@@ -72,8 +72,9 @@ typedef struct suta_param_seg {
 typedef struct suta_hyper {
   float em_coef, temp;
   int32_t reweight, not_blank;
-  int32_t opt_kind;                      /* 0 Adam/AdamW, 1 SGD */
+  int32_t opt_kind;                      /* 0 AdamW (decoupled weight decay), 1 SGD, 2 Adam (L2 weight decay) */
   float lr, beta1, beta2, eps, weight_decay;
+  float div_coef;                        /* REF/main.py:201-203 div_loss weight (0: skipped) */
 } suta_hyper;
 
 const char* suta_last_error(void);
@@ -117,6 +118,17 @@ float* suta_grads(const suta_engine* e);         /* DEV fp32 [U][n_params] */
 int32_t* suta_argmax_ids(const suta_engine* e);  /* DEV i32 [total_frames] */
 int32_t* suta_collapsed_ids(const suta_engine* e); /* DEV i32 [total_frames], utterance u at frame_off[u] */
 int32_t* suta_collapsed_len(const suta_engine* e); /* DEV i32 [U] */
+/* optimizer state of the live batch (torch.optim state_dict()['state'], REF/main.py:140,150): both Adam moments and the
+ * number of optimizer.step() calls since the last reset.  A caller that carries a NON-episodic ("continual", the
+ * reference's default without --episodic, REF/main.py:319-348) model from one utterance to the next copies P, both
+ * moments and the step count across suta_batch_begin with these. */
+/* call after writing suta_params() directly (model.load_state_dict, REF/main.py:149): refreshes the bf16 GEMM-operand
+ * copies of the per-utterance matrices and invalidates the cached CNN output */
+int suta_params_written(suta_engine* e, void* stream);
+float* suta_adam_exp_avg(const suta_engine* e);     /* DEV fp32 [U][n_params] */
+float* suta_adam_exp_avg_sq(const suta_engine* e);  /* DEV fp32 [U][n_params] */
+int suta_opt_steps(const suta_engine* e);
+int suta_set_opt_steps(suta_engine* e, int steps);
 const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype);
 int64_t suta_launch_count(const suta_engine* e); /* kernels launched by this engine since creation */
 /* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg). Reads and clears the counters collected
@@ -142,15 +154,20 @@ int suta_op_gemm_mn(const void* a, int64_t a_rows, int64_t a_row_stride, int a_m
 int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P, int64_t pstride,
                           int g_off, int b_off, float* y_f32, void* y_bf16, float* mean, float* rstd, int64_t M, int N,
                           float eps, void* stream);
+/* dgamma/dbeta are written (not accumulated) into G by a fixed-order two-stage reduction: bit-reproducible.
+ * tok_off / T describe the utterances' packed rows; scratch: suta_op_layernorm_bwd_scratch_floats(N, n_utts) floats */
 int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const void* x_bf16, const float* mean, const float* rstd,
                           const int32_t* row_utt, const float* P, int64_t pstride, int g_off, int b_off, float* G,
-                          float* dx_f32, void* dx_bf16, int64_t M, int N, void* stream);
+                          float* dx_f32, void* dx_bf16, int64_t M, int N, const int64_t* tok_off, const int32_t* T,
+                          int n_utts, float* scratch, void* stream);
+int64_t suta_op_layernorm_bwd_scratch_floats(int N, int n_utts);
 int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
                           int64_t M, void* stream);
 int suta_op_attention_bwd(const void* qkv, const void* O, const void* dO, const float* lse, float* D, void* dqkv,
                           const int32_t* blk_tab, int n_blk, int H, int heads, int64_t M, void* stream);
 int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef, float temp,
-                 int reweight, int not_blank, float* loss /*[3U]*/, float* dlogits_f32, void* dlogits_bf16, void* stream);
+                 int reweight, int not_blank, float div_coef, float* loss /*[3U]*/, float* dlogits_f32, void* dlogits_bf16,
+                 void* stream);
 /* out[row] = entropy(softmax(logits[row]/temp)), V = 32: softmax_entropy, REF/main.py:26-28 */
 int suta_op_softmax_entropy(const float* logits, int64_t rows, float temp, float* out, void* stream);
 int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,

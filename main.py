@@ -99,10 +99,16 @@ if __name__ == '__main__':
 
     if args.batch_utts > 1:
         # batched extension: many utterances per adaptation step, each with its own parameters
-        from suta_b200.engine import AdaptHyper
+        # (independent utterances = the reference's --episodic semantics; carrying state between utterances serialises them)
         from suta_b200.runner import SutaRunner
-        hp = AdaptHyper(em_coef=em_coef, temp=temp, reweight=reweight, not_blank=non_blank, opt=opt, lr=lr)
-        out = SutaRunner(model.engine, steps, hp, max_utts=args.batch_utts, vocab=vocab).run(dataset)
+        if not episodic:
+            raise SystemExit("--batch_utts adapts independent utterances: pass --episodic (without it the reference carries "
+                             "model and optimizer state from one utterance to the next, which cannot be batched)")
+        hp = optimizer.hp                      # the optimizer built by setup_optimizer above (opt, lr, betas, weight decay)
+        hp.em_coef, hp.temp, hp.reweight, hp.not_blank, hp.div_coef = em_coef, temp, reweight, non_blank, div_coef
+        out = SutaRunner(model.engine, steps, hp, max_utts=args.batch_utts, vocab=vocab,
+                         sched_gamma=scheduler.gamma if scheduler is not None else None,
+                         sched_step=scheduler.step_size if scheduler is not None else 1).run(dataset)
         for k, d in out["texts"].items():
             transcriptions[k] = [d[i] for i in sorted(d)]
         gt_texts = [u.text for u in dataset]
@@ -132,7 +138,7 @@ if __name__ == '__main__':
                 if episodic and (i + 1) in CK:
                     transcription = vocab.batch_to_text(model.engine.decode_ids())
                     ada_wer = wer(list(texts), list(transcription))
-                    print(f"adapt-{i + 1} WER:  ", ada_wer)
+                    print(f"adapt-{i + 1} WER:  " if i + 1 < 10 else f"adapt-{i + 1} WER: ", ada_wer)   # REF/main.py:355-396
                     if i + 1 == 10:
                         werrs.append(ori_wer - ada_wer)
                     transcriptions[i + 1] += transcription
@@ -150,7 +156,7 @@ if __name__ == '__main__':
     print('------------------------------------')
 
     if not os.path.exists(log_dir):
-        os.mkdir(log_dir)
+        os.makedirs(log_dir)
     with open(os.path.join(log_dir, exp_name), 'w') as f:
         f.write("\n".join(lines) + "\n")
         f.write(f'eposidic? {episodic}\n')

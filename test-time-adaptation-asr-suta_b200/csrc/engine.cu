@@ -149,8 +149,14 @@ struct suta_engine {
   float *logits = nullptr, *dlogits = nullptr, *losses = nullptr;
   bf16* dlogits16 = nullptr;
   float *P = nullptr, *G = nullptr, *Mom = nullptr, *Var = nullptr;
+  float* ln_part = nullptr;                        // dgamma/dbeta slots of the two-stage LayerNorm-backward reduction
   int *ids = nullptr, *collapsed = nullptr, *out_len = nullptr;
-  std::vector<uint8_t> host_tables;
+  // every device table of a batch lives in one contiguous region at the start of the workspace and is uploaded by ONE
+  // host-to-device copy from this pinned mirror (no pageable copies, no stream synchronisation in suta_batch_begin)
+  size_t tables_bytes = 0;
+  uint8_t* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  cudaEvent_t stage_ev = nullptr;                  // recorded after the upload: the mirror may be rewritten once it fired
 };
 
 namespace {
@@ -309,6 +315,21 @@ void carve(suta_engine* e, Bump& b) {
   e->d_row_utt = b.take<int>(M);
   for (int l = 1; l < c.n_conv; ++l) e->d_mblk[l] = b.take<int4>(e->n_mblk[l]);
   e->d_attn_tab = b.take<int4>(e->n_attn_blk);
+  if (e->train_feature) {
+    e->d_tok_mblk = b.take<int4>(e->n_tok_mblk);
+    e->d_dpre_off_last = b.take<long long>(U);
+    e->d_ztab[c.n_conv] = b.take<int4>(U);
+    for (int l = 0; l < c.n_conv; ++l) {
+      e->d_off[l] = b.take<long long>(U);
+      e->d_L[l] = b.take<int>(U);
+      if (l >= 1) {
+        e->d_mpair[l] = b.take<int4>(e->n_mpair[l]);
+        e->d_dgrad_mblk[l] = b.take<int4>(e->n_dg_mblk[l]);
+        e->d_ztab[l] = b.take<int4>(U);
+      }
+    }
+  }
+  e->tables_bytes = align_up(b.off, 256);          // everything above is uploaded by suta_batch_begin in one copy
   e->wav = b.take<float>(e->S); e->wav_norm = b.take<float>(e->S + 64);
   e->stats = b.take<double>((size_t)2 * U * (c.conv_dim[0] > 1 ? c.conv_dim[0] : 1) + 2 * U);
   e->mom = b.take<double>((size_t)U * (c.conv_kernel[0] + c.conv_kernel[0] * (c.conv_kernel[0] + 1) / 2));
@@ -347,23 +368,16 @@ void carve(suta_engine* e, Bump& b) {
   e->P = b.take<float>((size_t)U * e->n_params); e->G = b.take<float>((size_t)U * e->n_params);
   e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
   e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
+  e->ln_part = b.take<float>((size_t)layernorm_backward_scratch_floats(H > C ? H : C, U));
   if (e->train_feature) {
-    e->d_tok_mblk = b.take<int4>(e->n_tok_mblk);
-    e->d_dpre_off_last = b.take<long long>(U);
-    e->d_ztab[c.n_conv] = b.take<int4>(U);
     size_t zmax = 0;
     for (int l = 0; l < c.n_conv; ++l) {
       const bool last = l == c.n_conv - 1;
       const long long rows = last ? e->R64 : e->rows_total[l];
-      e->d_off[l] = b.take<long long>(U);
-      e->d_L[l] = b.take<int>(U);
       e->conv_pre[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
       // 128 leading rows (zero): the even-row dgrad GEMM reads row -1 of the first utterance
       e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
       if (l >= 1) {
-        e->d_mpair[l] = b.take<int4>(e->n_mpair[l]);
-        e->d_dgrad_mblk[l] = b.take<int4>(e->n_dg_mblk[l]);
-        e->d_ztab[l] = b.take<int4>(U);
         e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
         size_t z = dgrad_fused(e, l) ? 0 : (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
         zmax = z > zmax ? z : zmax;
@@ -447,6 +461,8 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int train_feature, 
 extern "C" void suta_engine_destroy(suta_engine* e) {
   if (!e) return;
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->stage_ev) cudaEventDestroy(e->stage_ev);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
   delete e;
 }
 extern "C" int64_t suta_engine_param_count(const suta_engine* e) { return e ? e->n_params : 0; }
@@ -498,7 +514,17 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
   const suta_model_cfg& c = e->cfg;
   const int U = e->U;
   cudaStream_t st = S(stream);
-  // ---- host tables -> device (one staging vector kept alive in the engine) ----
+  // ---- host tables -> pinned mirror of the table region -> device, one asynchronous copy ----
+  if (e->stage_ev) CUDA_TRY(cudaEventSynchronize(e->stage_ev));      // the previous batch's upload has left the mirror
+  else CUDA_TRY(cudaEventCreateWithFlags(&e->stage_ev, cudaEventDisableTiming));
+  if (e->h_stage_cap < e->tables_bytes) {
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->h_stage_cap = e->tables_bytes * 2;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&e->h_stage), e->h_stage_cap, cudaHostAllocDefault));
+  }
+  auto up = [&](void* dst, const void* src, size_t n) {
+    memcpy(e->h_stage + (reinterpret_cast<uint8_t*>(dst) - b.base), src, n);
+  };
   std::vector<int> row_utt(e->M);
   for (int u = 0; u < U; ++u)
     for (int t = 0; t < e->T[u]; ++t) row_utt[e->tok_off[u] + t] = u;
@@ -506,16 +532,15 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
   attn_tab.reserve(e->n_attn_blk);
   for (int u = 0; u < U; ++u)
     for (int m0 = 0; m0 < e->T[u]; m0 += 128) attn_tab.push_back(make_int4((int)e->tok_off[u], e->T[u], m0, 0));
-  auto up = [&](void* dst, const void* src, size_t n) { return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st); };
-  CUDA_TRY(up(e->d_samp_off, e->samp_off.data(), sizeof(long long) * U));
-  CUDA_TRY(up(e->d_tok_off, e->tok_off.data(), sizeof(long long) * U));
-  CUDA_TRY(up(e->d_pad_off, e->pad_off.data(), sizeof(long long) * U));
-  CUDA_TRY(up(e->d_off0, e->off[0].data(), sizeof(long long) * U));
-  CUDA_TRY(up(e->d_n_samples, e->n_samples.data(), sizeof(int) * U));
-  CUDA_TRY(up(e->d_T, e->T.data(), sizeof(int) * U));
-  CUDA_TRY(up(e->d_L0, e->L[0].data(), sizeof(int) * U));
-  CUDA_TRY(up(e->d_row_utt, row_utt.data(), sizeof(int) * e->M));
-  CUDA_TRY(up(e->d_attn_tab, attn_tab.data(), sizeof(int4) * attn_tab.size()));
+  up(e->d_samp_off, e->samp_off.data(), sizeof(long long) * U);
+  up(e->d_tok_off, e->tok_off.data(), sizeof(long long) * U);
+  up(e->d_pad_off, e->pad_off.data(), sizeof(long long) * U);
+  up(e->d_off0, e->off[0].data(), sizeof(long long) * U);
+  up(e->d_n_samples, e->n_samples.data(), sizeof(int) * U);
+  up(e->d_T, e->T.data(), sizeof(int) * U);
+  up(e->d_L0, e->L[0].data(), sizeof(int) * U);
+  up(e->d_row_utt, row_utt.data(), sizeof(int) * e->M);
+  up(e->d_attn_tab, attn_tab.data(), sizeof(int4) * attn_tab.size());
   for (int l = 1; l < c.n_conv; ++l) {
     std::vector<int4> tab;
     tab.reserve(e->n_mblk[l]);
@@ -527,16 +552,15 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
         tab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0), rows,
                                 e->train_feature ? u * c.conv_dim[l] : 0));
       }
-    CUDA_TRY(up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size()));
-    std::vector<int4> ptab;                // 256-row tiles for the CTA-pair kernel: utterance regions are 256-row aligned
-    if (e->train_feature) {
+    up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size());
+    if (e->train_feature) {                // 256-row tiles for the CTA-pair kernel: utterance regions are 256-row aligned
+      std::vector<int4> ptab;
       for (int u = 0; u < U; ++u)
         for (int m0 = 0; m0 < e->L[l][u]; m0 += 256)
           ptab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0),
                                    e->L[l][u] - m0 < 256 ? e->L[l][u] - m0 : 256, u * c.conv_dim[l]));
-      CUDA_TRY(up(e->d_mpair[l], ptab.data(), sizeof(int4) * ptab.size()));
+      up(e->d_mpair[l], ptab.data(), sizeof(int4) * ptab.size());
     }
-    CUDA_TRY(cudaStreamSynchronize(st));   // `tab` is pageable stack-owned memory
   }
   if (e->train_feature) {
     const int last = c.n_conv - 1;
@@ -545,12 +569,11 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
       for (int m0 = 0; m0 < e->T[u]; m0 += 128)
         tab.push_back(make_int4((int)(e->tok_off[u] + m0), (int)(e->tok_off[u] + m0), e->T[u] - m0 < 128 ? e->T[u] - m0 : 128,
                                 u * c.hidden));
-    CUDA_TRY(up(e->d_tok_mblk, tab.data(), sizeof(int4) * tab.size()));
-    CUDA_TRY(up(e->d_dpre_off_last, e->off64.data(), sizeof(long long) * U));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    up(e->d_tok_mblk, tab.data(), sizeof(int4) * tab.size());
+    up(e->d_dpre_off_last, e->off64.data(), sizeof(long long) * U);
     for (int l = 0; l < c.n_conv; ++l) {
-      CUDA_TRY(up(e->d_off[l], e->off[l].data(), sizeof(long long) * U));
-      CUDA_TRY(up(e->d_L[l], e->L[l].data(), sizeof(int) * U));
+      up(e->d_off[l], e->off[l].data(), sizeof(long long) * U);
+      up(e->d_L[l], e->L[l].data(), sizeof(int) * U);
       if (l >= 1) {
         // rows of d(pre-activation) of layer l: the layer's own (256-row-aligned) layout, except the last layer (token slab off64)
         std::vector<int4> dg, zt;
@@ -565,10 +588,9 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
                                    Lx - m0 < 128 ? Lx - m0 : 128, u * c.conv_dim[l]));
           zt.push_back(make_int4((int)dro, (int)(e->off[l - 1][u] / c.conv_stride[l]), e->L[l][u], 0));
         }
-        CUDA_TRY(up(e->d_dgrad_mblk[l], dg.data(), sizeof(int4) * dg.size()));
-        CUDA_TRY(up(e->d_ztab[l], zt.data(), sizeof(int4) * zt.size()));
+        up(e->d_dgrad_mblk[l], dg.data(), sizeof(int4) * dg.size());
+        up(e->d_ztab[l], zt.data(), sizeof(int4) * zt.size());
       }
-      CUDA_TRY(cudaStreamSynchronize(st));
       // gap rows between utterances must be exact zeros: they are reduced over by the weight-gradient GEMMs
       const long long rows = l == last ? e->R64 : e->rows_total[l];
       CUDA_TRY(cudaMemsetAsync(e->conv_out[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
@@ -578,11 +600,11 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
     }
     std::vector<int4> zt;
     for (int u = 0; u < U; ++u) zt.push_back(make_int4((int)e->off64[u], (int)e->tok_off[u], e->T[u], 0));
-    CUDA_TRY(up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size()));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size());
     CUDA_TRY(cudaMemsetAsync(e->dh0_pad, 0, sizeof(bf16) * (size_t)(e->R64 + 128) * c.hidden, st));
   }
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpyAsync(b.base, e->h_stage, e->tables_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(e->stage_ev, st));
   // zero rows of the padded positional-conv slabs never get written afterwards
   CUDA_TRY(cudaMemsetAsync(e->xg, 0, sizeof(bf16) * (size_t)(e->R + 8) * c.hidden, st));
   // conv buffers carry 128 slack rows read (never used) by partial implicit-GEMM tiles
@@ -676,6 +698,14 @@ extern "C" int suta_reset(suta_engine* e, void* stream) {
   e->opt_steps = 0;
   cudaStream_t st = S(stream);
   PROF("reset", params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, st));
+  return refresh_shadows(e, S(stream));
+}
+
+// The caller wrote the trainable vectors directly (model.load_state_dict, carrying a continual model into a new batch):
+// refresh everything derived from them.
+extern "C" int suta_params_written(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  e->frontend_done = false;
   return refresh_shadows(e, S(stream));
 }
 
@@ -830,10 +860,10 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   la.logits = e->logits; la.tok_off = e->d_tok_off; la.T = e->d_T;
   la.dlogits_f32 = e->dlogits; la.dlogits_bf16 = e->dlogits16; la.loss = e->losses; la.n_utts = e->U;
   la.em_coef = h->em_coef; la.temp = h->temp; la.reweight = h->reweight; la.not_blank = h->not_blank;
+  la.div_coef = h->div_coef;
   PROF("loss", suta_loss_forward_backward(la, st));
-  // only the LayerNorm segments are accumulated with atomics; every other gradient segment is written whole
-  CUDA_TRY(cudaMemset2DAsync(e->G, sizeof(float) * e->n_params, 0, sizeof(float) * e->ln_params, e->U, st));
-  e->launches += 2;
+  e->launches += 1;
+  // every gradient segment is written whole by exactly one kernel of this backward (no accumulation into G, no atomics)
 
   // two fp32 gradient streams, updated in place like the forward's residual stream: LayerNorm backward writes d(input)
   // into the other buffer and the following dgrad GEMM accumulates its product onto it (TMA reduce-add)
@@ -848,7 +878,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     const suta_layer_weights& w = e->w.layer[l];
     LayerBufs& x = e->lb[l];
     PROF("ln_bwd", layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
-                                e->G, db, e->b16, M, H, st));
+                                e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
     {  // output_dense dgrad, times GELU'(pre)
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
       p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
@@ -860,7 +890,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       SUTA_TRY(gemm(e, p, st));
     }
     PROF("ln_bwd", layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
-                                e->G, da, e->b16, M, H, st));
+                                e->G, da, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
       p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
@@ -872,11 +902,11 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.accumulate = 1; p.epi.out_f32 = da; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    e->launches += 5;
+    e->launches += 7;             // 2 x (LayerNorm backward + its dgamma/dbeta reduction), attention backward (3 launches)
   }
   // encoder.layer_norm
   PROF("ln_bwd", layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
-                              e->G, db, nullptr, M, H, st));
+                              e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
   PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
   if (use_posconv_tc(e)) {
@@ -906,7 +936,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   if (!e->train_feature) {
     // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
     return layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
-                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, st);
+                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, e->d_tok_off, e->d_T, e->U, e->ln_part, st);
   }
 
   // ================= train_feature: projection weight/bias, then the whole CNN (REF/main.py:88-94) =================
@@ -925,7 +955,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   }
   // feature_projection.layer_norm with input gradient
   PROF("ln_bwd", layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
-                              (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, st));
+                              (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
   // d(pre-activation) of the last conv layer, in the 128-row-aligned token slab
   PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
                                e->d_dpre_off_last, M, C, st));
@@ -1046,6 +1076,14 @@ extern "C" int32_t* suta_argmax_ids(const suta_engine* e) { return e->ids; }
 extern "C" int32_t* suta_collapsed_ids(const suta_engine* e) { return e->collapsed; }
 extern "C" int32_t* suta_collapsed_len(const suta_engine* e) { return e->out_len; }
 extern "C" int64_t suta_launch_count(const suta_engine* e) { return e->launches; }
+extern "C" float* suta_adam_exp_avg(const suta_engine* e) { return e->Mom; }
+extern "C" float* suta_adam_exp_avg_sq(const suta_engine* e) { return e->Var; }
+extern "C" int suta_opt_steps(const suta_engine* e) { return e ? e->opt_steps : 0; }
+extern "C" int suta_set_opt_steps(suta_engine* e, int steps) {
+  SUTA_CHECK_ARG(e && steps >= 0);
+  e->opt_steps = steps;
+  return SUTA_OK;
+}
 
 // dtype: 0 fp32, 1 bf16
 extern "C" const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype) {
@@ -1105,10 +1143,13 @@ extern "C" int suta_op_layernorm_fwd(const float* x_f32, const void* x_bf16, con
 }
 extern "C" int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const void* x_bf16, const float* mean,
                                      const float* rstd, const int32_t* row_utt, const float* P, int64_t pstride, int g_off,
-                                     int b_off, float* G, float* dx_f32, void* dx_bf16, int64_t M, int N, void* stream) {
+                                     int b_off, float* G, float* dx_f32, void* dx_bf16, int64_t M, int N,
+                                     const int64_t* tok_off, const int32_t* T, int n_utts, float* scratch, void* stream) {
   return layernorm_backward(dy, x_f32, reinterpret_cast<const bf16*>(x_bf16), mean, rstd, row_utt, UttParams{P, pstride}, g_off,
-                            b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N, S(stream));
+                            b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N,
+                            reinterpret_cast<const long long*>(tok_off), T, n_utts, scratch, S(stream));
 }
+extern "C" int64_t suta_op_layernorm_bwd_scratch_floats(int N, int n_utts) { return layernorm_backward_scratch_floats(N, n_utts); }
 extern "C" int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
                                      int64_t M, void* stream) {
   return attention_forward(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(O), lse,
@@ -1121,11 +1162,11 @@ extern "C" int suta_op_attention_bwd(const void* qkv, const void* O, const void*
                             reinterpret_cast<const int4*>(blk_tab), n_blk, H, heads, M, S(stream));
 }
 extern "C" int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef,
-                            float temp, int reweight, int not_blank, float* loss, float* dlogits_f32, void* dlogits_bf16,
-                            void* stream) {
+                            float temp, int reweight, int not_blank, float div_coef, float* loss, float* dlogits_f32,
+                            void* dlogits_bf16, void* stream) {
   LossArgs la{};
   la.logits = logits; la.tok_off = reinterpret_cast<const long long*>(tok_off); la.T = T; la.n_utts = n_utts;
-  la.em_coef = em_coef; la.temp = temp; la.reweight = reweight; la.not_blank = not_blank;
+  la.em_coef = em_coef; la.temp = temp; la.reweight = reweight; la.not_blank = not_blank; la.div_coef = div_coef;
   la.loss = loss; la.dlogits_f32 = dlogits_f32; la.dlogits_bf16 = reinterpret_cast<bf16*>(dlogits_bf16);
   return suta_loss_forward_backward(la, S(stream));
 }

@@ -22,10 +22,14 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
                       cudaStream_t stream, const float* y32_bias = nullptr);
-// dgamma/dbeta are accumulated (atomicAdd) into G (same layout as the parameter vector); dx outputs optional.
+// dgamma/dbeta are WRITTEN into G (same layout as the parameter vector) by a fixed-order two-stage reduction through
+// `scratch` (layernorm_backward_scratch_floats(N, n_utts) floats) -- bit-reproducible; G and the dx outputs are optional.
+// tok_off / T: first packed row and row count of every utterance (the rows row_utt describes).
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
-                       long long M, int N, cudaStream_t stream);
+                       long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
+                       cudaStream_t stream);
+long long layernorm_backward_scratch_floats(int N, int n_utts);
 
 // ---- frontend.cu ----------------------------------------------------------------------------
 // per-utterance (x - mean) / sqrt(var + 1e-7), optional additive noise is applied by the caller beforehand
@@ -126,6 +130,7 @@ struct LossArgs {
   int n_utts;
   float em_coef, temp;
   int reweight, not_blank;
+  float div_coef;              // REF/main.py:201-203 (0: term skipped)
 };
 int suta_loss_forward_backward(const LossArgs& a, cudaStream_t stream);
 // out[row] = entropy of softmax(logits[row] / temp)   (REF/main.py:26-28), V = 32
@@ -142,7 +147,7 @@ struct AdamArgs {
   int n_utts;
   int step_index;              // number of optimizer.step() calls already applied since reset
   float lr, beta1, beta2, eps, weight_decay;
-  int kind;                    // 0 Adam/AdamW, 1 SGD
+  int kind;                    // 0 AdamW (decoupled decay), 1 SGD (L2 decay), 2 Adam (L2 decay: g += wd p, torch/optim/adam.py)
   bf16* shadow;                // optional bf16 copy of P (GEMM operands of trainable weights), same layout
   // optional bf16 copies of selected segments, each stored [U][size] contiguously (the stacked per-utterance B operands
   // of the conv / projection GEMMs): written by the same pass that updates P

@@ -1,6 +1,7 @@
 // Fused SUTA loss: value and d loss / d logits in one kernel.
-// Restates REF/main.py:181-199 (forward_and_adapt's loss assembly), :26-28 (softmax_entropy) and :30-44
-// (mcc_loss, incl. the detached entropy re-weighting and the keepdim-less normalisation) for a batch of
+// Restates REF/main.py:181-203 (forward_and_adapt's loss assembly), :26-28 (softmax_entropy), :30-44
+// (mcc_loss, incl. the detached entropy re-weighting and the keepdim-less normalisation) and :46-60 (div_loss:
+// minus the entropy of softmax(mean-over-time raw logits[1:]), only when div_coef > 0) for a batch of
 // independent utterances; the gradient is the closed form verified against the reference's autograd
 // (oracle/suta_oracle.py: suta_loss_grad_closed).
 //
@@ -48,6 +49,8 @@ suta_loss_kernel(LossArgs a) {
   __shared__ float s_red[WARPS][4];         // nM, sum H over M, sum w
   __shared__ float s_scal[4];               // nM, sumH, sumW, (unused)
   __shared__ float s_r[V], s_col[V];
+  __shared__ float s_xsum[WARPS][V];        // per-warp column sums of the raw logits (div_loss)
+  __shared__ float s_gdiv[V];               // d div_loss / d logits[t][c] (same for every frame)
   const int u = blockIdx.x;
   const int T = a.T[u];
   const long long off = a.tok_off[u];
@@ -60,9 +63,10 @@ suta_loss_kernel(LossArgs a) {
   float colacc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) colacc[i] = 0.f;
-  float nM = 0.f, sumH = 0.f, sumW = 0.f;
+  float nM = 0.f, sumH = 0.f, sumW = 0.f, xsum = 0.f;
   for (int t = warp; t < T; t += WARPS) {
     float x = a.logits[(off + t) * V + lane];
+    xsum += x;
     RowStats r = row_softmax(x, inv_temp, lane);
     bool inM = a.not_blank ? (r.argmax != 0) : true;
     if (inM) { nM += 1.f; sumH += r.H; }
@@ -77,7 +81,25 @@ suta_loss_kernel(LossArgs a) {
 #pragma unroll
   for (int i = 0; i < V; ++i) sC[warp][i][lane] = colacc[i];
   if (lane == 0) { s_red[warp][0] = nM; s_red[warp][1] = sumH; s_red[warp][2] = sumW; }
+  s_xsum[warp][lane] = xsum;
   __syncthreads();
+  // div_loss (REF/main.py:46-60, called with the raw logits at :202): d = -H(q), q = softmax(mean_t x[t][1:]);
+  // d d / d x[t][c] = q_c (log q_c + H(q)) / T for c >= 1 -- every warp computes it redundantly (lane == class)
+  float d_loss = 0.f;
+  if (a.div_coef > 0.f) {
+    float m = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) m += s_xsum[w][lane];
+    m = (lane == 0) ? -INFINITY : m / (float)T;            // the blank column is dropped (:53-54)
+    const float mmax = warp_max(m);
+    const float em = (lane == 0) ? 0.f : __expf(m - mmax);
+    const float sm = warp_sum(em);
+    const float q = em / sm;
+    const float logq = (lane == 0) ? 0.f : (m - mmax) - __logf(sm);
+    const float Hq = -warp_sum(q * logq);
+    d_loss = -Hq;
+    if (warp == 0) s_gdiv[lane] = (lane == 0) ? 0.f : a.div_coef * q * (logq + Hq) / (float)T;
+  }
   for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
     int i = idx / V, j = idx % V;
     float s = 0.f;
@@ -133,6 +155,7 @@ suta_loss_kernel(LossArgs a) {
     float loss = 0.f;
     if (use_em) loss += a.em_coef * e_loss;
     if (use_mcc) loss += (1.0f - a.em_coef) * mcc;
+    if (a.div_coef > 0.f) loss += a.div_coef * d_loss;
     a.loss[u] = loss;
     a.loss[a.n_utts + u] = use_em ? e_loss : 0.f;
     a.loss[2 * a.n_utts + u] = mcc;
@@ -145,6 +168,8 @@ suta_loss_kernel(LossArgs a) {
   for (int k = 0; k < V; ++k) gg[k] = use_mcc ? sGG[lane][k] : 0.f;
   const float em_scale = (use_em && nM_tot > 0.f) ? a.em_coef / nM_tot : 0.f;   // empty selection: autograd gives 0
   const float mcc_scale = use_mcc ? (1.0f - a.em_coef) : 0.f;
+  __syncthreads();                   // s_gdiv (written by warp 0) is read by every warp below
+  const float gdiv = a.div_coef > 0.f ? s_gdiv[lane] : 0.f;
   for (int t = warp; t < T; t += WARPS) {
     float x = a.logits[(off + t) * V + lane];
     RowStats r = row_softmax(x, inv_temp, lane);
@@ -160,7 +185,7 @@ suta_loss_kernel(LossArgs a) {
       float s = warp_sum(r.p * gp);
       g += mcc_scale * r.p * (gp - s);
     }
-    g *= inv_temp;
+    g = g * inv_temp + gdiv;
     if (a.dlogits_f32) a.dlogits_f32[(off + t) * V + lane] = g;
     if (a.dlogits_bf16) a.dlogits_bf16[(off + t) * V + lane] = __float2bfloat16(g);
   }

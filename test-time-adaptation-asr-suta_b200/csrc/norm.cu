@@ -162,7 +162,10 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
 }
 
 // Backward.  One thread owns 4 fixed columns for all rows of its CTA (N/4 threads per CTA), so dgamma/dbeta live in 8
-// registers and are flushed with one atomicAdd per column per (CTA, utterance); the two row reductions are batched
+// registers and are flushed once per (CTA, utterance) into a scratch slot of their own (slot = CTA index + utterance
+// index: both are monotone along the packed rows, so the sum is unique); ln_bwd_reduce_kernel then adds the slots of
+// every utterance in a fixed order -- the result is bit-reproducible run to run (the first version used fp32
+// atomicAdd into G, whose order is not).  The two row reductions are batched
 // over R = 4 rows: every thread first issues the 8 independent 16-byte loads of the tile, then 8 warp reductions, one
 // exchange through shared memory, one __syncthreads.  (The first version kept whole rows per warp: 150 registers, one
 // CTA per SM, 3 TB/s.)
@@ -184,7 +187,7 @@ template <int N, typename TIn>
 __global__ void __launch_bounds__((N / 4 + 31) / 32 * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const int* __restrict__ row_utt, const float* __restrict__ P,
-              long long pstride, int g_off, int b_off, float* __restrict__ G, float* __restrict__ dx32,
+              long long pstride, int g_off, float* __restrict__ part, float* __restrict__ dx32,
               bf16* __restrict__ dx16, long long M, int rows_per_cta) {
   constexpr int NT = N / 4;                       // active threads
   constexpr int NW = (NT + 31) / 32;              // warps
@@ -199,11 +202,10 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
   int u_acc = -1;                                 // utterance the accumulators (and g) belong to
 
   auto flush = [&]() {
-    if (u_acc < 0 || !G || !act) return;
-    float* gg = G + (long long)u_acc * pstride + g_off + col;
-    float* gb = G + (long long)u_acc * pstride + b_off + col;
-    atomicAdd(gg + 0, ag.x); atomicAdd(gg + 1, ag.y); atomicAdd(gg + 2, ag.z); atomicAdd(gg + 3, ag.w);
-    atomicAdd(gb + 0, ab.x); atomicAdd(gb + 1, ab.y); atomicAdd(gb + 2, ab.z); atomicAdd(gb + 3, ab.w);
+    if (u_acc < 0 || !part || !act) return;
+    float* slot = part + ((long long)blockIdx.x + u_acc) * (2 * N);
+    *reinterpret_cast<float4*>(slot + col) = ag;
+    *reinterpret_cast<float4*>(slot + N + col) = ab;
     ag = ab = make_float4(0.f, 0.f, 0.f, 0.f);
   };
 
@@ -316,6 +318,20 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
   flush();
 }
 
+// G[u][g_off + c] = sum over the CTAs that saw rows of utterance u (ascending) of their dgamma slot; same for dbeta.
+__global__ void __launch_bounds__(256)
+ln_bwd_reduce_kernel(const float* __restrict__ part, const long long* __restrict__ tok_off, const int* __restrict__ T,
+                     int rows_per_cta, int N, float* __restrict__ G, long long pstride, int g_off, int b_off) {
+  const int u = blockIdx.x;
+  const long long r0 = tok_off[u], r1 = r0 + T[u] - 1;
+  const int b0 = (int)(r0 / rows_per_cta), b1 = (int)(r1 / rows_per_cta);
+  for (int c = threadIdx.x; c < 2 * N; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = b0; b <= b1; ++b) s += part[((long long)b + u) * (2 * N) + c];
+    G[(long long)u * pstride + (c < N ? g_off + c : b_off + c - N)] = s;
+  }
+}
+
 template <int N, typename TIn>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
                float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
@@ -334,9 +350,17 @@ int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
+// rows per CTA of the backward grid: one wave of at most (resident CTAs per SM) x (SMs) CTAs; 8 is the cap on `resident`,
+// so 8 x SMs + n_utts slots always suffice for the dgamma/dbeta scratch
+long long bwd_rows_per_cta(long long M, int resident) {
+  long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
+  return std::max<long long>(16, (rows + BWD_R - 1) / BWD_R * BWD_R);
+}
+
 template <int N, typename TIn>
 int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
-               int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, cudaStream_t stream) {
+               int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, const long long* tok_off, const int* T,
+               int n_utts, float* scratch, cudaStream_t stream) {
   constexpr int threads = (N / 4 + 31) / 32 * 32;
   using S = BwdSmem<N, TIn>;
   static int resident = 0;                         // CTAs of this instantiation that fit on one SM
@@ -345,12 +369,14 @@ int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rs
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_bwd_kernel<N, TIn>, threads, S::BYTES));
     resident = std::max(1, std::min(8, resident));
   }
-  // one wave: at most (resident CTAs per SM) x (SMs) CTAs, rows per CTA a multiple of the tile height
-  long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
-  rows = std::max<long long>(16, (rows + BWD_R - 1) / BWD_R * BWD_R);
+  const long long rows = bwd_rows_per_cta(M, resident);
   ln_bwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
-      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, b_off, G, dx32, dx16, M, (int)rows);
+      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, G ? scratch : nullptr, dx32, dx16, M, (int)rows);
   CUDA_TRY(cudaGetLastError());
+  if (G) {
+    ln_bwd_reduce_kernel<<<n_utts, 256, 0, stream>>>(scratch, tok_off, T, (int)rows, N, G, prm.stride, g_off, b_off);
+    CUDA_TRY(cudaGetLastError());
+  }
   return SUTA_OK;
 }
 
@@ -383,15 +409,19 @@ int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt
   return SUTA_OK;
 }
 
+long long layernorm_backward_scratch_floats(int N, int n_utts) { return ((long long)8 * n_sms() + n_utts + 1) * 2 * N; }
+
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
-                       long long M, int N, cudaStream_t stream) {
+                       long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
+                       cudaStream_t stream) {
   SUTA_CHECK_ARG((x_f32 != nullptr) != (x_bf16 != nullptr));
+  SUTA_CHECK_ARG(!G || (tok_off && T && n_utts > 0 && scratch));
   if (M <= 0) return SUTA_OK;
   if (x_f32) {
-    LN_DISPATCH(N, return (launch_bwd<NN, float>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, stream)));
+    LN_DISPATCH(N, return (launch_bwd<NN, float>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream)));
   } else {
-    LN_DISPATCH(N, return (launch_bwd<NN, bf16>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, stream)));
+    LN_DISPATCH(N, return (launch_bwd<NN, bf16>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream)));
   }
   return SUTA_OK;
 }

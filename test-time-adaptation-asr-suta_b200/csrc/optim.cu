@@ -33,13 +33,17 @@ __global__ void adam_kernel(AdamArgs a, AdamConsts c) {
     float p = a.P[i];
     const float g = a.G[i];
     if (a.kind == 1) {
-      for (int j = 0; j < k; ++j) p -= a.lr * g;
+      for (int j = 0; j < k; ++j) p -= a.lr * (g + a.weight_decay * p);          // torch/optim/sgd.py: grad.add(param, alpha=wd)
     } else {
       float m = a.Mom[i], v = a.Var[i];
       for (int j = 0; j < k; ++j) {
-        if (a.weight_decay != 0.f) p *= 1.0f - a.lr * a.weight_decay;
-        m = m + (g - m) * (1.0f - a.beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * a.beta2 + (1.0f - a.beta2) * g * g;         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+        float gj = g;
+        if (a.weight_decay != 0.f) {
+          if (a.kind == 2) gj = g + a.weight_decay * p;    // Adam: grad = grad.add(param, alpha=weight_decay)
+          else p *= 1.0f - a.lr * a.weight_decay;          // AdamW: param.mul_(1 - lr * weight_decay)
+        }
+        m = m + (gj - m) * (1.0f - a.beta1);                // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * a.beta2 + (1.0f - a.beta2) * gj * gj;       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
         const float denom = sqrtf(v) / c.bc2_sqrt[k][j] + a.eps;
         p = p - c.step_size[k][j] * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
       }
@@ -68,13 +72,13 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
   if (a.kind == 1) {
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      for (int j = 0; j < kv[t]; ++j) pv[t] -= a.lr * gv[t];
+      for (int j = 0; j < kv[t]; ++j) pv[t] -= a.lr * (gv[t] + a.weight_decay * pv[t]);
   } else {
     float4 m4 = __ldcs(reinterpret_cast<const float4*>(a.Mom + i)), v4 = __ldcs(reinterpret_cast<const float4*>(a.Var + i));
     float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
     const float omb1 = 1.0f - a.beta1, omb2 = 1.0f - a.beta2;
     const float decay = 1.0f - a.lr * a.weight_decay;
-    if (kv[0] == kv[1] && kv[1] == kv[2] && kv[2] == kv[3]) {
+    if (kv[0] == kv[1] && kv[1] == kv[2] && kv[2] == kv[3] && a.weight_decay == 0.f) {
       // the usual case (segment sizes are multiples of 4): the four elements advance through the k sub-steps
       // together.  With k = 4 on every conv weight (REF/main.py:88-94) the update is instruction-bound unless the
       // square root and the two divisions are single MUFU operations.
@@ -86,7 +90,6 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
         const float ss = c.step_size[k][j], ib = c.inv_bc2_sqrt[k][j];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          if (a.weight_decay != 0.f) pv[t] *= decay;
           mv[t] = fmaf(gv[t] - mv[t], omb1, mv[t]);
           vv[t] = fmaf(vv[t], a.beta2, gg[t]);
           const float denom = fmaf(sqrt_approx(vv[t]), ib, a.eps);
@@ -98,9 +101,13 @@ adam_vec4_kernel(AdamArgs a, AdamConsts c) {
       for (int t = 0; t < 4; ++t) {
         const int k = kv[t];
         for (int j = 0; j < k; ++j) {
-          if (a.weight_decay != 0.f) pv[t] *= decay;
-          mv[t] = fmaf(gv[t] - mv[t], omb1, mv[t]);
-          vv[t] = fmaf(vv[t], a.beta2, omb2 * gv[t] * gv[t]);
+          float gj = gv[t];
+          if (a.weight_decay != 0.f) {
+            if (a.kind == 2) gj = fmaf(a.weight_decay, pv[t], gj);   // Adam: L2 term joins the gradient
+            else pv[t] *= decay;                                     // AdamW: decoupled decay
+          }
+          mv[t] = fmaf(gj - mv[t], omb1, mv[t]);
+          vv[t] = fmaf(vv[t], a.beta2, omb2 * gj * gj);
           const float denom = fmaf(sqrt_approx(vv[t]), c.inv_bc2_sqrt[k][j], a.eps);
           pv[t] = fmaf(-c.step_size[k][j], __fdividef(mv[t], denom), pv[t]);
         }

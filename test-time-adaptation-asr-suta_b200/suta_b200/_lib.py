@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SUTA_B200_LIB") or os.path.join(os.path.dirname(_HERE
 
 MAX_LAYERS = 48
 MAX_CONV = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -46,7 +46,7 @@ class ParamSeg(C.Structure):
 class Hyper(C.Structure):
     _fields_ = [("em_coef", c_float), ("temp", c_float), ("reweight", c_int32), ("not_blank", c_int32),
                 ("opt_kind", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("weight_decay", c_float)]
+                ("weight_decay", c_float), ("div_coef", c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/suta_b200.h declares (tests check this)
@@ -79,6 +79,11 @@ SIGNATURES = {
     "suta_argmax_ids": (c_void_p, [c_void_p]),
     "suta_collapsed_ids": (c_void_p, [c_void_p]),
     "suta_collapsed_len": (c_void_p, [c_void_p]),
+    "suta_params_written": (c_int, [c_void_p, c_void_p]),
+    "suta_adam_exp_avg": (c_void_p, [c_void_p]),
+    "suta_adam_exp_avg_sq": (c_void_p, [c_void_p]),
+    "suta_opt_steps": (c_int, [c_void_p]),
+    "suta_set_opt_steps": (c_int, [c_void_p, c_int]),
     "suta_debug_buffer": (c_void_p, [c_void_p, C.c_char_p, C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(c_int)]),
     "suta_launch_count": (c_int64, [c_void_p]),
     "suta_profile": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
@@ -91,12 +96,14 @@ SIGNATURES = {
     "suta_op_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "suta_op_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p]),
+    "suta_op_layernorm_bwd_scratch_floats": (c_int64, [c_int, c_int]),
     "suta_op_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "suta_op_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int64, c_void_p]),
-    "suta_op_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
-                             c_void_p, c_void_p]),
+    "suta_op_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_float, c_void_p,
+                             c_void_p, c_void_p, c_void_p]),
     "suta_op_softmax_entropy": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "suta_op_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, C.POINTER(Hyper),
                              c_void_p, c_void_p]),

@@ -101,9 +101,13 @@ class SutaModel:
         self.cfg = ModelConfig.from_any(cfg)
         self.engine = SutaEngine(self.cfg, state_dict, train_feature=train_feature, trainable_mult={}, device=device)
         self._params = {name: SutaParam(self, name, off, size) for name, off, size in self.engine.segments}
-        self._x_key = None
+        self._x_ref = None              # strong reference to the bound input: its address cannot be recycled while bound
+        self._x_version = -1
         self._logits_valid = False
         self._shape = None
+        # model + optimizer state carried from one bound input to the next (REF/main.py:319-348 without --episodic):
+        # P = trainable vector, m / v = Adam moments (None = empty optimizer state), steps = optimizer.step() count
+        self._carry = dict(P=None, m=None, v=None, steps=0)
 
     # ---- what REF/main.py calls on `model` ----
     def eval(self):
@@ -125,27 +129,45 @@ class SutaModel:
         return list(self._params.items())
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        if self.engine.n_utts == 0:
-            return {"trainable": self.engine.params0.clone()}
-        return {"trainable": self.engine.params()[0].clone()}
+        if self.engine.n_utts:
+            return {"trainable": self.engine.params()[0].clone()}
+        p = self._carry["P"]
+        return {"trainable": (self.engine.params0 if p is None else p).clone()}
 
     def load_state_dict(self, state: Dict[str, torch.Tensor], strict: bool = True):
         if strict and set(state) != {"trainable"}:
             raise RuntimeError(f"unexpected keys in state_dict: {sorted(state)}")
+        p = state["trainable"].to(self.engine.device)
         if self.engine.n_utts:
-            self.engine.params().copy_(state["trainable"].to(self.engine.device)[None].expand(self.engine.n_utts, -1))
-        self._pending_state = state["trainable"]
+            self.engine.params().copy_(p[None].expand(self.engine.n_utts, -1))
+            self.engine.params_written()
+        self._carry["P"] = p.clone()
         self._logits_valid = False
+
+    def _clear_optimizer_state(self):
+        """optimizer.load_state_dict(<empty state>): both moments and the step count start over (REF/main.py:150)."""
+        self._carry.update(m=None, v=None, steps=0)
+        eng = self.engine
+        if eng.n_utts:
+            eng.exp_avg().zero_()
+            eng.exp_avg_sq().zero_()
+            eng.opt_steps = 0
 
     def _bind(self, x: torch.Tensor):
         if x.dim() != 2:
             raise ValueError("input_values must be [batch, samples]")
-        key = (x.data_ptr(), tuple(x.shape), x._version)
-        if key == self._x_key:
+        # identity of the tensor OBJECT (kept alive by _x_ref) + its version counter; never the storage address: the
+        # caching allocator hands the block of a deleted input to the next one of the same length (REF/main.py:400-401)
+        if x is self._x_ref and x._version == self._x_version:
             return
         B, N = x.shape
         eng = self.engine
-        keep = eng.params()[0].clone() if eng.n_utts else getattr(self, "_pending_state", None)
+        c = self._carry
+        if eng.n_utts:                     # the live batch IS the model: carry its state into the next input
+            if eng.n_utts > 1 and (c["steps"] or eng.opt_steps):
+                raise NotImplementedError("carrying adapted state across inputs (no --episodic) needs batch size 1, like "
+                                          "the reference (REF/main.py:32); restore a snapshot first or use B == 1")
+            c.update(P=eng.params()[0].clone(), m=eng.exp_avg()[0].clone(), v=eng.exp_avg_sq()[0].clone(), steps=eng.opt_steps)
         eng.begin_batch_lengths(np.full(B, N, dtype=np.int32))
         packed = torch.zeros(eng.total_samples, dtype=torch.float32, device=eng.device)
         xs = x.detach().to(device=eng.device, dtype=torch.float32)
@@ -153,12 +175,17 @@ class SutaModel:
             o = int(eng.sample_off[u])
             packed[o:o + N] = xs[u]
         eng.set_audio(packed, normalized=True)
-        # a new batch starts from the model's current parameters (continual mode) -- episodic callers restore
-        # the pristine snapshot through load_model_and_optimizer right before, exactly like the reference
+        # the new input starts from the model's CURRENT parameters and optimizer state (continual mode, the reference's
+        # default) -- episodic callers restored the pristine snapshot through load_model_and_optimizer right before
         eng.reset()
-        if keep is not None:
-            eng.params().copy_(keep.to(eng.device)[None].expand(B, -1))
-        self._x_key, self._logits_valid = key, False
+        if c["P"] is not None:
+            eng.params().copy_(c["P"][None].expand(B, -1))
+            eng.params_written()
+        if c["m"] is not None:
+            eng.exp_avg().copy_(c["m"][None].expand(B, -1))
+            eng.exp_avg_sq().copy_(c["v"][None].expand(B, -1))
+        eng.opt_steps = c["steps"]
+        self._x_ref, self._x_version, self._logits_valid = x, x._version, False
         self._shape = (B, int(eng.frames[0]), self.cfg.vocab_size)
 
     def __call__(self, x: torch.Tensor) -> _Out:
@@ -182,6 +209,7 @@ class SutaOptimizer:
         self.mult = mult
         self.model.engine.set_trainable(mult)
         self.hp = AdaptHyper(opt=opt_name, lr=lr, beta1=betas[0], beta2=betas[1], weight_decay=weight_decay)
+        self.model._optimizer = self
         self.param_groups = [dict(lr=lr, betas=betas, weight_decay=weight_decay, params=params)]
 
     def step(self):
@@ -200,11 +228,7 @@ class SutaOptimizer:
         if sd.get("state"):
             raise NotImplementedError("only pristine (empty-state) optimizer snapshots are supported")
         self.param_groups[0].update(sd["param_groups"][0])
-        eng = self.model.engine
-        if eng.n_utts:
-            keep = eng.params().clone()
-            eng.reset()
-            eng.params().copy_(keep)
+        self.model._clear_optimizer_state()
 
 
 class _StepLR:
@@ -269,13 +293,14 @@ def mcc_loss(x, reweight=False, dim=2, class_num=32):
     T = torch.full((1,), L, dtype=torch.int32, device=rows.device)
     loss = torch.empty(3, dtype=torch.float32, device=rows.device)
     p = lambda t: C.c_void_p(t.data_ptr())
-    check(_lib.load().suta_op_loss(p(rows), p(off), p(T), 1, 0.0, 1.0, int(bool(reweight)), 0, p(loss), None, None,
+    check(_lib.load().suta_op_loss(p(rows), p(off), p(T), 1, 0.0, 1.0, int(bool(reweight)), 0, 0.0, p(loss), None, None,
                                    _stream_ptr()))
     return loss[2] * (32.0 / class_num)
 
 
 def div_loss(x, non_blank=None, L_thd=64):
-    """REF/main.py:46-60 (not used by any script; value only)."""
+    """REF/main.py:46-60: minus the entropy of softmax(mean-over-time logits), blank column dropped whenever
+    `non_blank is not None` (value only: one 32-vector; the gradient used by forward_and_adapt is in the fused kernel)."""
     x = x.squeeze(0)
     cls_pred = x.mean(0)[1:] if non_blank is not None else x.mean(0)
     p = torch.softmax(cls_pred, 0)
@@ -342,11 +367,10 @@ def configure_model(model):
 def forward_and_adapt(x, model, optimizer, em_coef=0.9, reweight=False, temp=1., not_blank=True, scheduler=None,
                       div_coef=0, repeat_inference=True, skip_short_thd=None):
     """REF/main.py:172-215: forward, unsupervised loss (entropy + MCC), backward, optimizer step, forward again."""
-    if div_coef > 0:
-        raise NotImplementedError("div_loss adaptation (--div_coef > 0) is outside the hot path built here")
     outputs = model(x).logits
     hp = optimizer.hp
     hp.em_coef, hp.reweight, hp.temp, hp.not_blank = float(em_coef), bool(reweight), float(temp), bool(not_blank)
+    hp.div_coef = float(div_coef)
     model.engine.loss_backward(hp)
     optimizer.step()
     if scheduler is not None:

@@ -37,12 +37,15 @@ class AdaptHyper:
     beta2: float = 0.999
     eps: float = 1e-8
     weight_decay: float = 0.0
+    div_coef: float = 0.0          # REF/main.py:201-203 (no script sets it)
+
+    _OPT_KIND = {"AdamW": 0, "SGD": 1, "Adam": 2}     # Adam = L2 weight decay (torch.optim.Adam), AdamW = decoupled
 
     def to_c(self) -> Hyper:
-        if self.opt not in ("AdamW", "Adam", "SGD"):
+        if self.opt not in self._OPT_KIND:
             raise ValueError(f"unsupported optimizer {self.opt!r} (AdamW, Adam, SGD)")
-        return Hyper(self.em_coef, self.temp, int(self.reweight), int(self.not_blank), 1 if self.opt == "SGD" else 0,
-                     self.lr, self.beta1, self.beta2, self.eps, self.weight_decay)
+        return Hyper(self.em_coef, self.temp, int(self.reweight), int(self.not_blank), self._OPT_KIND[self.opt],
+                     self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.div_coef)
 
 
 def _stream_ptr() -> int:
@@ -282,6 +285,26 @@ class SutaEngine:
 
     def grads(self) -> torch.Tensor:
         return self._view(self.lib.suta_grads(self._h), (self.n_utts, self.n_params), torch.float32)
+
+    def params_written(self):
+        """Tell the engine that params() was written directly (bf16 operand copies / cached CNN output are stale)."""
+        check(self.lib.suta_params_written(self._h, _stream_ptr()))
+
+    def exp_avg(self) -> torch.Tensor:
+        """Adam first moment of every utterance of the live batch (torch.optim state 'exp_avg')."""
+        return self._view(self.lib.suta_adam_exp_avg(self._h), (self.n_utts, self.n_params), torch.float32)
+
+    def exp_avg_sq(self) -> torch.Tensor:
+        return self._view(self.lib.suta_adam_exp_avg_sq(self._h), (self.n_utts, self.n_params), torch.float32)
+
+    @property
+    def opt_steps(self) -> int:
+        """optimizer.step() calls since the last reset (bias correction uses multiplicity * opt_steps + j)."""
+        return int(self.lib.suta_opt_steps(self._h))
+
+    @opt_steps.setter
+    def opt_steps(self, n: int):
+        check(self.lib.suta_set_opt_steps(self._h, int(n)))
 
     def argmax_ids(self) -> torch.Tensor:
         return self._view(self.lib.suta_argmax_ids(self._h), (self.total_frames,), torch.int32)

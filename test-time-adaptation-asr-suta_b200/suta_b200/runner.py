@@ -26,21 +26,33 @@ class BatchResult:
 
 
 def adapt_batch(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarray, steps: int, hp: AdaptHyper,
-                vocab: CTCVocab, episodic: bool = True, collect_losses: bool = False) -> Dict[int, List[str]]:
+                vocab: CTCVocab, episodic: bool = True, collect_losses: bool = False,
+                sched_gamma: Optional[float] = None, sched_step: int = 1) -> Dict[int, List[str]]:
     """One adaptation batch = the body of REF/main.py:319-402 for len(lengths) utterances at once.
-    `wavs_packed` is the packed waveform buffer (pinned host or device) laid out by engine.begin_batch_lengths."""
+    `wavs_packed` is the packed waveform buffer (pinned host or device) laid out by engine.begin_batch_lengths.
+    Batches are always episodic: every utterance starts from the pristine parameters (REF/main.py:327-328) -- carrying
+    state from utterance to utterance serialises them (that mode lives in api.SutaModel, batch size 1).
+    sched_gamma / sched_step: the StepLR of REF/main.py:20-21, restarted for every utterance like the reference's
+    scheduler.load_state_dict (:151-153)."""
+    if not episodic:
+        raise ValueError("adapt_batch adapts independent utterances: episodic only (use the api.* surface for continual mode)")
     engine.set_audio(wavs_packed)
-    if episodic:
-        engine.reset()
+    engine.reset()
     engine.forward()                                               # vanilla forward, REF/main.py:331-334
     texts = {0: vocab.batch_to_text(engine.decode_ids())}
     losses = []
-    for i in range(steps):                                         # REF/main.py:347-348
-        engine.adapt_step(hp)
-        if collect_losses:
-            losses.append(engine.losses()[0].cpu().numpy().copy())
-        if episodic and (i + 1) in CHECKPOINT_STEPS:               # REF/main.py:349-398
-            texts[i + 1] = vocab.batch_to_text(engine.decode_ids())
+    lr0 = hp.lr
+    try:
+        for i in range(steps):                                     # REF/main.py:347-348
+            if sched_gamma is not None:
+                hp.lr = lr0 * sched_gamma ** (i // sched_step)
+            engine.adapt_step(hp)
+            if collect_losses:
+                losses.append(engine.losses()[0].cpu().numpy().copy())
+            if (i + 1) in CHECKPOINT_STEPS:                        # REF/main.py:349-398
+                texts[i + 1] = vocab.batch_to_text(engine.decode_ids())
+    finally:
+        hp.lr = lr0
     if collect_losses:
         texts["losses"] = losses
     return texts
@@ -62,8 +74,10 @@ class SutaRunner:
     """Dataset-level driver for one rank."""
 
     def __init__(self, engine: SutaEngine, steps: int = 10, hp: Optional[AdaptHyper] = None, max_utts: int = 64,
-                 max_frames: int = 32768, vocab: Optional[CTCVocab] = None, rank: int = 0, world_size: int = 1):
+                 max_frames: int = 32768, vocab: Optional[CTCVocab] = None, rank: int = 0, world_size: int = 1,
+                 sched_gamma: Optional[float] = None, sched_step: int = 1):
         self.engine, self.steps, self.hp = engine, steps, hp or AdaptHyper()
+        self.sched_gamma, self.sched_step = sched_gamma, sched_step
         self.max_utts, self.max_frames = max_utts, max_frames
         self.vocab = vocab or CTCVocab()
         self.rank, self.world_size = rank, world_size
@@ -82,7 +96,8 @@ class SutaRunner:
         for b in batches:
             sel = [utts[i] for i in b]
             packed = pack_batch(self.engine, sel)
-            out = adapt_batch(self.engine, packed, None, self.steps, self.hp, self.vocab)
+            out = adapt_batch(self.engine, packed, None, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
+                              sched_step=self.sched_step)
             for step, tl in out.items():
                 texts.setdefault(step, {}).update({i: t for i, t in zip(b, tl)})
         torch.cuda.synchronize()

@@ -29,16 +29,37 @@ from oracle import suta_oracle as O  # noqa: E402
 
 REF = "/root/reference"
 
-CASES = {
-    # name: (cfg factory, n_samples, audio seed, weight seed, blank_bias, ln_jitter, steps, train_feature)
-    "tiny_ln": ("tiny", 12000, 11, 3, 0.5, 0.1, 10, False),
-    "tiny_feat": ("tiny", 9000, 12, 4, 0.35, 0.1, 10, True),
-    "tiny_short": ("tiny", 2000, 13, 5, 0.35, 0.1, 5, False),
-    "base_ln_5s": ("base", 80000, 1234, 0, 1.75, 0.0, 10, False),
-    "base_ln_5s_noblank": ("base", 80000, 1234, 0, 0.0, 0.0, 3, False),
-    "base_feat_2s": ("base", 32000, 77, 0, 1.75, 0.0, 3, True),
-}
+def _case(cfg, n, aseed, wseed, bb, jit, steps, tf=False, **kw):
+    d = dict(cfg=cfg, n=n, aseed=aseed, wseed=wseed, blank_bias=bb, ln_jitter=jit, steps=steps, train_feature=tf,
+             extra_noise=0.0, opt="AdamW", beta=0.9, sched_gamma=None, bias_only=False, div_coef=0.0)
+    d.update(kw)
+    return d
+
+
 HYPER = dict(lr=2e-5, em_coef=0.3, reweight=True, temp=2.5, not_blank=True)   # REF/scripts/LS.sh:2-14
+CASES = {
+    # round 1
+    "tiny_ln": _case("tiny", 12000, 11, 3, 0.5, 0.1, 10),
+    "tiny_feat": _case("tiny", 9000, 12, 4, 0.35, 0.1, 10, True),
+    "tiny_short": _case("tiny", 2000, 13, 5, 0.35, 0.1, 5),
+    "base_ln_5s": _case("base", 80000, 1234, 0, 1.75, 0.0, 10),
+    "base_ln_5s_noblank": _case("base", 80000, 1234, 0, 0.0, 0.0, 3),
+    "base_feat_2s": _case("base", 32000, 77, 0, 1.75, 0.0, 3, True),
+    # round 2: the shapes bench.py measures (BASELINE.json configs[1], [3], [4]) and every optimizer / flag variant
+    "base_feat_5s": _case("base", 80000, 1234, 0, 1.75, 0.0, 10, True),                 # configs[1]: 10-step train_feature
+    "base_ln_30s": _case("base", 480000, 31, 0, 1.75, 0.0, 2),                          # T = 1499 end to end
+    "large_ln_2s": _case("large", 32000, 41, 0, 2.5, 0.0, 3),                          # configs[3] architecture
+    "tiny_feat_noise20": _case("tiny", 9000, 12, 4, 0.35, 0.1, 20, True, extra_noise=0.01),   # configs[4]: 20 steps + noise
+    "tiny_sgd": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, opt="SGD", lr=0.5),
+    "tiny_feat_sgd": _case("tiny", 9000, 12, 4, 0.35, 0.1, 5, True, opt="SGD", lr=0.02),
+    "tiny_adam_beta": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, opt="Adam", beta=0.8),
+    "tiny_steplr": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, sched_gamma=0.7),
+    "tiny_bias_only": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, bias_only=True),
+    "tiny_div": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, div_coef=0.1),
+    "tiny_em_only": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, em_coef=1.0, not_blank=False),
+    "tiny_mcc_plain": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, em_coef=0.0, reweight=False),
+    "tiny_temp1_allframes": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, temp=1.0, not_blank=False, reweight=False, em_coef=0.9),
+}
 BIG = 1 << 16      # tensors above this many elements are stored as (checksum, head) only
 
 
@@ -49,6 +70,7 @@ def import_reference():
     sys.path.insert(0, REF)
     import main as ref_main
     ref_main.scheduler = None           # module-global read by load_model_and_optimizer (REF/main.py:151)
+    import transformers.models.wav2vec2  # noqa: F401  (eval() of the scheduler string needs `torch` in main's globals)
     return ref_main
 
 
@@ -59,18 +81,22 @@ def build_processor():
     return Wav2Vec2Processor(fe, Wav2Vec2CTCTokenizer(os.path.join(REF, "vocab.json")))
 
 
-def run_reference(ref_main, processor, cfg, sd, wav, steps, train_feature):
+def run_reference(ref_main, processor, cfg, sd, wav, c, hy):
+    """Drive the reference's own functions through the loop of REF/main.py:306-311,319-402 for one utterance."""
     from transformers import Wav2Vec2ForCTC
     torch.manual_seed(0)
     model = Wav2Vec2ForCTC(cfg.to_hf()).eval()
     missing, unexpected = model.load_state_dict(sd, strict=False)
     missing = [m for m in missing if "masked_spec_embed" not in m]
     assert not missing and not unexpected, (missing, unexpected)
+    sched_name = "torch.optim.lr_scheduler.StepLR" if c["sched_gamma"] is not None else None
     with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model = ref_main.configure_model(model)
-        params, names = ref_main.collect_params(model, False, train_feature, False, True)
-        optimizer, scheduler = ref_main.setup_optimizer(params, "AdamW", HYPER["lr"], scheduler=None)
+        params, names = ref_main.collect_params(model, c["bias_only"], c["train_feature"], False, True)
+        optimizer, scheduler = ref_main.setup_optimizer(params, c["opt"], hy["lr"], beta=c["beta"], scheduler=sched_name,
+                                                        step_size=1, gamma=c["sched_gamma"] or 0.7)
+        ref_main.scheduler = scheduler      # module-global read by load_model_and_optimizer (REF/main.py:151)
         snap = ref_main.copy_model_and_optimizer(model, optimizer, scheduler)
         model, optimizer, scheduler = ref_main.load_model_and_optimizer(model, optimizer, *snap)
     x = processor([wav], return_tensors="pt", padding="longest").input_values
@@ -79,22 +105,30 @@ def run_reference(ref_main, processor, cfg, sd, wav, steps, train_feature):
         lg = model(x).logits
     out["logits"][0] = lg[0].numpy().copy()
     out["texts"][0] = processor.batch_decode(torch.argmax(lg, dim=-1))[0]
-    for i in range(steps):
+    for i in range(c["steps"]):
         with torch.no_grad():      # loss of the training forward, recomputed with the reference's functions
             lg = model(x).logits
             nb = torch.argmax(lg, -1) != 0
-            e = ref_main.softmax_entropy(lg / HYPER["temp"])[nb].mean(0).mean()
-            c = ref_main.mcc_loss(lg / HYPER["temp"], HYPER["reweight"], class_num=lg.shape[-1])
-            out["losses"].append(float(e * HYPER["em_coef"] + c * (1 - HYPER["em_coef"])))
+            loss = 0.0
+            if hy["em_coef"] > 0:
+                ent = ref_main.softmax_entropy(lg / hy["temp"])
+                loss += float((ent[nb] if hy["not_blank"] else ent).mean(0).mean()) * hy["em_coef"]
+            if 1 - hy["em_coef"] > 0:
+                # class_num: the reference hard-codes 32 = the vocabulary size of its checkpoints
+                loss += float(ref_main.mcc_loss(lg / hy["temp"], hy["reweight"], class_num=lg.shape[-1])) * (1 - hy["em_coef"])
+            if c["div_coef"] > 0:
+                loss += float(ref_main.div_loss(lg, hy["not_blank"])) * c["div_coef"]
+            out["losses"].append(loss)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            lg = ref_main.forward_and_adapt(x, model, optimizer, HYPER["em_coef"], HYPER["reweight"], HYPER["temp"],
-                                            HYPER["not_blank"], scheduler, 0)
-        if (i + 1) in O.CHECKPOINT_STEPS:
+            lg = ref_main.forward_and_adapt(x, model, optimizer, hy["em_coef"], hy["reweight"], hy["temp"],
+                                            hy["not_blank"], scheduler, c["div_coef"])
+        if (i + 1) in O.CHECKPOINT_STEPS or i + 1 == c["steps"]:
             out["logits"][i + 1] = lg[0].detach().numpy().copy()
             out["texts"][i + 1] = processor.batch_decode(torch.argmax(lg, dim=-1))[0]
     msd = model.state_dict()
     out["params"] = {n: msd[n].detach().numpy().copy() for n in dict.fromkeys(names)}
+    ref_main.scheduler = None
     return out
 
 
@@ -107,25 +141,29 @@ def pack_param(a):
 
 
 def make(case, ref_main, processor):
-    cfg_name, n, aseed, wseed, bb, jit, steps, tf = CASES[case]
+    c = CASES[case]
+    hy = {k: c.get(k, v) for k, v in HYPER.items()}
+    cfg_name, n, steps, tf = c["cfg"], c["n"], c["steps"], c["train_feature"]
     cfg = getattr(O.W2V2Config, cfg_name)()
-    sd = O.init_weights(cfg, wseed, blank_bias=bb, ln_jitter=jit)
-    wav = O.synth_audio(n, aseed)
-    ref = run_reference(ref_main, processor, cfg, sd, wav, steps, tf)
+    sd = O.init_weights(cfg, c["wseed"], blank_bias=c["blank_bias"], ln_jitter=c["ln_jitter"])
+    wav = O.synth_audio(n, c["aseed"], c["extra_noise"])        # REF/data.py:23: noise is added to the raw waveform
+    ref = run_reference(ref_main, processor, cfg, sd, wav, c, hy)
 
     # --- pin the oracle against the reference --------------------------------------------
     x = O.normalize_audio(wav)
     np.testing.assert_allclose(x, ref["x"], rtol=0, atol=2e-6)
-    names_o = O.collect_param_names(cfg, train_feature=tf)
+    names_o = O.collect_param_names(cfg, bias_only=c["bias_only"], train_feature=tf)
     assert sorted(names_o) == sorted(ref["names"]), "collect_params multiplicities differ"
-    ora = O.adapt_utterance(cfg, sd, x, steps=steps, train_feature=tf, **HYPER)
+    ora = O.adapt_utterance(cfg, sd, x, steps=steps, train_feature=tf, bias_only=c["bias_only"], opt=c["opt"], beta=c["beta"],
+                            sched_gamma=c["sched_gamma"], div_coef=c["div_coef"], keep_all_logits=True, **hy)
     assert ora.texts[0] == ref["texts"][0]
     np.testing.assert_allclose(ora.logits0, ref["logits"][0], rtol=0, atol=5e-5)
     np.testing.assert_allclose(ora.losses, ref["losses"], rtol=2e-5)
     for s, lg in ref["logits"].items():
         if s:
             np.testing.assert_allclose(ora.logits[s], lg, rtol=0, atol=2e-4)
-            assert ora.texts[s] == ref["texts"][s], (s, ora.texts[s], ref["texts"][s])
+            if s in ora.texts:
+                assert ora.texts[s] == ref["texts"][s], (s, ora.texts[s], ref["texts"][s])
     worst = 0.0
     for nme, p in ref["params"].items():
         d_ref = p - sd[nme].numpy()
@@ -133,17 +171,21 @@ def make(case, ref_main, processor):
         worst = max(worst, float(np.abs(d_ref - d_or).max() / (np.abs(d_ref).max() + 1e-12)))
     # closed-form gradient vs autograd on the reference's step-0 logits
     lg0 = torch.tensor(ref["logits"][0][None], requires_grad=True)
-    O.suta_loss(lg0, HYPER["em_coef"], HYPER["reweight"], HYPER["temp"], HYPER["not_blank"]).backward()
-    lv, gcf = O.suta_loss_grad_closed(ref["logits"][0], HYPER["em_coef"], HYPER["reweight"], HYPER["temp"], HYPER["not_blank"])
+    O.suta_loss(lg0, hy["em_coef"], hy["reweight"], hy["temp"], hy["not_blank"], c["div_coef"]).backward()
+    lv, gcf = O.suta_loss_grad_closed(ref["logits"][0], hy["em_coef"], hy["reweight"], hy["temp"], hy["not_blank"], c["div_coef"])
     np.testing.assert_allclose(gcf, lg0.grad[0].numpy(), rtol=1e-3, atol=1e-9)
     np.testing.assert_allclose(lv, ref["losses"][0], rtol=1e-5)
     blank_frac = float((ref["logits"][0].argmax(-1) == 0).mean())
+    dl = ref["logits"][max(ref["logits"])] - ref["logits"][0]
     print(f"[{case}] T={ref['logits'][0].shape[0]} blank_frac={blank_frac:.2f} losses={ref['losses'][0]:.6f}->"
-          f"{ref['losses'][-1]:.6f} oracle-vs-ref worst delta mismatch={worst:.2e} texts={ref['texts']}")
+          f"{ref['losses'][-1]:.6f} logit-change rms={float(np.sqrt((dl ** 2).mean())):.2e} "
+          f"oracle-vs-ref worst delta mismatch={worst:.2e} texts={ref['texts']}", flush=True)
     assert worst < 0.05, worst
 
-    meta = dict(case=case, cfg=cfg_name, n_samples=n, audio_seed=aseed, weight_seed=wseed, blank_bias=bb,
-                ln_jitter=jit, steps=steps, train_feature=tf, hyper=HYPER, blank_frac=blank_frac,
+    meta = dict(case=case, cfg=cfg_name, n_samples=n, audio_seed=c["aseed"], weight_seed=c["wseed"], blank_bias=c["blank_bias"],
+                ln_jitter=c["ln_jitter"], steps=steps, train_feature=tf, hyper=hy, blank_frac=blank_frac,
+                extra_noise=c["extra_noise"], opt=c["opt"], beta=c["beta"], sched_gamma=c["sched_gamma"],
+                bias_only=c["bias_only"], div_coef=c["div_coef"],
                 names=ref["names"], texts={str(k): v for k, v in ref["texts"].items()},
                 generator="tests/golden/make_golden.py", torch=torch.__version__,
                 transformers=__import__("transformers").__version__)
@@ -156,9 +198,55 @@ def make(case, ref_main, processor):
     np.savez_compressed(os.path.join(HERE, case + ".npz"), **arrs)
 
 
+def make_continual(ref_main, processor, case="tiny_continual"):
+    """The reference WITHOUT --episodic (its CLI default): model and optimizer state flow from one utterance into the
+    next (REF/main.py:319-348 with :327-328 skipped).  Three utterances, the last two of equal length."""
+    from transformers import Wav2Vec2ForCTC
+    cfg = O.W2V2Config.tiny()
+    sd = O.init_weights(cfg, 3, blank_bias=0.5, ln_jitter=0.1)
+    utts, steps = [(12000, 11), (9000, 12), (9000, 14)], 3
+    torch.manual_seed(0)
+    model = Wav2Vec2ForCTC(cfg.to_hf()).eval()
+    model.load_state_dict(sd, strict=False)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = ref_main.configure_model(model)
+        params, names = ref_main.collect_params(model, False, False, False, True)
+        optimizer, scheduler = ref_main.setup_optimizer(params, "AdamW", HYPER["lr"], scheduler=None)
+    arrs, carry = {}, None
+    for j, (n, seed) in enumerate(utts):
+        wav = O.synth_audio(n, seed)
+        x = processor([wav], return_tensors="pt", padding="longest").input_values
+        with torch.no_grad():
+            arrs[f"u{j}_logits_0"] = model(x).logits[0].numpy().copy()
+        for i in range(steps):
+            lg = ref_main.forward_and_adapt(x, model, optimizer, HYPER["em_coef"], HYPER["reweight"], HYPER["temp"],
+                                            HYPER["not_blank"], scheduler, 0)
+        arrs[f"u{j}_logits_{steps}"] = lg[0].detach().numpy().copy()
+        ora = O.adapt_utterance(cfg, sd, O.normalize_audio(wav), steps=steps, carry=carry, **HYPER)
+        carry = ora.carry
+        np.testing.assert_allclose(ora.logits0, arrs[f"u{j}_logits_0"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(ora.logits[steps], arrs[f"u{j}_logits_{steps}"], rtol=0, atol=2e-4)
+    msd = model.state_dict()
+    worst = 0.0
+    for nme in dict.fromkeys(names):
+        arrs["param:" + nme] = msd[nme].detach().numpy().copy()
+        d_ref, d_or = arrs["param:" + nme] - sd[nme].numpy(), carry["w"][nme].numpy() - sd[nme].numpy()
+        worst = max(worst, float(np.abs(d_ref - d_or).max() / (np.abs(d_ref).max() + 1e-12)))
+    print(f"[{case}] oracle-vs-ref worst delta mismatch after {len(utts)} utterances = {worst:.2e}", flush=True)
+    assert worst < 0.05
+    meta = dict(case=case, cfg="tiny", utts=utts, steps=steps, weight_seed=3, blank_bias=0.5, ln_jitter=0.1, hyper=HYPER,
+                names=names, generator="tests/golden/make_golden.py")
+    arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, case + ".npz"), **arrs)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     ref_main = import_reference()
     processor = build_processor()
-    for c in (sys.argv[1:] or list(CASES)):
-        make(c, ref_main, processor)
+    for c in (sys.argv[1:] or list(CASES) + ["tiny_continual"]):
+        if c == "tiny_continual":
+            make_continual(ref_main, processor)
+        else:
+            make(c, ref_main, processor)

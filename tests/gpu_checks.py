@@ -181,16 +181,28 @@ def check_layernorm(N=768, Ts=(70, 3, 129), seed=5, bf16_in=False):
     dy = torch.randn(M, N, device=DEV, generator=g)
     G = torch.zeros(U, n_par, device=DEV)
     dx32 = torch.zeros(M, N, device=DEV); dx16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    check(lib.suta_op_layernorm_bwd(P(dy), None if bf16_in else P(x), P(x) if bf16_in else None, P(mean), P(rstd), P(ru), P(Pm),
-                                    n_par, g_off, b_off, P(G), P(dx32), P(dx16), M, N, stream()))
+    tok_off = torch.tensor(np.concatenate([[0], np.cumsum(Ts)[:-1]]), dtype=torch.int64, device=DEV)
+    Tt = torch.tensor(Ts, dtype=torch.int32, device=DEV)
+    scratch = torch.empty(int(lib.suta_op_layernorm_bwd_scratch_floats(N, U)), device=DEV)
+    G = torch.full((U, n_par), float("nan"), device=DEV)        # dgamma/dbeta are WRITTEN, the rest of G is left alone
+    G2 = G.clone()
+    for Gx in (G, G2):                                          # twice: the two-stage reduction is bit-reproducible
+        check(lib.suta_op_layernorm_bwd(P(dy), None if bf16_in else P(x), P(x) if bf16_in else None, P(mean), P(rstd), P(ru),
+                                        P(Pm), n_par, g_off, b_off, P(Gx), P(dx32), P(dx16), M, N, P(tok_off), P(Tt), U,
+                                        P(scratch), stream()))
     torch.cuda.synchronize()
+    seg = slice(g_off, b_off + N)
+    bit_equal = bool(torch.equal(G[:, seg], G2[:, seg]))
+    untouched = bool(torch.isnan(G[:, :g_off]).all())
+    G = torch.where(torch.isnan(G), torch.zeros_like(G), G)
     xr = x.float().clone().requires_grad_(True)
     Pr = Pm.clone().requires_grad_(True)
     gam = Pr[ru.long(), g_off:g_off + N]; bet = Pr[ru.long(), b_off:b_off + N]
     yr = torch.nn.functional.layer_norm(xr, (N,), eps=1e-5) * gam + bet
     (yr * dy).sum().backward()
     return dict(y_rel=relerr(y32, yr), y16_rel=relerr(y16.float(), yr), dx_rel=relerr(dx32, xr.grad),
-                dx16_rel=relerr(dx16.float(), xr.grad), dparam_rel=relerr(G, Pr.grad))
+                dx16_rel=relerr(dx16.float(), xr.grad), dparam_rel=relerr(G, Pr.grad), dparam_bit_equal=bit_equal,
+                dparam_writes_only_its_segment=untouched)
 
 
 def attn_table(Ts):
@@ -230,7 +242,7 @@ def check_attention(Ts=(249, 64, 1, 130), heads=2, seed=6):
                 dv_rel=relerr(dqkv[:, 2 * H:].float(), x.grad[:, 2 * H:]), nan=int(torch.isnan(dqkv.float()).sum()))
 
 
-def check_loss(Ts=(249, 37, 6), seed=7, em_coef=0.3, reweight=True, not_blank=True, temp=2.5, blank_bias=1.0):
+def check_loss(Ts=(249, 37, 6), seed=7, em_coef=0.3, reweight=True, not_blank=True, temp=2.5, blank_bias=1.0, div_coef=0.0):
     lib = _lib.load()
     g = torch.Generator(device=DEV).manual_seed(seed)
     M, U = sum(Ts), len(Ts)
@@ -240,32 +252,44 @@ def check_loss(Ts=(249, 37, 6), seed=7, em_coef=0.3, reweight=True, not_blank=Tr
     Tt = torch.tensor(Ts, dtype=torch.int32, device=DEV)
     loss = torch.zeros(3 * U, device=DEV)
     d32 = torch.zeros(M, 32, device=DEV); d16 = torch.zeros(M, 32, device=DEV, dtype=torch.bfloat16)
-    check(lib.suta_op_loss(P(logits), P(off), P(Tt), U, em_coef, temp, int(reweight), int(not_blank), P(loss), P(d32), P(d16),
-                           stream()))
+    check(lib.suta_op_loss(P(logits), P(off), P(Tt), U, em_coef, temp, int(reweight), int(not_blank), div_coef, P(loss), P(d32),
+                           P(d16), stream()))
     torch.cuda.synchronize()
     lg = logits.cpu().numpy()
     worst_l = worst_g = 0.0
+    nan_loss, finite_grad, nan_agree = 0, True, True
     o = 0
     for u, T in enumerate(Ts):
-        lv, gr = O.suta_loss_grad_closed(lg[o:o + T], em_coef, reweight, temp, not_blank)
         lt = torch.tensor(lg[o:o + T][None], requires_grad=True)
-        lref = O.suta_loss(lt, em_coef, reweight, temp, not_blank)
+        lref = O.suta_loss(lt, em_coef, reweight, temp, not_blank, div_coef)
         lref.backward()
-        worst_l = max(worst_l, abs(float(loss[u]) - float(lref)) / abs(float(lref)))
         gk = d32[o:o + T].cpu().double()
+        if not np.isfinite(float(lref)):
+            # every frame blank with non_blank masking: REF/main.py:190 takes the mean of an empty selection -> the loss is
+            # NaN; torch's backward then poisons the gradient with NaN too.  The kernel reports the NaN loss and keeps the
+            # gradient finite (the entropy term contributes nothing): state which of the two happened
+            nan_loss += 1
+            nan_agree = nan_agree and not np.isfinite(float(loss[u]))
+            finite_grad = finite_grad and bool(torch.isfinite(gk).all())
+            o += T
+            continue
+        nan_agree = nan_agree and bool(np.isfinite(float(loss[u])))
+        worst_l = max(worst_l, abs(float(loss[u]) - float(lref)) / abs(float(lref)))
         worst_g = max(worst_g, float((gk - lt.grad[0].double()).norm() / lt.grad[0].double().norm()))
         o += T
-    return dict(loss_rel=worst_l, grad_rel=worst_g, bf16_rel=relerr(d16.float(), d32))
+    return dict(loss_rel=worst_l, grad_rel=worst_g, bf16_rel=relerr(d16.float(), d32), nan_loss_utts=nan_loss,
+                nan_where_the_reference_is_nan=nan_agree, grad_finite_where_loss_nan=finite_grad)
 
 
-def check_adam(n=5000, U=3, steps=4, seed=8):
+def check_adam(n=5000, U=3, steps=4, seed=8, opt="AdamW", lr=2e-5, beta1=0.9, wd=0.0):
+    """The fused update vs oracle.adam_update (= torch's single-tensor CPU loop, k sub-steps for multiplicity k)."""
     lib = _lib.load()
     rng = np.random.default_rng(seed)
     p0 = rng.standard_normal((U, n)).astype(np.float32)
     mult = rng.integers(0, 5, n).astype(np.uint8)
     Pd = torch.tensor(p0, device=DEV); Md = torch.zeros(U, n, device=DEV); Vd = torch.zeros(U, n, device=DEV)
     multd = torch.tensor(mult, device=DEV)
-    h = Hyper(0.3, 2.5, 1, 1, 0, 2e-5, 0.9, 0.999, 1e-8, 0.0)
+    h = Hyper(0.3, 2.5, 1, 1, {"AdamW": 0, "SGD": 1, "Adam": 2}[opt], lr, beta1, 0.999, 1e-8, wd, 0.0)
     p_ref = torch.tensor(p0.copy()); m_ref = torch.zeros(U, n); v_ref = torch.zeros(U, n)
     step_ref = np.zeros(n, dtype=np.int64)
     for s in range(steps):
@@ -278,7 +302,11 @@ def check_adam(n=5000, U=3, steps=4, seed=8):
             if len(idx) == 0:
                 continue
             pp, mm, vv = p_ref[:, idx].clone(), m_ref[:, idx].clone(), v_ref[:, idx].clone()
-            O.adam_update(pp, gt[:, idx], mm, vv, k * s, 2e-5, k=k)
+            if opt == "SGD":
+                for _ in range(k):
+                    pp -= lr * (gt[:, idx] + wd * pp)
+            else:
+                O.adam_update(pp, gt[:, idx], mm, vv, k * s, lr, k=k, beta1=beta1, weight_decay=wd, decoupled=(opt == "AdamW"))
             p_ref[:, idx], m_ref[:, idx], v_ref[:, idx] = pp, mm, vv
     torch.cuda.synchronize()
     d_ref = p_ref - torch.tensor(p0)
@@ -327,4 +355,8 @@ ALL = [("gemm_plain", check_gemm_plain), ("gemm_epilogue", check_gemm_epilogue),
        ("attention", check_attention), ("loss", check_loss),
        ("loss_variants", lambda: {f"{e}{r}{n}": check_loss(em_coef=e, reweight=r, not_blank=n)["grad_rel"]
                                   for e in (0.3, 1.0, 0.0) for r in (False, True) for n in (False, True)}),
-       ("adam", check_adam), ("decode", check_decode)]
+       ("loss_div", lambda: check_loss(div_coef=0.25)),
+       ("loss_all_blank", lambda: check_loss(Ts=(40, 5, 1), blank_bias=50.0)),
+       ("adam", check_adam), ("adam_beta_l2", lambda: check_adam(opt="Adam", beta1=0.8, wd=0.01, lr=1e-3)),
+       ("adamw_decay", lambda: check_adam(opt="AdamW", wd=0.01, lr=1e-3)), ("sgd_wd", lambda: check_adam(opt="SGD", lr=0.05, wd=0.01)),
+       ("decode", check_decode)]

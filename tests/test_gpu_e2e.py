@@ -1,17 +1,33 @@
-"""GPU: the whole adaptation path against the oracle (live, tiny model) and the reference's golden vectors (base).
+"""GPU: the whole adaptation path against the oracle (live, tiny model) and the reference's golden vectors (base, large).
 
-Stated tolerances (bf16 tensor-core operands, fp32 accumulation / norms / softmax / loss / optimizer):
-  logits          max |diff| < 0.05   (logit std ~0.6; observed ~0.02 on wav2vec2-base, 5 s)
-  per-step loss   relative   < 1e-3   (observed ~1e-5)
-  adapted params  relative   < 1e-3   in value (observed ~2e-5); the 10-step parameter DELTA is reproduced to ~10-20 %
-                                      in norm (Adam's first steps are sign-like, so bf16 gradient noise shows there)
-  CTC decode      bit-exact given the same logits
+Stated tolerances (bf16 tensor-core operands, fp32 accumulation / norms / softmax / loss / optimizer).  Every bound
+below is one an engine that does NOT adapt (or adapts wrongly) fails: the parameter DELTA and the logit CHANGE are
+compared, never just the values (a 10-step update at lr 2e-5 moves a parameter by ~2e-4 of its value).
+
+  logits            max |diff| < 0.05 (+ 15 % of the largest logit change the adaptation causes, which matters only
+                    under train_feature where 10 steps move logits by several units; logit std ~0.6, observed ~0.02)
+  per-step loss     relative   < 1e-3      (observed ~1e-5; 10-step train_feature on base: < 2e-3 at steps 9-10, where the
+                    bf16 emulation of tools/precision_study.py gives 1.15e-3 and the engine 1.0e-3 -- trajectories
+                    that differ by rounding noise diverge as the CNN weights move)
+  parameter delta   ||d_engine - d_ref|| / ||d_ref|| < 0.15   (observed 0.03-0.09; 1.0 for an engine that never adapted)
+  gradient, step 0  relative   < 0.05      (observed ~0.01) against fp32 autograd through the oracle
+  logit change produced by the engine's adapted parameters in the fp32 oracle forward vs the reference's logit change
+                    relative   < 0.15      (observed ~0.01 base, ~0.07 tiny)
+  CTC decode        bit-exact given the same logits; transcripts equal to the reference's wherever the reference's own
+                    top-2 logit gap exceeds the logit tolerance
+
+Why Adam amplifies: its first steps are sign-like (delta = lr * g / |g|), so a 1 % gradient error on the elements with
+the smallest gradients flips their whole step: 1 % gradient error -> ~8 % delta error, exactly what a CPU emulation
+of bf16 GEMM operands inside the fp32 oracle gives (tools/precision_study.py).  The looser
+bound applies only where the reference's own non-blank mask is decided by less than the logit tolerance (`mask_margin`).
 """
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.05
 
 
 @pytest.fixture(scope="module")
@@ -22,12 +38,20 @@ def E():
     return e2e_checks
 
 
-def _assert_parity(m):
-    assert m["logits0_maxabs"] < 0.05 and m["logitsN_maxabs"] < 0.05
-    assert m["loss_rel_max"] < 1e-3
-    assert m["param_value_rel"] < 1e-3
-    assert m["param_delta_rel"] < 0.5
+def _assert_parity(m, delta=0.15, grad=0.05, via=0.15, loss=1e-3):
+    assert m["logits0_maxabs"] < LOGIT_TOL and m["logitsN_maxabs"] < LOGIT_TOL + 0.15 * m["logit_change_maxabs"], m
+    assert m["loss_rel_max"] < loss, m
     assert m["decode_equal_given_logits"]
+    # the mask of the entropy term may legitimately differ on frames the reference decides by less than the engine's
+    # logit error (see e2e_checks.compare): one frame of n_M changes the entropy gradient by 1/n_M
+    loose = 2.5 if m["mask_margin"] < 2 * m["logits0_maxabs"] else 1.0
+    assert m["param_delta_rel"] < delta * loose, m
+    assert m["param_delta_rel"] < 0.5                      # never vacuous: an engine that does not adapt scores 1.0
+    if "grad0_rel" in m:
+        assert m["grad0_rel"] < grad * loose, m
+    if "dlogits_via_oracle_rel" in m:
+        assert m["dlogits_via_oracle_rel"] < via * loose, m
+    assert m["param_value_rel"] < 1e-3                     # sanity only (says nothing about the adaptation)
 
 
 def test_forward_stages_vs_oracle(E):
@@ -43,6 +67,28 @@ def test_batched_adaptation_matches_per_utterance_oracle(E):
 @pytest.mark.parametrize("case", ["tiny_ln", "tiny_short", "base_ln_5s", "base_ln_5s_noblank"])
 def test_against_reference_golden_vectors(E, case):
     m = E.check_golden(case)
+    print(case, m)
+    _assert_parity(m)
+    assert m["argmax_agree0"] > 0.95
+
+
+@pytest.mark.parametrize("case", ["tiny_sgd", "tiny_adam_beta", "tiny_steplr", "tiny_bias_only", "tiny_div", "tiny_em_only",
+                                  "tiny_mcc_plain", "tiny_temp1_allframes"])
+def test_optimizer_and_flag_variants_against_reference_golden_vectors(E, case):
+    """SGD, Adam(beta), StepLR, --bias_only, --div_coef, em_coef 1 / 0, temperature 1, entropy over all frames: each
+    driven through the unmodified reference by tests/golden/make_golden.py."""
+    m = E.check_golden(case)
+    print(case, m)
+    # SGD has no sign-like amplification: its delta is the gradient itself
+    _assert_parity(m, delta=0.05 if case == "tiny_sgd" else 0.15)
+
+
+@pytest.mark.parametrize("case", ["base_ln_30s", "large_ln_2s"])
+def test_long_utterance_and_large_model_against_reference_golden_vectors(E, case):
+    """T = 1499 frames end to end (BASELINE.json configs[3] length) and the wav2vec2-large architecture (H = 1024,
+    16 heads, 24 layers, I = 4096; HF/modeling_wav2vec2.py same code path)."""
+    m = E.check_golden(case)
+    print(case, m)
     _assert_parity(m)
     assert m["argmax_agree0"] > 0.95
 
@@ -51,17 +97,24 @@ def test_train_feature_batched_vs_oracle(E):
     """--train_feature: per-utterance CNN/projection weights and the reference's duplicate-parameter Adam semantics."""
     for name, m in E.check_tiny_feat_batch().items():
         _assert_parity(m)
-        assert m["param_delta_rel"] < 0.15           # the parameter DELTA itself is reproduced here (observed 3-5 %)
         for k, v in m.items():
             if k.startswith("delta:"):
                 assert v < 0.25, (name, k, v)
 
 
-@pytest.mark.parametrize("case", ["tiny_feat", "base_feat_2s"])
+@pytest.mark.parametrize("case", ["tiny_feat", "base_feat_2s", "base_feat_5s", "tiny_feat_noise20", "tiny_feat_sgd"])
 def test_train_feature_against_reference_golden_vectors(E, case):
+    """--train_feature incl. BASELINE.json configs[1]'s shape (base, 10 steps: base_feat_5s) and configs[4]'s recipe
+    (20 steps, extra_noise 0.01: tiny_feat_noise20).  Here the adaptation moves the logits far above the forward's
+    rounding noise, so the engine's own logit change is compared as well."""
     m = E.check_golden(case)
-    _assert_parity(m)
-    assert m["param_delta_rel"] < 0.15 and m["dlogits_rel"] < 0.15 and m["argmax_agree0"] > 0.95
+    print(case, m)
+    _assert_parity(m, loss=2e-3 if case == "base_feat_5s" else 1e-3)
+    assert m["argmax_agree0"] > 0.95
+    if m["logit_change_maxabs"] > 10 * m["logits0_maxabs"]:        # the change stands clear of the forward's rounding noise
+        assert m["dlogits_rel"] < 0.15
+    if "big_param_head_delta_rel" in m:
+        assert m["big_param_head_delta_rel"] < 0.15
 
 
 def test_batch_composition_does_not_change_results(E):
@@ -98,12 +151,68 @@ def test_drop_in_api_single_utterance(E, capsys):
         assert np.abs(out[0].cpu().numpy() - ref.logits[3]).max() < 0.05
         got = {p.name: p.data[0].cpu().numpy() for p in params}
         num = sum(float(((got[n] - ref.params[n]) ** 2).sum()) for n in got)
-        den = sum(float((ref.params[n] ** 2).sum()) for n in got)
-        assert (num / den) ** 0.5 < 1e-3
+        den = sum(float(((ref.params[n] - sd[n].numpy()) ** 2).sum()) for n in got)
+        assert (num / den) ** 0.5 < 0.4, (num / den) ** 0.5     # DELTA error (3 steps, T = 37: mask-margin case of _assert_parity)
     ent = api.softmax_entropy(out / 2.5)
     assert np.allclose(ent.cpu().numpy(), O.softmax_entropy(torch.tensor(out.cpu().numpy()) / 2.5).numpy(), atol=1e-5)
     mc = api.mcc_loss(out / 2.5, True)
     assert abs(float(mc) - float(O.mcc_loss(torch.tensor(out.cpu().numpy()) / 2.5, True))) < 1e-5
+    capsys.readouterr()
+
+
+def test_drop_in_api_without_episodic_carries_model_and_optimizer_state(E, capsys):
+    """The reference's default (no --episodic): adapted weights AND the AdamW state (exp_avg, exp_avg_sq, step) flow
+    from one utterance into the next (REF/main.py:319-348).  Fixture: the unmodified reference run over three
+    utterances without reset; the last two have the SAME length and each input tensor is deleted before the next
+    is created (REF/main.py:400-401), so the caching allocator hands the same address to a different utterance."""
+    from oracle import suta_oracle as O
+    from suta_b200 import ModelConfig, api
+    z, meta = E.load_golden("tiny_continual")
+    ocfg = O.W2V2Config.tiny()
+    sd = O.init_weights(ocfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"])
+    model = api.configure_model(api.SutaModel(ModelConfig.tiny(), sd))
+    params, names = api.collect_params(model, False, False, False, True)
+    assert names == meta["names"]
+    h = meta["hyper"]
+    opt, sched = api.setup_optimizer(params, "AdamW", h["lr"])
+    ptrs = []
+    for j, (n, seed) in enumerate(meta["utts"]):
+        x = torch.from_numpy(O.normalize_audio(O.synth_audio(n, seed)))[None].cuda()
+        ptrs.append((x.data_ptr(), n))
+        with torch.no_grad():
+            out0 = model(x).logits
+        assert np.abs(out0[0].cpu().numpy() - z[f"u{j}_logits_0"]).max() < LOGIT_TOL
+        for i in range(meta["steps"]):
+            out = api.forward_and_adapt(x, model, opt, h["em_coef"], h["reweight"], h["temp"], h["not_blank"], sched, 0)
+        assert np.abs(out[0].cpu().numpy() - z[f"u{j}_logits_{meta['steps']}"]).max() < LOGIT_TOL
+        del x, out0, out
+    assert model.engine.opt_steps == meta["steps"] * len(meta["utts"])          # bias correction did not restart
+    got = {p.name: p.data[0].cpu().numpy() for p in params}
+    num = sum(float(((got[n] - z["param:" + n]) ** 2).sum()) for n in got)
+    den = sum(float(((z["param:" + n] - sd[n].numpy()) ** 2).sum()) for n in got)
+    # 9 accumulated steps; restarting Adam's moments / bias correction at every utterance gives ~0.5 here
+    assert (num / den) ** 0.5 < 0.2, (num / den) ** 0.5
+    capsys.readouterr()
+
+
+def test_drop_in_api_rebinds_a_new_input_at_a_recycled_address(E, capsys):
+    """Two DIFFERENT utterances of equal length, the first deleted before the second exists: the second must not be
+    served the first one's audio, frame tables or logits (the model keyed its cache on data_ptr)."""
+    from oracle import suta_oracle as O
+    from suta_b200 import ModelConfig, api
+    ocfg = O.W2V2Config.tiny()
+    sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
+    model = api.configure_model(api.SutaModel(ModelConfig.tiny(), sd))
+    outs, ptrs = [], []
+    for seed in (21, 22):
+        x = torch.from_numpy(O.normalize_audio(O.synth_audio(8000, seed)))[None].cuda()
+        ptrs.append(x.data_ptr())
+        with torch.no_grad():
+            outs.append(model(x).logits[0].cpu().numpy().copy())
+        ref = O.model_forward(ocfg, sd, torch.from_numpy(O.normalize_audio(O.synth_audio(8000, seed)))[None])[0].detach().numpy()
+        assert np.abs(outs[-1] - ref).max() < LOGIT_TOL
+        del x
+    assert np.abs(outs[0] - outs[1]).max() > 0.1          # the two utterances really differ
     capsys.readouterr()
 
 

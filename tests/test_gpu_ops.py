@@ -56,6 +56,14 @@ def test_layernorm_forward_backward(K, N, bf16_in):
     r = K.check_layernorm(N, (70, 3, 129, 64), 5 + N, bf16_in)
     assert r["y_rel"] < F32 and r["dx_rel"] < F32 and r["dparam_rel"] < F32
     assert r["y16_rel"] < BF16 and r["dx16_rel"] < BF16
+    # dgamma/dbeta: fixed-order two-stage reduction (no atomics) -> the same bits on every run, nothing else touched
+    assert r["dparam_bit_equal"] and r["dparam_writes_only_its_segment"]
+
+
+def test_layernorm_backward_many_rows_many_utterances(K):
+    """Several CTAs per utterance and several utterances per CTA (the slot = CTA + utterance bookkeeping)."""
+    r = K.check_layernorm(768, (5000, 1, 1, 3, 12000, 2, 700), 77, False)
+    assert r["dx_rel"] < F32 and r["dparam_rel"] < F32 and r["dparam_bit_equal"]
 
 
 @pytest.mark.parametrize("Ts,heads", [((249, 64, 1, 130), 2), ((1749,), 1), ((63, 65, 128, 129), 12)])
@@ -71,9 +79,33 @@ def test_fused_loss_matches_reference_formulas(K, em, rew, nb):
     assert r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4 and r["bf16_rel"] < BF16
 
 
-def test_fused_loss_all_blank_and_single_frame(K):
-    r = K.check_loss(Ts=(1, 2, 1874), blank_bias=0.5)
+def test_fused_loss_single_frame_and_longest_utterance(K):
+    r = K.check_loss(Ts=(1, 2, 1874), blank_bias=0.5)       # a one-frame utterance whose frame is blank has a NaN loss in the reference too
+    assert r["nan_where_the_reference_is_nan"] and r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4
+
+
+def test_fused_loss_all_frames_blank(K):
+    """REF/main.py:190: with --non_blank and every frame predicted blank the entropy term is the mean of an empty
+    selection = NaN.  The kernel must report that NaN loss (not hide it) and keep d loss / d logits finite."""
+    r = K.check_loss(Ts=(40, 5, 1), blank_bias=50.0)
+    assert r["nan_loss_utts"] == 3 and r["nan_where_the_reference_is_nan"] and r["grad_finite_where_loss_nan"]
+    # strongly blank-dominated logits without the mask are an ordinary case
+    r = K.check_loss(Ts=(40, 5, 1), blank_bias=6.0, not_blank=False)
+    assert r["nan_loss_utts"] == 0 and r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-3
+
+
+@pytest.mark.parametrize("em,rew,nb,div", [(0.3, True, True, 0.25), (1.0, False, False, 0.3), (0.0, True, True, 0.1)])
+def test_fused_loss_with_div_loss(K, em, rew, nb, div):
+    """--div_coef > 0 (REF/main.py:46-60,201-203): minus the entropy of the time-averaged non-blank logits."""
+    r = K.check_loss(em_coef=em, reweight=rew, not_blank=nb, div_coef=div)
     assert r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4
+
+
+def test_gemm_mn_major_operands(K):
+    """Weight-gradient / per-utterance dgrad GEMMs read operands stored [K rows][M|N contiguous]."""
+    for args in ((), (128, 64, 64, 14), (768, 512, 4000, 15), (512, 1536, 2000, 16)):
+        for name, rel in K.check_gemm_mn(*args).items():
+            assert rel < 2e-5, (args, name, rel)
 
 
 def test_adam_with_multiplicities(K):

@@ -1,0 +1,115 @@
+"""GPU: the dataset-level driver (REF/main.py:319-454) -- SutaRunner's sharded plan, the main.py CLI in both the
+sequential (reference loop through the api.* surface) and the batched form, and the result files it writes."""
+import io
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def _tiny_engine(train_feature=False):
+    from suta_b200 import ModelConfig, SutaEngine
+    from suta_b200.api import reference_multiplicities
+    from suta_b200.weights import random_state_dict
+    cfg = ModelConfig.tiny()
+    return SutaEngine(cfg, random_state_dict(cfg, seed=0, blank_bias=0.5), train_feature=train_feature,
+                      trainable_mult=reference_multiplicities(cfg, train_feature=train_feature))
+
+
+@pytest.mark.parametrize("train_feature", [False, True])
+def test_shards_merged_equal_the_unsharded_run(train_feature):
+    """utterances are independent, so running shard k of n one after the other and merging transcripts and
+    WER counters must reproduce the unsharded run (the N-GPU job without the GPUs)."""
+    _need_gpu()
+    from suta_b200.data import librispeech_shaped
+    from suta_b200.runner import SutaRunner
+    utts = librispeech_shaped(23, seed=3)
+    eng = _tiny_engine(train_feature)
+    whole = SutaRunner(eng, steps=5, max_utts=6, max_frames=4096).run(utts)
+    merged_texts, merged_counts = {}, {}
+    seen = []
+    for r in range(3):
+        part = SutaRunner(eng, steps=5, max_utts=4, max_frames=4096, rank=r, world_size=3).run(utts)
+        for step, d in part["texts"].items():
+            merged_texts.setdefault(step, {}).update(d)
+        for step, (e, n) in part["wer_counts"].items():
+            pe, pn = merged_counts.get(step, (0, 0))
+            merged_counts[step] = (pe + e, pn + n)
+        seen += sorted(part["texts"][0])
+    assert sorted(seen) == list(range(len(utts)))                       # a partition: every utterance exactly once
+    assert set(whole["texts"]) == {0, 1, 3, 5}                          # REF/main.py:349-398 checkpoints <= steps
+    n_diff = 0
+    for step in whole["texts"]:
+        n_diff += sum(whole["texts"][step][i] != merged_texts[step][i] for i in whole["texts"][step])
+    if not train_feature:
+        # LayerNorm-only: every kernel's result for an utterance is independent of its position in the batch -> same bits
+        assert n_diff == 0 and merged_counts == whole["wer_counts"]
+    else:
+        # train_feature: the conv0 / GroupNorm backward sums in chunks sized by the LONGEST utterance of the batch, so
+        # the summation order (not the mathematics) depends on the batch; random-init logits are nearly tied, so a few
+        # frames may decode differently.  Same utterances, same reference texts, transcripts equal but for such frames.
+        assert n_diff <= 0.1 * len(utts) * len(whole["texts"]), n_diff
+        for step, (e, n) in whole["wer_counts"].items():
+            assert merged_counts[step][1] == n and abs(merged_counts[step][0] - e) <= 0.02 * n + 2
+    eng.close()
+
+
+def _run_main(tmp_path, *extra):
+    os.makedirs(str(tmp_path), exist_ok=True)
+    log_dir = str(tmp_path / "exps")
+    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", "random-tiny", "--num_utts", "7", "--steps", "10", "--episodic",
+           "--em_coef", "0.3", "--reweight", "--lr", "2e-5", "--non_blank", "--temp", "2.5", "--log_dir", log_dir, *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    files = sorted(os.listdir(log_dir))
+    assert len(files) == 2 and files[1] == files[0] + ".csv"
+    return r.stdout, files[0], open(os.path.join(log_dir, files[0])).read(), open(os.path.join(log_dir, files[1])).read()
+
+
+def test_main_cli_writes_the_reference_result_files(tmp_path):
+    """REF/main.py:267 (exp_name), :405-418 (stdout summary), :421-450 (log file), :452-454 (pandas CSV)."""
+    _need_gpu()
+    import pandas as pd
+    out, name, log, csv = _run_main(tmp_path)
+    assert name == ("synthetic_0.3_10_2.5_random-tiny_non_blankTrue_noise_0.0_rew_True_div_0.0_bias_False_feat_False_all_False_LN_True")
+    lines = log.splitlines()
+    assert [ln.split(":")[0] for ln in lines[:5]] == ["original WER", "TTA-1 WER", "TTA-3 WER", "TTA-5 WER", "TTA-10 WER"]
+    for ln in lines[:5]:
+        float(ln.split(": ")[1])
+    assert lines[5:] == ["eposidic? True", "lr = 2e-05", "optim = AdamW", "step = 10", "em_coef = 0.3", "reweight = True",
+                         "batch size = 1", "temperature = 2.5", "non_blank = True", "extra_noise = 0.0", "scheduler = None",
+                         "div_coef = 0.0", "bias_only = False", "train_feature = False", "train_all = False", "train_LN = True"]
+    for ln in lines[:5]:                                                 # the same summary goes to stdout (REF/main.py:408-415)
+        assert ln in out
+    assert out.count("original WER:  ") == 7 and out.count("adapt-10 WER: ") == 7 and "dataset num = 7" in out
+    df = pd.read_csv(io.StringIO(csv), index_col=0)
+    assert list(df.columns) == ["duration", "WERR"] and len(df) == 7
+    assert df.to_csv() == csv                                            # byte-identical to what pandas (the reference) writes
+
+
+def test_main_cli_batched_extension_matches_the_sequential_loop(tmp_path):
+    """--batch_utts adapts many utterances per step; the corpus WERs must equal the one-utterance-at-a-time loop."""
+    _need_gpu()
+    _, _, log_seq, csv_seq = _run_main(tmp_path / "a")
+    _, _, log_bat, csv_bat = _run_main(tmp_path / "b", "--batch_utts", "4")
+    assert log_seq == log_bat          # LayerNorm-only results do not depend on the batch composition (same bits)
+    assert csv_seq == csv_bat
+
+
+def test_main_cli_rejects_batching_without_episodic(tmp_path):
+    _need_gpu()
+    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", "random-tiny", "--num_utts", "3", "--steps", "3",
+           "--batch_utts", "2", "--log_dir", str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode != 0 and "--episodic" in (r.stdout + r.stderr)
