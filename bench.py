@@ -1,11 +1,18 @@
-"""Benchmark of the SUTA hot path: audio-seconds adapted per second for 10-step SUTA on wav2vec2-base.
+"""Benchmark of the SUTA hot path: audio-seconds adapted per second for S-step SUTA on wav2vec2.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine (one process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg4|cfg5|fullset]   # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...                                    # the reference on the host CPU
 
-A "step" is one adaptation batch: up to 64 utterances drawn from the LibriSpeech-test-other-shaped synthetic set
-(SURVEY.md 8d), each episodically reset, forwarded, adapted for 10 steps and decoded at the reference's checkpoints
-(REF/main.py:319-402).  Prints ONE JSON line on rank 0.
+Workloads (BASELINE.json `configs`):
+  cfg2 (default)  configs[1]: wav2vec2-base, LibriSpeech-test-other-shaped synthetic set, 10 steps, --train_feature
+  cfg3            configs[2]: wav2vec2-base, LayerNorm-only, 64 utterances per adaptation batch, length-bucketed
+  cfg4            configs[3]: wav2vec2-large (24 layers, 1024-d), LayerNorm-only, fixed 30 s utterances
+  cfg5            configs[4]: configs[1] + 0.01 noise, 20 adaptation steps
+  fullset         configs[1] over ALL 2939 utterances, LPT-sharded over the ranks (strong scaling), final gather included
+
+A "step" is one adaptation batch: up to 64 utterances, each episodically reset, forwarded, adapted for S steps and decoded
+at the reference's checkpoints (REF/main.py:319-402).  cfg* workloads time K batches spread over the length distribution
+(every rank the same batches: weak scaling); fullset times the rank's whole shard.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -20,9 +27,20 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "test-time-adaptation-asr-suta_b200")]
 
 METRIC = "audio_seconds_adapted_per_second"
 UNIT = "audio-s/s"
-SUTA_STEPS = 10
-MAX_UTTS = 64
-MAX_FRAMES = 36864
+N_UTTS = 2939
+
+WORKLOADS = {
+    "cfg2": dict(model="base", mode="feature", suta_steps=10, noise=0.0, dataset="ls", max_utts=64, max_frames=36864,
+                 desc="BASELINE.json configs[1]"),
+    "cfg3": dict(model="base", mode="ln", suta_steps=10, noise=0.0, dataset="ls", max_utts=64, max_frames=36864,
+                 desc="BASELINE.json configs[2]"),
+    "cfg4": dict(model="large", mode="ln", suta_steps=10, noise=0.0, dataset="fixed30", max_utts=64, max_frames=36864,
+                 desc="BASELINE.json configs[3]"),
+    "cfg5": dict(model="base", mode="feature", suta_steps=20, noise=0.01, dataset="ls", max_utts=64, max_frames=36864,
+                 desc="BASELINE.json configs[4]"),
+    "fullset": dict(model="base", mode="feature", suta_steps=10, noise=0.0, dataset="ls", max_utts=64, max_frames=36864,
+                    desc="BASELINE.json configs[1], whole set"),
+}
 
 
 def parse():
@@ -31,16 +49,38 @@ def parse():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
-    ap.add_argument("--mode", default="feature", choices=["feature", "ln"],
-                    help="feature = BASELINE.json configs[1] (--train_feature preset of REF/scripts/LS.sh); ln = LayerNorm-only")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", default=None, choices=["base", "large", "tiny"], help="override the workload's model")
+    ap.add_argument("--mode", default=None, choices=["feature", "ln"], help="override: feature = --train_feature, ln = LayerNorm-only")
+    ap.add_argument("--suta-steps", type=int, default=None, help="override the adaptation steps per utterance")
+    ap.add_argument("--extra-noise", type=float, default=None, help="override REF/data.py:23's noise level")
+    ap.add_argument("--max-utts", type=int, default=None, help="utterances per adaptation batch")
+    ap.add_argument("--max-frames", type=int, default=None, help="frames per adaptation batch")
+    ap.add_argument("--n-utts", type=int, default=N_UTTS, help="size of the synthetic set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--max-utts", type=int, default=MAX_UTTS, help="utterances per adaptation batch")
-    ap.add_argument("--max-frames", type=int, default=MAX_FRAMES, help="frames per adaptation batch")
-    ap.add_argument("--cpu-seconds", type=float, default=5.0, help="duration of the CPU-baseline utterance")
-    ap.add_argument("--suta-steps", type=int, default=10, help="adaptation steps per utterance (configs[4]: 20)")
-    ap.add_argument("--extra-noise", type=float, default=0.0, help="REF/data.py:23 noise added before normalisation (configs[4]: 0.01)")
-    return ap.parse_args()
+    ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--cpu-utts", type=int, default=5, help="utterances of the duration-stratified CPU-baseline sample")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    for k_arg, k_w in (("model", "model"), ("mode", "mode"), ("suta_steps", "suta_steps"), ("extra_noise", "noise"),
+                       ("max_utts", "max_utts"), ("max_frames", "max_frames")):
+        if getattr(a, k_arg) is not None:
+            w[k_w] = getattr(a, k_arg)
+    a.w = w
+    return a
+
+
+def make_config(a):
+    """`config` of the JSON line: identical for both arms (`--impl b200` and `--impl reference`)."""
+    w = a.w
+    tf = w["mode"] == "feature"
+    dataset = (f"LibriSpeech-test-other-shaped synthetic set ({a.n_utts} utts, 2-35 s"
+               + (f", + {w['noise']} noise" if w["noise"] else "") + ")") if w["dataset"] == "ls" else "fixed 30 s synthetic utterances"
+    return {"workload": f"{a.workload}: wav2vec2-{w['model']} CTC, {dataset}, {w['suta_steps']}-step EM+MCC SUTA, "
+                        + ("train_feature (LayerNorm + CNN front end + projection adapted per utterance)" if tf else "LayerNorm-only")
+                        + f", episodic ({w['desc']})",
+            "suta": {"steps": w["suta_steps"], "em_coef": 0.3, "temp": 2.5, "reweight": True, "non_blank": True, "lr": 2e-5,
+                     "opt": "AdamW", "episodic": True, "train_feature": tf, "extra_noise": w["noise"]}}
 
 
 def measured_peaks():
@@ -49,8 +89,20 @@ def measured_peaks():
         with open(p) as f:
             d = json.load(f)
         return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), hbm=float(d["hbm_gbs"]),
-                    source="MEASURED_PEAKS.json (bf16_tflops_sustained)")
+                    source="MEASURED_PEAKS.json (bf16_tflops_sustained, hbm_gbs)")
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` capture of THIS
+    workload's benched batches (profiles/r02_gemm_traffic.json, written by tools/ncu_traffic.py); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if workload in d:
+            return d[workload]
+    return None
 
 
 class ClockSampler:
@@ -89,6 +141,7 @@ class ClockSampler:
 
 
 def utt_flops(cfg, n_samples, steps, train_feature=False):
+    """ALGORITHMIC FLOPs of one utterance: (S+1) forwards + S backwards, CNN once in LayerNorm-only mode."""
     H, I, NL, V = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size
     Ls, L = [], n_samples
     for k, s in zip(cfg.conv_kernel, cfg.conv_stride):
@@ -105,29 +158,77 @@ def utt_flops(cfg, n_samples, steps, train_feature=False):
     f_head = 2.0 * T * H * V
     enc_f = f_proj + f_pos + NL * (f_lin + 4.0 * T * T * H) + f_head
     enc_b = f_proj + f_pos + NL * (f_lin + 8.0 * T * T * H) + f_head
-    if train_feature:   # SURVEY.md 8d: CNN forward every step, dgrad (no input grad for conv0) + wgrad in every backward
+    if train_feature:   # CNN forward every step, dgrad (no input grad for conv0) + wgrad in every backward
         f_conv0 = 2.0 * cfg.conv_dim[0] * cfg.conv_kernel[0] * Ls[0]
         return (steps + 1) * (f_conv + enc_f) + steps * (enc_b + f_proj + 2 * f_conv - f_conv0)
     return f_conv + (steps + 1) * enc_f + steps * enc_b
 
 
-def select_batches(utts, cfg, n_batches, offset=0, max_utts=MAX_UTTS, max_frames=MAX_FRAMES):
+def build_set(a, cfg=None):
+    from suta_b200.data import fixed_length, librispeech_shaped
+    if a.w["dataset"] == "fixed30":
+        return fixed_length(max(a.w["max_utts"] * 4, 96), 30.0)
+    return librispeech_shaped(a.n_utts, seed=0, extra_noise=a.w["noise"])
+
+
+def stratified_sample(utts, n):
+    """n utterances at the duration quantiles (i + 0.5) / n of the set: a bounded sample with the set's length mix."""
+    order = sorted(range(len(utts)), key=lambda i: (utts[i].n_samples, i))
+    return [utts[order[int((i + 0.5) * len(order) / n)]] for i in range(n)]
+
+
+def select_batches(utts, cfg, n_batches, max_utts, max_frames, offset=0.0):
     from suta_b200.shard import bucket_batches
     frames = [cfg.frames(u.n_samples) for u in utts]
     batches = bucket_batches(frames, list(range(len(utts))), max_utts, max_frames)
     nb = len(batches)
     pick = [int(round(offset + (i + 0.5) * nb / n_batches)) % nb for i in range(n_batches)]
-    return [[utts[i] for i in batches[j]] for j in pick]
+    return [batches[j] for j in pick]
 
 
 # ======================================================================================================
-def run_b200(args):
+def reference_times(a, device, n_utts, warmup):
+    """The reference's loop (oracle/hf_reference.py: real HF modules + autograd + torch.optim under main.py's driver) on a
+    duration-stratified sample of the workload's set; returns (utterances, seconds per utterance)."""
+    import torch
+    from oracle import suta_oracle as O
+    from oracle.hf_reference import ReferenceLoop, time_utterances
+    w = a.w
+    cfg = getattr(O.W2V2Config, w["model"])()
+    sd = O.init_weights(cfg, 0, blank_bias=1.75)
+    utts = stratified_sample(build_set(a), n_utts)
+    warm = utts[len(utts) // 2:len(utts) // 2 + 1] * warmup            # warm-up on a median-length utterance
+    loop = ReferenceLoop(cfg, sd, device, train_feature=w["mode"] == "feature", lr=2e-5)
+    secs = time_utterances(loop, [u.audio() for u in warm + utts], w["suta_steps"], warmup=len(warm))
+    del loop
+    if device != "cpu":
+        torch.cuda.empty_cache()
+    return utts, secs
+
+
+def baseline_record(a, device, n_utts, warmup, kind):
+    import torch
+    threads = os.cpu_count()
+    if device == "cpu":
+        torch.set_num_threads(threads)
+    utts, secs = reference_times(a, device, n_utts, warmup)
+    per = sorted(u.duration / s for u, s in zip(utts, secs))
+    tot_a, tot_s = sum(u.duration for u in utts), sum(secs)
+    rec = {"value": tot_a / tot_s, "unit": UNIT, "kind": kind, "median_utterance_value": per[len(per) // 2],
+           "sample": f"{len(utts)} utterances at the duration quantiles of the workload's set ({', '.join('%.1f' % u.duration for u in utts)} s; "
+                     f"{tot_a:.1f} audio-s in {tot_s:.1f} s wall), each: reset + vanilla forward + {a.w['suta_steps']} x "
+                     f"(forward, backward, AdamW, forward) + decodes, fp32, after {warmup} warm-up utterance(s)"}
+    if device == "cpu":
+        rec["cores"] = threads
+    return rec, utts, secs
+
+
+def run_b200(a):
     import numpy as np
     import torch
     import torch.distributed as dist
     from suta_b200 import AdaptHyper, ModelConfig, SutaEngine
-    from suta_b200.data import librispeech_shaped
-    from suta_b200.runner import adapt_batch
+    from suta_b200.runner import SutaRunner, adapt_batch, gather_results, pack_batch
     from suta_b200.text import CTCVocab
     from suta_b200.weights import random_state_dict
 
@@ -136,194 +237,209 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = getattr(ModelConfig, args.model)()
-    tf = args.mode == "feature"
+    w = a.w
+    cfg = getattr(ModelConfig, w["model"])()
+    tf = w["mode"] == "feature"
+    S = w["suta_steps"]
     mult = None
     if tf:              # multiplicities of REF/main.py:62-103 with train_feature (conv x4, proj LN x3, projection x2)
         from suta_b200.api import reference_multiplicities
         mult = reference_multiplicities(cfg, train_feature=True)
     eng = SutaEngine(cfg, random_state_dict(cfg, seed=0, blank_bias=1.75), train_feature=tf, trainable_mult=mult)
     hp, vocab = AdaptHyper(), CTCVocab()
-    utts = librispeech_shaped(2939, seed=rank, extra_noise=args.extra_noise)           # weak scaling: every rank adapts its own draw of the set
-    K, W = args.steps, max(args.warmup, 0)
-    timed = select_batches(utts, cfg, K, max_utts=args.max_utts, max_frames=args.max_frames)
-    warm = select_batches(utts, cfg, max(W, 1), offset=0.25, max_utts=args.max_utts, max_frames=args.max_frames)[:W]
+    utts = build_set(a)
+    K, W = a.steps, max(a.warmup, 0)
+    full = a.workload == "fullset"
+    runner = SutaRunner(eng, S, hp, max_utts=w["max_utts"], max_frames=w["max_frames"], vocab=vocab, rank=rank, world_size=world)
+    if full:            # strong scaling: this rank's LPT shard of the whole set, batch by batch
+        plan = runner.plan(utts)
+        timed_idx = plan
+        warm_idx = plan[len(plan) // 2:len(plan) // 2 + 1] * W
+    else:               # weak scaling: every rank adapts the same K batches spread over the length distribution
+        timed_idx = select_batches(utts, cfg, K, w["max_utts"], w["max_frames"])
+        warm_idx = select_batches(utts, cfg, max(W, 1), w["max_utts"], w["max_frames"], offset=0.25)[:W]
+    K_eff = len(timed_idx)
 
-    def stage(batch):                                     # synthetic-data generation is outside the timed region
-        lens = np.asarray([u.n_samples for u in batch], dtype=np.int32)
-        eng.begin_batch_lengths(lens)
-        host = torch.zeros(eng.total_samples, dtype=torch.float32).pin_memory()
-        hv = host.numpy()
-        for u, o in zip(batch, eng.sample_off):
-            hv[o:o + u.n_samples] = u.audio()
-        return lens, host
-
-    staged_w = [stage(b) for b in warm]
-    staged = [stage(b) for b in timed]
-    dev_audio = [h.cuda() for _, h in staged]
+    # synthetic-data generation is outside the timed region; pinned host buffers + device copies
+    staged_w = runner.stage(utts, warm_idx)
+    staged = runner.stage(utts, timed_idx)
+    dev_audio = [p.to(eng.device) for _b, _l, p in staged]
 
     def one_step(lens, audio):
         eng.begin_batch_lengths(lens)
-        return adapt_batch(eng, audio, lens, SUTA_STEPS, hp, vocab)
+        return adapt_batch(eng, audio, lens, S, hp, vocab)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(items):
+    def timed_region(items, with_gather):
+        """K steps between barriers; device time by CUDA events on the launching stream, max over ranks."""
         barrier()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(items) + 1)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(items) + 2)]
         l0 = eng.launch_count
+        texts = {}
         ev[0].record()
-        for i, (lens, audio) in enumerate(items):
-            one_step(lens, audio)
+        for i, (b, lens, audio) in enumerate(items):
+            out = one_step(lens, audio)
+            for step, tl in out.items():
+                texts.setdefault(step, {}).update({j: t for j, t in zip(b, tl)})
             ev[i + 1].record()
+        gathered = None
+        if with_gather:      # end-of-run exchange (SURVEY.md 8e): WER counters all-reduced, transcripts gathered
+            from suta_b200.wer import wer_counts
+            counts = {st: wer_counts([utts[j].text for j in sorted(d)], [d[j] for j in sorted(d)]) for st, d in texts.items()}
+            gathered = gather_results(dict(texts=texts, wer_counts=counts, wall_s=0.0, audio_s=0.0), sorted(texts))
+        ev[-1].record()
         barrier()
-        ms = torch.tensor([ev[0].elapsed_time(ev[-1])], device="cuda")
+        mine = ev[0].elapsed_time(ev[-1])
+        ms = torch.tensor([mine], device="cuda")
+        per_rank = [torch.zeros_like(ms) for _ in range(world)]
         if world > 1:
+            dist.all_gather(per_rank, ms)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        else:
+            per_rank = [ms]
         per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(items))]
-        return float(ms.item()), eng.launch_count - l0, per_step
+        return float(ms.item()), eng.launch_count - l0, per_step, [float(x.item()) for x in per_rank], gathered
 
-    for lens, host in staged_w:                           # warm-up (>= 3 by default)
+    for b, lens, host in staged_w:                        # warm-up (>= 3 by default)
         one_step(lens, host)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, step_ms = timed_region([(l, a) for (l, _), a in zip(staged, dev_audio)])   # inputs resident in HBM
-    ms_e2e, _, step_ms_e2e = timed_region([(l, h) for l, h in staged])                          # pinned host -> device
+    ms_dev, launches, step_ms, rank_ms, _ = timed_region([(b, l, d) for (b, l, _p), d in zip(staged, dev_audio)], full)   # inputs resident in HBM
+    ms_e2e, _, step_ms_e2e, rank_ms_e2e, gathered = timed_region(staged, full)                                          # pinned host -> device
     clocks = sampler.stop() if rank == 0 else None
 
-    # roofline leg: same steps with CUDA-event pairs around every tcgen05 GEMM launch
+    # roofline leg: the same steps again with CUDA-event pairs around every kernel launch (not part of `value`)
+    prof_items = staged[:min(len(staged), 6)]
     eng.profile(True)
-    for (l, _), a in zip(staged, dev_audio):
-        one_step(l, a)
+    for (b, lens, _p), d in zip(prof_items, dev_audio):
+        one_step(lens, d)
     gemm_ms, gemm_n, gemm_fl = eng.profile(False)
     rep = eng.profile_report()
     tot_ms = sum(v[0] for v in rep.values()) or 1.0
-    breakdown = [{"kernel": k, "share": round(v[0] / tot_ms, 4), "ms_per_step": round(v[0] / K, 3), "launches_per_step": v[2] / K,
-                  "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] else None}
+    KP = len(prof_items)
+    peaks = measured_peaks()
+    breakdown = [{"kernel": k, "share": round(v[0] / tot_ms, 4), "ms_per_step": round(v[0] / KP, 3), "launches_per_step": v[2] / KP,
+                  "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] else None,
+                  "gbs": round(v[3] / (v[0] * 1e-3) / 1e9, 1) if v[3] else None}
                  for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])]
+    # HBM-bound kernels against the measured copy bandwidth (algorithmic bytes: DESIGN.md section 3)
+    hbm_rooflines = [{"kernel": k, "bound": "hbm", "achieved": v[3] / (v[0] * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                      "frac": v[3] / (v[0] * 1e-3) / 1e9 / peaks["hbm"], "ms_per_step": v[0] / KP, "launches_per_step": v[2] / KP,
+                      "avg_launch_us": v[0] * 1e3 / v[2]}
+                     for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0]) if v[3] > 0 and v[0] > 0]
+    attn = [{"kernel": k, "bound": "tensor", "achieved": v[1] / (v[0] * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+             "frac": v[1] / (v[0] * 1e-3) / 1e12 / peaks["tflops"], "ms_per_step": v[0] / KP, "avg_launch_us": v[0] * 1e3 / v[2]}
+            for k, v in rep.items() if k.startswith("attn") and v[0] > 0]
 
-    audio_s = sum(u.duration for b in timed for u in b)
-    tot = torch.tensor([audio_s, float(sum(len(b) for b in timed)),
-                        sum(utt_flops(cfg, u.n_samples, SUTA_STEPS, tf) for b in timed for u in b)], device="cuda", dtype=torch.float64)
+    audio_s = sum(utts[j].duration for b, _l, _p in staged for j in b)
+    n_u = float(sum(len(b) for b, _l, _p in staged))
+    tot = torch.tensor([audio_s, n_u, sum(utt_flops(cfg, utts[j].n_samples, S, tf) for b, _l, _p in staged for j in b),
+                        float(K_eff)], device="cuda", dtype=torch.float64)
+    kmax = torch.tensor([float(K_eff)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    audio_all, utts_all, flops_all = (float(x) for x in tot.tolist())
-    peaks = measured_peaks()
-    h2d = sum(h.numel() * 4 for _, h in staged) / K
-    n_dec = 1 + sum(1 for c in (1, 3, 5, 10, 20, 40) if c <= SUTA_STEPS)      # REF/main.py:331-398 decode points
-    d2h = sum(sum(cfg.frames(u.n_samples) for u in b) * 4 * n_dec + len(b) * 4 * n_dec for b in timed) / K    # collapsed ids + lengths
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    audio_all, utts_all, flops_all, k_all = (float(x) for x in tot.tolist())
+    k_rep = int(kmax.item()) if full else K
+    h2d = sum(p.numel() * 4 for _b, _l, p in staged) / K_eff
+    n_dec = 1 + sum(1 for c in (1, 3, 5, 10, 20, 40) if c <= S)               # REF/main.py:331-398 decode points
+    d2h = sum(sum(cfg.frames(utts[j].n_samples) for j in b) * 4 * n_dec + len(b) * 4 * n_dec for b, _l, _p in staged) / K_eff
+    traffic = ncu_traffic(a.workload)
+    config = make_config(a)                              # identical in both arms
+    step_info = {"batching": f"<= {w['max_utts']} utts / {w['max_frames']} frames per adaptation batch, length-bucketed",
+                 "utts_per_step": utts_all / k_all, "audio_s_per_step": audio_all / k_all,
+                 "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2"}
+    if full:
+        step_info["sharding"] = ("LPT over estimated utterance cost (suta_b200.shard.shard_lpt), no collective inside the loop, "
+                                 "all_reduce of 2 x #checkpoints int64 WER counters + all_gather_object of transcripts inside the timed region")
     out = {
-        "metric": METRIC, "value": audio_all / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic (0.1*randn audio, random-init wav2vec2-base weights; no checkpoint/dataset offline)",
-        "config": {"workload": f"wav2vec2-{args.model} CTC, LibriSpeech-test-other-shaped synthetic set (2939 utts, 2-35 s), "
-                               f"{SUTA_STEPS}-step EM+MCC SUTA, " + ("train_feature (LayerNorm + CNN front end + projection adapted per utterance)"
-                                                                if tf else "LayerNorm-only") + ", "
-                               f"<= {args.max_utts} utts / {args.max_frames} frames per adaptation batch, length-bucketed",
-                   "utts_per_step": utts_all / K / world, "audio_s_per_step": audio_all / K / world,
-                   "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2",
-                   "suta": {"steps": SUTA_STEPS, "em_coef": hp.em_coef, "temp": hp.temp, "reweight": hp.reweight,
-                            "non_blank": hp.not_blank, "lr": hp.lr, "opt": hp.opt, "episodic": True}},
+        "metric": METRIC, "value": audio_all / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": k_rep, "warmup": W,
+        "ms_per_step": ms_dev / k_rep, "higher_is_better": True, "scaling": "strong" if full else "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": f"synthetic (0.1*randn audio, random-init wav2vec2-{w['model']} weights; no checkpoint/dataset offline)",
+        "config": config, "step": step_info,
         "e2e": {"value": audio_all / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm2_kernel (cta_group::2 pairs) + gemm_bf16_tc_kernel (tcgen05, all dense contractions)",
                      "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peaks["tflops"]) if gemm_ms else None,
-                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_note": traffic["note"] if traffic else "no ncu --set full capture of this workload committed",
+                     "algorithmic_bytes_per_launch": traffic.get("algorithmic_bytes_per_launch") if traffic else None,
                      "peak_source": peaks["source"], "launches": gemm_n,
                      "avg_launch_us": gemm_ms * 1e3 / gemm_n if gemm_n else None,
-                     "gemm_share_of_step": gemm_ms / ms_dev if ms_dev else None},
-        "path": {"algorithmic_tflop_per_step": flops_all / K / 1e12,
+                     "gemm_share_of_step": (gemm_ms / KP) / (sum(step_ms[:KP]) / KP) if KP else None},
+        "rooflines": attn + hbm_rooflines,
+        "path": {"algorithmic_tflop_per_step": flops_all / k_all / 1e12,
                  "achieved_tflops": flops_all / (ms_dev * 1e-3) / 1e12 / world,
                  "frac_of_peak": flops_all / (ms_dev * 1e-3) / 1e12 / world / peaks["tflops"]},
-        "rtf_p50": None,
+        "ms_per_rank": rank_ms, "ms_per_rank_e2e": rank_ms_e2e,
+        "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
         "breakdown": breakdown,
     }
     # p50 RTF: per-utterance latency (wall time of the batch that carried it, end to end) / its duration, this rank
-    rtfs = sorted((t / 1e3) / u.duration for b, t in zip(timed, step_ms_e2e) for u in b)
+    rtfs = sorted((t / 1e3) / utts[j].duration for (b, _l, _p), t in zip(staged, step_ms_e2e) for j in b)
     out["rtf_p50"] = rtfs[len(rtfs) // 2]
     out["rtf_throughput"] = (ms_e2e / 1e3) / (audio_all / world)      # GPU-seconds per audio-second
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.model, train_feature=tf)
+    if full and gathered is not None:
+        out["wer"] = {str(k): v for k, v in gathered["wer"].items()}
+        out["transcripts_gathered"] = {str(k): len(v) for k, v in gathered["texts"].items()}
+    eng.close()
+    del eng, dev_audio
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1:
+        if not a.no_gpu_eager:
+            # the bar SURVEY.md 8d names: the reference's eager fp32 GPU path (B = 1) on this same B200
+            try:
+                out["gpu_eager_baseline"] = baseline_record(a, "cuda", n_utts=5, warmup=1, kind="reference loop over HF Wav2Vec2ForCTC + "
+                                                            "torch.optim on cuda:0 (oracle/hf_reference.py), fp32 eager, batch 1")[0]
+            except Exception as e:       # reported, never fatal for the bench line
+                out["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if not a.no_cpu_baseline:
+            rec = baseline_record(a, "cpu", n_utts=a.cpu_utts, warmup=1, kind="port")[0]
+            out["cpu_baseline"] = rec
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per tcgen05 GEMM launch, from the committed `ncu --set full` capture
-# (profiles/r01g_ncu_full_pair_gemm_posconv.md: 10 launches of the CTA-pair kernel in tools/profile_step.py --utts 32
-# --seconds 6 --mode feature, 9.8 k frames per batch, i.e. about 1/2 of a bench batch; 72.6 MB on average).  Reads equal the
-# operand bytes -- e.g. the FFN dgrad launch reads 80.3 MB for 15 MB dY + 60 MB GELU' + 4.7 MB W, the accumulate launch
-# 95.3 MB for 60 MB dH + 4.7 MB W + 30 MB fp32 reduce target -- so no re-reads; results are mostly still in L2 at kernel end.
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 72.6e6
-NCU_GEMM_TRAFFIC_NOTE = ("ncu capture of the 9.8k-frame profile batch (profiles/r01g_ncu_full_pair_gemm_posconv.md), not of this run; "
-                         "tensor-bound kernel, traffic ~= algorithmic bytes")
-
-
-def cpu_baseline(seconds, model="base", threads=None, train_feature=False):
-    """The oracle (CPU restatement of the reference loop, pinned to the reference by tests/golden) on the host cores."""
-    import torch
-    from oracle import suta_oracle as O
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    cfg = getattr(O.W2V2Config, model)()
-    sd = O.init_weights(cfg, 0, blank_bias=1.75)
-    n = int(seconds * 16000)
-    x = O.normalize_audio(O.synth_audio(n, 1234))
-    t0 = time.time()
-    O.adapt_utterance(cfg, sd, x, steps=SUTA_STEPS, train_feature=train_feature)
-    dt = time.time() - t0
-    mode = "train_feature" if train_feature else "LayerNorm-only"
-    return {"value": seconds / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"one {seconds:g} s utterance, {SUTA_STEPS}-step {mode} SUTA, fp32 torch CPU oracle "
-                      f"(reset + vanilla forward + 10 x (forward, backward, AdamW, forward)), {dt:.1f} s wall"}
-
-
-def run_reference(args):
-    """Reference arm: the reference's own CPU algorithm (oracle port; /root/reference does not travel to the box)."""
+def run_reference(a):
+    """Reference arm: the reference's own CPU path (oracle/hf_reference.py: HF Wav2Vec2ForCTC + autograd + torch.optim
+    under a restatement of main.py's loop -- /root/reference is a script and does not travel to the box) on all host
+    cores; each step = ONE utterance of a duration-stratified sample of the same workload's set."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import torch
-    from oracle import suta_oracle as O
     threads = os.cpu_count()
     torch.set_num_threads(threads)
-    cfg = getattr(O.W2V2Config, args.model)()
-    sd = O.init_weights(cfg, 0, blank_bias=1.75)
-    seconds = args.cpu_seconds
-    n = int(seconds * 16000)
-    xs = [O.normalize_audio(O.synth_audio(n, 100 + i)) for i in range(args.warmup + args.steps)]
-    tf = args.mode == "feature"
-    mode = "train_feature (LayerNorm + CNN front end + projection)" if tf else "LayerNorm-only"
-    for i in range(args.warmup):
-        O.adapt_utterance(cfg, sd, xs[i], steps=SUTA_STEPS, train_feature=tf)
-    t0 = time.time()
-    for i in range(args.steps):
-        O.adapt_utterance(cfg, sd, xs[args.warmup + i], steps=SUTA_STEPS, train_feature=tf)
-    dt = time.time() - t0
-    val = seconds * args.steps / dt
-    sample = (f"each step = ONE {seconds:g} s utterance of the same synthetic generator (bounded sample of the batch the "
-              f"CUDA arm adapts per step), {SUTA_STEPS}-step {mode} SUTA, fp32 torch on {threads} host threads")
+    utts, secs = reference_times(a, "cpu", n_utts=max(a.steps, 1), warmup=max(a.warmup, 0))
+    per = sorted(u.duration / s for u, s in zip(utts, secs))
+    tot_a, tot_s = sum(u.duration for u in utts), sum(secs)
+    val = tot_a / tot_s
+    sample = (f"each step = ONE utterance; the {len(utts)} timed utterances sit at the duration quantiles of the workload's set "
+              f"({', '.join('%.1f' % u.duration for u in utts)} s), {threads} host threads, fp32; median per-utterance value "
+              f"{per[len(per) // 2]:.3f} {UNIT}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (0.1*randn audio, random-init wav2vec2 weights)",
-        "config": {"workload": f"wav2vec2-{args.model} CTC, LibriSpeech-test-other-shaped synthetic set, {SUTA_STEPS}-step EM+MCC SUTA, "
-                               f"{mode}, reference algorithm on the host CPU", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(utts),
+        "warmup": max(a.warmup, 0), "ms_per_step": tot_s / len(utts) * 1e3, "higher_is_better": True,
+        "scaling": "strong" if a.workload == "fullset" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": f"synthetic (0.1*randn audio, random-init wav2vec2-{a.w['model']} weights; no checkpoint/dataset offline)",
+        "config": make_config(a),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "median_utterance_value": per[len(per) // 2]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 if __name__ == "__main__":
     a = parse()
-    SUTA_STEPS = a.suta_steps
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -80,7 +80,7 @@ struct suta_engine {
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  struct ProfRec { std::string tag; double flops; bool is_gemm; };
+  struct ProfRec { std::string tag; double flops; bool is_gemm; double bytes; };
   std::vector<ProfRec> prof_recs;
   std::string prof_report;
   bool audio_normalized = false;
@@ -399,14 +399,15 @@ struct ProfScope {
   suta_engine* e;
   cudaStream_t st;
   bool on;
-  ProfScope(suta_engine* e_, cudaStream_t st_, const std::string& tag, double flops, bool is_gemm) : e(e_), st(st_), on(e_->profile) {
+  ProfScope(suta_engine* e_, cudaStream_t st_, const std::string& tag, double flops, bool is_gemm, double bytes = 0.0)
+      : e(e_), st(st_), on(e_->profile) {
     if (!on) return;
     if (e->ev_used + 2 > e->ev_pool.size()) {
       size_t old = e->ev_pool.size();
       e->ev_pool.resize(old + 1024);
       for (size_t i = old; i < e->ev_pool.size(); ++i) cudaEventCreate(&e->ev_pool[i]);
     }
-    e->prof_recs.push_back({tag, flops, is_gemm});
+    e->prof_recs.push_back({tag, flops, is_gemm, bytes});
     cudaEventRecord(e->ev_pool[e->ev_used], st);
   }
   ~ProfScope() {
@@ -421,6 +422,12 @@ struct ProfScope {
     SUTA_TRY(expr);                             \
   } while (0)
 #define PROF(tag, expr) PROF_F(tag, 0.0, expr)
+// HBM-bound kernels: ALGORITHMIC bytes of the launch (what must cross HBM once)
+#define PROF_B(tag, bytes, expr)                         \
+  do {                                                   \
+    ProfScope _ps(e, st, tag, 0.0, false, (double)(bytes)); \
+    SUTA_TRY(expr);                                      \
+  } while (0)
 
 int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   e->launches += 1;
@@ -648,7 +655,7 @@ extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t
     int64_t n = 0;
     e->prof_report.clear();
     std::vector<std::string> tags;
-    std::vector<double> tms, tfl;
+    std::vector<double> tms, tfl, tby;
     std::vector<long long> tn;
     for (size_t i = 0; i < e->prof_recs.size() && 2 * i + 1 < e->ev_used; ++i) {
       float t = 0.f;
@@ -657,12 +664,12 @@ extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t
       if (r.is_gemm) { ms += t; fl += r.flops; n += 1; }
       size_t k = 0;
       while (k < tags.size() && tags[k] != r.tag) ++k;
-      if (k == tags.size()) { tags.push_back(r.tag); tms.push_back(0); tfl.push_back(0); tn.push_back(0); }
-      tms[k] += t; tfl[k] += r.flops; tn[k] += 1;
+      if (k == tags.size()) { tags.push_back(r.tag); tms.push_back(0); tfl.push_back(0); tby.push_back(0); tn.push_back(0); }
+      tms[k] += t; tfl[k] += r.flops; tby[k] += r.bytes; tn[k] += 1;
     }
     for (size_t k = 0; k < tags.size(); ++k) {
       char line[256];
-      snprintf(line, sizeof(line), "%s\t%.4f\t%.6g\t%lld\n", tags[k].c_str(), tms[k], tfl[k], tn[k]);
+      snprintf(line, sizeof(line), "%s\t%.4f\t%.6g\t%lld\t%.6g\n", tags[k].c_str(), tms[k], tfl[k], tn[k], tby[k]);
       e->prof_report += line;
     }
     if (gemm_ms) *gemm_ms = ms;
@@ -734,7 +741,8 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
     a.pre_out = e->conv_pre[0];
   }
   a.n_utts = e->U; a.C = c.conv_dim[0]; a.k = c.conv_kernel[0]; a.stride = c.conv_stride[0]; a.max_L0 = e->max_L0;
-  PROF("conv0_fwd", conv0_groupnorm_gelu(a, st));
+  PROF_B("conv0_fwd", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2 * (e->train_feature ? 2 : 1),
+         conv0_groupnorm_gelu(a, st));
   e->launches += 2;
   for (int l = 1; l < c.n_conv; ++l) {
     const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l], s = c.conv_stride[l];
@@ -774,7 +782,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   const bf16* feat = e->conv_out[c.n_conv - 1];
 
   // feature projection: LayerNorm(C) -> Linear(C->H)        HF/modeling_wav2vec2.py:429-434
-  PROF("ln_fwd", layernorm_forward(nullptr, feat, e->d_row_utt, prm, (int)e->fp_g, (int)e->fp_b, nullptr, e->y_fp, e->fp_mean,
+  PROF_B("ln_fwd C", (double)M * C * (2 + 2), layernorm_forward(nullptr, feat, e->d_row_utt, prm, (int)e->fp_g, (int)e->fp_b, nullptr, e->y_fp, e->fp_mean,
                              e->fp_rstd, M, C, c.ln_eps, st));
   {
     GemmProblem p = dense(e->y_fp, M, C, reinterpret_cast<const bf16*>(e->w.proj_w), H);
@@ -806,7 +814,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   // the next pre-LayerNorm sum (lb[l].h1 / h2, kept per layer for the backward), and the following GEMM accumulates
   // "+= x W^T + b" into it with a TMA reduce-add -- the GEMM epilogue never loads the residual.
   // (the bias of that GEMM is added by the LayerNorm too, so its fp32 epilogue needs no bias and keeps 4 stages)
-  PROF("ln_fwd", layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, e->b16, e->enc_mean,
+  PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, e->b16, e->enc_mean,
                              e->enc_rstd, M, H, c.ln_eps, st, e->w.layer[0].bo));
   e->launches += 5;
   for (int l = 0; l < c.layers; ++l) {
@@ -823,7 +831,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
       p.epi.accumulate = 1; p.epi.out_f32 = x.h1; p.epi.out_ld = H;      // + bo: already in h1 (added by the LayerNorm)
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_fwd", layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
                                x.mean1, x.rstd1, M, H, c.ln_eps, st, w.b2));
     {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
@@ -835,7 +843,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
       p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;      // + b2: already in h2
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_fwd", layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
                                l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, e->b16, x.mean2, x.rstd2, M, H, c.ln_eps, st,
                                l + 1 < c.layers ? e->w.layer[l + 1].bo : nullptr));
     e->launches += 3;
@@ -877,7 +885,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   for (int l = c.layers - 1; l >= 0; --l) {
     const suta_layer_weights& w = e->w.layer[l];
     LayerBufs& x = e->lb[l];
-    PROF("ln_bwd", layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+    PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
                                 e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
     {  // output_dense dgrad, times GELU'(pre)
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
@@ -889,7 +897,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.accumulate = 1; p.epi.out_f32 = db; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF("ln_bwd", layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
+    PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
                                 e->G, da, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
@@ -905,7 +913,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     e->launches += 7;             // 2 x (LayerNorm backward + its dgamma/dbeta reduction), attention backward (3 launches)
   }
   // encoder.layer_norm
-  PROF("ln_bwd", layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
+  PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4), layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
                               e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
   PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
@@ -954,7 +962,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     PROF("colsum", colsum_per_utt(da, e->d_tok_off, e->d_T, e->G, e->n_params, e->proj_b_off, H, e->U, st));
   }
   // feature_projection.layer_norm with input gradient
-  PROF("ln_bwd", layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
+  PROF_B("ln_bwd C", (double)M * C * (4 + 2 + 4), layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
                               (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
   // d(pre-activation) of the last conv layer, in the 128-row-aligned token slab
   PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
@@ -1030,7 +1038,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   ba.P = e->P; ba.G = e->G; ba.pstride = e->n_params;
   ba.g_off = e->gn_g; ba.b_off = e->gn_b; ba.w_off = e->conv_w_off[0];
   ba.n_utts = e->U; ba.C = c.conv_dim[0]; ba.k = c.conv_kernel[0]; ba.stride = c.conv_stride[0]; ba.max_L0 = e->max_L0;
-  PROF("conv0_bwd", conv0_groupnorm_backward(ba, st));
+  PROF_B("conv0_bwd", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2, conv0_groupnorm_backward(ba, st));
   e->launches += 2;
   return SUTA_OK;
 }
@@ -1049,7 +1057,9 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
     e->frontend_done = false;    // the CNN output depends on the updated weights
   }
   cudaStream_t st = S(stream);
-  PROF("adam", optimizer_step(a, st));
+  double shadow_elems = 0.0;
+  for (int i = 0; i < a.n_seg; ++i) shadow_elems += (double)a.seg[i].size;
+  PROF_B("adam", (double)e->U * ((double)e->n_params * 28.0 + shadow_elems * 2.0), optimizer_step(a, st));
   e->opt_steps += 1;
   e->launches += 1;
   return SUTA_OK;

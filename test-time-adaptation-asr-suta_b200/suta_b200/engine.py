@@ -226,11 +226,11 @@ class SutaEngine:
         return ms.value, n.value, fl.value
 
     def profile_report(self):
-        """Per-kernel-class breakdown of the last profile() read-out: {tag: (ms, flops, launches)}."""
+        """Per-kernel-class breakdown of the last profile() read-out: {tag: (ms, flops, launches, algorithmic bytes)}."""
         out = {}
         for line in self.lib.suta_profile_report(self._h).decode().splitlines():
-            tag, ms, fl, n = line.split("\t")
-            out[tag] = (float(ms), float(fl), int(n))
+            tag, ms, fl, n, by = line.split("\t")
+            out[tag] = (float(ms), float(fl), int(n), float(by))
         return out
 
     def _view(self, ptr: int, shape, dtype) -> torch.Tensor:

@@ -89,14 +89,26 @@ class SutaRunner:
         mine = shard_lpt(costs, self.world_size)[self.rank]
         return bucket_batches(frames, mine, self.max_utts, self.max_frames)
 
-    def run(self, utts: Sequence[Utterance]) -> Dict[str, object]:
-        batches = self.plan(utts)
-        texts: Dict[int, Dict[int, str]] = {}
-        t0 = time.time()
-        for b in batches:
+    def stage(self, utts: Sequence[Utterance], batches: Optional[List[List[int]]] = None, device: bool = False):
+        """Materialise the packed waveform buffer of every batch of this rank's plan (pinned host memory, or device
+        memory with device=True): [(indices, lengths, packed)].  Data loading / synthesis is not part of the adaptation."""
+        out = []
+        for b in (self.plan(utts) if batches is None else batches):
             sel = [utts[i] for i in b]
             packed = pack_batch(self.engine, sel)
-            out = adapt_batch(self.engine, packed, None, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
+            out.append((b, np.asarray([u.n_samples for u in sel], dtype=np.int32), packed.to(self.engine.device) if device else packed))
+        return out
+
+    def run(self, utts: Sequence[Utterance], staged=None) -> Dict[str, object]:
+        """Adapt this rank's shard batch by batch (REF/main.py:319-402) and score it (REF/main.py:405-417).
+        `staged` = the result of stage(): skips building the waveform buffers."""
+        if staged is None:
+            staged = self.stage(utts)
+        texts: Dict[int, Dict[int, str]] = {}
+        t0 = time.time()
+        for b, lens, packed in staged:
+            self.engine.begin_batch_lengths(lens)
+            out = adapt_batch(self.engine, packed, lens, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
                               sched_step=self.sched_step)
             for step, tl in out.items():
                 texts.setdefault(step, {}).update({i: t for i, t in zip(b, tl)})
@@ -107,7 +119,7 @@ class SutaRunner:
             idx = sorted(d)
             counts[step] = wer_counts([utts[i].text for i in idx], [d[i] for i in idx])
         return dict(texts=texts, wer_counts=counts, wall_s=wall,
-                    audio_s=sum(utts[i].duration for b in batches for i in b), n_batches=len(batches))
+                    audio_s=sum(utts[i].duration for b, _l, _p in staged for i in b), n_batches=len(staged))
 
 
 def gather_results(local: Dict[str, object], steps_keys: Sequence[int]) -> Dict[str, object]:

@@ -70,6 +70,30 @@ def test_oracle_adaptation_reproduces_reference(case):
             assert np.abs(d_ref - d_got).max() <= 0.05 * np.abs(d_ref).max() + 1e-9
 
 
+@pytest.mark.parametrize("case", ["tiny_ln", "tiny_feat", "tiny_steplr", "tiny_adam_beta", "tiny_feat_sgd", "tiny_bias_only"])
+def test_hf_reference_loop_reproduces_reference(case):
+    """oracle/hf_reference.py (the loop bench.py times as the reference's CPU / eager-GPU path: real HF modules,
+    autograd and torch.optim under a restatement of main.py's driver) against what the unmodified reference produced."""
+    from oracle.hf_reference import ReferenceLoop
+    z, meta = load(case)
+    cfg = getattr(O.W2V2Config, meta["cfg"])()
+    sd = O.init_weights(cfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"])
+    x = O.normalize_audio(O.synth_audio(meta["n_samples"], meta["audio_seed"], meta.get("extra_noise", 0.0)))
+    h = meta["hyper"]
+    loop = ReferenceLoop(cfg, sd, "cpu", train_feature=meta["train_feature"], bias_only=meta.get("bias_only", False),
+                         opt=meta.get("opt", "AdamW"), lr=h["lr"], beta=meta.get("beta", 0.9), sched_gamma=meta.get("sched_gamma"))
+    assert loop.names == meta["names"]
+    for _ in range(2):                                   # twice: the episodic restore brings everything back
+        res = loop.adapt(x, steps=meta["steps"], em_coef=h["em_coef"], reweight=h["reweight"], temp=h["temp"],
+                         not_blank=h["not_blank"], div_coef=meta.get("div_coef", 0.0))
+        np.testing.assert_allclose(res.logits0, z["logits_0"], atol=1e-5)
+        np.testing.assert_allclose(res.losses, z["losses"], rtol=1e-5)
+        last = str(meta["steps"])
+        np.testing.assert_allclose(res.logits[meta["steps"]], z["logits_" + last], atol=2e-5)
+        for k, text in meta["texts"].items():
+            assert res.texts.get(int(k), text) == text
+
+
 def test_param_multiplicities_match_survey():
     names = O.collect_param_names(O.W2V2Config.base(), train_feature=True)
     mult = {}
