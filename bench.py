@@ -250,7 +250,8 @@ def run_b200(a):
     utts = build_set(a)
     K, W = a.steps, max(a.warmup, 0)
     full = a.workload == "fullset"
-    runner = SutaRunner(eng, S, hp, max_utts=w["max_utts"], max_frames=w["max_frames"], vocab=vocab, rank=rank, world_size=world)
+    runner = SutaRunner(eng, S, hp, max_utts=w["max_utts"], max_frames=w["max_frames"], vocab=vocab, rank=rank, world_size=world,
+                        extra_noise=w["noise"])
     if full:            # strong scaling: this rank's LPT shard of the whole set, batch by batch
         plan = runner.plan(utts)
         timed_idx = plan
@@ -265,9 +266,9 @@ def run_b200(a):
     staged = runner.stage(utts, timed_idx)
     dev_audio = [p.to(eng.device) for _b, _l, p in staged]
 
-    def one_step(lens, audio):
+    def one_step(lens, audio, ids):
         eng.begin_batch_lengths(lens)
-        return adapt_batch(eng, audio, lens, S, hp, vocab)
+        return adapt_batch(eng, audio, lens, S, hp, vocab, extra_noise=w["noise"], utt_ids=ids)   # noise: on the device
 
     def barrier():
         if world > 1:
@@ -282,7 +283,7 @@ def run_b200(a):
         texts = {}
         ev[0].record()
         for i, (b, lens, audio) in enumerate(items):
-            out = one_step(lens, audio)
+            out = one_step(lens, audio, b)
             for step, tl in out.items():
                 texts.setdefault(step, {}).update({j: t for j, t in zip(b, tl)})
             ev[i + 1].record()
@@ -305,7 +306,7 @@ def run_b200(a):
         return float(ms.item()), eng.launch_count - l0, per_step, [float(x.item()) for x in per_rank], gathered
 
     for b, lens, host in staged_w:                        # warm-up (>= 3 by default)
-        one_step(lens, host)
+        one_step(lens, host, b)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -317,7 +318,7 @@ def run_b200(a):
     prof_items = staged[:min(len(staged), 6)]
     eng.profile(True)
     for (b, lens, _p), d in zip(prof_items, dev_audio):
-        one_step(lens, d)
+        one_step(lens, d, b)
     gemm_ms, gemm_n, gemm_fl = eng.profile(False)
     rep = eng.profile_report()
     tot_ms = sum(v[0] for v in rep.values()) or 1.0

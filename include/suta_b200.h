@@ -100,6 +100,10 @@ int suta_batch_info(const suta_engine* e, int64_t* total_frames, int32_t* frames
  * by the caller (HF processor output, REF/main.py:322) so the device normalisation is skipped */
 int suta_batch_set_audio(suta_engine* e, const float* wav, int flags, void* stream);
 
+/* REF/data.py:23 (wav += extra_noise * randn_like(wav)) on the device, on the raw waveform of the live batch, before the
+ * normalisation; counter-based RNG keyed by (seed, utt_ids[u] -- host array, NULL = position in the batch) */
+int suta_batch_add_noise(suta_engine* e, float sigma, uint64_t seed, const int32_t* utt_ids /*HOST, may be NULL*/, void* stream);
+
 int suta_reset(suta_engine* e, void* stream);                       /* load_model_and_optimizer, REF/main.py:147-155 */
 int suta_frontend(suta_engine* e, void* stream);                    /* HF/feature_extraction_wav2vec2.py:95 + HF:409-419 */
 int suta_forward(suta_engine* e, void* stream);                     /* model(x).logits, REF/main.py:181/:214/:332 */

@@ -108,7 +108,7 @@ if __name__ == '__main__':
         hp.em_coef, hp.temp, hp.reweight, hp.not_blank, hp.div_coef = em_coef, temp, reweight, non_blank, div_coef
         out = SutaRunner(model.engine, steps, hp, max_utts=args.batch_utts, vocab=vocab,
                          sched_gamma=scheduler.gamma if scheduler is not None else None,
-                         sched_step=scheduler.step_size if scheduler is not None else 1).run(dataset)
+                         sched_step=scheduler.step_size if scheduler is not None else 1, extra_noise=extra_noise).run(dataset)
         for k, d in out["texts"].items():
             transcriptions[k] = [d[i] for i in sorted(d)]
         gt_texts = [u.text for u in dataset]

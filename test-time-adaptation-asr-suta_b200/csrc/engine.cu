@@ -150,6 +150,7 @@ struct suta_engine {
   bf16* dlogits16 = nullptr;
   float *P = nullptr, *G = nullptr, *Mom = nullptr, *Var = nullptr;
   float* ln_part = nullptr;                        // dgamma/dbeta slots of the two-stage LayerNorm-backward reduction
+  size_t ln_part_stride = 0;
   int *ids = nullptr, *collapsed = nullptr, *out_len = nullptr;
   // every device table of a batch lives in one contiguous region at the start of the workspace and is uploaded by ONE
   // host-to-device copy from this pinned mirror (no pageable copies, no stream synchronisation in suta_batch_begin)
@@ -368,7 +369,8 @@ void carve(suta_engine* e, Bump& b) {
   e->P = b.take<float>((size_t)U * e->n_params); e->G = b.take<float>((size_t)U * e->n_params);
   e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
   e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
-  e->ln_part = b.take<float>((size_t)layernorm_backward_scratch_floats(H > C ? H : C, U));
+  e->ln_part_stride = (size_t)layernorm_backward_scratch_floats(H > C ? H : C, U);
+  e->ln_part = b.take<float>(e->ln_part_stride * (2 * c.layers + 2));      // one slot set per LayerNorm: reduced together
   if (e->train_feature) {
     size_t zmax = 0;
     for (int l = 0; l < c.n_conv; ++l) {
@@ -699,6 +701,28 @@ static int refresh_shadows(suta_engine* e, cudaStream_t st) {
   return SUTA_OK;
 }
 
+// REF/data.py:23 on the device: adds sigma * N(0,1) to the RAW waveform the last suta_batch_set_audio copied in (before
+// the normalisation of suta_frontend).  utt_ids (host, optional): a stable id per utterance, so that an utterance gets
+// the same noise whatever batch it is adapted in; default = position in the batch.
+extern "C" int suta_batch_add_noise(suta_engine* e, float sigma, uint64_t seed, const int32_t* utt_ids, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0 && sigma >= 0.f);
+  if (e->audio_normalized) {
+    suta_set_last_error("suta_batch_add_noise: the audio was handed over already normalised; noise goes on the raw waveform");
+    return SUTA_ERR_ARG;
+  }
+  cudaStream_t st = S(stream);
+  int* d_ids = nullptr;
+  if (utt_ids) {                   // ids ride in the (otherwise unused until decode) argmax-id buffer
+    d_ids = e->ids;
+    CUDA_TRY(cudaMemcpyAsync(d_ids, utt_ids, sizeof(int) * e->U, cudaMemcpyHostToDevice, st));
+  }
+  e->launches += 1;
+  PROF("audio_noise", audio_add_noise(e->wav, e->d_samp_off, e->d_n_samples, d_ids, e->U, e->max_samples, sigma, seed, st));
+  e->frontend_done = false;
+  e->moments_done = false;
+  return SUTA_OK;
+}
+
 extern "C" int suta_reset(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   e->launches += 1;
@@ -875,6 +899,8 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
 
   // two fp32 gradient streams, updated in place like the forward's residual stream: LayerNorm backward writes d(input)
   // into the other buffer and the following dgrad GEMM accumulates its product onto it (TMA reduce-add)
+  LnReduceBatch lnred;                 // second stage of every LayerNorm's dgamma/dbeta reduction, launched once at the end
+  auto ln_slot = [&]() { return e->ln_part + e->ln_part_stride * (size_t)lnred.n; };
   float* da = e->fa;   // gradient w.r.t. the current LayerNorm output
   float* db = e->fb;   // gradient w.r.t. the pre-LayerNorm sum
   {  // lm_head dgrad
@@ -886,7 +912,8 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     const suta_layer_weights& w = e->w.layer[l];
     LayerBufs& x = e->lb[l];
     PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
-                                e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
+                                e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
     {  // output_dense dgrad, times GELU'(pre)
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
       p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
@@ -898,7 +925,8 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       SUTA_TRY(gemm(e, p, st));
     }
     PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
-                                e->G, da, e->b16, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
+                                e->G, da, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
       p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
@@ -910,11 +938,12 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.accumulate = 1; p.epi.out_f32 = da; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
-    e->launches += 7;             // 2 x (LayerNorm backward + its dgamma/dbeta reduction), attention backward (3 launches)
+    e->launches += 5;             // 2 x LayerNorm backward, attention backward (3 launches)
   }
   // encoder.layer_norm
   PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4), layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
-                              e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
+                              e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+  lnred.n += 1;
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
   PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
   if (use_posconv_tc(e)) {
@@ -943,8 +972,12 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   e->launches += 4;
   if (!e->train_feature) {
     // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
-    return layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
-                              (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, e->d_tok_off, e->d_T, e->U, e->ln_part, st);
+    SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
+                                (int)e->fp_g, (int)e->fp_b, e->G, nullptr, nullptr, M, C, e->d_tok_off, e->d_T, e->U, ln_slot(), st,
+                                &lnred.item[lnred.n]));
+    lnred.n += 1;
+    PROF("ln_bwd_reduce", layernorm_backward_reduce(lnred, e->d_tok_off, e->d_T, e->U, e->G, e->n_params, st));
+    return SUTA_OK;
   }
 
   // ================= train_feature: projection weight/bias, then the whole CNN (REF/main.py:88-94) =================
@@ -963,7 +996,9 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   }
   // feature_projection.layer_norm with input gradient
   PROF_B("ln_bwd C", (double)M * C * (4 + 2 + 4), layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
-                              (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, e->ln_part, st));
+                              (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+  lnred.n += 1;
+  PROF("ln_bwd_reduce", layernorm_backward_reduce(lnred, e->d_tok_off, e->d_T, e->U, e->G, e->n_params, st));
   // d(pre-activation) of the last conv layer, in the 128-row-aligned token slab
   PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, e->conv_pre[last], e->conv_dpre[last], e->d_row_utt, e->d_tok_off,
                                e->d_dpre_off_last, M, C, st));
@@ -1103,6 +1138,7 @@ extern "C" const void* suta_debug_buffer(const suta_engine* e, const char* name,
   auto ret = [&](const void* p, long long r, long long k, int dt) { *rows = r; *cols = k; *dtype = dt; return p; };
   std::string n(name);
   if (n == "wav_norm") return ret(e->wav_norm, 1, e->S, 0);
+  if (n == "wav") return ret(e->wav, 1, e->S, 0);
   if (n == "feat") return ret(e->conv_out[c.n_conv - 1], e->M, C, 1);
   if (n == "h0") return ret(e->h0, e->M, H, 0);
   if (n == "cpos") return ret(e->cpos, e->Rm, H, 0);

@@ -59,6 +59,47 @@ __global__ void audio_apply_kernel(const float* __restrict__ wav, float* __restr
   for (int i = i0 + threadIdx.x; i < min(n, i0 + NORM_CHUNK); i += blockDim.x) y[i] = (x[i] - m) * r;
 }
 
+// REF/data.py:23: wav += extra_noise * randn_like(wav), before the processor's normalisation.  Counter-based
+// Philox4x32-10 keyed by (seed, utterance id) and counted by sample index: the noise of an utterance depends on
+// nothing but (seed, its id, the sample position) -- not on the batch it happens to be adapted in.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;      // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;               // [0, 1)
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+__global__ void audio_noise_kernel(float* __restrict__ wav, const long long* __restrict__ samp_off,
+                                   const int* __restrict__ n_samples, const int* __restrict__ utt_id, float sigma,
+                                   unsigned long long seed) {
+  const int u = blockIdx.y;
+  const int n = n_samples[u];
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)(i >> 2), 0u, (uint32_t)(utt_id ? utt_id[u] : u), 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  float* x = wav + samp_off[u] + i;
+  const float z[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i + j < n) x[j] += sigma * z[j];
+}
+
 constexpr int C0_TT = 128;      // frames per CTA
 constexpr int C0_MAXK = 16;
 
@@ -225,6 +266,16 @@ int normalize_audio(const float* wav, float* out, const long long* samp_off, con
   dim3 grid(ceil_div(max_samples, NORM_CHUNK), n_utts);
   audio_stats_kernel<<<grid, 256, 0, stream>>>(wav, samp_off, n_samples, stats_scratch);
   audio_apply_kernel<<<grid, 256, 0, stream>>>(wav, out, samp_off, n_samples, stats_scratch);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int audio_add_noise(float* wav, const long long* samp_off, const int* n_samples, const int* utt_id, int n_utts,
+                    int max_samples, float sigma, unsigned long long seed, cudaStream_t stream) {
+  SUTA_CHECK_ARG(wav && n_utts > 0 && max_samples > 0 && sigma >= 0.f);
+  if (sigma == 0.f) return SUTA_OK;
+  audio_noise_kernel<<<dim3(ceil_div(ceil_div(max_samples, 4), 256), n_utts), 256, 0, stream>>>(wav, samp_off, n_samples, utt_id,
+                                                                                               sigma, seed);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

@@ -25,16 +25,32 @@ int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt
 // dgamma/dbeta are WRITTEN into G (same layout as the parameter vector) by a fixed-order two-stage reduction through
 // `scratch` (layernorm_backward_scratch_floats(N, n_utts) floats) -- bit-reproducible; G and the dx outputs are optional.
 // tok_off / T: first packed row and row count of every utterance (the rows row_utt describes).
+// defer != nullptr: the second stage is NOT launched; *defer describes it and the caller runs layernorm_backward_reduce
+// once for all the LayerNorms of a backward pass (each needs its own scratch until then).
+struct LnReduceItem {
+  const float* part;
+  int g_off, b_off, N, rows_per_cta;
+};
+constexpr int LN_REDUCE_MAX = 2 * 48 + 4;
+struct LnReduceBatch {
+  LnReduceItem item[LN_REDUCE_MAX];
+  int n = 0;
+};
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
                        long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
-                       cudaStream_t stream);
+                       cudaStream_t stream, LnReduceItem* defer = nullptr);
+int layernorm_backward_reduce(const LnReduceBatch& b, const long long* tok_off, const int* T, int n_utts, float* G,
+                              long long pstride, cudaStream_t stream);
 long long layernorm_backward_scratch_floats(int N, int n_utts);
 
 // ---- frontend.cu ----------------------------------------------------------------------------
 // per-utterance (x - mean) / sqrt(var + 1e-7), optional additive noise is applied by the caller beforehand
 int normalize_audio(const float* wav, float* out, const long long* samp_off, const int* n_samples, int n_utts,
                     int max_samples, double* stats_scratch /*[2*n_utts]*/, cudaStream_t stream);
+// wav[u][i] += sigma * N(0,1), REF/data.py:23; Philox keyed by (seed, utt_id[u] or u) and counted by the sample index
+int audio_add_noise(float* wav, const long long* samp_off, const int* n_samples, const int* utt_id, int n_utts,
+                    int max_samples, float sigma, unsigned long long seed, cudaStream_t stream);
 // conv0 (Cin=1) + GroupNorm(per channel over time) + GELU -> channels-last bf16
 struct Conv0Args {
   const float* x;              // normalised audio, packed

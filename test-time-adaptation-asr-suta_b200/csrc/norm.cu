@@ -332,6 +332,22 @@ ln_bwd_reduce_kernel(const float* __restrict__ part, const long long* __restrict
   }
 }
 
+// The same reduction for MANY LayerNorms in one launch (the engine defers the reductions of a whole backward pass:
+// 2 x layers + 2 small launches become one): blockIdx.y selects the LayerNorm.
+__global__ void __launch_bounds__(256)
+ln_bwd_reduce_many_kernel(const __grid_constant__ LnReduceBatch b, const long long* __restrict__ tok_off,
+                          const int* __restrict__ T, float* __restrict__ G, long long pstride) {
+  const LnReduceItem it = b.item[blockIdx.y];
+  const int u = blockIdx.x;
+  const long long r0 = tok_off[u], r1 = r0 + T[u] - 1;
+  const int b0 = (int)(r0 / it.rows_per_cta), b1 = (int)(r1 / it.rows_per_cta);
+  for (int c = threadIdx.x; c < 2 * it.N; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = b0; k <= b1; ++k) s += it.part[((long long)k + u) * (2 * it.N) + c];
+    G[(long long)u * pstride + (c < it.N ? it.g_off + c : it.b_off + c - it.N)] = s;
+  }
+}
+
 template <int N, typename TIn>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
                float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
@@ -360,7 +376,7 @@ long long bwd_rows_per_cta(long long M, int resident) {
 template <int N, typename TIn>
 int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
                int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, const long long* tok_off, const int* T,
-               int n_utts, float* scratch, cudaStream_t stream) {
+               int n_utts, float* scratch, cudaStream_t stream, LnReduceItem* defer) {
   constexpr int threads = (N / 4 + 31) / 32 * 32;
   using S = BwdSmem<N, TIn>;
   static int resident = 0;                         // CTAs of this instantiation that fit on one SM
@@ -373,7 +389,9 @@ int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rs
   ln_bwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
       dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, G ? scratch : nullptr, dx32, dx16, M, (int)rows);
   CUDA_TRY(cudaGetLastError());
-  if (G) {
+  if (G && defer) {
+    *defer = LnReduceItem{scratch, g_off, b_off, N, (int)rows};
+  } else if (G) {
     ln_bwd_reduce_kernel<<<n_utts, 256, 0, stream>>>(scratch, tok_off, T, (int)rows, N, G, prm.stride, g_off, b_off);
     CUDA_TRY(cudaGetLastError());
   }
@@ -414,14 +432,23 @@ long long layernorm_backward_scratch_floats(int N, int n_utts) { return ((long l
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
                        long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, LnReduceItem* defer) {
   SUTA_CHECK_ARG((x_f32 != nullptr) != (x_bf16 != nullptr));
   SUTA_CHECK_ARG(!G || (tok_off && T && n_utts > 0 && scratch));
   if (M <= 0) return SUTA_OK;
   if (x_f32) {
-    LN_DISPATCH(N, return (launch_bwd<NN, float>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream)));
+    LN_DISPATCH(N, return (launch_bwd<NN, float>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream, defer)));
   } else {
-    LN_DISPATCH(N, return (launch_bwd<NN, bf16>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream)));
+    LN_DISPATCH(N, return (launch_bwd<NN, bf16>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream, defer)));
   }
+  return SUTA_OK;
+}
+
+int layernorm_backward_reduce(const LnReduceBatch& b, const long long* tok_off, const int* T, int n_utts, float* G,
+                              long long pstride, cudaStream_t stream) {
+  SUTA_CHECK_ARG(b.n >= 0 && b.n <= LN_REDUCE_MAX && tok_off && T && n_utts > 0 && G);
+  if (b.n == 0) return SUTA_OK;
+  ln_bwd_reduce_many_kernel<<<dim3((unsigned)n_utts, (unsigned)b.n), 256, 0, stream>>>(b, tok_off, T, G, pstride);
+  CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "suta_batch_info": (c_int, [c_void_p, C.POINTER(c_int64), C.POINTER(c_int32), C.POINTER(c_int64),
                                 C.POINTER(c_int64), C.POINTER(c_int64)]),
     "suta_batch_set_audio": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "suta_batch_add_noise": (c_int, [c_void_p, c_float, C.c_uint64, C.POINTER(c_int32), c_void_p]),
     "suta_reset": (c_int, [c_void_p, c_void_p]),
     "suta_frontend": (c_int, [c_void_p, c_void_p]),
     "suta_forward": (c_int, [c_void_p, c_void_p]),

@@ -27,10 +27,12 @@ class Utterance:
     def duration(self) -> float:
         return self.n_samples / SAMPLE_RATE
 
-    def audio(self) -> np.ndarray:
+    def audio(self, with_noise: bool = True) -> np.ndarray:
+        """The waveform as the reference's collate function returns it (REF/data.py:15-23).  with_noise=False leaves the
+        extra_noise term out: the batched runner adds it on the device (suta_batch_add_noise)."""
         rng = np.random.default_rng(self.seed)
         wav = (0.1 * rng.standard_normal(self.n_samples)).astype(np.float32)
-        if self.extra_noise > 0:
+        if with_noise and self.extra_noise > 0:
             wav = wav + (self.extra_noise * rng.standard_normal(self.n_samples)).astype(np.float32)
         return wav
 

@@ -178,14 +178,18 @@ class SutaEngine:
         self.mult.copy_(m.to(self.device))
 
     # ------------------------------------------------------------------ batches
-    def begin_batch(self, wavs: Sequence[np.ndarray]):
-        """Start adapting a batch of raw (un-normalised) fp32 waveforms; copies them to the device."""
+    def begin_batch(self, wavs: Sequence[np.ndarray], max_samples: Optional[int] = 600000):
+        """Start adapting a batch of raw (un-normalised) fp32 waveforms; copies them to the device.
+        max_samples: REF/data.py:9,19-21 -- a waveform of >= 600000 samples keeps its first 600000 (the clamp is part of
+        the batch layout: samples beyond it never cross PCIe)."""
         lens = np.asarray([len(w) for w in wavs], dtype=np.int32)
+        if max_samples is not None:
+            lens = np.minimum(lens, max_samples).astype(np.int32)
         self.begin_batch_lengths(lens)
         host = torch.zeros(self.total_samples, dtype=torch.float32).pin_memory()
         hv = host.numpy()
-        for w, o in zip(wavs, self.sample_off):
-            hv[o:o + len(w)] = np.asarray(w, dtype=np.float32)
+        for w, n, o in zip(wavs, lens, self.sample_off):
+            hv[o:o + n] = np.asarray(w[:n], dtype=np.float32)
         self.set_audio(host)
 
     def begin_batch_lengths(self, lens: np.ndarray):
@@ -217,6 +221,16 @@ class SutaEngine:
         self._audio_keep = packed
         flags = int(not packed.is_cuda) | (2 if normalized else 0)
         check(self.lib.suta_batch_set_audio(self._h, C.c_void_p(packed.data_ptr()), flags, _stream_ptr()))
+
+    def add_noise(self, sigma: float, seed: int = 0, utt_ids: Optional[Sequence[int]] = None):
+        """REF/data.py:23 on the device: wav += sigma * N(0,1) on the raw waveform set by set_audio (before normalisation).
+        utt_ids: stable utterance ids, so the noise of an utterance does not depend on the batch it is adapted in."""
+        ids = None
+        if utt_ids is not None:
+            self._noise_ids = np.ascontiguousarray(utt_ids, dtype=np.int32)
+            assert len(self._noise_ids) == self.n_utts
+            ids = self._noise_ids.ctypes.data_as(C.POINTER(C.c_int32))
+        check(self.lib.suta_batch_add_noise(self._h, float(sigma), int(seed) & (2 ** 64 - 1), ids, _stream_ptr()))
 
     def profile(self, enable: bool):
         """Read-and-clear the per-launch GEMM timers, then switch collection on/off.

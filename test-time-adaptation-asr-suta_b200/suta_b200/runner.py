@@ -27,16 +27,20 @@ class BatchResult:
 
 def adapt_batch(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarray, steps: int, hp: AdaptHyper,
                 vocab: CTCVocab, episodic: bool = True, collect_losses: bool = False,
-                sched_gamma: Optional[float] = None, sched_step: int = 1) -> Dict[int, List[str]]:
+                sched_gamma: Optional[float] = None, sched_step: int = 1, extra_noise: float = 0.0, noise_seed: int = 0,
+                utt_ids: Optional[Sequence[int]] = None) -> Dict[int, List[str]]:
     """One adaptation batch = the body of REF/main.py:319-402 for len(lengths) utterances at once.
     `wavs_packed` is the packed waveform buffer (pinned host or device) laid out by engine.begin_batch_lengths.
     Batches are always episodic: every utterance starts from the pristine parameters (REF/main.py:327-328) -- carrying
     state from utterance to utterance serialises them (that mode lives in api.SutaModel, batch size 1).
     sched_gamma / sched_step: the StepLR of REF/main.py:20-21, restarted for every utterance like the reference's
-    scheduler.load_state_dict (:151-153)."""
+    scheduler.load_state_dict (:151-153).
+    extra_noise: REF/data.py:23, added to the raw waveform ON THE DEVICE (keyed by noise_seed and utt_ids)."""
     if not episodic:
         raise ValueError("adapt_batch adapts independent utterances: episodic only (use the api.* surface for continual mode)")
     engine.set_audio(wavs_packed)
+    if extra_noise > 0:
+        engine.add_noise(extra_noise, noise_seed, utt_ids)
     engine.reset()
     engine.forward()                                               # vanilla forward, REF/main.py:331-334
     texts = {0: vocab.batch_to_text(engine.decode_ids())}
@@ -58,7 +62,7 @@ def adapt_batch(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarr
     return texts
 
 
-def pack_batch(engine: SutaEngine, utts: Sequence[Utterance], pinned: bool = True) -> torch.Tensor:
+def pack_batch(engine: SutaEngine, utts: Sequence[Utterance], pinned: bool = True, with_noise: bool = True) -> torch.Tensor:
     lens = np.asarray([u.n_samples for u in utts], dtype=np.int32)
     engine.begin_batch_lengths(lens)
     host = torch.zeros(engine.total_samples, dtype=torch.float32)
@@ -66,7 +70,7 @@ def pack_batch(engine: SutaEngine, utts: Sequence[Utterance], pinned: bool = Tru
         host = host.pin_memory()
     hv = host.numpy()
     for u, o in zip(utts, engine.sample_off):
-        hv[o:o + u.n_samples] = u.audio()
+        hv[o:o + u.n_samples] = u.audio(with_noise)
     return host
 
 
@@ -75,9 +79,12 @@ class SutaRunner:
 
     def __init__(self, engine: SutaEngine, steps: int = 10, hp: Optional[AdaptHyper] = None, max_utts: int = 64,
                  max_frames: int = 32768, vocab: Optional[CTCVocab] = None, rank: int = 0, world_size: int = 1,
-                 sched_gamma: Optional[float] = None, sched_step: int = 1):
+                 sched_gamma: Optional[float] = None, sched_step: int = 1, extra_noise: float = 0.0, noise_seed: int = 0):
         self.engine, self.steps, self.hp = engine, steps, hp or AdaptHyper()
         self.sched_gamma, self.sched_step = sched_gamma, sched_step
+        # REF/data.py:23: the runner stages CLEAN waveforms and the engine adds the noise on the device, keyed by the
+        # utterance's index in the set (the same noise whichever rank / batch adapts it)
+        self.extra_noise, self.noise_seed = extra_noise, noise_seed
         self.max_utts, self.max_frames = max_utts, max_frames
         self.vocab = vocab or CTCVocab()
         self.rank, self.world_size = rank, world_size
@@ -95,7 +102,7 @@ class SutaRunner:
         out = []
         for b in (self.plan(utts) if batches is None else batches):
             sel = [utts[i] for i in b]
-            packed = pack_batch(self.engine, sel)
+            packed = pack_batch(self.engine, sel, with_noise=False)
             out.append((b, np.asarray([u.n_samples for u in sel], dtype=np.int32), packed.to(self.engine.device) if device else packed))
         return out
 
@@ -109,7 +116,7 @@ class SutaRunner:
         for b, lens, packed in staged:
             self.engine.begin_batch_lengths(lens)
             out = adapt_batch(self.engine, packed, lens, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
-                              sched_step=self.sched_step)
+                              sched_step=self.sched_step, extra_noise=self.extra_noise, noise_seed=self.noise_seed, utt_ids=b)
             for step, tl in out.items():
                 texts.setdefault(step, {}).update({i: t for i, t in zip(b, tl)})
         torch.cuda.synchronize()

@@ -113,3 +113,45 @@ def test_main_cli_rejects_batching_without_episodic(tmp_path):
            "--batch_utts", "2", "--log_dir", str(tmp_path)]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode != 0 and "--episodic" in (r.stdout + r.stderr)
+
+
+def test_device_side_noise_and_truncation():
+    """SURVEY.md 8f rank 1 (REF/data.py:19-23): waveforms are clamped to 600000 samples when the batch is laid out, and
+    `extra_noise * randn` is added on the device before the normalisation: N(0, sigma^2), reproducible for a seed,
+    different per utterance, and independent of the batch an utterance is adapted in."""
+    _need_gpu()
+    from oracle import suta_oracle as O
+    eng = _tiny_engine()
+    rng = np.random.default_rng(0)
+    wavs = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in (610000, 40000, 40000)]
+    eng.begin_batch(wavs)
+    assert list(eng.lengths) == [600000, 40000, 40000]                     # truncated like REF/data.py:19-21
+    raw = eng.debug_buffer("wav")[0].clone()
+    eng.add_noise(0.01, seed=7, utt_ids=[5, 6, 9])
+    noisy = eng.debug_buffer("wav")[0].clone()
+    d = (noisy - raw).cpu().numpy()
+    offs, lens = eng.sample_off, eng.lengths
+    z = [d[o:o + n] / 0.01 for o, n in zip(offs, lens)]
+    assert abs(z[0].mean()) < 0.01 and abs(z[0].std() - 1.0) < 0.01       # N(0,1) scaled by sigma
+    assert abs(np.mean(z[0] ** 3)) < 0.02 and abs(np.mean(z[0] ** 4) - 3.0) < 0.05
+    assert abs(np.corrcoef(z[1], z[2])[0, 1]) < 0.02                       # different utterance ids -> independent noise
+    assert abs(np.corrcoef(z[0][:-1], z[0][1:])[0, 1]) < 0.01              # white
+    eng.forward()
+    x = eng.debug_buffer("wav_norm")[0].cpu().numpy()
+    for o, n, w in zip(offs, lens, wavs):
+        np.testing.assert_allclose(x[o:o + n], O.normalize_audio(noisy[o:o + n].cpu().numpy()), atol=2e-5)   # noise first, then HF:95
+    # the same utterance id in another batch position / composition gets the same noise
+    eng.begin_batch([wavs[2], wavs[1]])
+    raw2 = eng.debug_buffer("wav")[0].clone()
+    eng.add_noise(0.01, seed=7, utt_ids=[9, 6])
+    d2 = (eng.debug_buffer("wav")[0] - raw2).cpu().numpy()
+    o2 = eng.sample_off
+    np.testing.assert_array_equal(d2[o2[0]:o2[0] + 40000], d[offs[2]:offs[2] + 40000])
+    np.testing.assert_array_equal(d2[o2[1]:o2[1] + 40000], d[offs[1]:offs[1] + 40000])
+    # another seed -> other noise
+    eng.begin_batch([wavs[1]])
+    raw3 = eng.debug_buffer("wav")[0].clone()
+    eng.add_noise(0.01, seed=8, utt_ids=[6])
+    d3 = (eng.debug_buffer("wav")[0] - raw3).cpu().numpy()[:40000]
+    assert abs(np.corrcoef(d3, d[offs[1]:offs[1] + 40000])[0, 1]) < 0.02
+    eng.close()
