@@ -75,6 +75,7 @@ typedef struct suta_hyper {
   int32_t opt_kind;                      /* 0 AdamW (decoupled weight decay), 1 SGD, 2 Adam (L2 weight decay) */
   float lr, beta1, beta2, eps, weight_decay;
   float div_coef;                        /* REF/main.py:201-203 div_loss weight (0: skipped) */
+  float pl_coef;                         /* REF/main_SDPL.py:176 pseudo-label CTC weight (0: skipped; needs SUTA_FLAG_PSEUDO_LABEL) */
 } suta_hyper;
 
 const char* suta_last_error(void);
@@ -83,7 +84,9 @@ int suta_device_sm_count(void);
 
 /* ---- engine lifecycle (replaces Wav2Vec2ForCTC.from_pretrained(...).eval().cuda() + configure_model +
  *      collect_params, REF/main.py:302-307; train_feature as REF/main.py:88-94) ---------------------------- */
-int suta_engine_create(const suta_model_cfg* cfg, int train_feature, suta_engine** out);
+#define SUTA_FLAG_TRAIN_FEATURE 1          /* REF/main.py:88-94: CNN front end + projection adapted per utterance */
+#define SUTA_FLAG_PSEUDO_LABEL 2           /* REF/main_SDPL.py: reserve the CTC scratch (alpha lattice) in every batch workspace */
+int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_engine** out);
 void suta_engine_destroy(suta_engine* e);
 int64_t suta_engine_param_count(const suta_engine* e);
 int suta_engine_param_layout(const suta_engine* e, suta_param_seg* segs, int max_segs, int* n_segs);
@@ -116,7 +119,7 @@ int suta_adapt_step(suta_engine* e, const suta_hyper* h, void* stream);
 /* device views into the workspace (valid until the next suta_batch_begin) */
 float* suta_logits(const suta_engine* e);        /* DEV fp32 [total_frames, V] */
 float* suta_dlogits(const suta_engine* e);       /* DEV fp32 [total_frames, V] */
-float* suta_losses(const suta_engine* e);        /* DEV fp32 [3][U]: total, entropy, mcc */
+float* suta_losses(const suta_engine* e);        /* DEV fp32 [4][U]: total, entropy, mcc, pseudo-label ctc */
 float* suta_params(const suta_engine* e);        /* DEV fp32 [U][n_params] */
 float* suta_grads(const suta_engine* e);         /* DEV fp32 [U][n_params] */
 int32_t* suta_argmax_ids(const suta_engine* e);  /* DEV i32 [total_frames] */
@@ -172,6 +175,12 @@ int suta_op_attention_bwd(const void* qkv, const void* O, const void* dO, const 
 int suta_op_loss(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, float em_coef, float temp,
                  int reweight, int not_blank, float div_coef, float* loss /*[3U]*/, float* dlogits_f32, void* dlogits_bf16,
                  void* stream);
+/* pseudo-label CTC loss (REF/main_SDPL.py:194-209) of every utterance against its own greedy transcript.
+ * collapsed / collapsed_len: output of suta_op_decode; alpha: sum_u T_u (2 T_u + 1) floats of scratch, g: [M,32] scratch;
+ * loss [U] and dlogits_f32 [M,32] are outputs (value of the CTC term alone, its gradient w.r.t. the logits) */
+int suta_op_ctc_pseudo_label(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts, const int32_t* collapsed,
+                             const int32_t* collapsed_len, float* alpha, float* g, float* loss, float* dlogits_f32,
+                             int32_t* target_len, void* stream);
 /* out[row] = entropy(softmax(logits[row]/temp)), V = 32: softmax_entropy, REF/main.py:26-28 */
 int suta_op_softmax_entropy(const float* logits, int64_t rows, float temp, float* out, void* stream);
 int suta_op_adam(float* P, const float* G, float* Mom, float* Var, const uint8_t* mult, int64_t n, int n_utts,

@@ -63,6 +63,7 @@ struct Seg { int kind, module, index; long long off, size; };
 struct suta_engine {
   suta_model_cfg cfg{};
   int train_feature = 0;
+  int pseudo_label = 0;                            // SUTA_FLAG_PSEUDO_LABEL: CTC scratch is part of every batch workspace
   suta_weights w{};
   bool have_weights = false;
   std::vector<Seg> segs;
@@ -149,6 +150,10 @@ struct suta_engine {
   float *logits = nullptr, *dlogits = nullptr, *losses = nullptr;
   bf16* dlogits16 = nullptr;
   float *P = nullptr, *G = nullptr, *Mom = nullptr, *Var = nullptr;
+  float *ctc_alpha = nullptr, *ctc_g = nullptr;    // pseudo-label CTC: alpha lattices, d loss / d log-prob scratch
+  long long* d_alpha_off = nullptr;
+  std::vector<long long> alpha_off;
+  int* ctc_tlen = nullptr;
   float* ln_part = nullptr;                        // dgamma/dbeta slots of the two-stage LayerNorm-backward reduction
   size_t ln_part_stride = 0;
   int *ids = nullptr, *collapsed = nullptr, *out_len = nullptr;
@@ -330,6 +335,7 @@ void carve(suta_engine* e, Bump& b) {
       }
     }
   }
+  if (e->pseudo_label) e->d_alpha_off = b.take<long long>(U);
   e->tables_bytes = align_up(b.off, 256);          // everything above is uploaded by suta_batch_begin in one copy
   e->wav = b.take<float>(e->S); e->wav_norm = b.take<float>(e->S + 64);
   e->stats = b.take<double>((size_t)2 * U * (c.conv_dim[0] > 1 ? c.conv_dim[0] : 1) + 2 * U);
@@ -365,7 +371,15 @@ void carve(suta_engine* e, Bump& b) {
   }
   e->logits = b.take<float>((size_t)M * V); e->dlogits = b.take<float>((size_t)M * V);
   e->dlogits16 = b.take<bf16>((size_t)M * V);
-  e->losses = b.take<float>(3 * U);
+  e->losses = b.take<float>(4 * U);
+  if (e->pseudo_label) {
+    long long tot = 0;
+    e->alpha_off.assign(U, 0);
+    for (int u = 0; u < U; ++u) { e->alpha_off[u] = tot; tot += ctc_alpha_floats(e->T[u]); }
+    e->ctc_alpha = b.take<float>((size_t)tot);
+    e->ctc_g = b.take<float>((size_t)M * V);
+    e->ctc_tlen = b.take<int>(U);
+  }
   e->P = b.take<float>((size_t)U * e->n_params); e->G = b.take<float>((size_t)U * e->n_params);
   e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
   e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
@@ -457,12 +471,13 @@ GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
 // =================================================================================================
 // C ABI
 // =================================================================================================
-extern "C" int suta_engine_create(const suta_model_cfg* cfg, int train_feature, suta_engine** out) {
-  SUTA_CHECK_ARG(cfg && out);
+extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_engine** out) {
+  SUTA_CHECK_ARG(cfg && out && (flags & ~(SUTA_FLAG_TRAIN_FEATURE | SUTA_FLAG_PSEUDO_LABEL)) == 0);
   SUTA_TRY(check_cfg(*cfg));
   suta_engine* e = new suta_engine();
   e->cfg = *cfg;
-  e->train_feature = train_feature ? 1 : 0;
+  e->train_feature = (flags & SUTA_FLAG_TRAIN_FEATURE) ? 1 : 0;
+  e->pseudo_label = (flags & SUTA_FLAG_PSEUDO_LABEL) ? 1 : 0;
   build_layout(e);
   *out = e;
   return SUTA_OK;
@@ -612,6 +627,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
     up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size());
     CUDA_TRY(cudaMemsetAsync(e->dh0_pad, 0, sizeof(bf16) * (size_t)(e->R64 + 128) * c.hidden, st));
   }
+  if (e->pseudo_label) up(e->d_alpha_off, e->alpha_off.data(), sizeof(long long) * U);
   CUDA_TRY(cudaMemcpyAsync(b.base, e->h_stage, e->tables_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(e->stage_ev, st));
   // zero rows of the padded positional-conv slabs never get written afterwards
@@ -895,6 +911,23 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   la.div_coef = h->div_coef;
   PROF("loss", suta_loss_forward_backward(la, st));
   e->launches += 1;
+  if (h->pl_coef > 0.f) {          // SDPL: CTC loss against the greedy transcript of these logits (REF/main_SDPL.py:176,194-209)
+    if (!e->pseudo_label) {
+      suta_set_last_error("pl_coef > 0 needs an engine created with SUTA_FLAG_PSEUDO_LABEL (the CTC scratch is part of the workspace)");
+      return SUTA_ERR_ARG;
+    }
+    SUTA_TRY(ctc_greedy_decode(e->logits, e->d_tok_off, e->d_T, e->ids, e->collapsed, e->out_len, e->U, V, st));
+    CtcArgs ca{};
+    ca.logits = e->logits; ca.tok_off = e->d_tok_off; ca.T = e->d_T; ca.collapsed = e->collapsed; ca.collapsed_len = e->out_len;
+    ca.alpha = e->ctc_alpha; ca.alpha_off = e->d_alpha_off; ca.g = e->ctc_g;
+    ca.dlogits_f32 = e->dlogits; ca.dlogits_bf16 = e->dlogits16; ca.loss = e->losses; ca.target_len = e->ctc_tlen;
+    ca.n_utts = e->U; ca.pl_coef = h->pl_coef;
+    int maxT = 0;
+    for (int u = 0; u < e->U; ++u) maxT = e->T[u] > maxT ? e->T[u] : maxT;
+    ca.max_states = 2 * maxT + 1;
+    PROF("ctc_pseudo_label", ctc_pseudo_label_loss(ca, st));
+    e->launches += 2;
+  }
   // every gradient segment is written whole by exactly one kernel of this backward (no accumulation into G, no atomics)
 
   // two fp32 gradient streams, updated in place like the forward's residual stream: LayerNorm backward writes d(input)
@@ -1215,6 +1248,31 @@ extern "C" int suta_op_loss(const float* logits, const int64_t* tok_off, const i
   la.em_coef = em_coef; la.temp = temp; la.reweight = reweight; la.not_blank = not_blank; la.div_coef = div_coef;
   la.loss = loss; la.dlogits_f32 = dlogits_f32; la.dlogits_bf16 = reinterpret_cast<bf16*>(dlogits_bf16);
   return suta_loss_forward_backward(la, S(stream));
+}
+extern "C" int suta_op_ctc_pseudo_label(const float* logits, const int64_t* tok_off, const int32_t* T, int n_utts,
+                                        const int32_t* collapsed, const int32_t* collapsed_len, float* alpha, float* g, float* loss,
+                                        float* dlogits_f32, int32_t* target_len, void* stream) {
+  SUTA_CHECK_ARG(n_utts > 0 && n_utts <= 4096 && T && tok_off && loss && dlogits_f32);
+  // host copies of T: lattice offsets (this entry point is for tests; the engine keeps its tables on the device)
+  std::vector<int> hT(n_utts);
+  CUDA_TRY(cudaMemcpyAsync(hT.data(), T, sizeof(int) * n_utts, cudaMemcpyDeviceToHost, S(stream)));
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  std::vector<long long> aoff(n_utts);
+  long long tot = 0, M = 0;
+  int maxT = 0;
+  for (int u = 0; u < n_utts; ++u) { aoff[u] = tot; tot += ctc_alpha_floats(hT[u]); M += hT[u]; maxT = hT[u] > maxT ? hT[u] : maxT; }
+  // the offsets ride at the end of the alpha scratch (caller sizes it sum_u T_u (2 T_u + 1) floats + 2 n_utts more)
+  long long* d_aoff = reinterpret_cast<long long*>(alpha + ((tot + 1) & ~1LL));
+  CUDA_TRY(cudaMemcpyAsync(d_aoff, aoff.data(), sizeof(long long) * n_utts, cudaMemcpyHostToDevice, S(stream)));
+  CUDA_TRY(cudaMemsetAsync(dlogits_f32, 0, sizeof(float) * M * 32, S(stream)));
+  CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float) * 4 * n_utts, S(stream)));
+  CtcArgs ca{};
+  ca.logits = logits; ca.tok_off = reinterpret_cast<const long long*>(tok_off); ca.T = T; ca.collapsed = collapsed;
+  ca.collapsed_len = collapsed_len; ca.alpha = alpha; ca.alpha_off = d_aoff; ca.g = g; ca.dlogits_f32 = dlogits_f32;
+  ca.loss = loss; ca.target_len = target_len; ca.n_utts = n_utts; ca.max_states = 2 * maxT + 1; ca.pl_coef = 1.0f;
+  SUTA_TRY(ctc_pseudo_label_loss(ca, S(stream)));
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));      // aoff (host) must outlive the upload
+  return SUTA_OK;
 }
 extern "C" int suta_op_softmax_entropy(const float* logits, int64_t rows, float temp, float* out, void* stream) {
   return softmax_entropy_rows(logits, rows, temp, out, S(stream));

@@ -152,6 +152,28 @@ int suta_loss_forward_backward(const LossArgs& a, cudaStream_t stream);
 // out[row] = entropy of softmax(logits[row] / temp)   (REF/main.py:26-28), V = 32
 int softmax_entropy_rows(const float* logits, long long rows, float temp, float* out, cudaStream_t stream);
 
+// ---- ctc.cu ---------------------------------------------------------------------------------
+// Pseudo-label CTC loss of the SDPL baseline (REF/main_SDPL.py:194-209), value + gradient, mixed into dlogits:
+// dlogits <- (1 - pl_coef) * dlogits + pl_coef * d ctc / d logits;  loss[u] <- (1 - pl_coef) * loss[u] + pl_coef * ctc
+struct CtcArgs {
+  const float* logits;         // [M, 32]
+  const long long* tok_off;    // [U]
+  const int* T;                // [U]
+  const int* collapsed;        // [M] greedy transcript ids (repeat-collapsed, blank dropped) of utterance u at tok_off[u]
+  const int* collapsed_len;    // [U]
+  float* alpha;                // scratch: utterance u uses ctc_alpha_floats(T_u) floats at alpha_off[u]
+  const long long* alpha_off;  // [U]
+  float* g;                    // scratch [M, 32]
+  float* dlogits_f32;          // in/out [M, 32] (may be null: treated as zero)
+  bf16* dlogits_bf16;          // out, optional
+  float* loss;                 // [4][U]: row 0 (total) is mixed, row 3 receives the CTC term; optional
+  int* target_len;             // [U] optional: pseudo-label length L
+  int n_utts, max_states;      // max_states >= 2 * max(T) + 1
+  float pl_coef;
+};
+int ctc_pseudo_label_loss(const CtcArgs& a, cudaStream_t stream);
+long long ctc_alpha_floats(int T);
+
 // ---- optim.cu -------------------------------------------------------------------------------
 struct AdamArgs {
   float* P;                    // [U][n]

@@ -46,7 +46,7 @@ class ParamSeg(C.Structure):
 class Hyper(C.Structure):
     _fields_ = [("em_coef", c_float), ("temp", c_float), ("reweight", c_int32), ("not_blank", c_int32),
                 ("opt_kind", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("weight_decay", c_float), ("div_coef", c_float)]
+                ("weight_decay", c_float), ("div_coef", c_float), ("pl_coef", c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/suta_b200.h declares (tests check this)
@@ -105,6 +105,8 @@ SIGNATURES = {
                                       c_int, c_int64, c_void_p]),
     "suta_op_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_float, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
+    "suta_op_ctc_pseudo_label": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "suta_op_softmax_entropy": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "suta_op_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, C.POINTER(Hyper),
                              c_void_p, c_void_p]),

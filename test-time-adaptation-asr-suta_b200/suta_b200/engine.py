@@ -38,6 +38,7 @@ class AdaptHyper:
     eps: float = 1e-8
     weight_decay: float = 0.0
     div_coef: float = 0.0          # REF/main.py:201-203 (no script sets it)
+    pl_coef: float = 0.0           # REF/main_SDPL.py:176 pseudo-label CTC weight (the SDPL baseline runs with 1.0)
 
     _OPT_KIND = {"AdamW": 0, "SGD": 1, "Adam": 2}     # Adam = L2 weight decay (torch.optim.Adam), AdamW = decoupled
 
@@ -45,7 +46,7 @@ class AdaptHyper:
         if self.opt not in self._OPT_KIND:
             raise ValueError(f"unsupported optimizer {self.opt!r} (AdamW, Adam, SGD)")
         return Hyper(self.em_coef, self.temp, int(self.reweight), int(self.not_blank), self._OPT_KIND[self.opt],
-                     self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.div_coef)
+                     self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.div_coef, self.pl_coef)
 
 
 def _stream_ptr() -> int:
@@ -56,7 +57,8 @@ class SutaEngine:
     """One frozen wav2vec2-CTC model on one GPU + the batched SUTA loop over independent utterances."""
 
     def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False,
-                 trainable_mult: Optional[Dict[str, int]] = None, device: Optional[torch.device] = None):
+                 trainable_mult: Optional[Dict[str, int]] = None, device: Optional[torch.device] = None,
+                 pseudo_label: bool = False):
         if not torch.cuda.is_available():
             raise _lib.SutaError("suta_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -72,7 +74,8 @@ class SutaEngine:
             cc.conv_dim[i], cc.conv_kernel[i], cc.conv_stride[i] = c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i]
         cc.pos_k, cc.pos_groups, cc.ln_eps = c.num_conv_pos_embeddings, c.num_conv_pos_embedding_groups, c.layer_norm_eps
         h = C.c_void_p()
-        check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature), C.byref(h)))
+        self.pseudo_label = bool(pseudo_label)         # SDPL: reserves the CTC lattice scratch in every batch workspace
+        check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature) | (2 if self.pseudo_label else 0), C.byref(h)))
         self._h = h
         self.n_params = int(self.lib.suta_engine_param_count(h))
         n = C.c_int()
@@ -292,7 +295,8 @@ class SutaEngine:
         return self._view(self.lib.suta_dlogits(self._h), (self.total_frames, self.cfg.vocab_size), torch.float32)
 
     def losses(self) -> torch.Tensor:
-        return self._view(self.lib.suta_losses(self._h), (3, self.n_utts), torch.float32)
+        """[4, U]: total, entropy term, MCC term, pseudo-label CTC term (REF/main.py:188-199, REF/main_SDPL.py:176)."""
+        return self._view(self.lib.suta_losses(self._h), (4, self.n_utts), torch.float32)
 
     def params(self) -> torch.Tensor:
         return self._view(self.lib.suta_params(self._h), (self.n_utts, self.n_params), torch.float32)

@@ -27,16 +27,17 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
-def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False, train_feature=False, mult=None, sched_gamma=None):
+def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False, train_feature=False, mult=None, sched_gamma=None,
+               pseudo_label=False):
     """Batched SUTA on the GPU: returns per-utterance dicts (logits at checkpoints, losses, params, ids).
     sched_gamma: StepLR(step_size=1) factor, applied by the caller between steps like REF/main.py:207-208."""
     _, mcfg = _cfgs(cfg_name)
     hp = hp or AdaptHyper()
     lr0 = hp.lr
-    eng = SutaEngine(mcfg, sd, train_feature=train_feature, trainable_mult=mult)
+    eng = SutaEngine(mcfg, sd, train_feature=train_feature, trainable_mult=mult, pseudo_label=pseudo_label)
     eng.begin_batch(wavs)
     eng.reset()
-    res = [dict(logits={}, losses=[], ids={}) for _ in wavs]
+    res = [dict(logits={}, losses=[], ids={}, pl_losses=[]) for _ in wavs]
     lg = eng.forward()
     ids = eng.decode_ids()
     for u in range(len(wavs)):
@@ -55,6 +56,7 @@ def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False, train_featu
         eng.forward()
         for u in range(len(wavs)):
             res[u]["losses"].append(float(losses[0, u]))
+            res[u]["pl_losses"].append(float(losses[3, u]))
         if (i + 1) in O.CHECKPOINT_STEPS or i + 1 == steps:
             ids = eng.decode_ids()
             for u in range(len(wavs)):
@@ -225,6 +227,37 @@ def check_tiny_stages():
     return out
 
 
+def check_golden_sdpl(case):
+    """The SDPL baseline (REF/main_SDPL.py): fixtures produced by the unmodified script's functions."""
+    z, meta = load_golden(case)
+    ocfg, _ = _cfgs(meta["cfg"])
+    sd = O.init_weights(ocfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"],
+                        special_bias=meta["special_bias"])
+    wav = O.synth_audio(meta["n_samples"], meta["audio_seed"])
+    hp = AdaptHyper(lr=meta["lr"], em_coef=meta["em_coef"], reweight=meta["reweight"], temp=meta["temp"], not_blank=meta["not_blank"],
+                    opt=meta["opt"], pl_coef=meta["pl_coef"])
+    tf = bool(meta["train_feature"])
+    res = run_engine(meta["cfg"], sd, [wav], meta["steps"], hp, keep_grads=True, train_feature=tf, mult=_mult(ocfg, tf),
+                     pseudo_label=True)[0]
+    skip = set(meta.get("zero_gradient_params", []))         # analytically zero gradient: Adam steps on rounding noise
+    ref_logits = {int(k.split("_")[1]): z[k] for k in z.files if k.startswith("logits_")}
+    ref_params = {k[6:]: z[k] for k in z.files if k.startswith("param:") and z[k].dtype == np.float32 and k[6:] not in skip}
+    x = O.normalize_audio(wav)
+    m = compare(res, ref_logits, [abs(v) + 1.0 for v in res["losses"]], ref_params, sd, ref_ids=True)   # total loss is not in the fixture
+    del m["loss_rel_max"]
+    m["pl_loss_rel_max"] = float(np.max(np.abs(np.asarray(res["pl_losses"]) - z["pl_losses"]) / np.abs(z["pl_losses"])))
+    # gradient at step 0 vs fp32 autograd through the oracle (the CTC term included)
+    w = {k: v.clone() for k, v in sd.items()}
+    uniq = [n for n in dict.fromkeys(meta["names"]) if n not in skip]
+    for n in uniq:
+        w[n].requires_grad_(True)
+    lg = O.model_forward(ocfg, w, torch.from_numpy(x)[None])
+    loss = O.suta_loss(lg, hp.em_coef, hp.reweight, hp.temp, hp.not_blank, 0.0, hp.pl_coef)
+    g0 = {n: g.numpy() for n, g in zip(uniq, torch.autograd.grad(loss, [w[n] for n in uniq]))}
+    m["grad0_rel"] = _grad_rel(res["grad0"], res["segments"], g0, res["to_layout"])
+    return m
+
+
 def check_determinism(cfg_name="base", train_feature=False, steps=3):
     """The same batch adapted twice: are gradients, parameters and logits the same BITS?"""
     ocfg, _ = _cfgs(cfg_name)
@@ -285,6 +318,7 @@ ALL = [("determinism_base_ln", check_determinism), ("determinism_tiny_feat", lam
        ("golden_tiny_ln", lambda: check_golden("tiny_ln")), ("golden_tiny_short", lambda: check_golden("tiny_short")),
        ("golden_base_ln_5s", lambda: check_golden("base_ln_5s")),
        ("golden_base_ln_5s_noblank", lambda: check_golden("base_ln_5s_noblank"))] + [
+       ("golden_tiny_sdpl", lambda: check_golden_sdpl("tiny_sdpl")), ("golden_tiny_sdpl_mix", lambda: check_golden_sdpl("tiny_sdpl_mix"))] + [
        ("golden_" + c, (lambda c=c: check_golden(c))) for c in
        ("tiny_sgd", "tiny_feat_sgd", "tiny_adam_beta", "tiny_steplr", "tiny_bias_only", "tiny_div", "tiny_em_only",
         "tiny_mcc_plain", "tiny_temp1_allframes", "tiny_feat_noise20", "large_ln_2s", "base_feat_5s", "base_ln_30s")]

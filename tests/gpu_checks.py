@@ -281,6 +281,58 @@ def check_loss(Ts=(249, 37, 6), seed=7, em_coef=0.3, reweight=True, not_blank=Tr
                 nan_where_the_reference_is_nan=nan_agree, grad_finite_where_loss_nan=finite_grad)
 
 
+def check_ctc(Ts=(249, 37, 1, 6, 700), seed=10, blank_bias=1.0, all_blank_utt=1):
+    """Pseudo-label CTC loss + gradient (csrc/ctc.cu) vs torch.nn.CTCLoss autograd on the CPU through the oracle's
+    restatement of REF/main_SDPL.py:194-209 (log_softmax over TIME, target = stripped greedy transcript)."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    M, U = sum(Ts), len(Ts)
+    logits = torch.randn(M, 32, device=DEV, generator=g) * 1.5
+    logits[:, 0] += blank_bias
+    logits[:, 1:4] -= 20.0                                       # no literal <s> </s> <unk> in the transcript (KeyError in the reference)
+    logits[:, 4] += 1.0                                          # plenty of word delimiters, also at the ends
+    off_np = np.concatenate([[0], np.cumsum(Ts)[:-1]])
+    if all_blank_utt is not None:
+        o = off_np[all_blank_utt]
+        logits[o:o + Ts[all_blank_utt], 0] += 50.0               # empty target
+    rep = torch.rand(M, device=DEV, generator=g) < 0.3           # repeated frames -> repeated characters need the blank path
+    lg = logits.cpu().numpy()
+    r = rep.cpu().numpy()
+    for i in range(1, M):
+        if r[i]:
+            lg[i] = lg[i - 1]
+    logits = torch.tensor(lg, device=DEV)
+    off = torch.tensor(off_np, dtype=torch.int64, device=DEV)
+    Tt = torch.tensor(Ts, dtype=torch.int32, device=DEV)
+    ids = torch.zeros(M, dtype=torch.int32, device=DEV); col = torch.zeros(M, dtype=torch.int32, device=DEV)
+    ln = torch.zeros(U, dtype=torch.int32, device=DEV)
+    check(lib.suta_op_decode(P(logits), P(off), P(Tt), U, 32, P(ids), P(col), P(ln), stream()))
+    n_alpha = sum(T * (2 * T + 1) for T in Ts) + 2 * U + 8
+    alpha = torch.empty(n_alpha, device=DEV); gbuf = torch.empty(M, 32, device=DEV)
+    loss = torch.zeros(4 * U, device=DEV); d32 = torch.zeros(M, 32, device=DEV); tl = torch.zeros(U, dtype=torch.int32, device=DEV)
+    outs = []
+    for _ in range(2):                                           # twice: bit-reproducible
+        check(lib.suta_op_ctc_pseudo_label(P(logits), P(off), P(Tt), U, P(col), P(ln), P(alpha), P(gbuf), P(loss), P(d32), P(tl),
+                                           stream()))
+        torch.cuda.synchronize()
+        outs.append((loss.clone(), d32.clone()))
+    worst_l = worst_g = 0.0
+    tlen_ok = True
+    o = 0
+    for u, T in enumerate(Ts):
+        lt = torch.tensor(lg[o:o + T][None], requires_grad=True)
+        tgt = O.pseudo_label_targets(lt)
+        lref = O.pseudo_labeling_loss(lt)
+        lref.backward()
+        tlen_ok = tlen_ok and int(tl[u]) == len(tgt)
+        worst_l = max(worst_l, abs(float(loss[3 * U + u]) - float(lref)) / max(abs(float(lref)), 1e-6))
+        gk = d32[o:o + T].cpu().double()
+        worst_g = max(worst_g, float((gk - lt.grad[0].double()).norm() / (lt.grad[0].double().norm() + 1e-30)))
+        o += T
+    return dict(loss_rel=worst_l, grad_rel=worst_g, target_len_equal=tlen_ok, finite=bool(torch.isfinite(d32).all()),
+                bit_equal=bool(torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])))
+
+
 def check_adam(n=5000, U=3, steps=4, seed=8, opt="AdamW", lr=2e-5, beta1=0.9, wd=0.0):
     """The fused update vs oracle.adam_update (= torch's single-tensor CPU loop, k sub-steps for multiplicity k)."""
     lib = _lib.load()
@@ -357,6 +409,7 @@ ALL = [("gemm_plain", check_gemm_plain), ("gemm_epilogue", check_gemm_epilogue),
                                   for e in (0.3, 1.0, 0.0) for r in (False, True) for n in (False, True)}),
        ("loss_div", lambda: check_loss(div_coef=0.25)),
        ("loss_all_blank", lambda: check_loss(Ts=(40, 5, 1), blank_bias=50.0)),
+       ("ctc", check_ctc), ("ctc_long", lambda: check_ctc(Ts=(1874, 2), seed=11, all_blank_utt=None)),
        ("adam", check_adam), ("adam_beta_l2", lambda: check_adam(opt="Adam", beta1=0.8, wd=0.01, lr=1e-3)),
        ("adamw_decay", lambda: check_adam(opt="AdamW", wd=0.01, lr=1e-3)), ("sgd_wd", lambda: check_adam(opt="SGD", lr=0.05, wd=0.01)),
        ("decode", check_decode)]

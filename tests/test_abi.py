@@ -39,7 +39,7 @@ def test_ctypes_structs_match_header_sizes():
     assert ctypes.sizeof(_lib.ModelCfg) == 4 * (6 + 3 * 8 + 2) + 4
     assert ctypes.sizeof(_lib.LayerWeights) == 12 * 8
     assert ctypes.sizeof(_lib.Weights) == 8 * (3 + 8 + 8 + 3 + 3 + 3 + 2) + 48 * 12 * 8
-    assert ctypes.sizeof(_lib.Hyper) == 44
+    assert ctypes.sizeof(_lib.Hyper) == 48
     assert ctypes.sizeof(_lib.ParamSeg) == 32
 
 

@@ -119,6 +119,17 @@ def test_train_feature_against_reference_golden_vectors(E, case):
         assert m["big_param_head_delta_rel"] < 0.15
 
 
+@pytest.mark.parametrize("case", ["tiny_sdpl", "tiny_sdpl_mix"])
+def test_sdpl_pseudo_label_baseline_against_reference_golden_vectors(E, case):
+    """REF/main_SDPL.py (the README's comparison row): adaptation by the CTC pseudo-label loss alone (pl_coef = 1, Adam,
+    lr 1e-4) and mixed half-and-half with the SUTA loss under --train_feature."""
+    m = E.check_golden_sdpl(case)
+    print(case, m)
+    assert m["pl_loss_rel_max"] < 1e-3
+    m["loss_rel_max"] = 0.0
+    _assert_parity(m)
+
+
 def test_batch_composition_does_not_change_results(E):
     """An utterance adapted alone and inside a batch of other lengths gives the same result (utterance independence)."""
     from oracle import suta_oracle as O

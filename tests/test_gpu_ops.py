@@ -101,6 +101,16 @@ def test_fused_loss_with_div_loss(K, em, rew, nb, div):
     assert r["loss_rel"] < 1e-5 and r["grad_rel"] < 1e-4
 
 
+@pytest.mark.parametrize("Ts,seed,blank_utt", [((249, 37, 1, 6, 700), 10, 1), ((1874, 2), 11, None), ((64, 65, 33), 12, 2)])
+def test_pseudo_label_ctc_loss_matches_torch_ctcloss(K, Ts, seed, blank_utt):
+    """SDPL baseline (REF/main_SDPL.py:194-209): value and gradient of nn.CTCLoss against the greedy transcript, with the
+    reference's log_softmax over TIME; empty targets (all frames blank), one-frame utterances, repeated characters, the
+    longest utterance the data loader lets through (T = 1874)."""
+    r = K.check_ctc(Ts, seed, all_blank_utt=blank_utt)
+    assert r["target_len_equal"] and r["finite"] and r["bit_equal"]
+    assert r["loss_rel"] < 1e-4 and r["grad_rel"] < 1e-3, r
+
+
 def test_gemm_mn_major_operands(K):
     """Weight-gradient / per-utterance dgrad GEMMs read operands stored [K rows][M|N contiguous]."""
     for args in ((), (128, 64, 64, 14), (768, 512, 4000, 15), (512, 1536, 2000, 16)):
