@@ -97,9 +97,11 @@ def reference_multiplicities(cfg, bias_only: bool = False, train_feature: bool =
 class SutaModel:
     """Engine-backed stand-in for the HF model object the reference functions touch."""
 
-    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False, device=None):
+    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False, device=None,
+                 pseudo_label: bool = False):
         self.cfg = ModelConfig.from_any(cfg)
-        self.engine = SutaEngine(self.cfg, state_dict, train_feature=train_feature, trainable_mult={}, device=device)
+        self.engine = SutaEngine(self.cfg, state_dict, train_feature=train_feature, trainable_mult={}, device=device,
+                                 pseudo_label=pseudo_label)
         self._params = {name: SutaParam(self, name, off, size) for name, off, size in self.engine.segments}
         self._x_ref = None              # strong reference to the bound input: its address cannot be recycled while bound
         self._x_version = -1
@@ -365,12 +367,13 @@ def configure_model(model):
 
 
 def forward_and_adapt(x, model, optimizer, em_coef=0.9, reweight=False, temp=1., not_blank=True, scheduler=None,
-                      div_coef=0, repeat_inference=True, skip_short_thd=None):
-    """REF/main.py:172-215: forward, unsupervised loss (entropy + MCC), backward, optimizer step, forward again."""
+                      div_coef=0, repeat_inference=True, skip_short_thd=None, pl_coef=0.0):
+    """REF/main.py:172-215: forward, unsupervised loss (entropy + MCC), backward, optimizer step, forward again.
+    pl_coef (keyword, extension): REF/main_SDPL.py:176's pseudo-label CTC mix (model built with pseudo_label=True)."""
     outputs = model(x).logits
     hp = optimizer.hp
     hp.em_coef, hp.reweight, hp.temp, hp.not_blank = float(em_coef), bool(reweight), float(temp), bool(not_blank)
-    hp.div_coef = float(div_coef)
+    hp.div_coef, hp.pl_coef = float(div_coef), float(pl_coef)
     model.engine.loss_backward(hp)
     optimizer.step()
     if scheduler is not None:
@@ -379,3 +382,46 @@ def forward_and_adapt(x, model, optimizer, em_coef=0.9, reweight=False, temp=1.,
     if repeat_inference:
         outputs = model(x).logits
     return outputs
+
+
+# --------------------------------------------------------------------------------------------------
+# REF/main_SDPL.py's variants of the same functions (the SDPL baseline)
+# --------------------------------------------------------------------------------------------------
+def sdpl_setup_optimizer(params, opt_name='Adam', lr=1e-4, beta=0.9, weight_decay=0., scheduler=None, step_size=1, gamma=0.85):
+    """REF/main_SDPL.py:17-32 (defaults: Adam, StepLR gamma 0.85)."""
+    return setup_optimizer(params, opt_name, lr, beta, weight_decay, scheduler, step_size, gamma)
+
+
+def sdpl_collect_params(model, bias_only=False, train_feature=False):
+    """REF/main_SDPL.py:71-104 (no train_all / train_LN switches)."""
+    return collect_params(model, bias_only, train_feature, False, True)
+
+
+def pseudo_labeling_loss(outputs, vocab=None, processor=None):
+    """REF/main_SDPL.py:194-209 (value): CTC loss of the logits [1, T, 32] against their own greedy transcript, with the
+    reference's log_softmax over the time axis.  `vocab` / `processor` are accepted for signature compatibility: the
+    transcript is decoded on the device with the built-in 32-symbol vocabulary."""
+    if outputs.dim() != 3 or outputs.shape[0] != 1:
+        raise RuntimeError("pseudo_labeling_loss expects logits of shape [1, T, 32]")
+    rows = _as_rows(outputs)
+    T = rows.shape[0]
+    dev = rows.device
+    lib = _lib.load()
+    off = torch.zeros(1, dtype=torch.int64, device=dev)
+    Tt = torch.full((1,), T, dtype=torch.int32, device=dev)
+    ids = torch.empty(T, dtype=torch.int32, device=dev); col = torch.empty(T, dtype=torch.int32, device=dev)
+    ln = torch.empty(1, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    check(lib.suta_op_decode(p(rows), p(off), p(Tt), 1, 32, p(ids), p(col), p(ln), _stream_ptr()))
+    alpha = torch.empty(T * (2 * T + 1) + 16, dtype=torch.float32, device=dev)
+    g = torch.empty(T, 32, dtype=torch.float32, device=dev); d = torch.empty(T, 32, dtype=torch.float32, device=dev)
+    loss = torch.empty(4, dtype=torch.float32, device=dev); tl = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.suta_op_ctc_pseudo_label(p(rows), p(off), p(Tt), 1, p(col), p(ln), p(alpha), p(g), p(loss), p(d), p(tl), _stream_ptr()))
+    return loss[3]
+
+
+def sdpl_forward_and_adapt(x, model, optimizer, em_coef=0.9, reweight=False, temp=1., not_blank=True, scheduler=None, div_coef=0,
+                           repeat_inference=True, pl_coef=1, vocab=None, processor=None):
+    """REF/main_SDPL.py:143-191: loss * (1 - pl_coef) + pseudo_labeling_loss * pl_coef, then the same update."""
+    return forward_and_adapt(x, model, optimizer, em_coef, reweight, temp, not_blank, scheduler, div_coef, repeat_inference,
+                             pl_coef=pl_coef)

@@ -10,7 +10,7 @@ import torch
 from .config import ModelConfig
 
 
-def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_bias: float = 0.0) -> Dict[str, torch.Tensor]:
+def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_bias: float = 0.0, special_bias: float = 0.0) -> Dict[str, torch.Tensor]:
     """State dict with HF parameter names and the scales of HF/modeling_wav2vec2.py:968-1003 (_init_weights).
     `blank_bias` shifts lm_head.bias[0] so that greedy decoding emits blanks like a trained CTC head does."""
     g = torch.Generator().manual_seed(seed)
@@ -46,6 +46,7 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_bias: float = 0.0) 
     sd["lm_head.weight"] = rn((cfg.vocab_size, H), 0.02)
     b = torch.zeros(cfg.vocab_size)
     b[0] = blank_bias
+    b[1:4] = special_bias              # <s>, </s>, <unk>: a trained CTC head never emits them
     sd["lm_head.bias"] = b
     return sd
 

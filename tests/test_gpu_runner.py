@@ -155,3 +155,23 @@ def test_device_side_noise_and_truncation():
     d3 = (eng.debug_buffer("wav")[0] - raw3).cpu().numpy()[:40000]
     assert abs(np.corrcoef(d3, d[offs[1]:offs[1] + 40000])[0, 1]) < 0.02
     eng.close()
+
+
+def test_main_sdpl_cli_writes_the_reference_log(tmp_path):
+    """REF/main_SDPL.py: exp_name (:272), log file ending in `pl_coef = ...` (:406-431), no CSV; sequential and batched agree."""
+    _need_gpu()
+    logs = []
+    for sub, extra in (("a", []), ("b", ["--batch_utts", "4"])):
+        log_dir = str(tmp_path / sub)
+        cmd = [sys.executable, os.path.join(ROOT, "main_SDPL.py"), "--asr", "random-tiny", "--num_utts", "6", "--steps", "10",
+               "--episodic", "--lr", "1e-4", "--log_dir", log_dir, *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        files = os.listdir(log_dir)
+        assert files == ["synthetic_1.0_10_2.5_random-tiny_non_blankFalse_noise_0.0_rew_False_div_0.0_bias_False_feat_False_se__pl_1"]
+        logs.append(open(os.path.join(log_dir, files[0])).read())
+        assert "pl_coef = 1" in r.stdout and "optim = Adam" in logs[-1]
+    lines = logs[0].splitlines()
+    assert [ln.split(":")[0] for ln in lines[:5]] == ["original WER", "TTA-1 WER", "TTA-3 WER", "TTA-5 WER", "TTA-10 WER"]
+    assert lines[-1] == "pl_coef = 1" and lines[-2] == "train_feature = False"
+    assert logs[0] == logs[1]
