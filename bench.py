@@ -303,15 +303,23 @@ def run_b200(a):
         else:
             per_rank = [ms]
         per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(items))]
-        return float(ms.item()), eng.launch_count - l0, per_step, [float(x.item()) for x in per_rank], gathered
+        # this rank's adaptation alone (before the blocking end-of-run exchange): the makespan the LPT shards aim to equalise
+        mk = torch.tensor([ev[0].elapsed_time(ev[len(items)])], device="cuda")
+        makespan = [torch.zeros_like(mk) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(makespan, mk)
+        else:
+            makespan = [mk]
+        return (float(ms.item()), eng.launch_count - l0, per_step, [float(x.item()) for x in per_rank], gathered,
+                [float(x.item()) for x in makespan])
 
     for b, lens, host in staged_w:                        # warm-up (>= 3 by default)
         one_step(lens, host, b)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, step_ms, rank_ms, _ = timed_region([(b, l, d) for (b, l, _p), d in zip(staged, dev_audio)], full)   # inputs resident in HBM
-    ms_e2e, _, step_ms_e2e, rank_ms_e2e, gathered = timed_region(staged, full)                                          # pinned host -> device
+    ms_dev, launches, step_ms, rank_ms, _, makespan = timed_region([(b, l, d) for (b, l, _p), d in zip(staged, dev_audio)], full)   # inputs resident in HBM
+    ms_e2e, _, step_ms_e2e, rank_ms_e2e, gathered, makespan_e2e = timed_region(staged, full)                                          # pinned host -> device
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline leg: the same steps again with CUDA-event pairs around every kernel launch (not part of `value`)
@@ -380,7 +388,8 @@ def run_b200(a):
                  "achieved_tflops": flops_all / (ms_dev * 1e-3) / 1e12 / world,
                  "frac_of_peak": flops_all / (ms_dev * 1e-3) / 1e12 / world / peaks["tflops"]},
         "ms_per_rank": rank_ms, "ms_per_rank_e2e": rank_ms_e2e,
-        "imbalance_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+        "ms_per_rank_before_gather": makespan,
+        "imbalance_max_over_mean": max(makespan) / (sum(makespan) / len(makespan)),
         "breakdown": breakdown,
     }
     # p50 RTF: per-utterance latency (wall time of the batch that carried it, end to end) / its duration, this rank

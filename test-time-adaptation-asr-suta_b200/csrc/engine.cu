@@ -445,8 +445,38 @@ struct ProfScope {
     SUTA_TRY(expr);                                      \
   } while (0)
 
+// ALGORITHMIC bytes of one GEMM launch: every operand element read once, every output element written once (an
+// accumulating fp32 output is read and written), saved / consumed auxiliary tensors included
+double gemm_algorithmic_bytes(const GemmProblem& p) {
+  const double M = p.M, N = p.N, K = p.K > 0 ? p.K : 0, nz = p.nz > 0 ? p.nz : 1;
+  double b = 0.0;
+  if (p.ztab) {                     // per-utterance reductions over time (weight gradients): flops = 2 M N sum_z K_z
+    const double ksum = p.flops > 0 ? p.flops / (2.0 * M * N) : 0.0;
+    b += (M + N) * ksum * 2.0 + M * N * 4.0 * nz;
+    return b;
+  }
+  b += M * K * 2.0 * (p.a_z_rows ? nz : 1.0);
+  b += N * K * 2.0 * nz;
+  const double out = M * N * (p.c_z_cols ? nz : 1.0);
+  if (p.epi.out_f32) b += out * (p.epi.accumulate ? 8.0 : 4.0);
+  if (p.epi.out_bf16) b += out * 2.0;
+  if (p.epi.aux_out) b += out * 2.0;
+  if (p.epi.aux_in) b += out * 2.0;
+  if (p.epi.residual) b += out * 4.0;
+  return b;
+}
+
 int gemm(suta_engine* e, const GemmProblem& p, cudaStream_t st) {
   e->launches += 1;
+  // SUTA_GEMM_LOG=<file>: one line per tcgen05 GEMM launch, in launch order (joined with an ncu capture by
+  // tools/ncu_traffic.py to compare DRAM traffic with the algorithmic bytes)
+  static FILE* glog = getenv("SUTA_GEMM_LOG") ? fopen(getenv("SUTA_GEMM_LOG"), "w") : nullptr;
+  static long long gidx = 0;
+  if (glog) {
+    fprintf(glog, "%lld\t%d\t%d\t%d\t%d\t%.0f\t%.0f\n", gidx++, p.M, p.N, p.K, p.nz, gemm_algorithmic_bytes(p),
+            p.flops > 0.0 ? p.flops : 2.0 * (double)p.M * p.N * p.K * p.nz);
+    fflush(glog);
+  }
   if (!e->profile) return gemm_bf16_tc(p, st);
   // algorithmic FLOPs of this launch: valid rows only (the M-block table may pad), all z slices
   const double flops = p.flops > 0.0 ? p.flops : 2.0 * (double)p.M * p.N * p.K * p.nz;
