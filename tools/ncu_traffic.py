@@ -21,7 +21,10 @@ TUNIT = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "mse
 
 def main():
     rep, log, skip, workload = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):        # `ncu --csv --page raw --log-file x.csv` written on the GPU box (reports are too big to ship)
+        raw = "".join(ln for ln in open(rep) if ln.startswith('"'))
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -57,7 +60,7 @@ def main():
     p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     d = json.load(open(p)) if os.path.exists(p) else {}
     d[workload] = {"dram_bytes_per_launch": tot_t / n, "algorithmic_bytes_per_launch": tot_a / n, "launches_captured": n,
-                   "note": f"ncu --set full of {n} consecutive tcgen05 GEMM launches (launch #{skip}..) of the benched batch, "
+                   "note": f"ncu dram-byte capture of {n} consecutive tcgen05 GEMM launches (launch #{skip}..) of the benched batch, "
                            f"`bench.py --workload {workload} --steps 1 --warmup 1`; see profiles/ for the per-launch table"}
     json.dump(d, open(p, "w"), indent=1)
 
