@@ -1,4 +1,4 @@
-// Attention backward on tcgen05 / TMEM (head_dim 64, per-utterance, non-causal).  See attention_tc.cu for the layouts.
+// Attention backward on tcgen05 / TMEM (head_dim 64, per-utterance, non-causal).  Layouts as in attention_fwd2_tc.cu.
 //
 //   S = Q K^T,  P = exp2(S * scale * log2e - LSE),  dP = dO V^T,  dS = P o (dP - D),  D = rowsum(dO o O)
 //   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K

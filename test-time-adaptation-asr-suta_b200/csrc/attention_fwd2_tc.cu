@@ -1,10 +1,9 @@
 // Variable-length multi-head self-attention forward on tcgen05 / TMEM, head_dim = 64: TWO INDEPENDENT PIPELINES per CTA.
-// Same contract as attention_tc.cu (HF/modeling_wav2vec2.py:500-544, non-causal, scale 64^-0.5, utterances never see
-// each other): qkv bf16 [M, 3H], O bf16 [M, H], LSE fp32 [heads, M] in base-2 units, block table int4 {utt_row0, T_u,
+// Contract (HF/modeling_wav2vec2.py:500-544, non-causal, scale 64^-0.5, utterances never see each other): qkv bf16 [M, 3H], O bf16 [M, H], LSE fp32 [heads, M] in base-2 units, block table int4 {utt_row0, T_u,
 // block_start_in_utt, 0} per 128 query rows.
 //
-// attention_tc.cu lets two softmax groups share one work item (even / odd key blocks, split-KV merge at the end): with the
-// short utterances of this workload (median 5 key blocks per item) the per-item drain -- last P V, three CTA-wide barriers
+// The first version (removed in round 2) let two softmax groups share one work item (even / odd key blocks, split-KV merge at
+// the end): with the short utterances of this workload (median 5 key blocks per item) the per-item drain -- last P V, three CTA-wide barriers
 // for the merge, normalise, store -- cost ~40 % of the item, and both groups paid it at the same time.  Here every softmax
 // group owns a complete pipeline and its own item stream (a kernel that allocates TMEM gets one CTA per SM, so the two
 // "virtual CTAs" live in one): its own TMA warp, MMA warp, Q double buffer, K/V ring, S / P double buffers and accumulator.
@@ -370,7 +369,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 }  // namespace
 
-int attention_forward_v2(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
+int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
                          cudaStream_t stream) {
   SUTA_CHECK_ARG(H == heads * HD);
   if (n_blk <= 0) return SUTA_OK;

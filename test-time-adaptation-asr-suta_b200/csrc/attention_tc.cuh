@@ -1,13 +1,8 @@
-// Helpers shared by the tcgen05 attention kernels (attention_tc.cu, attention_bwd_tc.cu).
+// Helpers shared by the tcgen05 attention kernels (attention_fwd2_tc.cu, attention_bwd_tc.cu).
 #pragma once
 #include <mutex>
 
 #include "kernels.cuh"
-
-// attention_fwd2_tc.cu: two independent item pipelines per CTA (the default forward); attention_tc.cu keeps the kernel in
-// which both softmax groups share one item
-int attention_forward_v2(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
-                         cudaStream_t stream);
 
 namespace attn_tc {
 

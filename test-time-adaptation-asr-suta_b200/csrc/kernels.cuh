@@ -8,7 +8,7 @@ struct UttParams {
   long long stride = 0;
 };
 
-// ---- attention_tc.cu / attention_bwd_tc.cu (tcgen05 / TMEM) -----------------------------------
+// ---- attention_fwd2_tc.cu / attention_bwd_tc.cu (tcgen05 / TMEM) -----------------------------------
 // qkv bf16 [M,3H], O bf16 [M,H], LSE fp32 [heads,M] (base 2), block table: one int4 {utt_row0, T_u, m0, 0} per 128 rows
 int attention_forward(const bf16* qkv, bf16* O, float* LSE, const int4* blk_tab, int n_blk, int H, int heads, long long M,
                       cudaStream_t stream);

@@ -234,7 +234,7 @@ def test_smoke_entry_point():
     __graft_entry__.smoke()
 
 
-@pytest.mark.parametrize("switches", ["SUTA_NO_GEMM2 SUTA_NO_TAIL_SPLIT", "SUTA_NO_POSCONV_TC SUTA_NO_FUSED_DGRAD SUTA_ATTN_FWD_V1"])
+@pytest.mark.parametrize("switches", ["SUTA_NO_GEMM2 SUTA_NO_TAIL_SPLIT", "SUTA_NO_POSCONV_TC SUTA_NO_FUSED_DGRAD"])
 def test_alternative_cuda_paths_keep_parity(switches):
     """The debug switches of INTEGRATION.md select other CUDA kernels for the same operators (one-SM GEMM instead of CTA
     pairs, generic-GEMM positional conv, col2im conv dgrad): the golden-vector parity must hold on those paths too.
