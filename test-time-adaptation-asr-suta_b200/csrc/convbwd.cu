@@ -135,7 +135,29 @@ conv0_bwd_accum_kernel(Conv0BwdArgs a) {
     const bf16* dyp = a.dy + row0 * a.C + c;
     int t = 0;
     const bool vec_ok = a.stride == 5 && k == 10;    // the wav2vec2 front end: 4 frames = 20 samples = five 16-byte words
-    for (; vec_ok && t + 4 <= nt; t += 4) {      // four independent loads in flight per thread (the kernel is latency-bound)
+    // eight independent 4-byte loads in flight per thread: the kernel is latency-bound (IPC ~0.2 per sub-partition with four),
+    // and by Little's law 2048 threads x 16 B barely cover the ~35 KB per SM that 6.5 TB/s x 800 ns call for
+    for (; vec_ok && t + 8 <= nt; t += 8) {
+      unsigned int rr[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rr[q] = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + q) * a.C));
+      // the 8 windows cover samples [5 t, 5 t + 45): twelve 16-byte broadcast loads instead of 80 scalar ones
+      float xw[48];
+#pragma unroll
+      for (int v = 0; v < 12; ++v) {
+        const float4 f = *reinterpret_cast<const float4*>(sx + 5 * t + 4 * v);
+        xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 dy = unpack_bf16x2(rr[q]);
+        const uint64_t dy2 = pk2(dy.x, dy.y);
+        s1 = add2(s1, dy2);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) A2[j] = fma2(dy2, dup2(xw[5 * q + j]), A2[j]);
+      }
+    }
+    for (; vec_ok && t + 4 <= nt; t += 4) {
       const unsigned int r0 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 0) * a.C));
       const unsigned int r1 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 1) * a.C));
       const unsigned int r2 = __ldg(reinterpret_cast<const unsigned int*>(dyp + (long long)(t + 2) * a.C));

@@ -175,3 +175,29 @@ def test_main_sdpl_cli_writes_the_reference_log(tmp_path):
     assert [ln.split(":")[0] for ln in lines[:5]] == ["original WER", "TTA-1 WER", "TTA-3 WER", "TTA-5 WER", "TTA-10 WER"]
     assert lines[-1] == "pl_coef = 1" and lines[-2] == "train_feature = False"
     assert logs[0] == logs[1]
+
+
+def test_local_hf_checkpoint_runs_through_the_engine(tmp_path):
+    """`--asr <local HF directory>` (the offline stand-in for from_pretrained, REF/main.py:302-303): weights written by
+    save_pretrained go through load_checkpoint into the engine; logits match the HF module's own CPU forward."""
+    _need_gpu()
+    from transformers import Wav2Vec2ForCTC
+    from oracle import suta_oracle as O
+    from suta_b200 import api
+    from suta_b200.weights import load_checkpoint
+    ocfg = O.W2V2Config.tiny()
+    hf = Wav2Vec2ForCTC(ocfg.to_hf()).eval()
+    hf.load_state_dict(O.init_weights(ocfg, 7, blank_bias=0.5, ln_jitter=0.1), strict=False)
+    hf.save_pretrained(str(tmp_path / "ckpt"))
+    cfg, sd = load_checkpoint(str(tmp_path / "ckpt"))
+    model = api.configure_model(api.SutaModel(cfg, sd))
+    x = torch.from_numpy(O.normalize_audio(O.synth_audio(9000, 5)))[None]
+    with torch.no_grad():
+        ref = hf(x).logits[0].numpy()
+    got = model(x.cuda()).logits[0].cpu().numpy()
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 0.05
+    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", str(tmp_path / "ckpt"), "--num_utts", "2", "--steps", "3", "--episodic",
+           "--log_dir", str(tmp_path / "exps")]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.exists(str(tmp_path / "exps" / "synthetic_1.0_3_2.5_ckpt_non_blankFalse_noise_0.0_rew_False_div_0.0_bias_False_feat_False_all_False_LN_True"))

@@ -88,3 +88,42 @@ def test_collect_params_names_and_duplicates_match_reference_walk(capsys):
     capsys.readouterr()
     with pytest.raises(NotImplementedError):
         api.collect_params(model, False, False, True, True)
+
+
+def test_load_checkpoint_reads_a_local_hf_directory(tmp_path):
+    """`--asr <local dir>` -- a Wav2Vec2ForCTC checkpoint written by save_pretrained (safetensors, new
+    weight-norm parametrisation) and one in the legacy layout (pytorch_model.bin, weight_g / weight_v) both load into
+    the names the engine packs, and unsupported architectures (stable LayerNorm / conv LayerNorm) are refused."""
+    import pytest
+    import torch
+    from transformers import Wav2Vec2Config, Wav2Vec2ForCTC
+    from oracle import suta_oracle as O
+    from suta_b200.config import ModelConfig
+    from suta_b200.weights import load_checkpoint
+    ocfg = O.W2V2Config.tiny()
+    model = Wav2Vec2ForCTC(ocfg.to_hf()).eval()
+    model.load_state_dict(O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1), strict=False)
+    d1 = tmp_path / "new"
+    model.save_pretrained(str(d1))
+    cfg, sd = load_checkpoint(str(d1))
+    assert cfg == ModelConfig.tiny()
+    ref = model.state_dict()
+    for k in ("wav2vec2.feature_extractor.conv_layers.3.conv.weight", "wav2vec2.encoder.layers.1.final_layer_norm.bias",
+              "wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original1", "lm_head.bias"):
+        assert torch.equal(sd[k], ref[k]), k
+    # legacy layout
+    d2 = tmp_path / "old"
+    d2.mkdir()
+    model.config.save_pretrained(str(d2))
+    old = {k: v for k, v in ref.items()}
+    old["wav2vec2.encoder.pos_conv_embed.conv.weight_g"] = old.pop("wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0")
+    old["wav2vec2.encoder.pos_conv_embed.conv.weight_v"] = old.pop("wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original1")
+    torch.save(old, str(d2 / "pytorch_model.bin"))
+    cfg2, sd2 = load_checkpoint(str(d2))
+    assert cfg2 == cfg and torch.equal(sd2["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0"],
+                                       ref["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0"])
+    # the lv60 family is refused loudly, not mis-computed
+    d3 = tmp_path / "lv60"
+    Wav2Vec2Config(feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True).save_pretrained(str(d3))
+    with pytest.raises(NotImplementedError):
+        load_checkpoint(str(d3))
