@@ -272,7 +272,7 @@ def run_b200(a):
         eng.begin_batch_lengths(lens)
         return adapt_batch(eng, audio, lens, S, hp, vocab, extra_noise=w["noise"], utt_ids=ids)   # noise: on the device
 
-    def count_launches():
+    def launches():
         return eng.launch_count + (runner._engine2.launch_count if runner._engine2 is not None else 0)
 
     def barrier():
@@ -285,7 +285,7 @@ def run_b200(a):
         the launching stream (the side streams are joined into it before the closing event), max over ranks."""
         barrier()
         ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        l0 = count_launches()
+        l0 = launches()
         ev0.record()
         res = runner.run(utts, staged=items, n_streams=a.streams)
         ev1.record()
@@ -306,7 +306,7 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         else:
             per_rank, makespan = [ms], [mk]
-        return (float(ms.item()), count_launches() - l0, res["batch_ms"], [float(x.item()) for x in per_rank], gathered,
+        return (float(ms.item()), launches() - l0, res["batch_ms"], [float(x.item()) for x in per_rank], gathered,
                 [float(x.item()) for x in makespan])
 
     for b, lens, host in staged_w:                        # warm-up (>= 3 by default)
