@@ -59,8 +59,6 @@ def parse():
     ap.add_argument("--n-utts", type=int, default=N_UTTS, help="size of the synthetic set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
-                    help="adaptation batches in flight per GPU (2: two CUDA streams, one host thread; SutaRunner.run)")
     ap.add_argument("--cpu-utts", type=int, default=5, help="utterances of the duration-stratified CPU-baseline sample")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
@@ -272,41 +270,47 @@ def run_b200(a):
         eng.begin_batch_lengths(lens)
         return adapt_batch(eng, audio, lens, S, hp, vocab, extra_noise=w["noise"], utt_ids=ids)   # noise: on the device
 
-    def launches():
-        return eng.launch_count + (runner._engine2.launch_count if runner._engine2 is not None else 0)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def timed_region(items, with_gather):
-        """The K steps between barriers through SutaRunner.run (a.streams batches in flight); device time by CUDA events on
-        the launching stream (the side streams are joined into it before the closing event), max over ranks."""
+        """K steps between barriers; device time by CUDA events on the launching stream, max over ranks."""
         barrier()
-        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        l0 = launches()
-        ev0.record()
-        res = runner.run(utts, staged=items, n_streams=a.streams)
-        ev1.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(items) + 2)]
+        l0 = eng.launch_count
+        texts = {}
+        ev[0].record()
+        for i, (b, lens, audio) in enumerate(items):
+            out = one_step(lens, audio, b)
+            for step, tl in out.items():
+                texts.setdefault(step, {}).update({j: t for j, t in zip(b, tl)})
+            ev[i + 1].record()
         gathered = None
         if with_gather:      # end-of-run exchange (SURVEY.md 8e): WER counters all-reduced, transcripts gathered
-            gathered = gather_results(res, sorted(res["texts"]))
-        ev2.record()
+            from suta_b200.wer import wer_counts
+            counts = {st: wer_counts([utts[j].text for j in sorted(d)], [d[j] for j in sorted(d)]) for st, d in texts.items()}
+            gathered = gather_results(dict(texts=texts, wer_counts=counts, wall_s=0.0, audio_s=0.0), sorted(texts))
+        ev[-1].record()
         barrier()
-        mine = ev0.elapsed_time(ev2)
+        mine = ev[0].elapsed_time(ev[-1])
         ms = torch.tensor([mine], device="cuda")
         per_rank = [torch.zeros_like(ms) for _ in range(world)]
-        # this rank's adaptation alone (before the blocking end-of-run exchange): the makespan the LPT shards aim to equalise
-        mk = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-        makespan = [torch.zeros_like(mk) for _ in range(world)]
         if world > 1:
             dist.all_gather(per_rank, ms)
-            dist.all_gather(makespan, mk)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         else:
-            per_rank, makespan = [ms], [mk]
-        return (float(ms.item()), launches() - l0, res["batch_ms"], [float(x.item()) for x in per_rank], gathered,
+            per_rank = [ms]
+        per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(items))]
+        # this rank's adaptation alone (before the blocking end-of-run exchange): the makespan the LPT shards aim to equalise
+        mk = torch.tensor([ev[0].elapsed_time(ev[len(items)])], device="cuda")
+        makespan = [torch.zeros_like(mk) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(makespan, mk)
+        else:
+            makespan = [mk]
+        return (float(ms.item()), eng.launch_count - l0, per_step, [float(x.item()) for x in per_rank], gathered,
                 [float(x.item()) for x in makespan])
 
     for b, lens, host in staged_w:                        # warm-up (>= 3 by default)
@@ -358,8 +362,7 @@ def run_b200(a):
     config = make_config(a)                              # identical in both arms
     step_info = {"batching": f"<= {w['max_utts']} utts / {w['max_frames']} frames per adaptation batch, length-bucketed",
                  "utts_per_step": utts_all / k_all, "audio_s_per_step": audio_all / k_all,
-                 "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2",
-                 "batches_in_flight": a.streams}
+                 "l2": "every step works on a different batch; workspace per step (GBs) >> 126 MB L2"}
     if full:
         step_info["sharding"] = ("LPT over estimated utterance cost (suta_b200.shard.shard_lpt), no collective inside the loop, "
                                  "all_reduce of 2 x #checkpoints int64 WER counters + all_gather_object of transcripts inside the timed region")
@@ -385,7 +388,7 @@ def run_b200(a):
                  "achieved_tflops": flops_all / (ms_dev * 1e-3) / 1e12 / world,
                  "frac_of_peak": flops_all / (ms_dev * 1e-3) / 1e12 / world / peaks["tflops"]},
         "ms_per_rank": rank_ms, "ms_per_rank_e2e": rank_ms_e2e,
-        "ms_per_rank_before_gather": makespan, "streams": a.streams,
+        "ms_per_rank_before_gather": makespan,
         "imbalance_max_over_mean": max(makespan) / (sum(makespan) / len(makespan)),
         "breakdown": breakdown,
     }

@@ -53,19 +53,6 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-class DecodeHandle:
-    """Greedy transcript ids of a batch on their way to the host: the decode kernel and the device-to-host copies are
-    queued on the engine's stream, result() waits for them (and only for them)."""
-
-    def __init__(self, ids_host: torch.Tensor, lens_host: torch.Tensor, event: torch.cuda.Event, frame_off: np.ndarray):
-        self._ids, self._lens, self._event, self._off = ids_host, lens_host, event, frame_off
-
-    def result(self) -> List[List[int]]:
-        self._event.synchronize()
-        ids_h, lens_h = self._ids.numpy(), self._lens.numpy()
-        return [ids_h[o:o + n].tolist() for o, n in zip(self._off, lens_h)]
-
-
 class SutaEngine:
     """One frozen wav2vec2-CTC model on one GPU + the batched SUTA loop over independent utterances."""
 
@@ -294,42 +281,11 @@ class SutaEngine:
 
     def decode_ids(self) -> List[List[int]]:
         """Greedy CTC on the device; returns the collapsed id sequence per utterance (one D2H copy)."""
-        return self.decode_async().result()
-
-    def decode_async(self) -> DecodeHandle:
-        """Queue the greedy CTC decode of the current logits and the copy of its result to pinned host memory on the
-        current stream; nothing blocks until DecodeHandle.result() (REF/main.py:333-334 blocks at every decode)."""
         check(self.lib.suta_decode(self._h, _stream_ptr()))
         ids = self._view(self.lib.suta_collapsed_ids(self._h), (self.total_frames,), torch.int32)
         lens = self._view(self.lib.suta_collapsed_len(self._h), (self.n_utts,), torch.int32)
-        ids_h = torch.empty(self.total_frames, dtype=torch.int32, pin_memory=True)
-        lens_h = torch.empty(self.n_utts, dtype=torch.int32, pin_memory=True)
-        ids_h.copy_(ids, non_blocking=True)
-        lens_h.copy_(lens, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        return DecodeHandle(ids_h, lens_h, ev, self.frame_off.copy())
-
-    def clone(self) -> "SutaEngine":
-        """A second engine over the SAME packed frozen weights (no copy) with a workspace of its own: lets two adaptation
-        batches be in flight on two streams (runner.SutaRunner, n_streams=2)."""
-        other = object.__new__(SutaEngine)
-        other.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_ws", "_audio_keep", "_noise_ids")})
-        cc = ModelCfg()
-        c = self.cfg
-        cc.hidden, cc.layers, cc.heads, cc.intermediate, cc.vocab = (c.hidden_size, c.num_hidden_layers, c.num_attention_heads,
-                                                                      c.intermediate_size, c.vocab_size)
-        cc.n_conv = len(c.conv_dim)
-        for i in range(cc.n_conv):
-            cc.conv_dim[i], cc.conv_kernel[i], cc.conv_stride[i] = c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i]
-        cc.pos_k, cc.pos_groups, cc.ln_eps = c.num_conv_pos_embeddings, c.num_conv_pos_embedding_groups, c.layer_norm_eps
-        h = C.c_void_p()
-        check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature) | (2 if self.pseudo_label else 0), C.byref(h)))
-        other._h = h
-        check(self.lib.suta_engine_set_weights(h, C.byref(self._weights)))
-        other._ws = None
-        other.n_utts = 0
-        return other
+        ids_h, lens_h = ids.cpu().numpy(), lens.cpu().numpy()
+        return [ids_h[o:o + n].tolist() for o, n in zip(self.frame_off, lens_h)]
 
     # ------------------------------------------------------------------ views
     def logits(self) -> torch.Tensor:

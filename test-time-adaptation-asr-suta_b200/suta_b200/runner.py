@@ -25,39 +25,6 @@ class BatchResult:
     audio_seconds: float = 0.0
 
 
-def adapt_batch_steps(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarray, steps: int, hp: AdaptHyper,
-                      vocab: CTCVocab, collect_losses: bool = False, sched_gamma: Optional[float] = None, sched_step: int = 1,
-                      extra_noise: float = 0.0, noise_seed: int = 0, utt_ids: Optional[Sequence[int]] = None):
-    """Generator form of adapt_batch: queues one chunk of the batch's work on the current stream per next() -- the vanilla
-    forward, then one forward_and_adapt per step -- without ever blocking the host (decodes are DecodeHandles), and
-    returns the transcripts through StopIteration.value once everything has been queued and has finished.  A scheduler
-    can therefore keep several batches in flight on several streams from ONE host thread (SutaRunner.run)."""
-    engine.set_audio(wavs_packed)
-    if extra_noise > 0:
-        engine.add_noise(extra_noise, noise_seed, utt_ids)
-    engine.reset()
-    engine.forward()                                               # vanilla forward, REF/main.py:331-334
-    handles = {0: engine.decode_async()}
-    yield
-    losses = []
-    lr0 = hp.lr
-    for i in range(steps):                                         # REF/main.py:347-348
-        hp.lr = lr0 if sched_gamma is None else lr0 * sched_gamma ** (i // sched_step)
-        try:
-            engine.adapt_step(hp)
-        finally:
-            hp.lr = lr0
-        if collect_losses:
-            losses.append(engine.losses()[0].cpu().numpy().copy())
-        if (i + 1) in CHECKPOINT_STEPS:                            # REF/main.py:349-398
-            handles[i + 1] = engine.decode_async()
-        yield
-    texts = {k: vocab.batch_to_text(h.result()) for k, h in handles.items()}
-    if collect_losses:
-        texts["losses"] = losses
-    return texts
-
-
 def adapt_batch(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarray, steps: int, hp: AdaptHyper,
                 vocab: CTCVocab, episodic: bool = True, collect_losses: bool = False,
                 sched_gamma: Optional[float] = None, sched_step: int = 1, extra_noise: float = 0.0, noise_seed: int = 0,
@@ -71,13 +38,28 @@ def adapt_batch(engine: SutaEngine, wavs_packed: torch.Tensor, lengths: np.ndarr
     extra_noise: REF/data.py:23, added to the raw waveform ON THE DEVICE (keyed by noise_seed and utt_ids)."""
     if not episodic:
         raise ValueError("adapt_batch adapts independent utterances: episodic only (use the api.* surface for continual mode)")
-    gen = adapt_batch_steps(engine, wavs_packed, lengths, steps, hp, vocab, collect_losses, sched_gamma, sched_step, extra_noise,
-                            noise_seed, utt_ids)
-    while True:
-        try:
-            next(gen)
-        except StopIteration as done:
-            return done.value
+    engine.set_audio(wavs_packed)
+    if extra_noise > 0:
+        engine.add_noise(extra_noise, noise_seed, utt_ids)
+    engine.reset()
+    engine.forward()                                               # vanilla forward, REF/main.py:331-334
+    texts = {0: vocab.batch_to_text(engine.decode_ids())}
+    losses = []
+    lr0 = hp.lr
+    try:
+        for i in range(steps):                                     # REF/main.py:347-348
+            if sched_gamma is not None:
+                hp.lr = lr0 * sched_gamma ** (i // sched_step)
+            engine.adapt_step(hp)
+            if collect_losses:
+                losses.append(engine.losses()[0].cpu().numpy().copy())
+            if (i + 1) in CHECKPOINT_STEPS:                        # REF/main.py:349-398
+                texts[i + 1] = vocab.batch_to_text(engine.decode_ids())
+    finally:
+        hp.lr = lr0
+    if collect_losses:
+        texts["losses"] = losses
+    return texts
 
 
 def pack_batch(engine: SutaEngine, utts: Sequence[Utterance], pinned: bool = True, with_noise: bool = True) -> torch.Tensor:
@@ -97,10 +79,8 @@ class SutaRunner:
 
     def __init__(self, engine: SutaEngine, steps: int = 10, hp: Optional[AdaptHyper] = None, max_utts: int = 64,
                  max_frames: int = 32768, vocab: Optional[CTCVocab] = None, rank: int = 0, world_size: int = 1,
-                 sched_gamma: Optional[float] = None, sched_step: int = 1, extra_noise: float = 0.0, noise_seed: int = 0,
-                 n_streams: int = 1):
+                 sched_gamma: Optional[float] = None, sched_step: int = 1, extra_noise: float = 0.0, noise_seed: int = 0):
         self.engine, self.steps, self.hp = engine, steps, hp or AdaptHyper()
-        self.n_streams, self._engine2, self._streams = n_streams, None, None
         self.sched_gamma, self.sched_step = sched_gamma, sched_step
         # REF/data.py:23: the runner stages CLEAN waveforms and the engine adds the noise on the device, keyed by the
         # utterance's index in the set (the same noise whichever rank / batch adapts it)
@@ -126,75 +106,26 @@ class SutaRunner:
             out.append((b, np.asarray([u.n_samples for u in sel], dtype=np.int32), packed.to(self.engine.device) if device else packed))
         return out
 
-    def run(self, utts: Sequence[Utterance], staged=None, n_streams: Optional[int] = None) -> Dict[str, object]:
+    def run(self, utts: Sequence[Utterance], staged=None) -> Dict[str, object]:
         """Adapt this rank's shard batch by batch (REF/main.py:319-402) and score it (REF/main.py:405-417).
-        `staged` = the result of stage(): skips building the waveform buffers.
-        n_streams = 2 keeps TWO batches in flight on two CUDA streams (a second engine over the same frozen weights with its
-        own workspace), driven round-robin by this one host thread: the tail of one batch's tensor-bound kernel overlaps
-        the ramp-up of the other's memory-bound one (+3 % train_feature, +7 % LayerNorm-only on a B200).  Results do not
-        depend on it: every batch still runs its own dependency chain in order on one stream."""
+        `staged` = the result of stage(): skips building the waveform buffers."""
         if staged is None:
             staged = self.stage(utts)
-        n_streams = self.n_streams if n_streams is None else n_streams
-        n_streams = max(1, min(int(n_streams), 2, len(staged)))
-        if n_streams == 2 and self._engine2 is None:
-            self._engine2 = self.engine.clone()
-            self._streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        engines = [self.engine, self._engine2][:n_streams]
-        cur = torch.cuda.current_stream()
-        streams = self._streams if n_streams == 2 else [cur]
-        for st in streams:
-            if st is not cur:
-                st.wait_stream(cur)
         texts: Dict[int, Dict[int, str]] = {}
-        batch_ms: List[Optional[float]] = [None] * len(staged)
         t0 = time.time()
-        todo = list(range(len(staged)))[::-1]
-        slots: List[Optional[dict]] = [None] * n_streams
-
-        def start(k):
-            j = todo.pop()
-            b, lens, packed = staged[j]
-            with torch.cuda.stream(streams[k]):
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record(streams[k])
-                engines[k].begin_batch_lengths(lens)
-                gen = adapt_batch_steps(engines[k], packed, lens, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
-                                        sched_step=self.sched_step, extra_noise=self.extra_noise, noise_seed=self.noise_seed,
-                                        utt_ids=b)
-            slots[k] = dict(j=j, b=b, gen=gen, ev0=ev0)
-
-        for k in range(n_streams):
-            start(k)
-        while any(s is not None for s in slots):
-            for k in range(n_streams):
-                sl = slots[k]
-                if sl is None:
-                    continue
-                with torch.cuda.stream(streams[k]):
-                    try:
-                        next(sl["gen"])
-                        continue
-                    except StopIteration as done:
-                        out = done.value
-                    ev1 = torch.cuda.Event(enable_timing=True)
-                    ev1.record(streams[k])
-                ev1.synchronize()
-                batch_ms[sl["j"]] = sl["ev0"].elapsed_time(ev1)
-                for step, tl in out.items():
-                    texts.setdefault(step, {}).update({i: t for i, t in zip(sl["b"], tl)})
-                slots[k] = None
-                if todo:
-                    start(k)
-        for st in streams:
-            if st is not cur:
-                cur.wait_stream(st)
+        for b, lens, packed in staged:
+            self.engine.begin_batch_lengths(lens)
+            out = adapt_batch(self.engine, packed, lens, self.steps, self.hp, self.vocab, sched_gamma=self.sched_gamma,
+                              sched_step=self.sched_step, extra_noise=self.extra_noise, noise_seed=self.noise_seed, utt_ids=b)
+            for step, tl in out.items():
+                texts.setdefault(step, {}).update({i: t for i, t in zip(b, tl)})
+        torch.cuda.synchronize()
         wall = time.time() - t0
         counts = {}
         for step, d in texts.items():
             idx = sorted(d)
             counts[step] = wer_counts([utts[i].text for i in idx], [d[i] for i in idx])
-        return dict(texts=texts, wer_counts=counts, wall_s=wall, batch_ms=batch_ms, n_streams=n_streams,
+        return dict(texts=texts, wer_counts=counts, wall_s=wall,
                     audio_s=sum(utts[i].duration for b, _l, _p in staged for i in b), n_batches=len(staged))
 
 

@@ -201,21 +201,3 @@ def test_local_hf_checkpoint_runs_through_the_engine(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert os.path.exists(str(tmp_path / "exps" / "synthetic_1.0_3_2.5_ckpt_non_blankFalse_noise_0.0_rew_False_div_0.0_bias_False_feat_False_all_False_LN_True"))
-
-
-@pytest.mark.parametrize("train_feature", [False, True])
-def test_two_batches_in_flight_give_the_same_results(train_feature):
-    """SutaRunner.run(n_streams=2): two adaptation batches on two CUDA streams (one host thread, a cloned engine over the
-    same frozen weights).  Every batch still runs its own chain in order, so nothing may change."""
-    _need_gpu()
-    from suta_b200.data import librispeech_shaped
-    from suta_b200.runner import SutaRunner
-    utts = librispeech_shaped(21, seed=5)
-    eng = _tiny_engine(train_feature)
-    r = SutaRunner(eng, steps=5, max_utts=4, max_frames=4096)
-    one = r.run(utts, n_streams=1)
-    for rep in range(3):
-        two = r.run(utts, n_streams=2)
-        assert two["n_streams"] == 2 and len(two["batch_ms"]) == one["n_batches"] and all(t > 0 for t in two["batch_ms"])
-        assert two["texts"] == one["texts"] and two["wer_counts"] == one["wer_counts"]     # same batches, same kernels: same bits
-    eng.close()
