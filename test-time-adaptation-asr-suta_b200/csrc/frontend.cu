@@ -10,6 +10,9 @@
 // (k + k(k+1)/2 numbers per utterance, computed ONCE per batch from the audio by audio_conv0_moments),
 //   sum_t y[t,c] = w_c . Sx        sum_t y[t,c]^2 = w_c^T R w_c
 // so a weight update (train_feature) only costs a 512 x 100-MAC kernel, not a pass over the waveform.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -100,12 +103,12 @@ __global__ void audio_noise_kernel(float* __restrict__ wav, const long long* __r
     if (i + j < n) x[j] += sigma * z[j];
 }
 
-constexpr int C0_TT = 128;      // frames per CTA
+constexpr int C0_TT_DEFAULT = 128;      // frames per CTA
 constexpr int C0_MAXK = 16;
 
 // MODE 0: accumulate per-channel sum / sum of squares;  MODE 1: normalise + GELU + store
-template <int MODE>
-__global__ void __launch_bounds__(256)
+template <int MODE, int C0_TT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 conv0_kernel(Conv0Args a, double* __restrict__ stats) {
   extern __shared__ float sx[];                  // C0_TT*stride + k samples
   const int u = blockIdx.y;
@@ -295,9 +298,11 @@ int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0
 int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream) {
   SUTA_CHECK_ARG(a.k <= C0_MAXK && a.C % 2 == 0 && a.n_utts > 0 && a.mom);
   conv0_stats_kernel<<<dim3(ceil_div(a.C, 128), a.n_utts), 128, 0, stream>>>(a);
-  dim3 grid(ceil_div(a.max_L0, C0_TT), a.n_utts);
-  size_t smem = sizeof(float) * (C0_TT * a.stride + a.k + 32);       // slack for the 16-byte window loads
-  conv0_kernel<1><<<grid, 256, smem, stream>>>(a, a.stats);
+  // frames per CTA x minimum resident CTAs were swept on the B200 (128/256/512 x 1/3/4: 9.4-10.0 ms per step, all within
+  // 6 %): the kernel is bound by instruction throughput (packed FMA + MUFU + bf16 packing), not by occupancy or latency
+  dim3 grid(ceil_div(a.max_L0, C0_TT_DEFAULT), a.n_utts);
+  size_t smem = sizeof(float) * (C0_TT_DEFAULT * a.stride + a.k + 32);       // slack for the 16-byte window loads
+  conv0_kernel<1, C0_TT_DEFAULT, 3><<<grid, 256, smem, stream>>>(a, a.stats);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
