@@ -1208,6 +1208,16 @@ extern "C" const void* suta_debug_buffer(const suta_engine* e, const char* name,
   if (n == "hE") return ret(e->hE, e->M, H, 0);
   if (n == "x_final") return ret(e->fa, e->M, H, 0);
   if (n == "d_yfp") return ret(e->d_yfp, e->M, C, 0);
+  if (n.rfind("dpre", 0) == 0 && e->train_feature) {      // d(pre-activation) of conv layer l (train_feature backward)
+    int l = atoi(n.c_str() + 4);
+    if (l >= 0 && l < c.n_conv) return ret(e->conv_dpre[l], l == c.n_conv - 1 ? e->R64 : e->rows_total[l], c.conv_dim[l], 1);
+  }
+  if (n.rfind("cpre", 0) == 0 && e->train_feature) {      // GELU'(pre-activation) saved by the forward
+    int l = atoi(n.c_str() + 4);
+    if (l >= 0 && l < c.n_conv) return ret(e->conv_pre[l], e->rows_total[l], c.conv_dim[l], 1);
+  }
+  if (n == "d_feat" && e->train_feature) return ret(e->d_feat, e->M, C, 0);
+  if (n == "dh0_pad" && e->train_feature) return ret(e->dh0_pad, e->R64, H, 1);
   if (n.rfind("conv", 0) == 0) {
     int l = atoi(n.c_str() + 4);
     if (l >= 0 && l < c.n_conv) return ret(e->conv_out[l], e->rows_total[l], c.conv_dim[l], 1);

@@ -675,7 +675,14 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
       if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
       return launch<64, true, true, false>(p, stream);
     }
-    const bool lean = dense && !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias);
+    // The 4-stage LEAN variant is NOT used with an MN-major B: on full-size train_feature batches (the parity-split conv
+    // dgrad: 300-600 k output rows, GELU' tiles fetched by TMA in the epilogue) it produced, in every run, a few dozen
+    // output rows (of ~10^6) whose accumulators were off by ~7 % -- the same rows in the even- and the odd-row launch, other
+    // rows in the next run (tests/test_gpu_e2e.py::test_full_size_batch_..., tools/determinism_probe.py).  The 3-stage
+    // variant with two epilogue patches is bit-reproducible and costs 0.35 % of the step; SUTA_LEAN_BMN=1 re-enables the
+    // 4-stage one for whoever hunts the race.
+    static const bool lean_bmn = getenv("SUTA_LEAN_BMN") != nullptr;
+    const bool lean = dense && !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias) && lean_bmn;
     if (dense) {
       if (p.N % 256 == 0 && lean) return launch<256, false, true, true, true>(p, stream);
       if (p.N % 256 == 0) return launch<256, false, true, true>(p, stream);

@@ -252,3 +252,47 @@ def test_alternative_cuda_paths_keep_parity(switches):
                         "golden_vectors and (base_ln_5s_noblank or base_feat_2s or tiny_feat)"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(here), timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_full_size_batch_is_reproducible_and_utterances_are_independent(E):
+    """BASELINE.json configs[1] at full size (wav2vec2-base, --train_feature, one 64-utterance batch of the
+    LibriSpeech-shaped set: ~20 k frames, CTA-pair GEMMs, tail split, fused conv dgrad): the oracle cannot follow at
+    this size, so size-independent properties are checked -- the same batch twice gives the same BITS, and an utterance
+    adapted alone gives the same result as inside the batch (independence; the reference adapts one at a time)."""
+    from suta_b200 import AdaptHyper, ModelConfig, SutaEngine
+    from suta_b200.api import reference_multiplicities
+    from suta_b200.data import librispeech_shaped
+    from suta_b200.shard import bucket_batches
+    from suta_b200.weights import random_state_dict
+    cfg = ModelConfig.base()
+    utts = librispeech_shaped(2939, seed=0)
+    frames = [cfg.frames(u.n_samples) for u in utts]
+    batch = bucket_batches(frames, list(range(len(utts))), 64, 36864)[22]           # a 64-utterance batch of ~6.5 s utterances (~20 k frames)
+    wavs = [utts[i].audio() for i in batch]
+    eng = SutaEngine(cfg, random_state_dict(cfg, 0, 1.75), train_feature=True,
+                     trainable_mult=reference_multiplicities(cfg, train_feature=True))
+    hp = AdaptHyper()
+
+    def adapt(ws, steps=2):
+        eng.begin_batch(ws)
+        eng.reset()
+        eng.forward()
+        for _ in range(steps):
+            eng.adapt_step(hp)
+        return eng.logits().clone(), eng.params().clone(), eng.losses()[0].clone(), [int(o) for o in eng.frame_off], [int(t) for t in eng.frames]
+
+    lg1, p1, l1, off, T = adapt(wavs)
+    assert len(batch) == 64 and lg1.shape[0] > 12000
+    lg2, p2, l2, _, _ = adapt(wavs)
+    assert torch.isfinite(lg1).all() and torch.isfinite(l1).all()
+    assert torch.equal(lg1, lg2) and torch.equal(p1, p2) and torch.equal(l1, l2)        # bit-reproducible at full size
+    for u in (0, 31, 63):
+        lga, pa, la, _, _ = adapt([wavs[u]])
+        inside = lg1[off[u]:off[u] + T[u]]
+        assert lga.shape == inside.shape
+        assert float((lga - inside).abs().max()) < 5e-3                               # summation order only (chunked reductions)
+        assert float((lga.argmax(-1) == inside.argmax(-1)).float().mean()) > 0.99
+        assert abs(float(la[0]) - float(l1[u])) < 1e-4 * abs(float(l1[u]))
+        d_in, d_al = p1[u] - eng.params0, pa[0] - eng.params0
+        assert float((d_in - d_al).norm() / d_al.norm()) < 0.02                       # the same adaptation, alone or in company
+    eng.close()
