@@ -337,16 +337,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             float4 uf[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) uf[j] = ld_shared_v4(arow + ((j ^ aswz) << 4));
-            if (LEAN) {                            // one patch: refill it as soon as everyone holds this chunk's tile
-              __syncwarp();
-              if (lane == 0 && kc + 1 < NCH) aux_issue(pc + 1, kc + 1);
-            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = make_uint4(__float_as_uint(uf[j].x), __float_as_uint(uf[j].y), __float_as_uint(uf[j].z), __float_as_uint(uf[j].w));
               const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
               v[8 * j] *= f0.x; v[8 * j + 1] *= f0.y; v[8 * j + 2] *= f1.x; v[8 * j + 3] *= f1.y;
               v[8 * j + 4] *= f2.x; v[8 * j + 5] *= f2.y; v[8 * j + 6] *= f3.x; v[8 * j + 7] *= f3.y;
+            }
+            if (LEAN) {
+              // one patch: refill it only once every lane has CONSUMED this chunk's tile (the multiplies above depend on the
+              // loads).  Issuing the refill right after the ld.shared instructions raced with them: under the mainloop's
+              // shared-memory traffic a queued ld.shared can take longer than the 2 KB TMA refill (L2 hit), and a few lanes
+              // then read the NEXT chunk's GELU' -- dozens of wrong rows per 10^6, different ones in every run
+              // (found by tests/test_gpu_e2e.py::test_full_size_batch_is_reproducible_and_utterances_are_independent)
+              asm volatile("" ::"f"(v[0]), "f"(v[8]), "f"(v[16]), "f"(v[24]) : "memory");
+              __syncwarp();
+              if (lane == 0 && kc + 1 < NCH) aux_issue(pc + 1, kc + 1);
             }
           } else if (p.epi.act == 2) {
 #pragma unroll
@@ -675,14 +681,9 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
       if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
       return launch<64, true, true, false>(p, stream);
     }
-    // The 4-stage LEAN variant is NOT used with an MN-major B: on full-size train_feature batches (the parity-split conv
-    // dgrad: 300-600 k output rows, GELU' tiles fetched by TMA in the epilogue) it produced, in every run, a few dozen
-    // output rows (of ~10^6) whose accumulators were off by ~7 % -- the same rows in the even- and the odd-row launch, other
-    // rows in the next run (tests/test_gpu_e2e.py::test_full_size_batch_..., tools/determinism_probe.py).  The 3-stage
-    // variant with two epilogue patches is bit-reproducible and costs 0.35 % of the step; SUTA_LEAN_BMN=1 re-enables the
-    // 4-stage one for whoever hunts the race.
-    static const bool lean_bmn = getenv("SUTA_LEAN_BMN") != nullptr;
-    const bool lean = dense && !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias) && lean_bmn;
+    // SUTA_NO_LEAN_BMN=1: the 3-stage variant (two epilogue patches) instead of the 4-stage LEAN one (debug switch)
+    static const bool no_lean_bmn = getenv("SUTA_NO_LEAN_BMN") != nullptr;
+    const bool lean = dense && !(p.epi.act == 1 && p.epi.aux_out) && !(p.epi.out_f32 && p.epi.bias) && !no_lean_bmn;
     if (dense) {
       if (p.N % 256 == 0 && lean) return launch<256, false, true, true, true>(p, stream);
       if (p.N % 256 == 0) return launch<256, false, true, true>(p, stream);
