@@ -20,7 +20,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "test-time-adaptation-asr-suta_b200")]
@@ -224,11 +223,10 @@ def baseline_record(a, device, n_utts, warmup, kind):
 
 
 def run_b200(a):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from suta_b200 import AdaptHyper, ModelConfig, SutaEngine
-    from suta_b200.runner import SutaRunner, adapt_batch, gather_results, pack_batch
+    from suta_b200.runner import SutaRunner, adapt_batch, gather_results
     from suta_b200.text import CTCVocab
     from suta_b200.weights import random_state_dict
 

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 from copy import deepcopy
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch
