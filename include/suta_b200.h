@@ -19,7 +19,7 @@ extern "C" {
 
 #define SUTA_MAX_LAYERS 48
 #define SUTA_MAX_CONV 8
-#define SUTA_ABI_VERSION 2
+#define SUTA_ABI_VERSION 3
 
 typedef struct suta_engine suta_engine;
 
@@ -30,6 +30,10 @@ typedef struct suta_model_cfg {
   int32_t conv_dim[SUTA_MAX_CONV], conv_kernel[SUTA_MAX_CONV], conv_stride[SUTA_MAX_CONV];
   int32_t pos_k, pos_groups;
   float ln_eps;
+  /* the "lv60" family (wav2vec2-large-960h-lv60[-self], large-robust; REF/main_SDPL.py:238-241) */
+  int32_t feat_norm_layer;               /* feat_extract_norm == "layer": every conv layer is Conv1d(+bias) -> LayerNorm(C)
+                                            -> GELU (HF:275-299); its 2 x n_conv LayerNorm vectors are trainable */
+  int32_t stable_layer_norm;             /* do_stable_layer_norm: pre-LN encoder layers + final encoder LayerNorm (HF:612-655,730-803) */
 } suta_model_cfg;
 
 /* Frozen weights, already in the engine's operand formats (see INTEGRATION.md for the packing recipe).
@@ -44,7 +48,8 @@ typedef struct suta_layer_weights {
 
 typedef struct suta_weights {
   const float* conv0_w;                  /* DEV fp32 [C0,k0]                                  HF:319 */
-  const float *gn_g, *gn_b;              /* DEV fp32 [C0] GroupNorm affine                    HF:320 */
+  const float *gn_g, *gn_b;              /* DEV fp32 [C0] GroupNorm affine (NULL with feat_norm_layer) HF:320 */
+  const float* conv_b[SUTA_MAX_CONV];    /* DEV fp32 [C_l] conv bias (feat_norm_layer only; NULL = none)  HF:286 */
   const void* conv_w[SUTA_MAX_CONV];     /* DEV bf16 [C_l, k_l*C_{l-1}], K order (tap,cin)    HF:269 */
   const void* conv_w_t[SUTA_MAX_CONV];   /* DEV bf16 [k_l*C_{l-1}, C_l] (train_feature dgrad)        */
   const void *proj_w, *proj_w_t;         /* DEV bf16 [H,C], [C,H]                             HF:431 */
@@ -62,7 +67,8 @@ typedef struct suta_weights {
 /* One segment of the per-utterance trainable vector. kind: 0 LN gamma, 1 LN beta, 2 GroupNorm gamma, 3 GroupNorm beta,
  * 4 conv weight (layer index in `index`), 5 projection weight, 6 projection bias.
  * module: 0 feature_projection.layer_norm, 1 encoder.layer_norm, 2 layers[index].layer_norm,
- *         3 layers[index].final_layer_norm, 4 feature_extractor.conv_layers[index], 5 feature_projection.projection */
+ *         3 layers[index].final_layer_norm, 4 feature_extractor.conv_layers[index], 5 feature_projection.projection,
+ *         6 feature_extractor.conv_layers[index].layer_norm (feat_norm_layer: kinds 0 / 1) */
 typedef struct suta_param_seg {
   int32_t kind, module, index;
   int64_t offset, size;

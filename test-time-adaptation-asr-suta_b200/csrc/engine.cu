@@ -63,6 +63,10 @@ struct Seg { int kind, module, index; long long off, size; };
 struct suta_engine {
   suta_model_cfg cfg{};
   int train_feature = 0;
+  // the "lv60" family: conv_ln = every conv layer is Conv1d(+bias) -> LayerNorm(C) -> GELU with TRAINABLE LayerNorms (so the
+  // backward spans the CNN even in LayerNorm-only mode, through the frozen shared conv weights); stable = pre-LN encoder;
+  // cnn_bwd = the batch layout / tables / buffers a backward through the CNN needs (train_feature or conv_ln)
+  int conv_ln = 0, stable = 0, cnn_bwd = 0;
   int pseudo_label = 0;                            // SUTA_FLAG_PSEUDO_LABEL: CTC scratch is part of every batch workspace
   suta_weights w{};
   bool have_weights = false;
@@ -71,6 +75,7 @@ struct suta_engine {
   // segment offsets
   long long fp_g = 0, fp_b = 0, enc_g = 0, enc_b = 0;
   std::vector<long long> ln1_g, ln1_b, ln2_g, ln2_b;
+  std::vector<long long> cln_g, cln_b;             // conv-layer LayerNorms (conv_ln)
   // train_feature segments (REF/main.py:88-94): GroupNorm affine, every conv weight, projection weight + bias
   long long ln_params = 0;                         // size of the LayerNorm-only prefix of the trainable vector
   long long gn_g = 0, gn_b = 0, proj_w_off = 0, proj_b_off = 0;
@@ -122,6 +127,11 @@ struct suta_engine {
   int* d_L[SUTA_MAX_CONV] = {};                    // [U] valid rows per layer
   bf16* conv_pre[SUTA_MAX_CONV] = {};              // GELU'(pre-activation) saved by the forward (bf16)
   bf16* conv_dpre[SUTA_MAX_CONV] = {};             // d(pre-activation), zero outside valid rows
+  // conv_ln only: conv output before its LayerNorm (bf16, saved), per-row statistics, row -> utterance tables of the
+  // layer's row space (-1 in the gaps; the last layer is token-packed and uses d_row_utt)
+  bf16* conv_z[SUTA_MAX_CONV] = {};
+  float *conv_mean[SUTA_MAX_CONV] = {}, *conv_rstd[SUTA_MAX_CONV] = {};
+  int* d_conv_row_utt[SUTA_MAX_CONV] = {};
   bf16* w_shadow[SUTA_MAX_CONV] = {};              // bf16 copies of the per-utterance conv weights [U][Cout][k*Cin]
   bf16* proj_shadow = nullptr;                     // [U][H][C]
   bf16* zbuf = nullptr;                            // dgrad GEMM output [rows_l, k*Cin]
@@ -189,6 +199,13 @@ int build_layout(suta_engine* e) {
     e->ln2_g[l] = add(0, 3, l, H);
     e->ln2_b[l] = add(1, 3, l, H);
   }
+  if (e->conv_ln) {                  // HF/modeling_wav2vec2.py:288: one LayerNorm(C_l) per conv layer, collected by REF/main.py:81-87
+    e->cln_g.resize(c.n_conv); e->cln_b.resize(c.n_conv);
+    for (int l = 0; l < c.n_conv; ++l) {
+      e->cln_g[l] = add(0, 6, l, c.conv_dim[l]);
+      e->cln_b[l] = add(1, 6, l, c.conv_dim[l]);
+    }
+  }
   e->ln_params = o;
   if (e->train_feature) {
     e->gn_g = add(2, 4, 0, c.conv_dim[0]);
@@ -226,7 +243,7 @@ static bool use_posconv_tc(const suta_engine* e) {
 // dY[j] W_0 + dY[j-1] W_2, odd rows 2j+1 = dY[j] W_1).
 static bool dgrad_fused(const suta_engine* e, int l) {
   const suta_model_cfg& c = e->cfg;
-  return e->train_feature && l >= 1 && c.conv_stride[l] == 2 && (c.conv_kernel[l] == 2 || c.conv_kernel[l] == 3) &&
+  return e->cnn_bwd && l >= 1 && c.conv_stride[l] == 2 && (c.conv_kernel[l] == 2 || c.conv_kernel[l] == 3) &&
          c.conv_dim[l] % 64 == 0 && c.conv_dim[l - 1] % 64 == 0 && getenv("SUTA_NO_FUSED_DGRAD") == nullptr;
 }
 
@@ -272,7 +289,7 @@ int plan_batch(suta_engine* e, int U, const int32_t* n_samples) {
       // time in 64-row steps and (b) every 128-row GEMM tile owns its output rows outright (TMA-store epilogue)
       // (c) the parity-split conv dgrad (conv_backward) writes 256 rows of layer l per 128-row tile of layer l + 1 and
       // reads one zero row past the utterance's last gradient row: 256-row alignment with at least one spare row
-      r += last ? e->L[l][u] : (e->train_feature ? ((e->L[l][u] + 1 + 255) & ~255) : ((e->L[l][u] + 7) & ~7));
+      r += last ? e->L[l][u] : (e->cnn_bwd ? ((e->L[l][u] + 1 + 255) & ~255) : ((e->L[l][u] + 7) & ~7));
       if (l >= 1) {
         e->n_mblk[l] += ceil_div(e->L[l][u], 128);
         e->n_mpair[l] += ceil_div(e->L[l][u], 256);
@@ -321,17 +338,19 @@ void carve(suta_engine* e, Bump& b) {
   e->d_row_utt = b.take<int>(M);
   for (int l = 1; l < c.n_conv; ++l) e->d_mblk[l] = b.take<int4>(e->n_mblk[l]);
   e->d_attn_tab = b.take<int4>(e->n_attn_blk);
-  if (e->train_feature) {
-    e->d_tok_mblk = b.take<int4>(e->n_tok_mblk);
+  if (e->cnn_bwd) {
+    if (e->train_feature) {
+      e->d_tok_mblk = b.take<int4>(e->n_tok_mblk);
+      e->d_ztab[c.n_conv] = b.take<int4>(U);
+    }
     e->d_dpre_off_last = b.take<long long>(U);
-    e->d_ztab[c.n_conv] = b.take<int4>(U);
     for (int l = 0; l < c.n_conv; ++l) {
       e->d_off[l] = b.take<long long>(U);
       e->d_L[l] = b.take<int>(U);
       if (l >= 1) {
         e->d_mpair[l] = b.take<int4>(e->n_mpair[l]);
         e->d_dgrad_mblk[l] = b.take<int4>(e->n_dg_mblk[l]);
-        e->d_ztab[l] = b.take<int4>(U);
+        if (e->train_feature) e->d_ztab[l] = b.take<int4>(U);
       }
     }
   }
@@ -384,7 +403,21 @@ void carve(suta_engine* e, Bump& b) {
   e->Mom = b.take<float>((size_t)U * e->n_params); e->Var = b.take<float>((size_t)U * e->n_params);
   e->ids = b.take<int>(M); e->collapsed = b.take<int>(M); e->out_len = b.take<int>(U);
   e->ln_part_stride = (size_t)layernorm_backward_scratch_floats(H > C ? H : C, U);
-  e->ln_part = b.take<float>(e->ln_part_stride * (2 * c.layers + 2));      // one slot set per LayerNorm: reduced together
+  e->ln_part = b.take<float>(e->ln_part_stride * (2 * c.layers + 2 + (e->conv_ln ? c.n_conv : 0)));   // one slot set per LayerNorm: reduced together
+  if (e->conv_ln) {
+    for (int l = 0; l < c.n_conv; ++l) {
+      const bool last = l == c.n_conv - 1;
+      const long long rows = last ? e->R64 : e->rows_total[l];
+      e->conv_z[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
+      e->conv_mean[l] = b.take<float>((size_t)e->rows_total[l] + 128);
+      e->conv_rstd[l] = b.take<float>((size_t)e->rows_total[l] + 128);
+      if (!last) e->d_conv_row_utt[l] = b.take<int>((size_t)e->rows_total[l] + 128);
+      // gradient of the layer's output, turned IN PLACE into the gradient of its pre-LayerNorm value (128 leading zero
+      // rows: the even-row dgrad GEMM reads row -1 of the first utterance)
+      e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
+    }
+    e->d_feat = b.take<float>((size_t)M * C);
+  }
   if (e->train_feature) {
     size_t zmax = 0;
     for (int l = 0; l < c.n_conv; ++l) {
@@ -508,6 +541,22 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_eng
   e->cfg = *cfg;
   e->train_feature = (flags & SUTA_FLAG_TRAIN_FEATURE) ? 1 : 0;
   e->pseudo_label = (flags & SUTA_FLAG_PSEUDO_LABEL) ? 1 : 0;
+  e->conv_ln = cfg->feat_norm_layer ? 1 : 0;
+  e->stable = cfg->stable_layer_norm ? 1 : 0;
+  e->cnn_bwd = e->train_feature || e->conv_ln;
+  if (e->conv_ln && e->train_feature) {
+    suta_set_last_error("train_feature is not built for the LayerNorm feature extractor (feat_extract_norm == \"layer\"): "
+                        "LayerNorm-only adaptation, which already trains its 2 x n_conv conv LayerNorm vectors, is");
+    delete e;
+    return SUTA_ERR_ARG;
+  }
+  if (e->conv_ln)
+    for (int l = 1; l < cfg->n_conv; ++l)
+      if (!dgrad_fused(e, l)) {
+        suta_set_last_error("LayerNorm feature extractor: conv layer %d needs stride 2 and kernel 2 or 3 (parity-split dgrad)", l);
+        delete e;
+        return SUTA_ERR_ARG;
+      }
   build_layout(e);
   *out = e;
   return SUTA_OK;
@@ -533,7 +582,7 @@ extern "C" int suta_engine_param_layout(const suta_engine* e, suta_param_seg* se
 extern "C" int suta_engine_set_weights(suta_engine* e, const suta_weights* w) {
   SUTA_CHECK_ARG(e && w);
   const suta_model_cfg& c = e->cfg;
-  SUTA_CHECK_ARG(w->conv0_w && w->gn_g && w->gn_b && w->proj_w && w->proj_w_t && w->proj_b);
+  SUTA_CHECK_ARG(w->conv0_w && (e->conv_ln || (w->gn_g && w->gn_b)) && w->proj_w && w->proj_w_t && w->proj_b);
   SUTA_CHECK_ARG(w->pos_w && w->pos_w_t && w->pos_b && w->lm_w && w->lm_w_t && w->lm_b && w->params0 && w->mult);
   for (int l = 1; l < c.n_conv; ++l) SUTA_CHECK_ARG(w->conv_w[l]);
   for (int l = 0; l < c.layers; ++l) {
@@ -607,23 +656,25 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
                                 e->train_feature ? u * c.conv_dim[l] : 0));
       }
     up(e->d_mblk[l], tab.data(), sizeof(int4) * tab.size());
-    if (e->train_feature) {                // 256-row tiles for the CTA-pair kernel: utterance regions are 256-row aligned
+    if (e->cnn_bwd) {                      // 256-row tiles for the CTA-pair kernel: utterance regions are 256-row aligned
       std::vector<int4> ptab;
       for (int u = 0; u < U; ++u)
         for (int m0 = 0; m0 < e->L[l][u]; m0 += 256)
           ptab.push_back(make_int4((int)(e->off[l - 1][u] / s + m0), (int)(e->off[l][u] + m0),
-                                   e->L[l][u] - m0 < 256 ? e->L[l][u] - m0 : 256, u * c.conv_dim[l]));
+                                   e->L[l][u] - m0 < 256 ? e->L[l][u] - m0 : 256, e->train_feature ? u * c.conv_dim[l] : 0));
       up(e->d_mpair[l], ptab.data(), sizeof(int4) * ptab.size());
     }
   }
-  if (e->train_feature) {
+  if (e->cnn_bwd) {
     const int last = c.n_conv - 1;
-    std::vector<int4> tab;
-    for (int u = 0; u < U; ++u)
-      for (int m0 = 0; m0 < e->T[u]; m0 += 128)
-        tab.push_back(make_int4((int)(e->tok_off[u] + m0), (int)(e->tok_off[u] + m0), e->T[u] - m0 < 128 ? e->T[u] - m0 : 128,
-                                u * c.hidden));
-    up(e->d_tok_mblk, tab.data(), sizeof(int4) * tab.size());
+    if (e->train_feature) {
+      std::vector<int4> tab;
+      for (int u = 0; u < U; ++u)
+        for (int m0 = 0; m0 < e->T[u]; m0 += 128)
+          tab.push_back(make_int4((int)(e->tok_off[u] + m0), (int)(e->tok_off[u] + m0), e->T[u] - m0 < 128 ? e->T[u] - m0 : 128,
+                                  u * c.hidden));
+      up(e->d_tok_mblk, tab.data(), sizeof(int4) * tab.size());
+    }
     up(e->d_dpre_off_last, e->off64.data(), sizeof(long long) * U);
     for (int l = 0; l < c.n_conv; ++l) {
       up(e->d_off[l], e->off[l].data(), sizeof(long long) * U);
@@ -639,27 +690,37 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
           const int Lx = e->L[l][u] + (fused && l != last ? 1 : 0);
           for (int m0 = 0; m0 < Lx; m0 += 128)
             dg.push_back(make_int4((int)(dro + m0), fused ? (int)(e->off[l - 1][u] / 2 + m0) : (int)(dro + m0),
-                                   Lx - m0 < 128 ? Lx - m0 : 128, u * c.conv_dim[l]));
+                                   Lx - m0 < 128 ? Lx - m0 : 128, e->train_feature ? u * c.conv_dim[l] : 0));
           zt.push_back(make_int4((int)dro, (int)(e->off[l - 1][u] / c.conv_stride[l]), e->L[l][u], 0));
         }
         up(e->d_dgrad_mblk[l], dg.data(), sizeof(int4) * dg.size());
-        up(e->d_ztab[l], zt.data(), sizeof(int4) * zt.size());
+        if (e->train_feature) up(e->d_ztab[l], zt.data(), sizeof(int4) * zt.size());
       }
       // gap rows between utterances must be exact zeros: they are reduced over by the weight-gradient GEMMs
       const long long rows = l == last ? e->R64 : e->rows_total[l];
       CUDA_TRY(cudaMemsetAsync(e->conv_out[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
       CUDA_TRY(cudaMemsetAsync(e->conv_dpre[l] - (size_t)128 * c.conv_dim[l], 0, sizeof(bf16) * (size_t)(rows + 256) * c.conv_dim[l], st));
       // GELU' of rows no forward tile covers is multiplied with zero gradients by the fused dgrad: must be finite
-      CUDA_TRY(cudaMemsetAsync(e->conv_pre[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
+      if (e->train_feature)
+        CUDA_TRY(cudaMemsetAsync(e->conv_pre[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
+      // conv_ln: rows of the pre-LayerNorm buffer that no conv tile writes are still streamed through the LayerNorm
+      // kernels' shared-memory ring (and skipped): keep them finite
+      if (e->conv_ln)
+        CUDA_TRY(cudaMemsetAsync(e->conv_z[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
     }
-    std::vector<int4> zt;
-    for (int u = 0; u < U; ++u) zt.push_back(make_int4((int)e->off64[u], (int)e->tok_off[u], e->T[u], 0));
-    up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size());
-    CUDA_TRY(cudaMemsetAsync(e->dh0_pad, 0, sizeof(bf16) * (size_t)(e->R64 + 128) * c.hidden, st));
+    if (e->train_feature) {
+      std::vector<int4> zt;
+      for (int u = 0; u < U; ++u) zt.push_back(make_int4((int)e->off64[u], (int)e->tok_off[u], e->T[u], 0));
+      up(e->d_ztab[c.n_conv], zt.data(), sizeof(int4) * zt.size());
+      CUDA_TRY(cudaMemsetAsync(e->dh0_pad, 0, sizeof(bf16) * (size_t)(e->R64 + 128) * c.hidden, st));
+    }
   }
   if (e->pseudo_label) up(e->d_alpha_off, e->alpha_off.data(), sizeof(long long) * U);
   CUDA_TRY(cudaMemcpyAsync(b.base, e->h_stage, e->tables_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(e->stage_ev, st));
+  if (e->conv_ln)                      // row -> utterance tables of the conv layers' row spaces, built on the device
+    for (int l = 0; l < c.n_conv - 1; ++l)
+      SUTA_TRY(fill_row_utt(e->d_conv_row_utt[l], e->rows_total[l] + 128, e->d_off[l], e->d_L[l], U, e->max_L[l], st));
   // zero rows of the padded positional-conv slabs never get written afterwards
   CUDA_TRY(cudaMemsetAsync(e->xg, 0, sizeof(bf16) * (size_t)(e->R + 8) * c.hidden, st));
   // conv buffers carry 128 slack rows read (never used) by partial implicit-GEMM tiles
@@ -775,6 +836,7 @@ extern "C" int suta_reset(suta_engine* e, void* stream) {
   e->opt_steps = 0;
   cudaStream_t st = S(stream);
   PROF("reset", params_reset(e->P, e->w.params0, e->Mom, e->Var, nullptr, e->n_params, e->U, st));
+  if (e->conv_ln) e->frontend_done = false;        // the CNN output depends on the (trainable) conv LayerNorms
   return refresh_shadows(e, S(stream));
 }
 
@@ -786,12 +848,60 @@ extern "C" int suta_params_written(suta_engine* e, void* stream) {
   return refresh_shadows(e, S(stream));
 }
 
+// LayerNorm feature extractor (feat_extract_norm == "layer", HF/modeling_wav2vec2.py:275-299): every layer is
+// Conv1d(+bias, frozen) -> LayerNorm(C) with the utterance's own gamma/beta (trainable, REF/main.py:81-87) -> GELU.  The
+// pre-LayerNorm value z_l and the row statistics are kept for the backward; runs on every forward (the LayerNorms move).
+static int frontend_layer_norm(suta_engine* e, cudaStream_t st) {
+  const suta_model_cfg& c = e->cfg;
+  UttParams prm{e->P, e->n_params};
+  const int last = c.n_conv - 1;
+  PROF_B("conv0_bias", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2,
+         conv0_bias(e->wav_norm, e->d_samp_off, e->d_L0, e->d_off0, e->w.conv0_w, e->w.conv_b[0], e->conv_z[0], e->U, c.conv_dim[0],
+                    c.conv_kernel[0], c.conv_stride[0], e->max_L0, st));
+  e->launches += 1;
+  for (int l = 0; l < c.n_conv; ++l) {
+    const int Cout = c.conv_dim[l];
+    long long rows_valid = 0;
+    for (int u = 0; u < e->U; ++u) rows_valid += e->L[l][u];
+    if (l >= 1) {
+      const int Cin = c.conv_dim[l - 1], k = c.conv_kernel[l], s = c.conv_stride[l];
+      GemmProblem p;
+      const long long rows_in = e->rows_total[l - 1] + 128;      // overlapping-row view, as in suta_frontend
+      p.a = {e->conv_out[l - 1], (rows_in - k) / s + 1, (long long)s * Cin};
+      p.b = {reinterpret_cast<const bf16*>(e->w.conv_w[l]), Cout, (long long)k * Cin};
+      p.M = (int)rows_valid; p.N = Cout; p.K = k * Cin;
+      p.mblk = e->d_mblk[l]; p.num_mblk = e->n_mblk[l];
+      p.epi.bias = e->w.conv_b[l];
+      p.epi.out_bf16 = e->conv_z[l]; p.epi.out_ld = Cout;
+      if (l < last) {            // 256-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
+        p.tiles_own_rows = 1;
+        p.out_rows = e->rows_total[l] + 128;
+        p.mpair = e->d_mpair[l]; p.num_mpair = e->n_mpair[l];
+      }
+      SUTA_TRY(gemm(e, p, st));
+    }
+    const long long rows = l == last ? e->M : e->rows_total[l];
+    PROF_B("ln_gelu_fwd C", (double)rows_valid * Cout * (2 + 2),
+           layernorm_forward(nullptr, e->conv_z[l], l == last ? e->d_row_utt : e->d_conv_row_utt[l], prm, (int)e->cln_g[l],
+                             (int)e->cln_b[l], nullptr, e->conv_out[l], e->conv_mean[l], e->conv_rstd[l], rows, Cout, 1e-5f, st,
+                             nullptr, LN_GELU));
+    e->launches += 1;
+  }
+  e->frontend_done = true;
+  return SUTA_OK;
+}
+
 extern "C" int suta_frontend(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   const suta_model_cfg& c = e->cfg;
   cudaStream_t st = S(stream);
   if (!e->audio_normalized && !e->moments_done)     // once per set_audio
     PROF("normalize", normalize_audio(e->wav, e->wav_norm, e->d_samp_off, e->d_n_samples, e->U, e->max_samples, e->stats, st));
+  if (e->conv_ln) {
+    if (!e->moments_done) e->launches += 2;
+    e->moments_done = true;
+    return frontend_layer_norm(e, st);
+  }
   if (!e->moments_done) {      // second moments of the conv0 input windows: depend on the audio only, once per batch
     PROF("conv0_moments", audio_conv0_moments(e->wav_norm, e->d_samp_off, e->d_L0, e->mom, c.conv_kernel[0], c.conv_stride[0], e->U,
                                               e->max_L0, st));
@@ -841,6 +951,59 @@ extern "C" int suta_frontend(suta_engine* e, void* stream) {
   return SUTA_OK;
 }
 
+// Pre-LN encoder (do_stable_layer_norm, HF/modeling_wav2vec2.py:638-645, :790): per layer
+//   r' = r + out_proj(attention(LN1(r))),   r'' = r' + FFN(LN2(r')),   logits = lm_head(LN_enc(r_final)).
+// Same buffers and the same in-place residual scheme as the post-LN path: lb[l].h1 = r entering layer l (LN1's input, kept
+// for the backward), lb[l].h2 = r'; each LayerNorm writes its normalised bf16 output for the GEMM AND seeds the next
+// residual buffer with its INPUT plus the bias of the GEMM that then accumulates onto it (LN_KEEP_INPUT).
+static int forward_stable(suta_engine* e, cudaStream_t st) {
+  const suta_model_cfg& c = e->cfg;
+  const int H = c.hidden, I = c.intermediate, V = c.vocab;
+  const long long M = e->M;
+  UttParams prm{e->P, e->n_params};
+  for (int l = 0; l < c.layers; ++l) {
+    const suta_layer_weights& w = e->w.layer[l];
+    LayerBufs& x = e->lb[l];
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
+                               x.mean1, x.rstd1, M, H, c.ln_eps, st, w.bo, LN_KEEP_INPUT));
+    {
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
+      p.epi.bias = w.bqkv; p.epi.out_bf16 = x.qkv; p.epi.out_ld = 3 * H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    PROF_F("attn_fwd", 4.0 * H * e->sumT2, attention_forward(x.qkv, x.attn, x.lse, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+    {
+      GemmProblem p = dense(x.attn, M, H, reinterpret_cast<const bf16*>(w.wo), H);
+      p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    float* next = l + 1 < c.layers ? e->lb[l + 1].h1 : e->hE;        // hE: the residual stream after the last layer
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], next, e->b16,
+                               x.mean2, x.rstd2, M, H, c.ln_eps, st, w.b2, LN_KEEP_INPUT));
+    {
+      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
+      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->gelu16; p.epi.out_ld = I;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    {
+      GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
+      p.epi.accumulate = 1; p.epi.out_f32 = next; p.epi.out_ld = H;
+      SUTA_TRY(gemm(e, p, st));
+    }
+    e->launches += 3;
+  }
+  // encoder.layer_norm AFTER the layers (HF:790): only the bf16 operand of lm_head is needed
+  PROF_B("ln_fwd", (double)M * H * (4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, nullptr, e->b16,
+                             e->enc_mean, e->enc_rstd, M, H, c.ln_eps, st));
+  e->launches += 1;
+  {
+    GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.lm_w), V);
+    p.epi.bias = e->w.lm_b; p.epi.out_f32 = e->logits; p.epi.out_ld = V;
+    SUTA_TRY(gemm(e, p, st));
+  }
+  return SUTA_OK;
+}
+
 extern "C" int suta_forward(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   if (!e->frontend_done) SUTA_TRY(suta_frontend(e, stream));
@@ -878,7 +1041,13 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
     p.epi.bias = e->w.pos_b; p.epi.out_f32 = e->cpos; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
-  PROF("posconv_combine", posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->hE, M, H, -(c.pos_k / 2), st));
+  // pre-LN ("stable") encoder: no LayerNorm here -- h0 + pos-conv IS the residual stream entering layer 0 (HF:760-762)
+  PROF("posconv_combine", posconv_combine(e->h0, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->stable ? e->lb[0].h1 : e->hE, M, H,
+                                          -(c.pos_k / 2), st));
+  if (e->stable) {
+    e->launches += 4;
+    return forward_stable(e, st);
+  }
   // encoder.layer_norm                                          HF/modeling_wav2vec2.py:692
   // The residual stream is updated IN PLACE: every LayerNorm writes its fp32 output straight into the buffer that holds
   // the next pre-LayerNorm sum (lb[l].h1 / h2, kept per layer for the backward), and the following GEMM accumulates
@@ -971,7 +1140,46 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     p.epi.out_f32 = da; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
-  for (int l = c.layers - 1; l >= 0; --l) {
+  if (e->stable) {
+    // Pre-LN encoder (HF:638-645, :790).  db carries d(residual stream); every branch gradient comes back through its
+    // LayerNorm's backward, which adds it onto db in place (dx_add = dx = db) and emits the bf16 operand of the next dgrad.
+    PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
+                                e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
+    for (int l = c.layers - 1; l >= 0; --l) {
+      const suta_layer_weights& w = e->w.layer[l];
+      LayerBufs& x = e->lb[l];
+      {  // output_dense dgrad, times GELU'(pre)
+        GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
+        p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      {  // intermediate_dense dgrad -> d(final_layer_norm output)
+        GemmProblem p = dense(e->dpre16, M, I, reinterpret_cast<const bf16*>(w.w1_t), H);
+        p.epi.out_f32 = da; p.epi.out_ld = H;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
+                                  e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n], db));
+      lnred.n += 1;
+      {  // out_proj dgrad
+        GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
+        p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      PROF_F("attn_bwd", 8.0 * H * e->sumT2, attention_backward(x.qkv, x.attn, e->dO16, x.lse, e->Dbuf, e->dqkv16, e->d_attn_tab, e->n_attn_blk, H, c.heads, M, st));
+      {  // q,k,v dgrad -> d(layer_norm output)
+        GemmProblem p = dense(e->dqkv16, M, 3 * H, reinterpret_cast<const bf16*>(w.wqkv_t), H);
+        p.epi.out_f32 = da; p.epi.out_ld = H;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 4 + 2), layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
+                                  e->G, db, l > 0 ? e->b16 : nullptr, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n], db));
+      lnred.n += 1;
+      e->launches += 5;
+    }
+  }
+  for (int l = e->stable ? -1 : c.layers - 1; l >= 0; --l) {
     const suta_layer_weights& w = e->w.layer[l];
     LayerBufs& x = e->lb[l];
     PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
@@ -1003,10 +1211,12 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     }
     e->launches += 5;             // 2 x LayerNorm backward, attention backward (3 launches)
   }
-  // encoder.layer_norm
-  PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4), layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
-                              e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
-  lnred.n += 1;
+  // encoder.layer_norm (post-LN: in front of the layers)
+  if (!e->stable) {
+    PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4), layernorm_backward(da, e->hE, nullptr, e->enc_mean, e->enc_rstd, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b,
+                                e->G, db, nullptr, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
+  }
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
   PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
   if (use_posconv_tc(e)) {
@@ -1033,6 +1243,65 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     SUTA_TRY(gemm(e, p, st));
   }
   e->launches += 4;
+  if (e->conv_ln) {
+    // ============ LayerNorm feature extractor: the trainable conv LayerNorms put the whole CNN on the backward path ==========
+    const int last = c.n_conv - 1;
+    // feature_projection.layer_norm with input gradient (its input, the last conv layer's output, is bf16)
+    PROF_B("ln_bwd C", (double)M * C * (4 + 2 + 4), layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
+                                (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
+    // last conv layer: GELU(LayerNorm(z)) backward, in place on the dense fp32 gradient, then into the 128-row-aligned slab
+    PROF_B("ln_gelu_bwd C", (double)M * C * (4 + 2 + 4), layernorm_gelu_backward(e->d_feat, nullptr, e->conv_z[last], e->conv_mean[last], e->conv_rstd[last], e->d_row_utt, prm,
+                                   (int)e->cln_g[last], (int)e->cln_b[last], e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U,
+                                   ln_slot(), st, &lnred.item[lnred.n]));
+    lnred.n += 1;
+    PROF("gelu_grad_pad", gelu_grad_to_padded(e->d_feat, nullptr, e->conv_dpre[last], e->d_row_utt, e->d_tok_off, e->d_dpre_off_last, M, C, st));
+    e->launches += 3;
+    for (int l = last; l >= 1; --l) {
+      const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], k = c.conv_kernel[l];
+      const long long dpre_rows = (l == last ? e->R64 : e->rows_total[l]) + 128;
+      long long rows_valid = 0, rows_below = 0;
+      for (int u = 0; u < e->U; ++u) { rows_valid += e->L[l][u]; rows_below += e->L[l - 1][u]; }
+      // d a_{l-1} = transposed conv of d z_l through the frozen, shared W_l, split by the parity of the input row exactly as
+      // under train_feature (conv_backward above) -- no GELU' factor here: the LayerNorm backward below applies it
+      GemmProblem p;
+      p.b = {reinterpret_cast<const bf16*>(e->w.conv_w[l]), Cout, (long long)k * Cin, 1, (long long)k * Cin};
+      p.M = (int)rows_valid; p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_dg_mblk[l];
+      p.tiles_own_rows = 1; p.out_rows = (e->rows_total[l - 1] + 128) / 2;
+      p.epi.out_ld = 2 * Cin;
+      if (k == 2) {
+        p.a = {e->conv_dpre[l], dpre_rows, Cout};
+        p.N = 2 * Cin; p.K = Cout;
+        p.epi.out_bf16 = e->conv_dpre[l - 1];
+        SUTA_TRY(gemm(e, p, st));
+      } else {
+        p.a = {e->conv_dpre[l] - Cout, dpre_rows + 1, Cout};
+        p.N = Cin; p.K = 2 * Cout; p.b_kwrap = Cout; p.b_tap_col[0] = 2 * Cin; p.b_tap_col[1] = 0;
+        p.epi.out_bf16 = e->conv_dpre[l - 1];
+        p.flops = 2.0 * (2 * Cout) * Cin * (double)rows_valid;
+        SUTA_TRY(gemm(e, p, st));
+        p.a = {e->conv_dpre[l], dpre_rows, Cout};
+        p.K = Cout; p.b_tap_col[0] = Cin; p.b_tap_col[1] = Cin;
+        p.epi.out_bf16 = e->conv_dpre[l - 1] + Cin;
+        p.flops = 2.0 * Cout * Cin * (double)rows_valid;
+        SUTA_TRY(gemm(e, p, st));
+      }
+      // layer l-1: d z = LayerNorm-backward(d a * GELU'), in place (valid rows only; the gaps stay zero); layer 0 has
+      // nothing below it that is trainable: parameter gradients only
+      PROF_B("ln_gelu_bwd C", (double)rows_below * Cin * (2 + 2 + (l > 1 ? 2 : 0)),
+             layernorm_gelu_backward(nullptr, e->conv_dpre[l - 1], e->conv_z[l - 1], e->conv_mean[l - 1], e->conv_rstd[l - 1],
+                                     e->d_conv_row_utt[l - 1], prm, (int)e->cln_g[l - 1], (int)e->cln_b[l - 1], e->G, nullptr,
+                                     l > 1 ? e->conv_dpre[l - 1] : nullptr, e->rows_total[l - 1], Cin, e->d_off[l - 1], e->d_L[l - 1], e->U,
+                                     ln_slot(), st, &lnred.item[lnred.n]));
+      lnred.item[lnred.n].tok_off = e->d_off[l - 1];
+      lnred.item[lnred.n].T = e->d_L[l - 1];
+      lnred.n += 1;
+      e->launches += 1;
+    }
+    PROF("ln_bwd_reduce", layernorm_backward_reduce(lnred, e->d_tok_off, e->d_T, e->U, e->G, e->n_params, st));
+    e->launches += 1;
+    return SUTA_OK;
+  }
   if (!e->train_feature) {
     // feature_projection.layer_norm: parameter gradients only (the CNN below it is frozen)
     SUTA_TRY(layernorm_backward(e->d_yfp, nullptr, e->conv_out[c.n_conv - 1], e->fp_mean, e->fp_rstd, e->d_row_utt, prm,
@@ -1154,6 +1423,7 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
     a.seg[a.n_seg++] = {e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->proj_shadow};
     e->frontend_done = false;    // the CNN output depends on the updated weights
   }
+  if (e->conv_ln) e->frontend_done = false;
   cudaStream_t st = S(stream);
   double shadow_elems = 0.0;
   for (int i = 0; i < a.n_seg; ++i) shadow_elems += (double)a.seg[i].size;

@@ -306,3 +306,74 @@ int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream) {
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
+
+// ---- LayerNorm feature extractor (feat_extract_norm == "layer", HF/modeling_wav2vec2.py:275-299) ----------------------
+// Layer 0 there is Conv1d(1 -> C, k, stride, bias) with NO statistics over time: z0[t, c] = b[c] + sum_j w[c][j] x[s t + j],
+// written channels-last in bf16; the per-frame LayerNorm(C) + GELU that follows is norm.cu's LN_GELU forward.
+namespace {
+
+constexpr int C0B_ROWS = 128;      // output frames per CTA
+
+__global__ void __launch_bounds__(256)
+conv0_bias_kernel(const float* __restrict__ x, const long long* __restrict__ samp_off, const int* __restrict__ L0,
+                  const long long* __restrict__ out_off, const float* __restrict__ w, const float* __restrict__ bias,
+                  bf16* __restrict__ out, int C, int k, int stride) {
+  extern __shared__ float wsm[];                 // [k][C] taps (transposed: a channel octet reads 8 consecutive floats), then [C] bias
+  const int u = blockIdx.y;
+  const int L = L0[u];
+  const int t0 = blockIdx.x * C0B_ROWS;
+  if (t0 >= L) return;
+  for (int i = threadIdx.x; i < C * k; i += blockDim.x) wsm[(i % k) * C + i / k] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[k * C + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int n_oct = C >> 3;
+  const int oct = threadIdx.x % n_oct, rsub = threadIdx.x / n_oct, rstep = blockDim.x / n_oct;
+  const float* xu = x + samp_off[u];
+  const int t1 = min(L, t0 + C0B_ROWS);
+  for (int t = t0 + rsub; t < t1; t += rstep) {
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = wsm[k * C + oct * 8 + c];
+    for (int j = 0; j < k; ++j) {
+      const float xv = __ldg(xu + (long long)t * stride + j);
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + j * C + oct * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + j * C + oct * 8 + 4);
+      acc[0] = fmaf(w0.x, xv, acc[0]); acc[1] = fmaf(w0.y, xv, acc[1]); acc[2] = fmaf(w0.z, xv, acc[2]); acc[3] = fmaf(w0.w, xv, acc[3]);
+      acc[4] = fmaf(w1.x, xv, acc[4]); acc[5] = fmaf(w1.y, xv, acc[5]); acc[6] = fmaf(w1.z, xv, acc[6]); acc[7] = fmaf(w1.w, xv, acc[7]);
+    }
+    *reinterpret_cast<uint4*>(out + (out_off[u] + t) * C + oct * 8) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// row -> utterance table of a conv layer's row space (gap rows keep the -1 of the caller's memset)
+__global__ void fill_row_utt_kernel(int* __restrict__ row_utt, const long long* __restrict__ off, const int* __restrict__ L) {
+  const int u = blockIdx.y;
+  const long long o = off[u];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L[u]; t += gridDim.x * blockDim.x) row_utt[o + t] = u;
+}
+
+}  // namespace
+
+int conv0_bias(const float* x, const long long* samp_off, const int* L0, const long long* out_off, const float* w,
+               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream) {
+  SUTA_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && k > 0 && k <= 32);
+  const size_t smem = sizeof(float) * ((size_t)k * C + C);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv0_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  conv0_bias_kernel<<<dim3((unsigned)ceil_div(max_L0, C0B_ROWS), (unsigned)n_utts), 256, smem, stream>>>(
+      x, samp_off, L0, out_off, w, bias, out, C, k, stride);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int fill_row_utt(int* row_utt, long long rows, const long long* off, const int* L, int n_utts, int max_L, cudaStream_t stream) {
+  CUDA_TRY(cudaMemsetAsync(row_utt, 0xFF, sizeof(int) * (size_t)rows, stream));
+  const int gx = max_L / 1024 + 1;
+  fill_row_utt_kernel<<<dim3((unsigned)(gx > 64 ? 64 : gx), (unsigned)n_utts), 256, 0, stream>>>(row_utt, off, L);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}

@@ -19,9 +19,13 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
 // y = LayerNorm(x) * gamma[u] + beta[u]; x is fp32 (x_f32) or bf16 (x_bf16), exactly one non-null.
 // y32_bias (optional, fp32 [N]) is added to the fp32 output only: that copy seeds the residual sum the next GEMM accumulates
 // into, so the GEMM's bias is folded in here.
+// mode: LN_PLAIN; LN_GELU (bf16 input): the outputs are GELU(LN(x)) -- conv layers of the LayerNorm feature extractor,
+// HF/modeling_wav2vec2.py:291-299; LN_KEEP_INPUT (fp32 input): y_f32 = x (+ y32_bias) instead of LN(x) -- the pre-LN encoder
+// keeps the residual stream beside the normalised branch, HF:638-645.  Rows with row_utt < 0 are skipped in every mode.
+enum { LN_PLAIN = 0, LN_GELU = 1, LN_KEEP_INPUT = 2 };
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
-                      cudaStream_t stream, const float* y32_bias = nullptr);
+                      cudaStream_t stream, const float* y32_bias = nullptr, int mode = LN_PLAIN);
 // dgamma/dbeta are WRITTEN into G (same layout as the parameter vector) by a fixed-order two-stage reduction through
 // `scratch` (layernorm_backward_scratch_floats(N, n_utts) floats) -- bit-reproducible; G and the dx outputs are optional.
 // tok_off / T: first packed row and row count of every utterance (the rows row_utt describes).
@@ -30,8 +34,10 @@ int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt
 struct LnReduceItem {
   const float* part;
   int g_off, b_off, N, rows_per_cta;
+  const long long* tok_off;    // optional: first row / row count of every utterance in THIS LayerNorm's row space
+  const int* T;                //   (conv-layer layouts); null = the arguments of layernorm_backward_reduce
 };
-constexpr int LN_REDUCE_MAX = 2 * 48 + 4;
+constexpr int LN_REDUCE_MAX = 2 * 48 + 4 + 8;
 struct LnReduceBatch {
   LnReduceItem item[LN_REDUCE_MAX];
   int n = 0;
@@ -39,7 +45,14 @@ struct LnReduceBatch {
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
                        long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
-                       cudaStream_t stream, LnReduceItem* defer = nullptr);
+                       cudaStream_t stream, LnReduceItem* defer = nullptr, const float* dx_add = nullptr);
+// dx_add (fp32 [M,N], fp32 x only; may alias dx_f32): added to dx -- the residual path of the pre-LN encoder.
+// Backward of GELU(LayerNorm(x)) (forward mode LN_GELU): dy is the gradient of the GELU output, fp32 or bf16 (exactly one
+// non-null); dx_bf16 may alias dy_bf16.
+int layernorm_gelu_backward(const float* dy_f32, const bf16* dy_bf16, const bf16* x_bf16, const float* mean, const float* rstd,
+                            const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
+                            long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
+                            cudaStream_t stream, LnReduceItem* defer = nullptr);
 int layernorm_backward_reduce(const LnReduceBatch& b, const long long* tok_off, const int* T, int n_utts, float* G,
                               long long pstride, cudaStream_t stream);
 long long layernorm_backward_scratch_floats(int N, int n_utts);
@@ -73,6 +86,13 @@ int conv0_groupnorm_gelu(const Conv0Args& a, cudaStream_t stream);
 // Sx[j] = sum_t x[s t + j] (k values) then R[j][j'] = sum_t x[s t + j] x[s t + j'] for j <= j', per utterance, in double
 int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0, double* mom, int k, int stride, int n_utts,
                         int max_L0, cudaStream_t stream);
+
+// LayerNorm feature extractor, layer 0 (HF/modeling_wav2vec2.py:281-292): z0 = Conv1d(1 -> C, k, stride) + bias, channels-last
+// bf16 at out_off[u] + t (bias may be null); w fp32 [C][k]
+int conv0_bias(const float* x, const long long* samp_off, const int* L0, const long long* out_off, const float* w,
+               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream);
+// row_utt[off[u] + t] = u for t < L[u], every other row of [0, rows) = -1
+int fill_row_utt(int* row_utt, long long rows, const long long* off, const int* L, int n_utts, int max_L, cudaStream_t stream);
 
 // ---- convbwd.cu (train_feature backward of the CNN front end) ---------------------------------
 int cast_params_bf16(const float* P, long long pstride, long long seg_off, long long size, int n_utts, bf16* out,

@@ -61,7 +61,12 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src,
 // One warp per row, 8 rows per tile; the tiles of a CTA's row range stream through a 3-deep shared-memory ring filled by
 // 1-D bulk copies issued two tiles ahead (the register-only version was latency-bound at 41 % of the HBM rate: its loads
 // could not start before the previous row's dependent chain -- statistics, per-utterance gamma/beta, stores -- had drained).
-template <int N, typename TIn>
+// MODE 0: y = LN(x) (the post-LN encoder, feature projection).  MODE 1: the bf16 output is GELU(LN(x)) -- the conv layers of
+// the LayerNorm feature extractor (HF/modeling_wav2vec2.py:291-299).  MODE 2: the fp32 output is x (+ y32_bias), NOT
+// LN(x): the pre-LN ("stable") encoder keeps the residual stream beside the normalised branch (HF:638-645), so the
+// LayerNorm seeds the next residual buffer with its own INPUT.  Rows with row_utt < 0 (gaps between utterances in the conv
+// layouts) are skipped.
+template <int N, typename TIn, int MODE>
 __global__ void __launch_bounds__(FWD_W * 32)
 ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const float* __restrict__ P, long long pstride,
               int g_off, int b_off, float* __restrict__ y32, bf16* __restrict__ y16, float* __restrict__ mean_out,
@@ -98,7 +103,7 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
     const long long row = cta_row0 + (long long)it * FWD_W + warp;
     const int u = u_next;
     u_next = row + FWD_W < M ? __ldg(row_utt + row + FWD_W) : 0;
-    if (u != u_cur && row < M) {                   // per-utterance gamma/beta stay in registers until the utterance changes
+    if (u != u_cur && u >= 0 && row < M) {         // per-utterance gamma/beta stay in registers until the utterance changes
       u_cur = u;
       const float* gam = P + (long long)u * pstride + g_off;
       const float* bet = P + (long long)u * pstride + b_off;
@@ -111,7 +116,7 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
         }
     }
     mbar_wait(&full[it % FWD_STAGES], (uint32_t)((it / FWD_STAGES) & 1));
-    if (row < M) {
+    if (row < M && u >= 0) {
       const TIn* xr = reinterpret_cast<const TIn*>(ring + (it % FWD_STAGES) * S::TILE_BYTES) + warp * N;
       float4 v[NV];
       float s = 0.f;
@@ -147,7 +152,9 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
           o.y = (v[i].y - mean) * rstd * g.y + b.y;
           o.z = (v[i].z - mean) * rstd * g.z + b.z;
           o.w = (v[i].w - mean) * rstd * g.w + b.w;
+          if (MODE == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
           if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+          if (MODE == 2) o = v[i];
           if (y32) {
             if (y32_bias) {   // the fp32 copy seeds the next residual sum: the bias of the GEMM that accumulates into it rides along
               const float4 nb = nbv[i];
@@ -172,10 +179,10 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
 constexpr int BWD_R = 4;          // rows per tile
 constexpr int BWD_STAGES = 3;     // tiles in flight per CTA (bulk-async copies into shared memory)
 
-template <int N, typename TIn>
+template <int N, typename TIn, typename TDy = float>
 struct BwdSmem {
   static constexpr int X_BYTES = BWD_R * N * (int)sizeof(TIn);
-  static constexpr int D_BYTES = BWD_R * N * 4;
+  static constexpr int D_BYTES = BWD_R * N * (int)sizeof(TDy);
   static constexpr int STAGE_BYTES = X_BYTES + D_BYTES;
   static constexpr int BYTES = BWD_STAGES * STAGE_BYTES + 64;
 };
@@ -183,22 +190,27 @@ struct BwdSmem {
 // The tiles (4 rows of x and of dy: 24 KB at N = 768) stream through a 3-deep shared-memory ring filled by 1-D bulk
 // copies that one thread issues two tiles ahead -- with register-only loads the kernel had ~45 KB in flight per SM and
 // reached 34 % of the HBM rate (profiles/r01e); the __syncthreads of the row reduction doubles as the "stage is free" signal.
-template <int N, typename TIn>
+// MODE 0: plain LayerNorm backward.  MODE 1: the forward applied GELU after the LayerNorm (conv layers of the LayerNorm
+// feature extractor): dy is the gradient of the GELU OUTPUT; y = xhat gamma + beta is recomputed and dy * GELU'(y) takes
+// dy's place (needs beta: b_off).  MODE 2: dx += dx_add (fp32, may alias dx32): the pre-LN encoder's residual path,
+// d(residual) = d(residual after the branch) + LayerNorm-backward(d branch input).  Rows with row_utt < 0 are skipped.
+// dx32 / dx16 may alias dy (rows are staged in shared memory before their outputs are written).
+template <int N, typename TIn, typename TDy, int MODE>
 __global__ void __launch_bounds__((N / 4 + 31) / 32 * 32)
-ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
+ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const int* __restrict__ row_utt, const float* __restrict__ P,
-              long long pstride, int g_off, float* __restrict__ part, float* __restrict__ dx32,
-              bf16* __restrict__ dx16, long long M, int rows_per_cta) {
+              long long pstride, int g_off, int b_off, float* __restrict__ part, float* dx32,
+              bf16* dx16, const float* dx_add, long long M, int rows_per_cta) {
   constexpr int NT = N / 4;                       // active threads
   constexpr int NW = (NT + 31) / 32;              // warps
-  using S = BwdSmem<N, TIn>;
+  using S = BwdSmem<N, TIn, TDy>;
   extern __shared__ __align__(128) uint8_t ring[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + BWD_STAGES * S::STAGE_BYTES);
   __shared__ float red[2][2][NW][BWD_R];          // [tile parity][c1 | c2][warp][row]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool act = tid < NT;
   const int col = 4 * tid;
-  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, g = ag;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, g = ag, bb = ag;
   int u_acc = -1;                                 // utterance the accumulators (and g) belong to
 
   auto flush = [&]() {
@@ -216,9 +228,9 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
     const int nr = (int)min((long long)BWD_R, M - r0);
     uint64_t* bar = &full[t % BWD_STAGES];
     const uint32_t dst = smem_u32(ring + (t % BWD_STAGES) * S::STAGE_BYTES);
-    mbar_expect_tx(bar, (uint32_t)(nr * N * (sizeof(TIn) + 4)));
+    mbar_expect_tx(bar, (uint32_t)(nr * N * (sizeof(TIn) + sizeof(TDy))));
     bulk_load_1d(dst, x + r0 * N, (uint32_t)(nr * N * sizeof(TIn)), bar);
-    bulk_load_1d(dst + S::X_BYTES, dy + r0 * N, (uint32_t)(nr * N * 4), bar);
+    bulk_load_1d(dst + S::X_BYTES, dy + r0 * N, (uint32_t)(nr * N * sizeof(TDy)), bar);
   };
   if (tid == 0) {
     for (int s2 = 0; s2 < BWD_STAGES; ++s2) mbar_init(&full[s2], 1);
@@ -233,8 +245,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
     for (int r = 0; r < BWD_R; ++r) {
       const bool ok = r0 + r < M;
       uu_n[r] = ok ? __ldg(row_utt + r0 + r) : -1;
-      mu_n[r] = ok ? __ldg(mean + r0 + r) : 0.f;
-      rs_n[r] = ok ? __ldg(rstd + r0 + r) : 0.f;
+      mu_n[r] = ok && uu_n[r] >= 0 ? __ldg(mean + r0 + r) : 0.f;     // gap rows: no statistics were written
+      rs_n[r] = ok && uu_n[r] >= 0 ? __ldg(rstd + r0 + r) : 0.f;
     }
   };
   load_scalars(cta_row0);
@@ -249,14 +261,22 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
 #pragma unroll
     for (int r = 0; r < BWD_R; ++r) { uu[r] = uu_n[r]; mu[r] = mu_n[r]; rs[r] = rs_n[r]; }
     load_scalars(row0 + BWD_R);                    // next tile's row constants: their L2 latency hides behind this tile
+    float4 av[MODE == 2 ? BWD_R : 1];
+    if (MODE == 2) {                               // residual-path gradient: fetched now, consumed after the reductions
+#pragma unroll
+      for (int r = 0; r < BWD_R; ++r) {
+        av[MODE == 2 ? r : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M && act && uu[r] >= 0) av[MODE == 2 ? r : 0] = *reinterpret_cast<const float4*>(dx_add + (row0 + r) * N + col);
+      }
+    }
     mbar_wait(&full[it % BWD_STAGES], (uint32_t)((it / BWD_STAGES) & 1));
     const uint8_t* st = ring + (it % BWD_STAGES) * S::STAGE_BYTES;
 #pragma unroll
     for (int r = 0; r < BWD_R; ++r) {
       xv[r] = dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < M && act) {
+      if (row0 + r < M && act && uu[r] >= 0) {
         xv[r] = Loader<TIn>::ld4(reinterpret_cast<const TIn*>(st) + r * N + col);
-        dv[r] = *reinterpret_cast<const float4*>(st + S::X_BYTES + (r * N + col) * 4);
+        dv[r] = Loader<TDy>::ld4(reinterpret_cast<const TDy*>(st + S::X_BYTES) + r * N + col);
       }
     }
     float p1[BWD_R], p2[BWD_R];
@@ -266,9 +286,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
         flush();
         u_acc = uu[r];
         if (act) g = __ldg(reinterpret_cast<const float4*>(P + (long long)u_acc * pstride + g_off + col));
+        if (act && MODE == 1) bb = __ldg(reinterpret_cast<const float4*>(P + (long long)u_acc * pstride + b_off + col));
       }
-      const float4 d = dv[r];
+      float4 d = dv[r];
       float4 xh = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);
+      if (MODE == 1) {                            // through the GELU that followed the LayerNorm
+        d.x *= gelu_erf_grad(fmaf(xh.x, g.x, bb.x)); d.y *= gelu_erf_grad(fmaf(xh.y, g.y, bb.y));
+        d.z *= gelu_erf_grad(fmaf(xh.z, g.z, bb.z)); d.w *= gelu_erf_grad(fmaf(xh.w, g.w, bb.w));
+      }
       ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
       ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
       const float4 dxh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -294,7 +319,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
 #pragma unroll
       for (int r = 0; r < BWD_R; ++r) {
         const long long row = row0 + r;
-        if (row >= M || !act) continue;
+        if (row >= M || !act || uu[r] < 0) continue;
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -308,6 +333,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x, const flo
         o.y = rs[r] * (dv[r].y - c1 - xv[r].y * c2);
         o.z = rs[r] * (dv[r].z - c1 - xv[r].z * c2);
         o.w = rs[r] * (dv[r].w - c1 - xv[r].w * c2);
+        if (MODE == 2) { const float4 a = av[MODE == 2 ? r : 0]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         if (dx32) *reinterpret_cast<float4*>(dx32 + row * N + col) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
@@ -339,6 +365,7 @@ ln_bwd_reduce_many_kernel(const __grid_constant__ LnReduceBatch b, const long lo
                           const int* __restrict__ T, float* __restrict__ G, long long pstride) {
   const LnReduceItem it = b.item[blockIdx.y];
   const int u = blockIdx.x;
+  if (it.tok_off) { tok_off = it.tok_off; T = it.T; }      // a LayerNorm over rows of its own (conv layer layouts)
   const long long r0 = tok_off[u], r1 = r0 + T[u] - 1;
   const int b0 = (int)(r0 / it.rows_per_cta), b1 = (int)(r1 / it.rows_per_cta);
   for (int c = threadIdx.x; c < 2 * it.N; c += blockDim.x) {
@@ -348,20 +375,20 @@ ln_bwd_reduce_many_kernel(const __grid_constant__ LnReduceBatch b, const long lo
   }
 }
 
-template <int N, typename TIn>
+template <int N, typename TIn, int MODE>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
                float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
   using S = FwdSmem<N, TIn>;
   static int resident = 0;                         // CTAs of this instantiation that fit on one SM
   if (!resident) {
-    CUDA_TRY(cudaFuncSetAttribute(ln_fwd_kernel<N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_fwd_kernel<N, TIn>, FWD_W * 32, S::BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(ln_fwd_kernel<N, TIn, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_fwd_kernel<N, TIn, MODE>, FWD_W * 32, S::BYTES));
     resident = std::max(1, std::min(8, resident));
   }
   // one wave: at most (resident CTAs per SM) x (SMs) CTAs, rows per CTA a multiple of the tile height
   long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
   rows = std::max<long long>(FWD_W, (rows + FWD_W - 1) / FWD_W * FWD_W);
-  ln_fwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), FWD_W * 32, S::BYTES, stream>>>(
+  ln_fwd_kernel<N, TIn, MODE><<<(unsigned)((M + rows - 1) / rows), FWD_W * 32, S::BYTES, stream>>>(
       x, row_utt, prm.P, prm.stride, g_off, b_off, y32, y16, mean, rstd, M, eps, y32_bias, (int)rows);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
@@ -373,24 +400,24 @@ long long bwd_rows_per_cta(long long M, int resident) {
   return std::max<long long>(16, (rows + BWD_R - 1) / BWD_R * BWD_R);
 }
 
-template <int N, typename TIn>
-int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
-               int g_off, int b_off, float* G, float* dx32, bf16* dx16, long long M, const long long* tok_off, const int* T,
-               int n_utts, float* scratch, cudaStream_t stream, LnReduceItem* defer) {
+template <int N, typename TIn, typename TDy, int MODE>
+int launch_bwd(const TDy* dy, const TIn* x, const float* mean, const float* rstd, const int* row_utt, UttParams prm,
+               int g_off, int b_off, float* G, float* dx32, bf16* dx16, const float* dx_add, long long M,
+               const long long* tok_off, const int* T, int n_utts, float* scratch, cudaStream_t stream, LnReduceItem* defer) {
   constexpr int threads = (N / 4 + 31) / 32 * 32;
-  using S = BwdSmem<N, TIn>;
+  using S = BwdSmem<N, TIn, TDy>;
   static int resident = 0;                         // CTAs of this instantiation that fit on one SM
   if (!resident) {
-    CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_bwd_kernel<N, TIn>, threads, S::BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<N, TIn, TDy, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_bwd_kernel<N, TIn, TDy, MODE>, threads, S::BYTES));
     resident = std::max(1, std::min(8, resident));
   }
   const long long rows = bwd_rows_per_cta(M, resident);
-  ln_bwd_kernel<N, TIn><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
-      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, G ? scratch : nullptr, dx32, dx16, M, (int)rows);
+  ln_bwd_kernel<N, TIn, TDy, MODE><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
+      dy, x, mean, rstd, row_utt, prm.P, prm.stride, g_off, b_off, G ? scratch : nullptr, dx32, dx16, dx_add, M, (int)rows);
   CUDA_TRY(cudaGetLastError());
   if (G && defer) {
-    *defer = LnReduceItem{scratch, g_off, b_off, N, (int)rows};
+    *defer = LnReduceItem{scratch, g_off, b_off, N, (int)rows, nullptr, nullptr};
   } else if (G) {
     ln_bwd_reduce_kernel<<<n_utts, 256, 0, stream>>>(scratch, tok_off, T, (int)rows, N, G, prm.stride, g_off, b_off);
     CUDA_TRY(cudaGetLastError());
@@ -415,14 +442,19 @@ int launch_bwd(const float* dy, const TIn* x, const float* mean, const float* rs
 
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,
-                      cudaStream_t stream, const float* y32_bias) {
+                      cudaStream_t stream, const float* y32_bias, int mode) {
   SUTA_CHECK_ARG((x_f32 != nullptr) != (x_bf16 != nullptr));
   SUTA_CHECK_ARG(g_off % 4 == 0 && b_off % 4 == 0 && prm.stride % 4 == 0);
+  SUTA_CHECK_ARG(mode == LN_PLAIN || (mode == LN_GELU && x_bf16) || (mode == LN_KEEP_INPUT && x_f32));
   if (M <= 0) return SUTA_OK;
-  if (x_f32) {
-    LN_DISPATCH(N, return (launch_fwd<NN, float>(x_f32, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
+  if (mode == LN_GELU) {
+    LN_DISPATCH(N, return (launch_fwd<NN, bf16, 1>(x_bf16, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
+  } else if (mode == LN_KEEP_INPUT) {
+    LN_DISPATCH(N, return (launch_fwd<NN, float, 2>(x_f32, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
+  } else if (x_f32) {
+    LN_DISPATCH(N, return (launch_fwd<NN, float, 0>(x_f32, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
   } else {
-    LN_DISPATCH(N, return (launch_fwd<NN, bf16>(x_bf16, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
+    LN_DISPATCH(N, return (launch_fwd<NN, bf16, 0>(x_bf16, row_utt, prm, g_off, b_off, y_f32, y_bf16, mean, rstd, M, eps, y32_bias, stream)));
   }
   return SUTA_OK;
 }
@@ -432,14 +464,33 @@ long long layernorm_backward_scratch_floats(int N, int n_utts) { return ((long l
 int layernorm_backward(const float* dy, const float* x_f32, const bf16* x_bf16, const float* mean, const float* rstd,
                        const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
                        long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
-                       cudaStream_t stream, LnReduceItem* defer) {
+                       cudaStream_t stream, LnReduceItem* defer, const float* dx_add) {
   SUTA_CHECK_ARG((x_f32 != nullptr) != (x_bf16 != nullptr));
   SUTA_CHECK_ARG(!G || (tok_off && T && n_utts > 0 && scratch));
+  SUTA_CHECK_ARG(!dx_add || x_f32);
   if (M <= 0) return SUTA_OK;
-  if (x_f32) {
-    LN_DISPATCH(N, return (launch_bwd<NN, float>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream, defer)));
+  if (dx_add) {
+    LN_DISPATCH(N, return (launch_bwd<NN, float, float, 2>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, dx_add, M, tok_off, T, n_utts, scratch, stream, defer)));
+  } else if (x_f32) {
+    LN_DISPATCH(N, return (launch_bwd<NN, float, float, 0>(dy, x_f32, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, nullptr, M, tok_off, T, n_utts, scratch, stream, defer)));
   } else {
-    LN_DISPATCH(N, return (launch_bwd<NN, bf16>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, M, tok_off, T, n_utts, scratch, stream, defer)));
+    LN_DISPATCH(N, return (launch_bwd<NN, bf16, float, 0>(dy, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, nullptr, M, tok_off, T, n_utts, scratch, stream, defer)));
+  }
+  return SUTA_OK;
+}
+
+// backward of GELU(LayerNorm(x)) with a bf16 input x: dy (gradient of the GELU output) is fp32 or bf16, exactly one non-null
+int layernorm_gelu_backward(const float* dy_f32, const bf16* dy_bf16, const bf16* x_bf16, const float* mean, const float* rstd,
+                            const int* row_utt, UttParams prm, int g_off, int b_off, float* G, float* dx_f32, bf16* dx_bf16,
+                            long long M, int N, const long long* tok_off, const int* T, int n_utts, float* scratch,
+                            cudaStream_t stream, LnReduceItem* defer) {
+  SUTA_CHECK_ARG((dy_f32 != nullptr) != (dy_bf16 != nullptr) && x_bf16);
+  SUTA_CHECK_ARG(!G || (tok_off && T && n_utts > 0 && scratch));
+  if (M <= 0) return SUTA_OK;
+  if (dy_f32) {
+    LN_DISPATCH(N, return (launch_bwd<NN, bf16, float, 1>(dy_f32, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, nullptr, M, tok_off, T, n_utts, scratch, stream, defer)));
+  } else {
+    LN_DISPATCH(N, return (launch_bwd<NN, bf16, bf16, 1>(dy_bf16, x_bf16, mean, rstd, row_utt, prm, g_off, b_off, G, dx_f32, dx_bf16, nullptr, M, tok_off, T, n_utts, scratch, stream, defer)));
   }
   return SUTA_OK;
 }

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SUTA_B200_LIB") or os.path.join(os.path.dirname(_HERE
 
 MAX_LAYERS = 48
 MAX_CONV = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -21,7 +21,8 @@ class ModelCfg(C.Structure):
     _fields_ = [("hidden", c_int32), ("layers", c_int32), ("heads", c_int32), ("intermediate", c_int32),
                 ("vocab", c_int32), ("n_conv", c_int32), ("conv_dim", c_int32 * MAX_CONV),
                 ("conv_kernel", c_int32 * MAX_CONV), ("conv_stride", c_int32 * MAX_CONV),
-                ("pos_k", c_int32), ("pos_groups", c_int32), ("ln_eps", c_float)]
+                ("pos_k", c_int32), ("pos_groups", c_int32), ("ln_eps", c_float),
+                ("feat_norm_layer", c_int32), ("stable_layer_norm", c_int32)]
 
 
 class LayerWeights(C.Structure):
@@ -30,7 +31,7 @@ class LayerWeights(C.Structure):
 
 
 class Weights(C.Structure):
-    _fields_ = [("conv0_w", c_void_p), ("gn_g", c_void_p), ("gn_b", c_void_p),
+    _fields_ = [("conv0_w", c_void_p), ("gn_g", c_void_p), ("gn_b", c_void_p), ("conv_b", c_void_p * MAX_CONV),
                 ("conv_w", c_void_p * MAX_CONV), ("conv_w_t", c_void_p * MAX_CONV),
                 ("proj_w", c_void_p), ("proj_w_t", c_void_p), ("proj_b", c_void_p),
                 ("pos_w", c_void_p), ("pos_w_t", c_void_p), ("pos_b", c_void_p),

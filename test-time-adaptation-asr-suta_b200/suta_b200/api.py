@@ -60,8 +60,10 @@ def _module_order(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
     mods = [("wav2vec2.feature_extractor", "container", []), ("wav2vec2.feature_extractor.conv_layers", "container", [])]
     for i in range(len(cfg.conv_dim)):
         b = f"wav2vec2.feature_extractor.conv_layers.{i}"
-        mods += [(b, "container", []), (b + ".conv", "conv", ["weight"])]
-        if i == 0:
+        mods += [(b, "container", []), (b + ".conv", "conv", ["weight", "bias"] if cfg.conv_bias else ["weight"])]
+        if cfg.feat_extract_norm == "layer":       # every conv layer carries a LayerNorm(C) (HF/modeling_wav2vec2.py:288)
+            mods.append((b + ".layer_norm", "layernorm", ["weight", "bias"]))
+        elif i == 0:
             mods.append((b + ".layer_norm", "groupnorm", ["weight", "bias"]))
     mods += [("wav2vec2.feature_projection", "container", []),
              ("wav2vec2.feature_projection.layer_norm", "layernorm", ["weight", "bias"]),

@@ -20,7 +20,8 @@ CHECKPOINT_STEPS = (1, 3, 5, 10, 20, 40)       # REF/main.py:350-398
 
 _MODULE_NAMES = {0: "wav2vec2.feature_projection.layer_norm", 1: "wav2vec2.encoder.layer_norm",
                  2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm",
-                 4: "wav2vec2.feature_extractor.conv_layers.{i}", 5: "wav2vec2.feature_projection.projection"}
+                 4: "wav2vec2.feature_extractor.conv_layers.{i}", 5: "wav2vec2.feature_projection.projection",
+                 6: "wav2vec2.feature_extractor.conv_layers.{i}.layer_norm"}
 _KIND_LEAF = {0: "weight", 1: "bias", 2: "layer_norm.weight", 3: "layer_norm.bias", 4: "conv.weight", 5: "weight", 6: "bias"}
 
 
@@ -73,6 +74,10 @@ class SutaEngine:
         for i in range(cc.n_conv):
             cc.conv_dim[i], cc.conv_kernel[i], cc.conv_stride[i] = c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i]
         cc.pos_k, cc.pos_groups, cc.ln_eps = c.num_conv_pos_embeddings, c.num_conv_pos_embedding_groups, c.layer_norm_eps
+        cc.feat_norm_layer, cc.stable_layer_norm = int(c.feat_extract_norm == "layer"), int(c.do_stable_layer_norm)
+        if self.train_feature and c.feat_extract_norm == "layer":
+            raise NotImplementedError("--train_feature is not built for the LayerNorm feature extractor (lv60 family); "
+                                      "LayerNorm-only adaptation (which trains its conv LayerNorms) is")
         h = C.c_void_p()
         self.pseudo_label = bool(pseudo_label)         # SDPL: reserves the CTC lattice scratch in every batch workspace
         check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature) | (2 if self.pseudo_label else 0), C.byref(h)))
@@ -112,8 +117,13 @@ class SutaEngine:
 
         fe = "wav2vec2.feature_extractor.conv_layers."
         w.conv0_w = p(self._dev(g(fe + "0.conv.weight").reshape(c.conv_dim[0], c.conv_kernel[0]), f32))
-        w.gn_g = p(self._dev(g(fe + "0.layer_norm.weight"), f32))
-        w.gn_b = p(self._dev(g(fe + "0.layer_norm.bias"), f32))
+        if c.feat_extract_norm == "layer":     # conv LayerNorms are trainable segments; the conv biases are frozen
+            for l in range(len(c.conv_dim)):
+                if c.conv_bias:
+                    w.conv_b[l] = p(self._dev(g(fe + f"{l}.conv.bias"), f32))
+        else:
+            w.gn_g = p(self._dev(g(fe + "0.layer_norm.weight"), f32))
+            w.gn_b = p(self._dev(g(fe + "0.layer_norm.bias"), f32))
         for l in range(1, len(c.conv_dim)):
             cw = g(fe + f"{l}.conv.weight")                       # [Cout, Cin, k] -> [Cout, (k, Cin)]
             w.conv_w[l] = p(self._dev(cw.permute(0, 2, 1).reshape(cw.shape[0], -1), bf))

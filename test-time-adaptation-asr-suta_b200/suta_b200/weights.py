@@ -21,12 +21,15 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_bias: float = 0.0, 
     cin = 1
     for i, (c, k) in enumerate(zip(cfg.conv_dim, cfg.conv_kernel)):
         sd[f"wav2vec2.feature_extractor.conv_layers.{i}.conv.weight"] = rn((c, cin, k), math.sqrt(2.0 / (cin * k)))
+        if cfg.conv_bias:
+            sd[f"wav2vec2.feature_extractor.conv_layers.{i}.conv.bias"] = ru((c,), math.sqrt(1.0 / (cin * k)))
         cin = c
 
     def ln(prefix, n):
         sd[prefix + ".weight"], sd[prefix + ".bias"] = torch.ones(n), torch.zeros(n)
 
-    ln("wav2vec2.feature_extractor.conv_layers.0.layer_norm", cfg.conv_dim[0])
+    for i in range(len(cfg.conv_dim) if cfg.feat_extract_norm == "layer" else 1):      # LayerNorm per layer / one GroupNorm
+        ln(f"wav2vec2.feature_extractor.conv_layers.{i}.layer_norm", cfg.conv_dim[i])
     ln("wav2vec2.feature_projection.layer_norm", cfg.conv_dim[-1])
     kk = math.sqrt(1.0 / cfg.conv_dim[-1])
     sd["wav2vec2.feature_projection.projection.weight"] = ru((H, cfg.conv_dim[-1]), kk)

@@ -139,12 +139,12 @@ def compare(res_u, ref_logits, ref_losses, ref_params, sd, ref_ids=None, ocfg=No
     return m
 
 
-def check_tiny_batch(steps=10):
-    ocfg, _ = _cfgs("tiny")
+def check_tiny_batch(steps=10, cfg_name="tiny"):
+    ocfg, _ = _cfgs(cfg_name)
     sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
     lens, seeds = [12000, 9000, 2000, 16001], [11, 12, 13, 14]
     wavs = [O.synth_audio(n, s) for n, s in zip(lens, seeds)]
-    res = run_engine("tiny", sd, wavs, steps, keep_grads=True)
+    res = run_engine(cfg_name, sd, wavs, steps, keep_grads=True)
     out = {}
     for u, w in enumerate(wavs):
         ora = O.adapt_utterance(ocfg, sd, O.normalize_audio(w), steps=steps)
@@ -199,9 +199,10 @@ def check_tiny_feat_batch(steps=5):
     return out
 
 
-def check_tiny_stages():
+def check_tiny_stages(cfg_name="tiny"):
     """Intermediate activations of the forward vs the oracle's taps (localises a broken stage)."""
-    ocfg, mcfg = _cfgs("tiny")
+    ocfg, mcfg = _cfgs(cfg_name)
+    stable = ocfg.do_stable_layer_norm
     sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
     wavs = [O.synth_audio(9000, 21), O.synth_audio(5000, 22)]
     eng = SutaEngine(mcfg, sd)
@@ -219,12 +220,37 @@ def check_tiny_stages():
         out[f"u{u}_wav_norm"] = _rel(eng.debug_buffer("wav_norm")[0, so:so + len(w)].cpu().numpy(), x)
         out[f"u{u}_feat"] = _rel(eng.debug_buffer("feat")[o:o + T].float().cpu().numpy(), taps["conv6"][0].t().numpy())
         out[f"u{u}_h0"] = _rel(eng.debug_buffer("h0")[o:o + T].cpu().numpy(), taps["proj"][0].numpy())
-        out[f"u{u}_hE"] = _rel(eng.debug_buffer("hE")[o:o + T].cpu().numpy(), taps["pos"][0].numpy())
-        out[f"u{u}_h2_0"] = _rel(eng.debug_buffer("h2_0")[o:o + T].cpu().numpy(), taps["pre_ln2_0"][0].numpy())
-        out[f"u{u}_x_final"] = _rel(eng.debug_buffer("x_final")[o:o + T].cpu().numpy(), taps[f"layer{ocfg.num_hidden_layers - 1}"][0].numpy())
+        for l in (0, 3, 6):
+            out[f"u{u}_conv{l}"] = _rel(_conv_rows(eng, l, u).float().cpu().numpy(), taps[f"conv{l}"][0].t().numpy())
+        if stable:      # pre-LN: h0 + pos-conv enters layer 0 directly (buffer h1_0); "hE" holds the stream after the last layer
+            out[f"u{u}_h1_0"] = _rel(eng.debug_buffer("h1_0")[o:o + T].cpu().numpy(), taps["pos"][0].numpy())
+            out[f"u{u}_h2_0"] = _rel(eng.debug_buffer("h2_0")[o:o + T].cpu().numpy(), taps["pre_ln2_0"][0].numpy())
+            out[f"u{u}_hE"] = _rel(eng.debug_buffer("hE")[o:o + T].cpu().numpy(), taps[f"layer{ocfg.num_hidden_layers - 1}"][0].numpy())
+        else:
+            out[f"u{u}_hE"] = _rel(eng.debug_buffer("hE")[o:o + T].cpu().numpy(), taps["pos"][0].numpy())
+            out[f"u{u}_h2_0"] = _rel(eng.debug_buffer("h2_0")[o:o + T].cpu().numpy(), taps["pre_ln2_0"][0].numpy())
+            out[f"u{u}_x_final"] = _rel(eng.debug_buffer("x_final")[o:o + T].cpu().numpy(), taps[f"layer{ocfg.num_hidden_layers - 1}"][0].numpy())
         out[f"u{u}_logits"] = _rel(eng.utt_logits(u).cpu().numpy(), lg[0].numpy())
     eng.close()
     return out
+
+
+def _conv_rows(eng, l, u):
+    """Valid rows of utterance u in conv layer l's output (the engine's row offsets follow csrc/engine.cu::plan_batch)."""
+    c = eng.cfg
+    Ls = []
+    for n in eng.lengths:
+        L, per = int(n), []
+        for k, s in zip(c.conv_kernel, c.conv_stride):
+            L = (L - k) // s + 1
+            per.append(L)
+        Ls.append(per)
+    last = l == len(c.conv_dim) - 1
+    cnn_bwd = eng.train_feature or c.feat_extract_norm == "layer"
+    off = 0
+    for v in range(u):
+        off += Ls[v][l] if last else (((Ls[v][l] + 1 + 255) & ~255) if cnn_bwd else ((Ls[v][l] + 7) & ~7))
+    return eng.debug_buffer(f"conv{l}")[off:off + Ls[u][l]]
 
 
 def check_golden_sdpl(case):

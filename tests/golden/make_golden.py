@@ -59,6 +59,11 @@ CASES = {
     "tiny_em_only": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, em_coef=1.0, not_blank=False),
     "tiny_mcc_plain": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, em_coef=0.0, reweight=False),
     "tiny_temp1_allframes": _case("tiny", 12000, 11, 3, 0.5, 0.1, 5, temp=1.0, not_blank=False, reweight=False, em_coef=0.9),
+    # the "lv60" family (REF/main_SDPL.py:238-241): LayerNorm feature extractor with conv bias + pre-LN encoder; the
+    # LayerNorm-only set then holds the 7 conv LayerNorms, so the backward spans the CNN (HF:275-299,612-655,730-803)
+    "tiny_lv60_ln": _case("tiny_lv60", 12000, 11, 3, 0.5, 0.1, 10),
+    "tiny_lv60_short": _case("tiny_lv60", 2000, 13, 5, 0.35, 0.1, 5),
+    "large_lv60_2s": _case("large_lv60", 32000, 41, 0, 2.5, 0.0, 3),
 }
 BIG = 1 << 16      # tensors above this many elements are stored as (checksum, head) only
 

@@ -36,9 +36,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_structs_match_header_sizes():
     from suta_b200 import _lib
-    assert ctypes.sizeof(_lib.ModelCfg) == 4 * (6 + 3 * 8 + 2) + 4
+    assert ctypes.sizeof(_lib.ModelCfg) == 4 * (6 + 3 * 8 + 2) + 4 + 2 * 4
     assert ctypes.sizeof(_lib.LayerWeights) == 12 * 8
-    assert ctypes.sizeof(_lib.Weights) == 8 * (3 + 8 + 8 + 3 + 3 + 3 + 2) + 48 * 12 * 8
+    assert ctypes.sizeof(_lib.Weights) == 8 * (3 + 8 + 8 + 8 + 3 + 3 + 3 + 2) + 48 * 12 * 8
     assert ctypes.sizeof(_lib.Hyper) == 48
     assert ctypes.sizeof(_lib.ParamSeg) == 32
 

@@ -95,6 +95,28 @@ def test_long_utterance_and_large_model_against_reference_golden_vectors(E, case
     assert m["argmax_agree0"] > 0.95
 
 
+@pytest.mark.parametrize("case", ["tiny_lv60_ln", "tiny_lv60_short", "large_lv60_2s"])
+def test_lv60_family_against_reference_golden_vectors(E, case):
+    """The stable-LayerNorm / conv-LayerNorm checkpoints the authors list (REF/main_SDPL.py:238-241; HF/modeling_wav2vec2.py
+    :275-299,612-655,730-803): Conv1d(+bias) -> LayerNorm(C) -> GELU in every conv layer, pre-LN encoder.  The LayerNorm-only
+    set then contains the 7 conv LayerNorms (114 tensors on large-lv60), so the backward runs through the whole CNN."""
+    m = E.check_golden(case)
+    print(case, m)
+    _assert_parity(m)
+    assert m["argmax_agree0"] > 0.95
+
+
+def test_lv60_batched_adaptation_matches_per_utterance_oracle(E):
+    for name, m in E.check_tiny_batch(cfg_name="tiny_lv60").items():
+        print(name, m)
+        _assert_parity(m)
+
+
+def test_lv60_forward_stages_vs_oracle(E):
+    for name, rel in E.check_tiny_stages(cfg_name="tiny_lv60").items():
+        assert rel < 0.03, (name, rel)
+
+
 def test_train_feature_batched_vs_oracle(E):
     """--train_feature: per-utterance CNN/projection weights and the reference's duplicate-parameter Adam semantics."""
     for name, m in E.check_tiny_feat_batch().items():

@@ -93,7 +93,7 @@ def test_collect_params_names_and_duplicates_match_reference_walk(capsys):
 def test_load_checkpoint_reads_a_local_hf_directory(tmp_path):
     """`--asr <local dir>` -- a Wav2Vec2ForCTC checkpoint written by save_pretrained (safetensors, new
     weight-norm parametrisation) and one in the legacy layout (pytorch_model.bin, weight_g / weight_v) both load into
-    the names the engine packs, and unsupported architectures (stable LayerNorm / conv LayerNorm) are refused."""
+    the names the engine packs; so does a checkpoint of the lv60 family (stable LayerNorm / conv LayerNorm / conv bias)."""
     import pytest
     import torch
     from transformers import Wav2Vec2Config, Wav2Vec2ForCTC
@@ -122,8 +122,18 @@ def test_load_checkpoint_reads_a_local_hf_directory(tmp_path):
     cfg2, sd2 = load_checkpoint(str(d2))
     assert cfg2 == cfg and torch.equal(sd2["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0"],
                                        ref["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0"])
-    # the lv60 family is refused loudly, not mis-computed
+    # the lv60 family (REF/main_SDPL.py:238-241): conv LayerNorms and conv biases come along
+    lcfg = O.W2V2Config.tiny_lv60()
+    m3 = Wav2Vec2ForCTC(lcfg.to_hf()).eval()
+    m3.load_state_dict(O.init_weights(lcfg, 3, blank_bias=0.5, ln_jitter=0.1), strict=False)
     d3 = tmp_path / "lv60"
-    Wav2Vec2Config(feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True).save_pretrained(str(d3))
+    m3.save_pretrained(str(d3))
+    cfg3, sd3 = load_checkpoint(str(d3))
+    assert cfg3 == ModelConfig.tiny_lv60()
+    for k in ("wav2vec2.feature_extractor.conv_layers.5.layer_norm.weight", "wav2vec2.feature_extractor.conv_layers.0.conv.bias"):
+        assert torch.equal(sd3[k], m3.state_dict()[k]), k
+    # a combination no checkpoint uses is refused loudly, not mis-computed
+    d4 = tmp_path / "odd"
+    Wav2Vec2Config(feat_extract_norm="group", conv_bias=True).save_pretrained(str(d4))
     with pytest.raises(NotImplementedError):
-        load_checkpoint(str(d3))
+        load_checkpoint(str(d4))

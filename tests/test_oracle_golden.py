@@ -10,8 +10,9 @@ from oracle import suta_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TINY = ["tiny_ln", "tiny_feat", "tiny_short", "tiny_feat_noise20", "tiny_sgd", "tiny_feat_sgd", "tiny_adam_beta", "tiny_steplr",
-        "tiny_bias_only", "tiny_div", "tiny_em_only", "tiny_mcc_plain", "tiny_temp1_allframes"]
-CASES = TINY + ["base_ln_5s", "base_ln_5s_noblank", "base_feat_2s", "base_feat_5s", "base_ln_30s", "large_ln_2s"]
+        "tiny_bias_only", "tiny_div", "tiny_em_only", "tiny_mcc_plain", "tiny_temp1_allframes",
+        "tiny_lv60_ln", "tiny_lv60_short"]      # lv60: LayerNorm feature extractor + conv bias + pre-LN encoder
+CASES = TINY + ["base_ln_5s", "base_ln_5s_noblank", "base_feat_2s", "base_feat_5s", "base_ln_30s", "large_ln_2s", "large_lv60_2s"]
 
 
 def oracle_kwargs(meta):
@@ -70,7 +71,8 @@ def test_oracle_adaptation_reproduces_reference(case):
             assert np.abs(d_ref - d_got).max() <= 0.05 * np.abs(d_ref).max() + 1e-9
 
 
-@pytest.mark.parametrize("case", ["tiny_ln", "tiny_feat", "tiny_steplr", "tiny_adam_beta", "tiny_feat_sgd", "tiny_bias_only"])
+@pytest.mark.parametrize("case", ["tiny_ln", "tiny_feat", "tiny_steplr", "tiny_adam_beta", "tiny_feat_sgd", "tiny_bias_only",
+                                  "tiny_lv60_ln"])
 def test_hf_reference_loop_reproduces_reference(case):
     """oracle/hf_reference.py (the loop bench.py times as the reference's CPU / eager-GPU path: real HF modules,
     autograd and torch.optim under a restatement of main.py's driver) against what the unmodified reference produced."""
@@ -92,6 +94,16 @@ def test_hf_reference_loop_reproduces_reference(case):
         np.testing.assert_allclose(res.logits[meta["steps"]], z["logits_" + last], atol=2e-5)
         for k, text in meta["texts"].items():
             assert res.texts.get(int(k), text) == text
+
+
+def test_lv60_layernorm_only_set_matches_survey():
+    """the large-lv60 shape lists 114 tensors / 108 544 elements, incl. 7 conv LayerNorm(512)."""
+    cfg = O.W2V2Config.large_lv60()
+    names = O.collect_param_names(cfg)
+    assert len(names) == 114 and len(set(names)) == 114
+    sd_shapes = {n: (cfg.conv_dim[0] if "feature_" in n else cfg.hidden_size) for n in names}
+    assert sum(sd_shapes.values()) == 108544
+    assert sum("feature_extractor.conv_layers" in n for n in names) == 14
 
 
 def test_param_multiplicities_match_survey():
