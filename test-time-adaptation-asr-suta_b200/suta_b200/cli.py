@@ -2,9 +2,10 @@
 per-utterance loop, same stdout lines and result files.  main.py and main_SDPL.py at the repository root are the two
 entry points; the function surface they re-export lives in suta_b200.api.
 
-Offline differences: `--asr` takes `random-base` / `random-large` / `random-tiny` or a LOCAL HuggingFace
-checkpoint directory (no network), `--dataset_name synthetic` generates the LibriSpeech-test-other-shaped set instead
-of reading a corpus from `--dataset_dir`.  Extensions: `--num_utts`, `--batch_utts N` (N utterances per adaptation step,
+Offline differences: `--asr` takes `random-base` / `random-large` / `random-large_lv60` / `random-tiny` or a
+LOCAL HuggingFace checkpoint directory (no network); `--dataset_name synthetic` (the default) generates the
+LibriSpeech-test-other-shaped set, `librispeech` / `chime` / `ted` / `commonvoice` read a corpus from `--dataset_dir` the
+way REF/corpus/*.py do (suta_b200/corpus.py).  Extensions: `--num_utts`, `--batch_utts N` (N utterances per adaptation step,
 each with its own parameters; needs --episodic).
 """
 from __future__ import annotations
@@ -76,11 +77,13 @@ def main(argv=None, sdpl: bool = False):
     from .data import librispeech_shaped
     from .text import CTCVocab
     from .weights import load_checkpoint, random_state_dict
-    if dataset_name != 'synthetic':
-        raise SystemExit("only --dataset_name synthetic is available offline (corpus loaders: SURVEY.md 8f rank 4)")
     if batch_size != 1:
         raise SystemExit("--batch_size: the reference only works with 1 (REF/main.py:32); use --batch_utts for batching")
-    dataset = librispeech_shaped(args.num_utts, extra_noise=extra_noise)
+    if dataset_name == 'synthetic':
+        dataset = librispeech_shaped(args.num_utts, extra_noise=extra_noise)
+    else:                                                                # REF/main.py:299: load_dataset(split, name, dir, ...)
+        from .corpus import create_dataset
+        dataset = create_dataset(args.split, dataset_name, args.dataset_dir, batch_size, extra_noise)
     vocab = CTCVocab()
 
     print('------------------------------------')

@@ -163,15 +163,18 @@ def test_batch_composition_does_not_change_results(E):
     assert alone["ids"][5] == mixed["ids"][5] or np.abs(alone["logits"][5] - mixed["logits"][5]).max() < 2e-3
 
 
-def test_drop_in_api_single_utterance(E, capsys):
-    """forward_and_adapt & co. (the reference's function surface) drive the same engine path."""
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_lv60"])
+def test_drop_in_api_single_utterance(E, capsys, cfg_name):
+    """forward_and_adapt & co. (the reference's function surface) drive the same engine path -- for the group-norm /
+    post-LN family and for the lv60 family (conv LayerNorms in the collected set, as REF/main.py:81-87 finds them)."""
     from oracle import suta_oracle as O
     from suta_b200 import ModelConfig, api
-    ocfg = O.W2V2Config.tiny()
+    ocfg = getattr(O.W2V2Config, cfg_name)()
     sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
     wav = O.synth_audio(12000, 11)
-    model = api.configure_model(api.SutaModel(ModelConfig.tiny(), sd))
+    model = api.configure_model(api.SutaModel(getattr(ModelConfig, cfg_name)(), sd))
     params, names = api.collect_params(model, False, False, False, True)
+    assert sorted(names) == sorted(O.collect_param_names(ocfg))
     opt, sched = api.setup_optimizer(params, "AdamW", 2e-5)
     snap = api.copy_model_and_optimizer(model, opt, sched)
     x = torch.from_numpy(O.normalize_audio(wav))[None].cuda()

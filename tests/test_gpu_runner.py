@@ -201,3 +201,32 @@ def test_local_hf_checkpoint_runs_through_the_engine(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert os.path.exists(str(tmp_path / "exps" / "synthetic_1.0_3_2.5_ckpt_non_blankFalse_noise_0.0_rew_False_div_0.0_bias_False_feat_False_all_False_LN_True"))
+
+
+def test_main_cli_reads_a_corpus_directory_with_an_lv60_model(tmp_path):
+    """`--dataset_name ted --dataset_dir <tree>` walks a TED-LIUM-shaped directory of WAV segments
+    like REF/corpus/ted.py (suta_b200/corpus.py), with a model of the lv60 family (LayerNorm feature extractor, pre-LN
+    encoder); the batched extension reproduces the one-utterance-at-a-time loop bit for bit."""
+    _need_gpu()
+    import wave
+    root = tmp_path / "ted"
+    os.makedirs(root / "wav_segment"); os.makedirs(root / "transcription")
+    rng = np.random.default_rng(0)
+    for j, (n, text) in enumerate(((9000, "THE OF AND"), (14000, "HE WAS THAT IT HIS"), (6000, "A"), (11000, "WITH AS HAD FOR"))):
+        with wave.open(str(root / "wav_segment" / f"seg_{j:03d}.wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+            f.writeframes((rng.standard_normal(n) * 3000).astype("<i2").tobytes())
+        (root / "transcription" / f"seg_{j:03d}.txt").write_text(text + "\n")
+    logs = []
+    for k, extra in enumerate(([], ["--batch_utts", "3"])):
+        log_dir = str(tmp_path / f"exps{k}")
+        cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", "random-tiny_lv60", "--dataset_name", "ted", "--dataset_dir", str(root),
+               "--steps", "5", "--episodic", "--em_coef", "0.3", "--reweight", "--lr", "2e-5", "--non_blank", "--log_dir", log_dir, *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        assert "There are 4 samples" in r.stdout and "dataset num = 4" in r.stdout
+        assert "conv_layers.6.layer_norm.weight" in r.stdout               # print(param_names): the conv LayerNorms are collected
+        name = "ted_0.3_5_2.5_random-tiny_lv60_non_blankTrue_noise_0.0_rew_True_div_0.0_bias_False_feat_False_all_False_LN_True"
+        logs.append(open(os.path.join(log_dir, name)).read())
+        assert logs[-1].splitlines()[0].startswith("original WER: ") and logs[-1].splitlines()[3].startswith("TTA-5 WER: ")
+    assert logs[0] == logs[1]

@@ -76,7 +76,8 @@ def test_synthetic_set_shape():
 
 def test_collect_params_names_and_duplicates_match_reference_walk(capsys):
     from suta_b200 import api
-    for cfg, ocfg in ((ModelConfig.base(), O.W2V2Config.base()), (ModelConfig.tiny(), O.W2V2Config.tiny())):
+    for cfg, ocfg in ((ModelConfig.base(), O.W2V2Config.base()), (ModelConfig.tiny(), O.W2V2Config.tiny()),
+                      (ModelConfig.large_lv60(), O.W2V2Config.large_lv60())):
         names_all = {f"{nm}.{leaf}" for nm, _k, leaves in api._module_order(cfg) for leaf in leaves}
         model = types.SimpleNamespace(cfg=cfg, engine=types.SimpleNamespace(train_feature=True),
                                       _params={n: types.SimpleNamespace(name=n, requires_grad=False) for n in names_all})
