@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--model", default=None, choices=["base", "large", "tiny"], help="override the workload's model")
+    ap.add_argument("--model", default=None, choices=["base", "large", "tiny", "large_lv60", "tiny_lv60"],
+                    help="override the workload's model (large_lv60: LayerNorm feature extractor + pre-LN encoder, LayerNorm-only mode)")
     ap.add_argument("--mode", default=None, choices=["feature", "ln"], help="override: feature = --train_feature, ln = LayerNorm-only")
     ap.add_argument("--suta-steps", type=int, default=None, help="override the adaptation steps per utterance")
     ap.add_argument("--extra-noise", type=float, default=None, help="override REF/data.py:23's noise level")
@@ -157,9 +158,13 @@ def utt_flops(cfg, n_samples, steps, train_feature=False):
     f_head = 2.0 * T * H * V
     enc_f = f_proj + f_pos + NL * (f_lin + 4.0 * T * T * H) + f_head
     enc_b = f_proj + f_pos + NL * (f_lin + 8.0 * T * T * H) + f_head
+    f_conv0 = 2.0 * cfg.conv_dim[0] * cfg.conv_kernel[0] * Ls[0]
     if train_feature:   # CNN forward every step, dgrad (no input grad for conv0) + wgrad in every backward
-        f_conv0 = 2.0 * cfg.conv_dim[0] * cfg.conv_kernel[0] * Ls[0]
         return (steps + 1) * (f_conv + enc_f) + steps * (enc_b + f_proj + 2 * f_conv - f_conv0)
+    if getattr(cfg, "feat_extract_norm", "group") == "layer":
+        # lv60 family: the conv LayerNorms are in the LayerNorm-only set, so the CNN runs in every forward and its dgrad
+        # (frozen weights: no wgrad; nothing below conv0) in every backward
+        return (steps + 1) * (f_conv + enc_f) + steps * (enc_b + f_conv - f_conv0)
     return f_conv + (steps + 1) * enc_f + steps * enc_b
 
 

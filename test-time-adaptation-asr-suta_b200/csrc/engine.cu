@@ -140,6 +140,7 @@ struct suta_engine {
   float* c0_scratch = nullptr;
   double* mom = nullptr;                           // [U][k + k(k+1)/2] audio moments (conv0 GroupNorm statistics / backward)
   bool moments_done = false;
+  bool z0_done = false;                            // conv_ln: conv0 + bias of the current audio is in conv_z[0]
   int max_L[SUTA_MAX_CONV] = {};
   // device buffers
   float *wav = nullptr, *wav_norm = nullptr;
@@ -727,7 +728,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
   for (int l = 0; l < c.n_conv; ++l)
     CUDA_TRY(cudaMemsetAsync(e->conv_out[l] + (size_t)e->rows_total[l] * c.conv_dim[l], 0, sizeof(bf16) * 128 * c.conv_dim[l], st));
   e->frontend_done = false;
-  e->moments_done = false;
+  e->moments_done = false; e->z0_done = false;
   e->opt_steps = 0;
   return SUTA_OK;
 }
@@ -752,7 +753,7 @@ extern "C" int suta_batch_set_audio(suta_engine* e, const float* wav, int flags,
   CUDA_TRY(cudaMemcpyAsync(e->audio_normalized ? e->wav_norm : e->wav, wav, sizeof(float) * e->S,
                            is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, S(stream)));
   e->frontend_done = false;
-  e->moments_done = false;
+  e->moments_done = false; e->z0_done = false;
   return SUTA_OK;
 }
 
@@ -826,7 +827,7 @@ extern "C" int suta_batch_add_noise(suta_engine* e, float sigma, uint64_t seed, 
   e->launches += 1;
   PROF("audio_noise", audio_add_noise(e->wav, e->d_samp_off, e->d_n_samples, d_ids, e->U, e->max_samples, sigma, seed, st));
   e->frontend_done = false;
-  e->moments_done = false;
+  e->moments_done = false; e->z0_done = false;
   return SUTA_OK;
 }
 
@@ -855,10 +856,13 @@ static int frontend_layer_norm(suta_engine* e, cudaStream_t st) {
   const suta_model_cfg& c = e->cfg;
   UttParams prm{e->P, e->n_params};
   const int last = c.n_conv - 1;
-  PROF_B("conv0_bias", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2,
-         conv0_bias(e->wav_norm, e->d_samp_off, e->d_L0, e->d_off0, e->w.conv0_w, e->w.conv_b[0], e->conv_z[0], e->U, c.conv_dim[0],
-                    c.conv_kernel[0], c.conv_stride[0], e->max_L0, st));
-  e->launches += 1;
+  if (!e->z0_done) {       // conv0 and its bias are frozen: z_0 depends on the audio only, once per batch (only its LayerNorm moves)
+    PROF_B("conv0_bias", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2,
+           conv0_bias(e->wav_norm, e->d_samp_off, e->d_L0, e->d_off0, e->w.conv0_w, e->w.conv_b[0], e->conv_z[0], e->U, c.conv_dim[0],
+                      c.conv_kernel[0], c.conv_stride[0], e->max_L0, st));
+    e->launches += 1;
+    e->z0_done = true;
+  }
   for (int l = 0; l < c.n_conv; ++l) {
     const int Cout = c.conv_dim[l];
     long long rows_valid = 0;

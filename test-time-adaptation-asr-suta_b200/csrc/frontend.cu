@@ -346,6 +346,46 @@ conv0_bias_kernel(const float* __restrict__ x, const long long* __restrict__ sam
   }
 }
 
+// The usual shape (k = 10): every thread keeps the K taps + bias of its 8 channels in registers and walks rows; the x
+// window of a row is one broadcast load per tap for the 32 lanes (= 32 channel octets) of a warp.  80 FMA per 16-byte
+// store: about the HBM time of the output at C = 512.
+template <int K>
+__global__ void __launch_bounds__(256)
+conv0_bias_reg_kernel(const float* __restrict__ x, const long long* __restrict__ samp_off, const int* __restrict__ L0,
+                      const long long* __restrict__ out_off, const float* __restrict__ w, const float* __restrict__ bias,
+                      bf16* __restrict__ out, int C, int stride, int rows_per_cta) {
+  const int u = blockIdx.y;
+  const int L = L0[u];
+  const int t0 = blockIdx.x * rows_per_cta;
+  if (t0 >= L) return;
+  const int n_oct = C >> 3;
+  const int oct = threadIdx.x % n_oct, rsub = threadIdx.x / n_oct, rstep = blockDim.x / n_oct;
+  float wr[8][K], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias ? __ldg(bias + oct * 8 + c) : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[c][j] = __ldg(w + (oct * 8 + c) * K + j);
+  }
+  const float* xu = x + samp_off[u];
+  bf16* ou = out + out_off[u] * C + oct * 8;
+  const int t1 = min(L, t0 + rows_per_cta);
+  for (int t = t0 + rsub; t < t1; t += rstep) {
+    float xv[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) xv[j] = __ldg(xu + (long long)t * stride + j);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[c] = br[c];
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc[c] = fmaf(wr[c][j], xv[j], acc[c]);
+    }
+    *reinterpret_cast<uint4*>(ou + (long long)t * C) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 // row -> utterance table of a conv layer's row space (gap rows keep the -1 of the caller's memset)
 __global__ void fill_row_utt_kernel(int* __restrict__ row_utt, const long long* __restrict__ off, const int* __restrict__ L) {
   const int u = blockIdx.y;
@@ -358,6 +398,15 @@ __global__ void fill_row_utt_kernel(int* __restrict__ row_utt, const long long* 
 int conv0_bias(const float* x, const long long* samp_off, const int* L0, const long long* out_off, const float* w,
                const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream) {
   SUTA_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && k > 0 && k <= 32);
+  if (k == 10) {
+    // ~4 CTAs per SM and utterance column; at least 256 rows per CTA so the 88 register-resident weights amortise
+    int rows = ceil_div(max_L0, 4 * 148);
+    rows = rows < 256 ? 256 : (rows + 63) / 64 * 64;
+    conv0_bias_reg_kernel<10><<<dim3((unsigned)ceil_div(max_L0, rows), (unsigned)n_utts), 256, 0, stream>>>(
+        x, samp_off, L0, out_off, w, bias, out, C, stride, rows);
+    CUDA_TRY(cudaGetLastError());
+    return SUTA_OK;
+  }
   const size_t smem = sizeof(float) * ((size_t)k * C + C);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {

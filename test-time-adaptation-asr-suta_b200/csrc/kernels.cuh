@@ -21,7 +21,7 @@ int attention_backward(const bf16* qkv, const bf16* O, const bf16* dO, const flo
 // into, so the GEMM's bias is folded in here.
 // mode: LN_PLAIN; LN_GELU (bf16 input): the outputs are GELU(LN(x)) -- conv layers of the LayerNorm feature extractor,
 // HF/modeling_wav2vec2.py:291-299; LN_KEEP_INPUT (fp32 input): y_f32 = x (+ y32_bias) instead of LN(x) -- the pre-LN encoder
-// keeps the residual stream beside the normalised branch, HF:638-645.  Rows with row_utt < 0 are skipped in every mode.
+// keeps the residual stream beside the normalised branch, HF:638-645.  LN_GELU skips rows with row_utt < 0 (conv-layout gaps).
 enum { LN_PLAIN = 0, LN_GELU = 1, LN_KEEP_INPUT = 2 };
 int layernorm_forward(const float* x_f32, const bf16* x_bf16, const int* row_utt, UttParams prm, int g_off, int b_off,
                       float* y_f32, bf16* y_bf16, float* mean, float* rstd, long long M, int N, float eps,

@@ -45,12 +45,14 @@ struct Cols {
 };
 
 constexpr int FWD_W = 8;          // warps per CTA = rows per tile
-constexpr int FWD_STAGES = 3;     // tiles in flight per CTA
-
+// tiles in flight per CTA: 3 for the wide fp32 rows of the encoder (24-32 KB tiles); narrow bf16 rows (the conv-layer and
+// feature-projection LayerNorms: 8 KB tiles at N = 512) need more of them to keep enough bytes in flight per SM -- with 3
+// stages those kernels sat at ~0.48 of the HBM rate (48 KB in flight per SM), the wide ones at 0.8
 template <int N, typename TIn>
 struct FwdSmem {
   static constexpr int TILE_BYTES = FWD_W * N * (int)sizeof(TIn);
-  static constexpr int BYTES = FWD_STAGES * TILE_BYTES + 64;
+  static constexpr int STAGES = TILE_BYTES <= 8192 ? 6 : (TILE_BYTES <= 16384 ? 4 : 3);
+  static constexpr int BYTES = STAGES * TILE_BYTES + 64;
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -64,8 +66,8 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src,
 // MODE 0: y = LN(x) (the post-LN encoder, feature projection).  MODE 1: the bf16 output is GELU(LN(x)) -- the conv layers of
 // the LayerNorm feature extractor (HF/modeling_wav2vec2.py:291-299).  MODE 2: the fp32 output is x (+ y32_bias), NOT
 // LN(x): the pre-LN ("stable") encoder keeps the residual stream beside the normalised branch (HF:638-645), so the
-// LayerNorm seeds the next residual buffer with its own INPUT.  Rows with row_utt < 0 (gaps between utterances in the conv
-// layouts) are skipped.
+// LayerNorm seeds the next residual buffer with its own INPUT.  MODE 1 only: rows with row_utt < 0 (gaps between utterances
+// in the conv layouts) are skipped.
 template <int N, typename TIn, int MODE>
 __global__ void __launch_bounds__(FWD_W * 32)
 ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const float* __restrict__ P, long long pstride,
@@ -73,6 +75,7 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
               float* __restrict__ rstd_out, long long M, float eps, const float* __restrict__ y32_bias, int rows_per_cta) {
   constexpr int NV = Cols<N>::NV;
   using S = FwdSmem<N, TIn>;
+  constexpr int FWD_STAGES = S::STAGES;
   extern __shared__ __align__(128) uint8_t ring[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + FWD_STAGES * S::TILE_BYTES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,7 +106,7 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
     const long long row = cta_row0 + (long long)it * FWD_W + warp;
     const int u = u_next;
     u_next = row + FWD_W < M ? __ldg(row_utt + row + FWD_W) : 0;
-    if (u != u_cur && u >= 0 && row < M) {         // per-utterance gamma/beta stay in registers until the utterance changes
+    if (u != u_cur && (MODE != 1 || u >= 0) && row < M) {         // per-utterance gamma/beta stay in registers until the utterance changes
       u_cur = u;
       const float* gam = P + (long long)u * pstride + g_off;
       const float* bet = P + (long long)u * pstride + b_off;
@@ -116,7 +119,7 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
         }
     }
     mbar_wait(&full[it % FWD_STAGES], (uint32_t)((it / FWD_STAGES) & 1));
-    if (row < M && u >= 0) {
+    if (row < M && (MODE != 1 || u >= 0)) {
       const TIn* xr = reinterpret_cast<const TIn*>(ring + (it % FWD_STAGES) * S::TILE_BYTES) + warp * N;
       float4 v[NV];
       float s = 0.f;
@@ -193,7 +196,7 @@ struct BwdSmem {
 // MODE 0: plain LayerNorm backward.  MODE 1: the forward applied GELU after the LayerNorm (conv layers of the LayerNorm
 // feature extractor): dy is the gradient of the GELU OUTPUT; y = xhat gamma + beta is recomputed and dy * GELU'(y) takes
 // dy's place (needs beta: b_off).  MODE 2: dx += dx_add (fp32, may alias dx32): the pre-LN encoder's residual path,
-// d(residual) = d(residual after the branch) + LayerNorm-backward(d branch input).  Rows with row_utt < 0 are skipped.
+// d(residual) = d(residual after the branch) + LayerNorm-backward(d branch input).  MODE 1 only: rows with row_utt < 0 are skipped.
 // dx32 / dx16 may alias dy (rows are staged in shared memory before their outputs are written).
 template <int N, typename TIn, typename TDy, int MODE>
 __global__ void __launch_bounds__((N / 4 + 31) / 32 * 32)
@@ -203,6 +206,7 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
               bf16* dx16, const float* dx_add, long long M, int rows_per_cta) {
   constexpr int NT = N / 4;                       // active threads
   constexpr int NW = (NT + 31) / 32;              // warps
+  constexpr bool GAPS = MODE == 1;                // only the conv-layer row spaces have gap rows (row_utt < 0)
   using S = BwdSmem<N, TIn, TDy>;
   extern __shared__ __align__(128) uint8_t ring[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + BWD_STAGES * S::STAGE_BYTES);
@@ -245,8 +249,8 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
     for (int r = 0; r < BWD_R; ++r) {
       const bool ok = r0 + r < M;
       uu_n[r] = ok ? __ldg(row_utt + r0 + r) : -1;
-      mu_n[r] = ok && uu_n[r] >= 0 ? __ldg(mean + r0 + r) : 0.f;     // gap rows: no statistics were written
-      rs_n[r] = ok && uu_n[r] >= 0 ? __ldg(rstd + r0 + r) : 0.f;
+      mu_n[r] = ok && (!GAPS || uu_n[r] >= 0) ? __ldg(mean + r0 + r) : 0.f;     // gap rows: no statistics were written
+      rs_n[r] = ok && (!GAPS || uu_n[r] >= 0) ? __ldg(rstd + r0 + r) : 0.f;
     }
   };
   load_scalars(cta_row0);
@@ -266,7 +270,7 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
 #pragma unroll
       for (int r = 0; r < BWD_R; ++r) {
         av[MODE == 2 ? r : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < M && act && uu[r] >= 0) av[MODE == 2 ? r : 0] = *reinterpret_cast<const float4*>(dx_add + (row0 + r) * N + col);
+        if (row0 + r < M && act) av[MODE == 2 ? r : 0] = *reinterpret_cast<const float4*>(dx_add + (row0 + r) * N + col);
       }
     }
     mbar_wait(&full[it % BWD_STAGES], (uint32_t)((it / BWD_STAGES) & 1));
@@ -274,7 +278,7 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
 #pragma unroll
     for (int r = 0; r < BWD_R; ++r) {
       xv[r] = dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < M && act && uu[r] >= 0) {
+      if (row0 + r < M && act && (!GAPS || uu[r] >= 0)) {
         xv[r] = Loader<TIn>::ld4(reinterpret_cast<const TIn*>(st) + r * N + col);
         dv[r] = Loader<TDy>::ld4(reinterpret_cast<const TDy*>(st + S::X_BYTES) + r * N + col);
       }
@@ -319,7 +323,7 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
 #pragma unroll
       for (int r = 0; r < BWD_R; ++r) {
         const long long row = row0 + r;
-        if (row >= M || !act || uu[r] < 0) continue;
+        if (row >= M || !act || (GAPS && uu[r] < 0)) continue;
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {

@@ -226,6 +226,9 @@ SDPL_CASES = {
                       temp=2.5, not_blank=False, train_feature=False),
     "tiny_sdpl_mix": dict(n=9000, aseed=12, wseed=4, steps=5, opt="Adam", lr=1e-4, pl_coef=0.5, em_coef=0.3, reweight=True,
                           temp=2.5, not_blank=True, train_feature=True),
+    # the checkpoints REF/main_SDPL.py:238-241 lists are of the lv60 family: the same loss over that architecture
+    "tiny_lv60_sdpl": dict(cfg="tiny_lv60", n=7000, aseed=43, wseed=8, steps=5, opt="Adam", lr=1e-4, pl_coef=1.0, em_coef=1.0,
+                           reweight=False, temp=2.5, not_blank=False, train_feature=False),
 }
 
 
@@ -233,7 +236,7 @@ def make_sdpl(case, processor):
     from transformers import Wav2Vec2ForCTC
     ref = import_reference_sdpl()
     c = SDPL_CASES[case]
-    cfg = O.W2V2Config.tiny()
+    cfg = getattr(O.W2V2Config, c.get("cfg", "tiny"))()
     sd = O.init_weights(cfg, c["wseed"], blank_bias=0.5, ln_jitter=0.1, special_bias=-10.0)
     wav = O.synth_audio(c["n"], c["aseed"])
     vocab = json.load(open(os.path.join(REF, "vocab.json")))
@@ -269,7 +272,9 @@ def make_sdpl(case, processor):
     # log_softmax over TIME makes d loss / d logits sum to zero over the frames of every class, so the gradient of the last
     # LayerNorm's bias (which shifts every frame alike) is analytically ZERO under the pure CTC loss: Adam turns its rounding
     # noise into +-lr steps that no two implementations share.  Excluded from every parameter comparison (listed in meta).
-    noise = [f"wav2vec2.encoder.layers.{cfg.num_hidden_layers - 1}.final_layer_norm.bias"] if c["pl_coef"] == 1.0 else []
+    # (the pre-LN encoder of the lv60 family ends in encoder.layer_norm: there it is that LayerNorm's bias)
+    last_ln = "wav2vec2.encoder.layer_norm" if cfg.do_stable_layer_norm else f"wav2vec2.encoder.layers.{cfg.num_hidden_layers - 1}.final_layer_norm"
+    noise = [last_ln + ".bias"] if c["pl_coef"] == 1.0 else []
     for nme in dict.fromkeys(names):
         arrs["param:" + nme] = pack_param(msd[nme].detach().numpy())
         if nme in noise:
@@ -280,7 +285,7 @@ def make_sdpl(case, processor):
           f"ctc losses={losses[0]:.5f}->{losses[-1]:.5f} oracle-vs-ref worst delta mismatch={worst:.2e}", flush=True)
     assert worst < 0.05
     arrs["pl_losses"] = np.asarray(losses)
-    meta = dict(case=case, cfg="tiny", n_samples=c["n"], audio_seed=c["aseed"], weight_seed=c["wseed"], blank_bias=0.5, ln_jitter=0.1,
+    meta = dict(case=case, cfg=c.get("cfg", "tiny"), n_samples=c["n"], audio_seed=c["aseed"], weight_seed=c["wseed"], blank_bias=0.5, ln_jitter=0.1,
                 special_bias=-10.0, names=names, zero_gradient_params=noise, generator="tests/golden/make_golden.py (REF/main_SDPL.py)", **{k: c[k] for k in
                 ("steps", "opt", "lr", "pl_coef", "em_coef", "reweight", "temp", "not_blank", "train_feature")})
     arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -141,10 +141,11 @@ def test_train_feature_against_reference_golden_vectors(E, case):
         assert m["big_param_head_delta_rel"] < 0.15
 
 
-@pytest.mark.parametrize("case", ["tiny_sdpl", "tiny_sdpl_mix"])
+@pytest.mark.parametrize("case", ["tiny_sdpl", "tiny_sdpl_mix", "tiny_lv60_sdpl"])
 def test_sdpl_pseudo_label_baseline_against_reference_golden_vectors(E, case):
     """REF/main_SDPL.py (the README's comparison row): adaptation by the CTC pseudo-label loss alone (pl_coef = 1, Adam,
-    lr 1e-4) and mixed half-and-half with the SUTA loss under --train_feature."""
+    lr 1e-4), mixed half-and-half with the SUTA loss under --train_feature, and the pure CTC case on the lv60 architecture
+    (the checkpoints REF/main_SDPL.py:238-241 names)."""
     m = E.check_golden_sdpl(case)
     print(case, m)
     assert m["pl_loss_rel_max"] < 1e-3

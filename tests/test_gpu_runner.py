@@ -221,12 +221,12 @@ def test_main_cli_reads_a_corpus_directory_with_an_lv60_model(tmp_path):
     for k, extra in enumerate(([], ["--batch_utts", "3"])):
         log_dir = str(tmp_path / f"exps{k}")
         cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", "random-tiny_lv60", "--dataset_name", "ted", "--dataset_dir", str(root),
-               "--steps", "5", "--episodic", "--em_coef", "0.3", "--reweight", "--lr", "2e-5", "--non_blank", "--log_dir", log_dir, *extra]
+               "--steps", "10", "--episodic", "--em_coef", "0.3", "--reweight", "--lr", "2e-5", "--non_blank", "--log_dir", log_dir, *extra]
         r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "There are 4 samples" in r.stdout and "dataset num = 4" in r.stdout
         assert "conv_layers.6.layer_norm.weight" in r.stdout               # print(param_names): the conv LayerNorms are collected
-        name = "ted_0.3_5_2.5_random-tiny_lv60_non_blankTrue_noise_0.0_rew_True_div_0.0_bias_False_feat_False_all_False_LN_True"
+        name = "ted_0.3_10_2.5_random-tiny_lv60_non_blankTrue_noise_0.0_rew_True_div_0.0_bias_False_feat_False_all_False_LN_True"
         logs.append(open(os.path.join(log_dir, name)).read())
-        assert logs[-1].splitlines()[0].startswith("original WER: ") and logs[-1].splitlines()[3].startswith("TTA-5 WER: ")
+        assert logs[-1].splitlines()[0].startswith("original WER: ") and logs[-1].splitlines()[4].startswith("TTA-10 WER: ")
     assert logs[0] == logs[1]

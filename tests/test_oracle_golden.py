@@ -96,6 +96,28 @@ def test_hf_reference_loop_reproduces_reference(case):
             assert res.texts.get(int(k), text) == text
 
 
+@pytest.mark.parametrize("case", ["tiny_sdpl", "tiny_sdpl_mix", "tiny_lv60_sdpl"])
+def test_oracle_sdpl_loop_reproduces_reference(case):
+    """REF/main_SDPL.py through the unmodified script's functions (make_golden.make_sdpl): the oracle's pseudo-label CTC
+    loss and the adapted logits / parameters after the fixture's steps."""
+    z, meta = load(case)
+    cfg = getattr(O.W2V2Config, meta["cfg"])()
+    sd = O.init_weights(cfg, meta["weight_seed"], blank_bias=meta["blank_bias"], ln_jitter=meta["ln_jitter"], special_bias=meta["special_bias"])
+    x = O.normalize_audio(O.synth_audio(meta["n_samples"], meta["audio_seed"]))
+    res = O.adapt_utterance(cfg, sd, x, steps=meta["steps"], lr=meta["lr"], em_coef=meta["em_coef"], reweight=meta["reweight"],
+                            temp=meta["temp"], not_blank=meta["not_blank"], train_feature=meta["train_feature"], opt=meta["opt"],
+                            pl_coef=meta["pl_coef"], keep_all_logits=True)
+    np.testing.assert_allclose(res.logits0, z["logits_0"], atol=5e-5)
+    np.testing.assert_allclose(res.logits[meta["steps"]], z[f"logits_{meta['steps']}"], atol=3e-4)
+    np.testing.assert_allclose(float(O.pseudo_labeling_loss(torch.tensor(z["logits_0"][None]))), z["pl_losses"][0], rtol=1e-5)
+    skip = set(meta.get("zero_gradient_params", []))
+    for n in set(meta["names"]) - skip:
+        ref = z["param:" + n]
+        if ref.dtype == np.float32:
+            d_ref, d_got = ref - sd[n].numpy(), res.params[n] - sd[n].numpy()
+            assert np.abs(d_ref - d_got).max() <= 0.05 * np.abs(d_ref).max() + 1e-9, n
+
+
 def test_lv60_layernorm_only_set_matches_survey():
     """the large-lv60 shape lists 114 tensors / 108 544 elements, incl. 7 conv LayerNorm(512)."""
     cfg = O.W2V2Config.large_lv60()
