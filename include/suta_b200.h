@@ -173,6 +173,19 @@ int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const void* x_bf1
                           const int32_t* row_utt, const float* P, int64_t pstride, int g_off, int b_off, float* G,
                           float* dx_f32, void* dx_bf16, int64_t M, int N, const int64_t* tok_off, const int32_t* T,
                           int n_utts, float* scratch, void* stream);
+/* The LayerNorm variants of the lv60 family.  mode 1: y = GELU(LN(x)) with a bf16 x -- a conv layer of the LayerNorm
+ * feature extractor (HF:291-299); rows with row_utt < 0 (gaps of the conv layouts) are skipped.  mode 2: y_f32 = x +
+ * y32_bias while y_bf16 = LN(x) -- the pre-LN encoder keeps the residual stream beside the normalised branch (HF:638-645).
+ * mode 0: suta_op_layernorm_fwd (+ y32_bias on the fp32 output). */
+int suta_op_layernorm_fwd_mode(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P, int64_t pstride,
+                               int g_off, int b_off, float* y_f32, void* y_bf16, float* mean, float* rstd, int64_t M, int N,
+                               float eps, const float* y32_bias, int mode, void* stream);
+/* Their backward.  mode 1: dy (fp32 or bf16, exactly one non-null) is the gradient of the GELU output, x is bf16; dx_bf16
+ * may alias dy_bf16.  mode 2: fp32 x and dy, dx += dx_add (may alias dx_f32). */
+int suta_op_layernorm_bwd_mode(const float* dy_f32, const void* dy_bf16, const float* x_f32, const void* x_bf16, const float* mean,
+                               const float* rstd, const int32_t* row_utt, const float* P, int64_t pstride, int g_off, int b_off,
+                               float* G, float* dx_f32, void* dx_bf16, const float* dx_add, int mode, int64_t M, int N,
+                               const int64_t* tok_off, const int32_t* T, int n_utts, float* scratch, void* stream);
 int64_t suta_op_layernorm_bwd_scratch_floats(int N, int n_utts);
 int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
                           int64_t M, void* stream);

@@ -1542,6 +1542,27 @@ extern "C" int suta_op_layernorm_bwd(const float* dy, const float* x_f32, const 
                             b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N,
                             reinterpret_cast<const long long*>(tok_off), T, n_utts, scratch, S(stream));
 }
+extern "C" int suta_op_layernorm_fwd_mode(const float* x_f32, const void* x_bf16, const int32_t* row_utt, const float* P,
+                                          int64_t pstride, int g_off, int b_off, float* y_f32, void* y_bf16, float* mean,
+                                          float* rstd, int64_t M, int N, float eps, const float* y32_bias, int mode, void* stream) {
+  return layernorm_forward(x_f32, reinterpret_cast<const bf16*>(x_bf16), row_utt, UttParams{P, pstride}, g_off, b_off, y_f32,
+                           reinterpret_cast<bf16*>(y_bf16), mean, rstd, M, N, eps, S(stream), y32_bias, mode);
+}
+extern "C" int suta_op_layernorm_bwd_mode(const float* dy_f32, const void* dy_bf16, const float* x_f32, const void* x_bf16,
+                                          const float* mean, const float* rstd, const int32_t* row_utt, const float* P,
+                                          int64_t pstride, int g_off, int b_off, float* G, float* dx_f32, void* dx_bf16,
+                                          const float* dx_add, int mode, int64_t M, int N, const int64_t* tok_off,
+                                          const int32_t* T, int n_utts, float* scratch, void* stream) {
+  const long long* to = reinterpret_cast<const long long*>(tok_off);
+  if (mode == LN_GELU)
+    return layernorm_gelu_backward(dy_f32, reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), mean, rstd,
+                                   row_utt, UttParams{P, pstride}, g_off, b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N, to,
+                                   T, n_utts, scratch, S(stream));
+  SUTA_CHECK_ARG(dy_f32 && !dy_bf16 && (mode == LN_PLAIN || (mode == LN_KEEP_INPUT && dx_add)));
+  return layernorm_backward(dy_f32, x_f32, reinterpret_cast<const bf16*>(x_bf16), mean, rstd, row_utt, UttParams{P, pstride}, g_off,
+                            b_off, G, dx_f32, reinterpret_cast<bf16*>(dx_bf16), M, N, to, T, n_utts, scratch, S(stream), nullptr,
+                            mode == LN_KEEP_INPUT ? dx_add : nullptr);
+}
 extern "C" int64_t suta_op_layernorm_bwd_scratch_floats(int N, int n_utts) { return layernorm_backward_scratch_floats(N, n_utts); }
 extern "C" int suta_op_attention_fwd(const void* qkv, void* O, float* lse, const int32_t* blk_tab, int n_blk, int H, int heads,
                                      int64_t M, void* stream) {

@@ -101,6 +101,11 @@ SIGNATURES = {
                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                       c_void_p, c_void_p]),
     "suta_op_layernorm_bwd_scratch_floats": (c_int64, [c_int, c_int]),
+    "suta_op_layernorm_fwd_mode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "suta_op_layernorm_bwd_mode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
+                                           c_void_p, c_int, c_void_p, c_void_p]),
     "suta_op_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "suta_op_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_int64, c_void_p]),

@@ -205,6 +205,91 @@ def check_layernorm(N=768, Ts=(70, 3, 129), seed=5, bf16_in=False):
                 dparam_writes_only_its_segment=untouched)
 
 
+def check_layernorm_gelu(N=512, Ts=(70, 3, 129), gaps=(5, 0, 250), seed=9, dy_bf16=True):
+    """GELU(LayerNorm(x)) forward / backward of the LayerNorm feature extractor (HF/modeling_wav2vec2.py:291-299) in a conv
+    layer's row space: bf16 x, utterance regions separated by GAP rows (row_utt = -1) that must be left untouched, the
+    gradient arriving in bf16 and replaced IN PLACE by d x (valid rows only), per-utterance gamma / beta."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    U = len(Ts)
+    offs, ru, r = [], [], 0
+    for u, (T, gp) in enumerate(zip(Ts, gaps)):
+        offs.append(r); ru += [u] * T + [-1] * gp; r += T + gp
+    M = r
+    ru = torch.tensor(ru, dtype=torch.int32, device=DEV)
+    valid = ru >= 0
+    x = (torch.randn(M, N, device=DEV, generator=g) * 2 + 0.3).bfloat16()
+    n_par = 2 * N + 64
+    Pm = torch.randn(U, n_par, device=DEV, generator=g) * 0.5 + 0.5
+    g_off, b_off = 64, 64 + N
+    y16 = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    mean = torch.full((M,), float("nan"), device=DEV); rstd = torch.full((M,), float("nan"), device=DEV)   # gap rows stay NaN: must not leak
+    check(lib.suta_op_layernorm_fwd_mode(None, P(x), P(ru), P(Pm), n_par, g_off, b_off, None, P(y16), P(mean), P(rstd), M, N, 1e-5,
+                                         None, 1, stream()))
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    dy[~valid] = 0
+    dyb = dy.bfloat16() if dy_bf16 else dy.clone()
+    dy_ref = dyb.float().clone()
+    tok_off = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    Tt = torch.tensor(Ts, dtype=torch.int32, device=DEV)
+    scratch = torch.empty(int(lib.suta_op_layernorm_bwd_scratch_floats(N, U)), device=DEV)
+    G = torch.full((U, n_par), float("nan"), device=DEV)
+    dx32 = torch.zeros(M, N, device=DEV) if not dy_bf16 else None
+    check(lib.suta_op_layernorm_bwd_mode(None if dy_bf16 else P(dyb), P(dyb) if dy_bf16 else None, None, P(x), P(mean), P(rstd), P(ru),
+                                         P(Pm), n_par, g_off, b_off, P(G), None if dy_bf16 else P(dx32), P(dyb) if dy_bf16 else None,
+                                         None, 1, M, N, P(tok_off), P(Tt), U, P(scratch), stream()))
+    torch.cuda.synchronize()
+    dx = dyb.float() if dy_bf16 else dx32                     # bf16: written in place over dy
+    G = torch.where(torch.isnan(G), torch.zeros_like(G), G)
+    xr = x.float().clone().requires_grad_(True)
+    Pr = Pm.clone().requires_grad_(True)
+    idx = ru.long().clamp(min=0)
+    gam = Pr[idx, g_off:g_off + N]; bet = Pr[idx, b_off:b_off + N]
+    yr = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xr, (N,), eps=1e-5) * gam + bet)
+    (yr * dy_ref)[valid].sum().backward()
+    return dict(y16_rel=relerr(y16.float()[valid], yr[valid]), gaps_untouched=bool((y16[~valid] == 7.0).all()) if (~valid).any() else True,
+                dx_rel=relerr(dx[valid], xr.grad[valid]), dx_gaps_zero=bool((dx[~valid] == 0).all()) if (~valid).any() else True,
+                dparam_rel=relerr(G, Pr.grad), nan=int(torch.isnan(dx).sum()) + int(torch.isnan(G).sum()))
+
+
+def check_layernorm_keep_input(N=768, Ts=(70, 3, 129), seed=10):
+    """The pre-LN encoder's LayerNorm (HF:638-645): forward y_bf16 = LN(x), y_f32 = x + bias (the residual stream seeded
+    for the GEMM that accumulates the branch onto it); backward d x = d_residual + LayerNorm-backward(d branch), in place."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    M, U = sum(Ts), len(Ts)
+    x = torch.randn(M, N, device=DEV, generator=g) * 2 + 0.3
+    n_par = 2 * N + 64
+    Pm = torch.randn(U, n_par, device=DEV, generator=g)
+    g_off, b_off = 64, 64 + N
+    ru = _row_utt(Ts)
+    bias = torch.randn(N, device=DEV, generator=g)
+    y32 = torch.zeros(M, N, device=DEV); y16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    mean = torch.zeros(M, device=DEV); rstd = torch.zeros(M, device=DEV)
+    check(lib.suta_op_layernorm_fwd_mode(P(x), None, P(ru), P(Pm), n_par, g_off, b_off, P(y32), P(y16), P(mean), P(rstd), M, N, 1e-5,
+                                         P(bias), 2, stream()))
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    dres = torch.randn(M, N, device=DEV, generator=g)
+    dres0 = dres.clone()
+    tok_off = torch.tensor(np.concatenate([[0], np.cumsum(Ts)[:-1]]), dtype=torch.int64, device=DEV)
+    Tt = torch.tensor(Ts, dtype=torch.int32, device=DEV)
+    scratch = torch.empty(int(lib.suta_op_layernorm_bwd_scratch_floats(N, U)), device=DEV)
+    G = torch.full((U, n_par), float("nan"), device=DEV)
+    dx16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    check(lib.suta_op_layernorm_bwd_mode(P(dy), None, P(x), None, P(mean), P(rstd), P(ru), P(Pm), n_par, g_off, b_off, P(G), P(dres),
+                                         P(dx16), P(dres), 2, M, N, P(tok_off), P(Tt), U, P(scratch), stream()))
+    torch.cuda.synchronize()
+    G = torch.where(torch.isnan(G), torch.zeros_like(G), G)
+    xr = x.clone().requires_grad_(True)
+    Pr = Pm.clone().requires_grad_(True)
+    gam = Pr[ru.long(), g_off:g_off + N]; bet = Pr[ru.long(), b_off:b_off + N]
+    yr = torch.nn.functional.layer_norm(xr, (N,), eps=1e-5) * gam + bet
+    (yr * dy).sum().backward()
+    want = dres0 + xr.grad
+    return dict(y32_rel=relerr(y32, x + bias), y16_rel=relerr(y16.float(), yr), dx_rel=relerr(dres, want),
+                dx16_rel=relerr(dx16.float(), want), dparam_rel=relerr(G, Pr.grad))
+
+
 def attn_table(Ts):
     tab, off = [], 0
     for T in Ts:

@@ -60,6 +60,29 @@ def test_layernorm_forward_backward(K, N, bf16_in):
     assert r["dparam_bit_equal"] and r["dparam_writes_only_its_segment"]
 
 
+@pytest.mark.parametrize("N,dy_bf16", [(512, True), (512, False), (64, True)])
+def test_layernorm_gelu_conv_layout(K, N, dy_bf16):
+    """lv60 conv layers: GELU(LayerNorm(x)), gap rows skipped, bf16 gradient replaced in place (HF:291-299)."""
+    r = K.check_layernorm_gelu(N, (70, 3, 129, 300), (5, 0, 250, 13), 9 + N, dy_bf16)
+    assert r["nan"] == 0 and r["gaps_untouched"] and r["dx_gaps_zero"], r
+    # GELU / GELU' use the engine's erf polynomial (common.cuh: ~1e-6 absolute): 1e-4 instead of the 1e-5 of plain LayerNorm
+    assert r["y16_rel"] < BF16 and r["dparam_rel"] < 1e-4, r
+    assert r["dx_rel"] < (BF16 if dy_bf16 else 1e-4), r
+
+
+def test_layernorm_gelu_many_rows(K):
+    r = K.check_layernorm_gelu(512, (5000, 1, 3, 12000, 700), (250, 255, 1, 0, 100), 78, True)
+    assert r["nan"] == 0 and r["dx_rel"] < BF16 and r["dparam_rel"] < 1e-4 and r["gaps_untouched"], r
+
+
+@pytest.mark.parametrize("N", [768, 1024, 128])
+def test_layernorm_keep_input_and_residual_backward(K, N):
+    """lv60 pre-LN encoder: the LayerNorm seeds the residual buffer with its input + bias; its backward adds onto d residual."""
+    r = K.check_layernorm_keep_input(N, (70, 3, 129, 64), 10 + N)
+    assert r["y32_rel"] < F32 and r["dx_rel"] < F32 and r["dparam_rel"] < F32, r
+    assert r["y16_rel"] < BF16 and r["dx16_rel"] < BF16, r
+
+
 def test_layernorm_backward_many_rows_many_utterances(K):
     """Several CTAs per utterance and several utterances per CTA (the slot = CTA + utterance bookkeeping)."""
     r = K.check_layernorm(768, (5000, 1, 1, 3, 12000, 2, 700), 77, False)

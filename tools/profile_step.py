@@ -17,8 +17,9 @@ ap.add_argument("--utts", type=int, default=24)
 ap.add_argument("--seconds", type=float, default=6.0)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--mode", default="ln")
+ap.add_argument("--model", default="base", help="base | large | large_lv60 | tiny ...")
 a = ap.parse_args()
-cfg = ModelConfig.base()
+cfg = getattr(ModelConfig, a.model)()
 mult = None
 if a.mode == "feature":
     sys.path.insert(0, ROOT)
