@@ -395,6 +395,25 @@ def run_b200(a):
         "imbalance_max_over_mean": max(makespan) / (sum(makespan) / len(makespan)),
         "breakdown": breakdown,
     }
+    # batch-1 latency: the reference's own operating point (one utterance at a time, REF/main.py:319-402; its README quotes
+    # RTF ~0.1).  The median-duration utterance of the set adapted ALONE, pinned host audio in, decoded ids out; not part of
+    # `value` (at M ~ 300 tokens the path is launch-bound, not roofline-bound)
+    if rank == 0 and not full:
+        order = sorted(range(len(utts)), key=lambda j: utts[j].n_samples)
+        one = runner.stage(utts, [[order[len(order) // 2]]])[0]
+        ts = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            one_step(one[1], one[2], one[0])
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms1 = sorted(ts[1:])[1]
+        d1 = utts[one[0][0]].duration
+        out["latency_batch1"] = {"utt_seconds": d1, "ms": ms1, "rtf": ms1 / 1e3 / d1,
+                                 "note": f"one utterance adapted alone ({S} steps, reset, decodes), median of 3 after 1 warm-up"}
     # p50 RTF: per-utterance latency (wall time of the batch that carried it, end to end) / its duration, this rank
     rtfs = sorted((t / 1e3) / utts[j].duration for (b, _l, _p), t in zip(staged, step_ms_e2e) for j in b)
     out["rtf_p50"] = rtfs[len(rtfs) // 2]

@@ -156,6 +156,39 @@ def check_tiny_batch(steps=10, cfg_name="tiny"):
     return out
 
 
+def check_ragged_batch(cfg_name="tiny", steps=2):
+    """Edge shapes in ONE batch (empty-ish and ragged inputs, tile boundaries): the shortest possible utterance
+    (T = 1), T = 2, exactly 128 and 129 frames (one GEMM / attention tile and one row more), 256 frames, a long one, and
+    40 more short ones so that the batch exceeds one 64-utterance wave of per-utterance tables.  Forward parity for every
+    utterance; `steps` adaptation steps must reproduce the oracle's logits for the utterances whose loss is defined."""
+    ocfg, mcfg = _cfgs(cfg_name)
+    sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
+
+    def n_for(T):
+        n = 400
+        while ocfg.frames(n) < T:
+            n += 1
+        return n
+    lens = [n_for(1), n_for(2), n_for(128), n_for(129), n_for(256) + 3, 130001, 3001] + [2000 + 37 * i for i in range(40)]
+    wavs = [O.synth_audio(n, 100 + i) for i, n in enumerate(lens)]
+    res = run_engine(cfg_name, sd, wavs, steps)
+    out = {"frames": [int(r["logits"][0].shape[0]) for r in res[:7]]}
+    worst0 = worstN = 0.0
+    for u in list(range(7)) + [10, 46]:
+        x = O.normalize_audio(wavs[u])
+        with torch.no_grad():
+            ref0 = O.model_forward(ocfg, sd, torch.from_numpy(x)[None])[0].numpy()
+        worst0 = max(worst0, float(np.abs(res[u]["logits"][0] - ref0).max()))
+        if u >= 2:                                        # T = 1 / 2: the loss of a one-frame utterance is degenerate
+            ora = O.adapt_utterance(ocfg, sd, x, steps=steps, keep_all_logits=True)
+            if np.isfinite(ora.losses).all():
+                worstN = max(worstN, float(np.abs(res[u]["logits"][steps] - ora.logits[steps]).max()))
+                out[f"loss_rel_u{u}"] = float(np.max(np.abs(np.asarray(res[u]["losses"]) - np.asarray(ora.losses)) / np.abs(ora.losses)))
+    out["logits0_maxabs"], out["logitsN_maxabs"] = worst0, worstN
+    out["all_finite"] = bool(all(np.isfinite(r["logits"][steps]).all() for r in res[2:]))
+    return out
+
+
 def _grad_rel(flat, segments, g0, to_layout):
     num = den = 0.0
     for name, off, size in segments:

@@ -117,6 +117,16 @@ def test_lv60_forward_stages_vs_oracle(E):
         assert rel < 0.03, (name, rel)
 
 
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_lv60"])
+def test_ragged_batch_edge_shapes(E, cfg_name):
+    """T = 1, T = 2, exactly one 128-row tile and one row more, 256 frames, a long utterance and 40 short ones in one batch."""
+    m = E.check_ragged_batch(cfg_name)
+    print(cfg_name, m)
+    assert m["frames"][:5] == [1, 2, 128, 129, 256]
+    assert m["logits0_maxabs"] < LOGIT_TOL and m["logitsN_maxabs"] < LOGIT_TOL and m["all_finite"], m
+    assert all(v < 1e-3 for k, v in m.items() if k.startswith("loss_rel_")), m
+
+
 def test_train_feature_batched_vs_oracle(E):
     """--train_feature: per-utterance CNN/projection weights and the reference's duplicate-parameter Adam semantics."""
     for name, m in E.check_tiny_feat_batch().items():
