@@ -113,6 +113,34 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// gelu_erf / gelu_erf_grad on two values (packed fp32): the same rounded operations as the scalar forms
+__device__ __forceinline__ uint64_t erf_fast2(uint64_t z, float z0, float z1) {      // z = (z0, z1)
+  const uint64_t t = pk2(fabsf(z0), fabsf(z1));
+  uint64_t p = fma2(dup2(-0.002944157226011157f), t, dup2(0.02959004044532776f));
+  p = fma2(p, t, dup2(-0.1486656218767166f));
+  p = fma2(p, t, dup2(-0.9185093641281128f));
+  p = fma2(p, t, dup2(-1.6278890371322632f));
+  p = mul2(p, t);
+  float p0, p1;
+  upk2(p, p0, p1);
+  return pk2(copysignf(1.0f - ex2_approx(p0), z0), copysignf(1.0f - ex2_approx(p1), z1));
+}
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
+  const uint64_t z = mul2(x, dup2(0.70710678118654752f));
+  float z0, z1;
+  upk2(z, z0, z1);
+  const uint64_t hx = mul2(x, dup2(0.5f));
+  return fma2(hx, erf_fast2(z, z0, z1), hx);
+}
+__device__ __forceinline__ uint64_t gelu_erf_grad2(uint64_t x) {
+  const uint64_t z = mul2(x, dup2(0.70710678118654752f));
+  float z0, z1, q0, q1;
+  upk2(z, z0, z1);
+  const uint64_t cdf = fma2(dup2(0.5f), erf_fast2(z, z0, z1), dup2(0.5f));
+  upk2(mul2(mul2(x, x), dup2(-0.72134752044448170f)), q0, q1);
+  const uint64_t pdf = mul2(pk2(ex2_approx(q0), ex2_approx(q1)), dup2(0.39894228040143268f));
+  return fma2(x, pdf, cdf);
+}
 // gelu_erf_both on two values: identical arithmetic (every step is the same rounded fp32 operation), half the
 // FMA-pipe instructions -- the GELU epilogues and conv0 are bound by instruction issue, not by memory
 __device__ __forceinline__ void gelu_erf_both2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {

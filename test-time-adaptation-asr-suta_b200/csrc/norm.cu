@@ -134,9 +134,22 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
       }
       const float mean = warp_sum(s) * (1.0f / N);
       float ss = 0.f;
+      if (MODE == 1) {
+        uint64_t acc = 0ull;
+        const uint64_t nmean = dup2(-mean);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (Cols<N>::active(lane, i)) {
+            const uint64_t a = add2(pk2(v[i].x, v[i].y), nmean), c = add2(pk2(v[i].z, v[i].w), nmean);
+            acc = fma2(a, a, fma2(c, c, acc));
+          }
+        float s0, s1;
+        upk2(acc, s0, s1);
+        ss = s0 + s1;
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (Cols<N>::active(lane, i)) {
+        if (MODE != 1 && Cols<N>::active(lane, i)) {
           float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
           ss += a * a + b * b + c * c + d * d;
         }
@@ -145,9 +158,27 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
         mean_out[row] = mean;
         rstd_out[row] = rstd;
       }
+      if (MODE == 1) {
+        // GELU(LayerNorm) is bound by instruction issue (ncu: 72 % issue, 26 instructions per element): the affine and
+        // the erf polynomial run on packed fp32 pairs (FFMA2), half the FMA-pipe instructions
+        const uint64_t rs2 = dup2(rstd), nm2 = dup2(-mean * rstd);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (Cols<N>::active(lane, i)) {
+            const int col = 4 * lane + 128 * i;
+            const float4 g = gv[i], b = bv[i];
+            const uint64_t y01 = gelu_erf2(fma2(fma2(pk2(v[i].x, v[i].y), rs2, nm2), pk2(g.x, g.y), pk2(b.x, b.y)));
+            const uint64_t y23 = gelu_erf2(fma2(fma2(pk2(v[i].z, v[i].w), rs2, nm2), pk2(g.z, g.w), pk2(b.z, b.w)));
+            float4 o;
+            upk2(y01, o.x, o.y);
+            upk2(y23, o.z, o.w);
+            if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            if (y32) *reinterpret_cast<float4*>(y32 + row * N + col) = o;
+          }
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (Cols<N>::active(lane, i)) {
+        if (MODE != 1 && Cols<N>::active(lane, i)) {
           const int col = 4 * lane + 128 * i;
           const float4 g = gv[i], b = bv[i];
           float4 o;
@@ -155,7 +186,6 @@ ln_fwd_kernel(const TIn* __restrict__ x, const int* __restrict__ row_utt, const 
           o.y = (v[i].y - mean) * rstd * g.y + b.y;
           o.z = (v[i].z - mean) * rstd * g.z + b.z;
           o.w = (v[i].w - mean) * rstd * g.w + b.w;
-          if (MODE == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
           if (y16) *reinterpret_cast<uint2*>(y16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
           if (MODE == 2) o = v[i];
           if (y32) {
@@ -292,12 +322,30 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
         if (act) g = __ldg(reinterpret_cast<const float4*>(P + (long long)u_acc * pstride + g_off + col));
         if (act && MODE == 1) bb = __ldg(reinterpret_cast<const float4*>(P + (long long)u_acc * pstride + b_off + col));
       }
+      if (MODE == 1) {
+        // through the GELU that followed the LayerNorm; packed fp32 pairs (FFMA2): this kernel is bound by instruction
+        // issue, not by memory (profiles/r02g_ncu_full_lv60_kernels.md)
+        const uint64_t rs2 = dup2(rs[r]), nm2 = dup2(-mu[r] * rs[r]);
+        const uint64_t g01 = pk2(g.x, g.y), g23 = pk2(g.z, g.w);
+        const uint64_t xh01 = fma2(pk2(xv[r].x, xv[r].y), rs2, nm2), xh23 = fma2(pk2(xv[r].z, xv[r].w), rs2, nm2);
+        const uint64_t d01 = mul2(pk2(dv[r].x, dv[r].y), gelu_erf_grad2(fma2(xh01, g01, pk2(bb.x, bb.y))));
+        const uint64_t d23 = mul2(pk2(dv[r].z, dv[r].w), gelu_erf_grad2(fma2(xh23, g23, pk2(bb.z, bb.w))));
+        upk2(fma2(d01, xh01, pk2(ag.x, ag.y)), ag.x, ag.y);
+        upk2(fma2(d23, xh23, pk2(ag.z, ag.w)), ag.z, ag.w);
+        upk2(add2(pk2(ab.x, ab.y), d01), ab.x, ab.y);
+        upk2(add2(pk2(ab.z, ab.w), d23), ab.z, ab.w);
+        const uint64_t dxh01 = mul2(d01, g01), dxh23 = mul2(d23, g23);
+        float a0, a1, b0, b1;
+        upk2(add2(dxh01, dxh23), a0, a1);
+        upk2(fma2(dxh01, xh01, mul2(dxh23, xh23)), b0, b1);
+        p1[r] = a0 + a1;
+        p2[r] = b0 + b1;
+        upk2(xh01, xv[r].x, xv[r].y); upk2(xh23, xv[r].z, xv[r].w);
+        upk2(dxh01, dv[r].x, dv[r].y); upk2(dxh23, dv[r].z, dv[r].w);
+        continue;
+      }
       float4 d = dv[r];
       float4 xh = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);
-      if (MODE == 1) {                            // through the GELU that followed the LayerNorm
-        d.x *= gelu_erf_grad(fmaf(xh.x, g.x, bb.x)); d.y *= gelu_erf_grad(fmaf(xh.y, g.y, bb.y));
-        d.z *= gelu_erf_grad(fmaf(xh.z, g.z, bb.z)); d.w *= gelu_erf_grad(fmaf(xh.w, g.w, bb.w));
-      }
       ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
       ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
       const float4 dxh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -333,10 +381,16 @@ ln_bwd_kernel(const TDy* __restrict__ dy, const TIn* __restrict__ x, const float
         c1 *= 1.0f / N;
         c2 *= 1.0f / N;
         float4 o;
-        o.x = rs[r] * (dv[r].x - c1 - xv[r].x * c2);
-        o.y = rs[r] * (dv[r].y - c1 - xv[r].y * c2);
-        o.z = rs[r] * (dv[r].z - c1 - xv[r].z * c2);
-        o.w = rs[r] * (dv[r].w - c1 - xv[r].w * c2);
+        if (MODE == 1) {
+          const uint64_t rs2 = dup2(rs[r]), nc1 = dup2(-c1), nc2 = dup2(-c2);
+          upk2(mul2(rs2, fma2(pk2(xv[r].x, xv[r].y), nc2, add2(pk2(dv[r].x, dv[r].y), nc1))), o.x, o.y);
+          upk2(mul2(rs2, fma2(pk2(xv[r].z, xv[r].w), nc2, add2(pk2(dv[r].z, dv[r].w), nc1))), o.z, o.w);
+        } else {
+          o.x = rs[r] * (dv[r].x - c1 - xv[r].x * c2);
+          o.y = rs[r] * (dv[r].y - c1 - xv[r].y * c2);
+          o.z = rs[r] * (dv[r].z - c1 - xv[r].z * c2);
+          o.w = rs[r] * (dv[r].w - c1 - xv[r].w * c2);
+        }
         if (MODE == 2) { const float4 a = av[MODE == 2 ? r : 0]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         if (dx32) *reinterpret_cast<float4*>(dx32 + row * N + col) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + row * N + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
