@@ -245,7 +245,8 @@ static bool use_posconv_tc(const suta_engine* e) {
 static bool dgrad_fused(const suta_engine* e, int l) {
   const suta_model_cfg& c = e->cfg;
   return e->cnn_bwd && l >= 1 && c.conv_stride[l] == 2 && (c.conv_kernel[l] == 2 || c.conv_kernel[l] == 3) &&
-         c.conv_dim[l] % 64 == 0 && c.conv_dim[l - 1] % 64 == 0 && getenv("SUTA_NO_FUSED_DGRAD") == nullptr;
+         c.conv_dim[l] % 64 == 0 && c.conv_dim[l - 1] % 64 == 0 &&
+         (e->conv_ln || getenv("SUTA_NO_FUSED_DGRAD") == nullptr);   // the debug switch selects train_feature's col2im path only
 }
 
 // geometry of a batch; fills host vectors, returns workspace size through the bump allocator

@@ -112,6 +112,13 @@ def test_lv60_batched_adaptation_matches_per_utterance_oracle(E):
         _assert_parity(m)
 
 
+def test_lv60_adaptation_is_bit_reproducible(E):
+    """Same batch twice: gradients, adapted parameters and logits are the same BITS (two-stage fixed-order reductions of
+    the 2 x (7 + 1 + 2 x layers + 1) LayerNorm gradients, conv layers included)."""
+    r = E.check_determinism("tiny_lv60", False, steps=3)
+    assert r["grad0"] and r["params"] and r["logits"], r
+
+
 def test_lv60_forward_stages_vs_oracle(E):
     for name, rel in E.check_tiny_stages(cfg_name="tiny_lv60").items():
         assert rel < 0.03, (name, rel)
