@@ -5,6 +5,7 @@
 // Backward: see ln_bwd_kernel.  HBM-bound.
 #include "kernels.cuh"
 #include <algorithm>
+#include <atomic>
 
 namespace {
 
@@ -437,11 +438,15 @@ template <int N, typename TIn, int MODE>
 int launch_fwd(const TIn* x, const int* row_utt, UttParams prm, int g_off, int b_off, float* y32, bf16* y16, float* mean,
                float* rstd, long long M, float eps, const float* y32_bias, cudaStream_t stream) {
   using S = FwdSmem<N, TIn>;
-  static int resident = 0;                         // CTAs of this instantiation that fit on one SM
+  // CTAs of this instantiation that fit on one SM.  Published only once it is final (attribute set, value clamped): a second
+  // host thread driving another engine must never see the raw occupancy (> 8 would overrun the backward's slot scratch)
+  static std::atomic<int> resident_pub{0};
+  int resident = resident_pub.load(std::memory_order_acquire);
   if (!resident) {
     CUDA_TRY(cudaFuncSetAttribute(ln_fwd_kernel<N, TIn, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_fwd_kernel<N, TIn, MODE>, FWD_W * 32, S::BYTES));
     resident = std::max(1, std::min(8, resident));
+    resident_pub.store(resident, std::memory_order_release);
   }
   // one wave: at most (resident CTAs per SM) x (SMs) CTAs, rows per CTA a multiple of the tile height
   long long rows = (M + (long long)resident * n_sms() - 1) / ((long long)resident * n_sms());
@@ -464,11 +469,13 @@ int launch_bwd(const TDy* dy, const TIn* x, const float* mean, const float* rstd
                const long long* tok_off, const int* T, int n_utts, float* scratch, cudaStream_t stream, LnReduceItem* defer) {
   constexpr int threads = (N / 4 + 31) / 32 * 32;
   using S = BwdSmem<N, TIn, TDy>;
-  static int resident = 0;                         // CTAs of this instantiation that fit on one SM
+  static std::atomic<int> resident_pub{0};         // see launch_fwd: published only once final
+  int resident = resident_pub.load(std::memory_order_acquire);
   if (!resident) {
     CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<N, TIn, TDy, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ln_bwd_kernel<N, TIn, TDy, MODE>, threads, S::BYTES));
     resident = std::max(1, std::min(8, resident));
+    resident_pub.store(resident, std::memory_order_release);
   }
   const long long rows = bwd_rows_per_cta(M, resident);
   ln_bwd_kernel<N, TIn, TDy, MODE><<<(unsigned)((M + rows - 1) / rows), threads, S::BYTES, stream>>>(
