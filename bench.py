@@ -239,6 +239,8 @@ def run_b200(a):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner on STDOUT, next to the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = a.w
     cfg = getattr(ModelConfig, w["model"])()
