@@ -65,7 +65,7 @@ typedef struct suta_weights {
 } suta_weights;
 
 /* One segment of the per-utterance trainable vector. kind: 0 LN gamma, 1 LN beta, 2 GroupNorm gamma, 3 GroupNorm beta,
- * 4 conv weight (layer index in `index`), 5 projection weight, 6 projection bias.
+ * 4 conv weight (layer index in `index`), 5 projection weight, 6 projection bias, 7 conv bias (feat_norm_layer + TRAIN_FEATURE).
  * module: 0 feature_projection.layer_norm, 1 encoder.layer_norm, 2 layers[index].layer_norm,
  *         3 layers[index].final_layer_norm, 4 feature_extractor.conv_layers[index], 5 feature_projection.projection,
  *         6 feature_extractor.conv_layers[index].layer_norm (feat_norm_layer: kinds 0 / 1) */

@@ -218,6 +218,12 @@ __global__ void conv0_bwd_finalize_kernel(Conv0BwdArgs a) {
     for (int j = 0; j < C0B_MAXK; ++j)
       if (j < k) A[j] += (double)pp[(long long)(1 + j) * a.C];
   }
+  if (a.plain) {                                       // conv + bias only: the accumulated sums ARE the gradients
+    float* Gp = a.G + (long long)u * a.pstride;
+    Gp[a.b_off + c] = (float)S1;
+    for (int j = 0; j < k; ++j) Gp[a.w_off + (long long)c * k + j] = (float)A[j];
+    return;
+  }
   const double* st = a.stats + ((long long)u * a.C + c) * 2;
   const double mu = st[0] / L0;
   const double rstd = 1.0 / sqrt(st[1] / L0 - mu * mu + 1e-5);
@@ -255,6 +261,32 @@ __global__ void colsum_kernel(const float* __restrict__ x, const long long* __re
   G[(long long)u * gstride + g_off + c] = s;
 }
 
+// 8 row lanes x 32 column pairs per CTA; every lane sums its rows in order, the lanes are added in order: same bits every run
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, const long long* __restrict__ row_off, const int* __restrict__ L,
+                   float* __restrict__ G, long long gstride, long long g_off, int C) {
+  __shared__ float2 red[8][32];
+  const int u = blockIdx.y;
+  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cp) * 2;
+  float2 s = make_float2(0.f, 0.f);
+  if (c < C) {
+    const bf16* p = x + row_off[u] * C + c;
+    const int n = L[u];
+    for (int t = lane_r; t < n; t += 8) {
+      const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(p + (long long)t * C)));
+      s.x += v.x; s.y += v.y;
+    }
+  }
+  red[lane_r][cp] = s;
+  __syncthreads();
+  if (lane_r == 0 && c < C) {
+    float2 a = red[0][cp];
+    for (int r = 1; r < 8; ++r) { a.x += red[r][cp].x; a.y += red[r][cp].y; }
+    *reinterpret_cast<float2*>(G + (long long)u * gstride + g_off + c) = a;
+  }
+}
+
 int grid_for(long long total) {
   long long b = (total + 255) / 256, cap = 148LL * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
@@ -290,7 +322,7 @@ int conv_col2im_gelu_grad(const Col2imArgs& a, cudaStream_t stream) {
 }
 
 int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream) {
-  SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0 && a.C % 2 == 0 && a.mom && a.part);
+  SUTA_CHECK_ARG(a.k <= C0B_MAXK && a.n_utts > 0 && a.C % 2 == 0 && (a.mom || a.plain) && a.part);
   SUTA_CHECK_ARG(a.n_chunk >= ceil_div(a.max_L0, C0B_TT));
   dim3 grid(ceil_div(a.max_L0, C0B_TT), a.n_utts);
   size_t smem = sizeof(float) * (C0B_TT * a.stride + a.k + 32);      // slack for the 16-byte window loads
@@ -303,6 +335,14 @@ int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream) {
 int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
                    int C, int n_utts, cudaStream_t stream) {
   colsum_kernel<<<dim3(ceil_div(C, 128), n_utts), 128, 0, stream>>>(x, tok_off, T, G, gstride, g_off, C);
+  CUDA_TRY(cudaGetLastError());
+  return SUTA_OK;
+}
+
+int colsum_per_utt_bf16(const bf16* x, const long long* row_off, const int* L, float* G, long long gstride, long long g_off,
+                        int C, int n_utts, cudaStream_t stream) {
+  SUTA_CHECK_ARG(C % 2 == 0 && g_off % 2 == 0 && gstride % 2 == 0);
+  colsum_bf16_kernel<<<dim3(ceil_div(C, 64), n_utts), 256, 0, stream>>>(x, row_off, L, G, gstride, g_off, C);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

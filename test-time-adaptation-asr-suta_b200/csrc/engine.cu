@@ -81,6 +81,7 @@ struct suta_engine {
   long long gn_g = 0, gn_b = 0, proj_w_off = 0, proj_b_off = 0;
   long long conv_w_off[SUTA_MAX_CONV] = {};
   long long conv_w_size[SUTA_MAX_CONV] = {};
+  long long conv_b_off[SUTA_MAX_CONV] = {};        // conv biases (lv60 family under train_feature)
   long long launches = 0;
   // optional per-launch GEMM timing (bench.py roofline leg): CUDA event pairs around every tcgen05 GEMM launch
   bool profile = false;
@@ -209,12 +210,16 @@ int build_layout(suta_engine* e) {
   }
   e->ln_params = o;
   if (e->train_feature) {
-    e->gn_g = add(2, 4, 0, c.conv_dim[0]);
-    e->gn_b = add(3, 4, 0, c.conv_dim[0]);
+    if (!e->conv_ln) {
+      e->gn_g = add(2, 4, 0, c.conv_dim[0]);
+      e->gn_b = add(3, 4, 0, c.conv_dim[0]);
+    }
     for (int l = 0; l < c.n_conv; ++l) {
       e->conv_w_size[l] = (long long)c.conv_dim[l] * c.conv_kernel[l] * (l ? c.conv_dim[l - 1] : 1);
       e->conv_w_off[l] = add(4, 4, l, e->conv_w_size[l]);     // packed [Cout][(tap, Cin)]
     }
+    if (e->conv_ln)                                           // HF:286 conv_bias=True: Conv1d biases are parameters of the feature extractor too
+      for (int l = 0; l < c.n_conv; ++l) e->conv_b_off[l] = add(7, 4, l, c.conv_dim[l]);
     e->proj_w_off = add(5, 5, 0, (long long)H * C);
     e->proj_b_off = add(6, 5, 0, H);
   }
@@ -425,9 +430,11 @@ void carve(suta_engine* e, Bump& b) {
     for (int l = 0; l < c.n_conv; ++l) {
       const bool last = l == c.n_conv - 1;
       const long long rows = last ? e->R64 : e->rows_total[l];
-      e->conv_pre[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
-      // 128 leading rows (zero): the even-row dgrad GEMM reads row -1 of the first utterance
-      e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
+      if (!e->conv_ln) {         // (the LayerNorm feature extractor keeps z_l instead of GELU' and owns its d z_l buffers above)
+        e->conv_pre[l] = b.take<bf16>((size_t)(e->rows_total[l] + 128) * c.conv_dim[l]);
+        // 128 leading rows (zero): the even-row dgrad GEMM reads row -1 of the first utterance
+        e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
+      }
       if (l >= 1) {
         e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
         size_t z = dgrad_fused(e, l) ? 0 : (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
@@ -437,7 +444,7 @@ void carve(suta_engine* e, Bump& b) {
     e->zbuf = b.take<bf16>(zmax);
     e->proj_shadow = b.take<bf16>((size_t)U * H * C);
     e->dh0_pad = b.take<bf16>((size_t)(e->R64 + 128) * H);
-    e->d_feat = b.take<float>((size_t)M * C);
+    if (!e->conv_ln) e->d_feat = b.take<float>((size_t)M * C);
     e->c0_scratch = b.take<float>((size_t)conv0_bwd_scratch_floats(U, c.conv_dim[0], c.conv_kernel[0], e->max_L0));
   }
   b.off = align_up(b.off, 256);
@@ -546,12 +553,6 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_eng
   e->conv_ln = cfg->feat_norm_layer ? 1 : 0;
   e->stable = cfg->stable_layer_norm ? 1 : 0;
   e->cnn_bwd = e->train_feature || e->conv_ln;
-  if (e->conv_ln && e->train_feature) {
-    suta_set_last_error("train_feature is not built for the LayerNorm feature extractor (feat_extract_norm == \"layer\"): "
-                        "LayerNorm-only adaptation, which already trains its 2 x n_conv conv LayerNorm vectors, is");
-    delete e;
-    return SUTA_ERR_ARG;
-  }
   if (e->conv_ln)
     for (int l = 1; l < cfg->n_conv; ++l)
       if (!dgrad_fused(e, l)) {
@@ -703,7 +704,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
       CUDA_TRY(cudaMemsetAsync(e->conv_out[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
       CUDA_TRY(cudaMemsetAsync(e->conv_dpre[l] - (size_t)128 * c.conv_dim[l], 0, sizeof(bf16) * (size_t)(rows + 256) * c.conv_dim[l], st));
       // GELU' of rows no forward tile covers is multiplied with zero gradients by the fused dgrad: must be finite
-      if (e->train_feature)
+      if (e->train_feature && !e->conv_ln)
         CUDA_TRY(cudaMemsetAsync(e->conv_pre[l], 0, sizeof(bf16) * (size_t)(e->rows_total[l] + 128) * c.conv_dim[l], st));
       // conv_ln: rows of the pre-LayerNorm buffer that no conv tile writes are still streamed through the LayerNorm
       // kernels' shared-memory ring (and skipped): keep them finite
@@ -857,7 +858,13 @@ static int frontend_layer_norm(suta_engine* e, cudaStream_t st) {
   const suta_model_cfg& c = e->cfg;
   UttParams prm{e->P, e->n_params};
   const int last = c.n_conv - 1;
-  if (!e->z0_done) {       // conv0 and its bias are frozen: z_0 depends on the audio only, once per batch (only its LayerNorm moves)
+  const bool tf = e->train_feature != 0;
+  if (tf) {                // per-utterance taps and bias inside the trainable vector: every forward
+    PROF_B("conv0_bias", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2,
+           conv0_bias(e->wav_norm, e->d_samp_off, e->d_L0, e->d_off0, e->P + e->conv_w_off[0], e->P + e->conv_b_off[0], e->conv_z[0], e->U,
+                      c.conv_dim[0], c.conv_kernel[0], c.conv_stride[0], e->max_L0, st, e->n_params, e->n_params));
+    e->launches += 1;
+  } else if (!e->z0_done) {  // conv0 and its bias are frozen: z_0 depends on the audio only, once per batch (only its LayerNorm moves)
     PROF_B("conv0_bias", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2,
            conv0_bias(e->wav_norm, e->d_samp_off, e->d_L0, e->d_off0, e->w.conv0_w, e->w.conv_b[0], e->conv_z[0], e->U, c.conv_dim[0],
                       c.conv_kernel[0], c.conv_stride[0], e->max_L0, st));
@@ -878,7 +885,10 @@ static int frontend_layer_norm(suta_engine* e, cudaStream_t st) {
       p.mblk = e->d_mblk[l]; p.num_mblk = e->n_mblk[l];
       p.epi.bias = e->w.conv_b[l];
       p.epi.out_bf16 = e->conv_z[l]; p.epi.out_ld = Cout;
-      if (l < last) {            // 256-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
+      if (tf) {                  // the utterance's own weights (stacked bf16 copies) and bias: row-masked epilogue, the gap
+        p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin};       // rows of z_l keep their zeros
+        p.epi.bias = e->P + e->conv_b_off[l]; p.epi.bias_utt_stride = e->n_params;
+      } else if (l < last) {     // 256-row-aligned utterances: tiles own their rows (the last layer packs tokens densely)
         p.tiles_own_rows = 1;
         p.out_rows = e->rows_total[l] + 128;
         p.mpair = e->d_mpair[l]; p.num_mpair = e->n_mpair[l];
@@ -1251,6 +1261,20 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   if (e->conv_ln) {
     // ============ LayerNorm feature extractor: the trainable conv LayerNorms put the whole CNN on the backward path ==========
     const int last = c.n_conv - 1;
+    const bool tf = e->train_feature != 0;
+    if (tf) {  // d W_proj[u] = d h0[u]^T y_fp[u], d b_proj[u] = column sums of d h0[u]  (as in the GroupNorm family below)
+      PROF("gelu_grad_pad", gelu_grad_to_padded(da, nullptr, e->dh0_pad, e->d_row_utt, e->d_tok_off, e->d_dpre_off_last, M, H, st));
+      GemmProblem p;
+      p.a = {e->dh0_pad, e->R64 + 128, H, 1, H};
+      p.b = {e->y_fp, M, C, 1, C};
+      p.M = H; p.N = C; p.K = 0; p.nz = e->U;
+      p.ztab = e->d_ztab[c.n_conv];
+      p.epi.out_f32 = e->G + e->proj_w_off; p.epi.out_ld = C; p.out_z_stride = e->n_params;
+      p.flops = 2.0 * H * C * (double)M;
+      SUTA_TRY(gemm(e, p, st));
+      PROF("colsum", colsum_per_utt(da, e->d_tok_off, e->d_T, e->G, e->n_params, e->proj_b_off, H, e->U, st));
+      e->launches += 2;
+    }
     // feature_projection.layer_norm with input gradient (its input, the last conv layer's output, is bf16)
     PROF_B("ln_bwd C", (double)M * C * (4 + 2 + 4), layernorm_backward(e->d_yfp, nullptr, e->conv_out[last], e->fp_mean, e->fp_rstd, e->d_row_utt, prm, (int)e->fp_g,
                                 (int)e->fp_b, e->G, e->d_feat, nullptr, M, C, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
@@ -1267,10 +1291,26 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       const long long dpre_rows = (l == last ? e->R64 : e->rows_total[l]) + 128;
       long long rows_valid = 0, rows_below = 0;
       for (int u = 0; u < e->U; ++u) { rows_valid += e->L[l][u]; rows_below += e->L[l - 1][u]; }
-      // d a_{l-1} = transposed conv of d z_l through the frozen, shared W_l, split by the parity of the input row exactly as
-      // under train_feature (conv_backward above) -- no GELU' factor here: the LayerNorm backward below applies it
+      if (tf) {  // d W_l[u] = d z_l[u]^T im2col(a_{l-1}[u]) (reduction over time), d b_l[u] = column sums of d z_l[u]
+        const int s = c.conv_stride[l];
+        GemmProblem p;
+        p.a = {e->conv_dpre[l], dpre_rows, Cout, 1, Cout};
+        p.b = {e->conv_out[l - 1], (e->rows_total[l - 1] + 128 - k) / s + 1, (long long)s * Cin, 1, (long long)k * Cin};
+        p.M = Cout; p.N = k * Cin; p.K = 0; p.nz = e->U;
+        p.ztab = e->d_ztab[l];
+        p.epi.out_f32 = e->G + e->conv_w_off[l]; p.epi.out_ld = k * Cin; p.out_z_stride = e->n_params;
+        p.flops = 2.0 * Cout * k * Cin * (double)rows_valid;
+        SUTA_TRY(gemm(e, p, st));
+        PROF("colsum", colsum_per_utt_bf16(e->conv_dpre[l], l == last ? e->d_dpre_off_last : e->d_off[l], e->d_L[l], e->G, e->n_params,
+                                           e->conv_b_off[l], Cout, e->U, st));
+        e->launches += 1;
+      }
+      // d a_{l-1} = transposed conv of d z_l through W_l (frozen and shared, or the utterance's own under train_feature), split
+      // by the parity of the input row exactly as in the GroupNorm family below -- no GELU' factor here: the LayerNorm
+      // backward that follows applies it
       GemmProblem p;
       p.b = {reinterpret_cast<const bf16*>(e->w.conv_w[l]), Cout, (long long)k * Cin, 1, (long long)k * Cin};
+      if (tf) p.b = {e->w_shadow[l], (long long)e->U * Cout, (long long)k * Cin, 1, (long long)k * Cin};
       p.M = (int)rows_valid; p.mblk = e->d_dgrad_mblk[l]; p.num_mblk = e->n_dg_mblk[l];
       p.tiles_own_rows = 1; p.out_rows = (e->rows_total[l - 1] + 128) / 2;
       p.epi.out_ld = 2 * Cin;
@@ -1293,15 +1333,25 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       }
       // layer l-1: d z = LayerNorm-backward(d a * GELU'), in place (valid rows only; the gaps stay zero); layer 0 has
       // nothing below it that is trainable: parameter gradients only
-      PROF_B("ln_gelu_bwd C", (double)rows_below * Cin * (2 + 2 + (l > 1 ? 2 : 0)),
+      PROF_B("ln_gelu_bwd C", (double)rows_below * Cin * (2 + 2 + (l > 1 || tf ? 2 : 0)),
              layernorm_gelu_backward(nullptr, e->conv_dpre[l - 1], e->conv_z[l - 1], e->conv_mean[l - 1], e->conv_rstd[l - 1],
                                      e->d_conv_row_utt[l - 1], prm, (int)e->cln_g[l - 1], (int)e->cln_b[l - 1], e->G, nullptr,
-                                     l > 1 ? e->conv_dpre[l - 1] : nullptr, e->rows_total[l - 1], Cin, e->d_off[l - 1], e->d_L[l - 1], e->U,
-                                     ln_slot(), st, &lnred.item[lnred.n]));
+                                     l > 1 || tf ? e->conv_dpre[l - 1] : nullptr, e->rows_total[l - 1], Cin, e->d_off[l - 1], e->d_L[l - 1],
+                                     e->U, ln_slot(), st, &lnred.item[lnred.n]));
       lnred.item[lnred.n].tok_off = e->d_off[l - 1];
       lnred.item[lnred.n].T = e->d_L[l - 1];
       lnred.n += 1;
       e->launches += 1;
+    }
+    if (tf) {  // layer 0: d w_0[c][j] = sum_t d z_0[t,c] x[s t + j], d b_0[c] = sum_t d z_0[t,c]
+      Conv0BwdArgs ba{};
+      ba.x = e->wav_norm; ba.samp_off = e->d_samp_off; ba.L0 = e->d_L0; ba.out_off = e->d_off0;
+      ba.dy = e->conv_dpre[0]; ba.part = e->c0_scratch; ba.n_chunk = conv0_bwd_chunks(e->max_L0);
+      ba.G = e->G; ba.pstride = e->n_params; ba.b_off = e->conv_b_off[0]; ba.w_off = e->conv_w_off[0];
+      ba.n_utts = e->U; ba.C = c.conv_dim[0]; ba.k = c.conv_kernel[0]; ba.stride = c.conv_stride[0]; ba.max_L0 = e->max_L0;
+      ba.plain = 1;
+      PROF_B("conv0_bwd", (double)e->S * 4 + (double)e->rows_total[0] * c.conv_dim[0] * 2, conv0_groupnorm_backward(ba, st));
+      e->launches += 2;
     }
     PROF("ln_bwd_reduce", layernorm_backward_reduce(lnred, e->d_tok_off, e->d_T, e->U, e->G, e->n_params, st));
     e->launches += 1;

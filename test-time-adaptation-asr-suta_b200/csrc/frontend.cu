@@ -317,9 +317,11 @@ constexpr int C0B_ROWS = 128;      // output frames per CTA
 __global__ void __launch_bounds__(256)
 conv0_bias_kernel(const float* __restrict__ x, const long long* __restrict__ samp_off, const int* __restrict__ L0,
                   const long long* __restrict__ out_off, const float* __restrict__ w, const float* __restrict__ bias,
-                  bf16* __restrict__ out, int C, int k, int stride) {
+                  bf16* __restrict__ out, int C, int k, int stride, long long w_stride, long long b_stride) {
   extern __shared__ float wsm[];                 // [k][C] taps (transposed: a channel octet reads 8 consecutive floats), then [C] bias
   const int u = blockIdx.y;
+  w += (long long)u * w_stride;
+  if (bias) bias += (long long)u * b_stride;
   const int L = L0[u];
   const int t0 = blockIdx.x * C0B_ROWS;
   if (t0 >= L) return;
@@ -353,8 +355,10 @@ template <int K>
 __global__ void __launch_bounds__(256)
 conv0_bias_reg_kernel(const float* __restrict__ x, const long long* __restrict__ samp_off, const int* __restrict__ L0,
                       const long long* __restrict__ out_off, const float* __restrict__ w, const float* __restrict__ bias,
-                      bf16* __restrict__ out, int C, int stride, int rows_per_cta) {
+                      bf16* __restrict__ out, int C, int stride, int rows_per_cta, long long w_stride, long long b_stride) {
   const int u = blockIdx.y;
+  w += (long long)u * w_stride;
+  if (bias) bias += (long long)u * b_stride;
   const int L = L0[u];
   const int t0 = blockIdx.x * rows_per_cta;
   if (t0 >= L) return;
@@ -396,14 +400,15 @@ __global__ void fill_row_utt_kernel(int* __restrict__ row_utt, const long long* 
 }  // namespace
 
 int conv0_bias(const float* x, const long long* samp_off, const int* L0, const long long* out_off, const float* w,
-               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream) {
+               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream,
+               long long w_stride, long long b_stride) {
   SUTA_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && k > 0 && k <= 32);
   if (k == 10) {
     // ~4 CTAs per SM and utterance column; at least 256 rows per CTA so the 88 register-resident weights amortise
     int rows = ceil_div(max_L0, 4 * 148);
     rows = rows < 256 ? 256 : (rows + 63) / 64 * 64;
     conv0_bias_reg_kernel<10><<<dim3((unsigned)ceil_div(max_L0, rows), (unsigned)n_utts), 256, 0, stream>>>(
-        x, samp_off, L0, out_off, w, bias, out, C, stride, rows);
+        x, samp_off, L0, out_off, w, bias, out, C, stride, rows, w_stride, b_stride);
     CUDA_TRY(cudaGetLastError());
     return SUTA_OK;
   }
@@ -414,7 +419,7 @@ int conv0_bias(const float* x, const long long* samp_off, const int* L0, const l
     smem_set = smem;
   }
   conv0_bias_kernel<<<dim3((unsigned)ceil_div(max_L0, C0B_ROWS), (unsigned)n_utts), 256, smem, stream>>>(
-      x, samp_off, L0, out_off, w, bias, out, C, k, stride);
+      x, samp_off, L0, out_off, w, bias, out, C, k, stride, w_stride, b_stride);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }

@@ -89,8 +89,10 @@ int audio_conv0_moments(const float* x, const long long* samp_off, const int* L0
 
 // LayerNorm feature extractor, layer 0 (HF/modeling_wav2vec2.py:281-292): z0 = Conv1d(1 -> C, k, stride) + bias, channels-last
 // bf16 at out_off[u] + t (bias may be null); w fp32 [C][k]
+// w_stride / b_stride != 0: per-utterance taps / bias inside the trainable vector (w + u * w_stride), train_feature
 int conv0_bias(const float* x, const long long* samp_off, const int* L0, const long long* out_off, const float* w,
-               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream);
+               const float* bias, bf16* out, int n_utts, int C, int k, int stride, int max_L0, cudaStream_t stream,
+               long long w_stride = 0, long long b_stride = 0);
 // row_utt[off[u] + t] = u for t < L[u], every other row of [0, rows) = -1
 int fill_row_utt(int* row_utt, long long rows, const long long* off, const int* L, int n_utts, int max_L, cudaStream_t stream);
 
@@ -126,12 +128,17 @@ struct Conv0BwdArgs {
   long long pstride;
   long long g_off, b_off, w_off;
   int n_utts, C, k, stride, max_L0;
+  int plain;                   // 1: no GroupNorm behind the conv (lv60 family): dy is d(conv output), the result is just
+                               //    d w[c][j] = sum_t dy[t,c] x[s t + j] -> G[w_off ..], d bias[c] = sum_t dy[t,c] -> G[b_off ..]
 };
 int conv0_groupnorm_backward(const Conv0BwdArgs& a, cudaStream_t stream);
 long long conv0_bwd_scratch_floats(int n_utts, int C, int k, int max_L0);
 int conv0_bwd_chunks(int max_L0);
 int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float* G, long long gstride, long long g_off,
                    int C, int n_utts, cudaStream_t stream);
+// the same over bf16 rows (conv bias gradient of the lv60 family: column sums of d z_l over an utterance's rows), fixed order
+int colsum_per_utt_bf16(const bf16* x, const long long* row_off, const int* L, float* G, long long gstride, long long g_off,
+                        int C, int n_utts, cudaStream_t stream);
 
 // ---- posconv_tc.cu --------------------------------------------------------------------------
 // grouped positional conv on tcgen05 with a shared-memory-resident input window (CG = H/G in {48, 64})

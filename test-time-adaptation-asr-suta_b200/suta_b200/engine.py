@@ -22,7 +22,8 @@ _MODULE_NAMES = {0: "wav2vec2.feature_projection.layer_norm", 1: "wav2vec2.encod
                  2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm",
                  4: "wav2vec2.feature_extractor.conv_layers.{i}", 5: "wav2vec2.feature_projection.projection",
                  6: "wav2vec2.feature_extractor.conv_layers.{i}.layer_norm"}
-_KIND_LEAF = {0: "weight", 1: "bias", 2: "layer_norm.weight", 3: "layer_norm.bias", 4: "conv.weight", 5: "weight", 6: "bias"}
+_KIND_LEAF = {0: "weight", 1: "bias", 2: "layer_norm.weight", 3: "layer_norm.bias", 4: "conv.weight", 5: "weight", 6: "bias",
+              7: "conv.bias"}
 
 
 @dataclass
@@ -75,9 +76,8 @@ class SutaEngine:
             cc.conv_dim[i], cc.conv_kernel[i], cc.conv_stride[i] = c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i]
         cc.pos_k, cc.pos_groups, cc.ln_eps = c.num_conv_pos_embeddings, c.num_conv_pos_embedding_groups, c.layer_norm_eps
         cc.feat_norm_layer, cc.stable_layer_norm = int(c.feat_extract_norm == "layer"), int(c.do_stable_layer_norm)
-        if self.train_feature and c.feat_extract_norm == "layer":
-            raise NotImplementedError("--train_feature is not built for the LayerNorm feature extractor (lv60 family); "
-                                      "LayerNorm-only adaptation (which trains its conv LayerNorms) is")
+        if self.train_feature and c.feat_extract_norm == "layer" and not c.conv_bias:
+            raise NotImplementedError("--train_feature on a LayerNorm feature extractor without conv bias (no checkpoint has one)")
         h = C.c_void_p()
         self.pseudo_label = bool(pseudo_label)         # SDPL: reserves the CTC lattice scratch in every batch workspace
         check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature) | (2 if self.pseudo_label else 0), C.byref(h)))
@@ -185,6 +185,8 @@ class SutaEngine:
 
     def set_trainable(self, mult_by_name: Dict[str, int]):
         """Re-select what the optimizer updates (collect_params' result): name -> multiplicity (0 = frozen)."""
+        if max(list(mult_by_name.values()) + [0]) > 6:
+            raise ValueError("a parameter listed more than 6 times (csrc/optim.cu MAXK)")
         m = torch.zeros(self.n_params, dtype=torch.uint8)
         for name, off, size in self.segments:
             m[off:off + size] = int(mult_by_name.get(name, 0))

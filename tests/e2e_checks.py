@@ -205,20 +205,21 @@ def _mult(ocfg, train_feature, bias_only=False):
     return m
 
 
-def check_tiny_feat_batch(steps=5):
+def check_tiny_feat_batch(steps=5, cfg_name="tiny"):
     """train_feature: per-utterance CNN + projection weights, duplicate-parameter Adam semantics (REF/main.py:88-94)."""
-    ocfg, _ = _cfgs("tiny")
+    ocfg, _ = _cfgs(cfg_name)
     sd = O.init_weights(ocfg, 4, blank_bias=0.35, ln_jitter=0.1)
     lens, seeds = [9000, 12000, 3000], [12, 15, 16]
     wavs = [O.synth_audio(n, s) for n, s in zip(lens, seeds)]
-    res = run_engine("tiny", sd, wavs, steps, keep_grads=True, train_feature=True, mult=_mult(ocfg, True))
+    res = run_engine(cfg_name, sd, wavs, steps, keep_grads=True, train_feature=True, mult=_mult(ocfg, True))
     out = {}
     for u, w in enumerate(wavs):
         ora = O.adapt_utterance(ocfg, sd, O.normalize_audio(w), steps=steps, train_feature=True)
         ref_logits = dict(ora.logits); ref_logits[0] = ora.logits0
         m = compare(res[u], ref_logits, ora.losses, ora.params, sd, ref_ids=True, ocfg=ocfg, x=O.normalize_audio(w))
         # per-group delta errors localise a broken gradient
-        for grp in ("conv_layers.0.conv", "conv_layers.0.layer_norm", "conv_layers.3.conv", "conv_layers.6.conv",
+        for grp in ("conv_layers.0.conv.weight", "conv_layers.0.conv.bias", "conv_layers.0.layer_norm", "conv_layers.3.conv.weight",
+                    "conv_layers.3.conv.bias", "conv_layers.3.layer_norm", "conv_layers.6.conv.weight", "conv_layers.6.layer_norm",
                     "feature_projection.projection.weight", "feature_projection.projection.bias", "feature_projection.layer_norm",
                     "encoder.layers.0.layer_norm"):
             num = den = 0.0
@@ -227,7 +228,8 @@ def check_tiny_feat_batch(steps=5):
                     p0 = sd[name].numpy().reshape(-1)
                     num += float(np.sum((res[u]["params"][name] - p.reshape(-1)) ** 2))
                     den += float(np.sum((p.reshape(-1) - p0) ** 2))
-            m["delta:" + grp] = float(np.sqrt(num / max(den, 1e-30)))
+            if den > 0:
+                m["delta:" + grp] = float(np.sqrt(num / max(den, 1e-30)))
         out[f"utt{u}_T{ora.logits0.shape[0]}"] = m
     return out
 

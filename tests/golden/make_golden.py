@@ -64,6 +64,9 @@ CASES = {
     "tiny_lv60_ln": _case("tiny_lv60", 12000, 11, 3, 0.5, 0.1, 10),
     "tiny_lv60_short": _case("tiny_lv60", 2000, 13, 5, 0.35, 0.1, 5),
     "large_lv60_2s": _case("large_lv60", 32000, 41, 0, 2.5, 0.0, 3),
+    # --train_feature on that family: conv weights AND biases x4, conv LayerNorms x5 (once as LayerNorm + four enclosing modules)
+    # (audio seed chosen so that the reference's own non-blank decisions stand clear of the engine's logit error: T = 27 frames)
+    "tiny_lv60_feat": _case("tiny_lv60", 9000, 53, 4, 0.35, 0.1, 10, True),
 }
 BIG = 1 << 16      # tensors above this many elements are stored as (checksum, head) only
 

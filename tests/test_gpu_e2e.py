@@ -134,16 +134,19 @@ def test_ragged_batch_edge_shapes(E, cfg_name):
     assert all(v < 1e-3 for k, v in m.items() if k.startswith("loss_rel_")), m
 
 
-def test_train_feature_batched_vs_oracle(E):
-    """--train_feature: per-utterance CNN/projection weights and the reference's duplicate-parameter Adam semantics."""
-    for name, m in E.check_tiny_feat_batch().items():
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_lv60"])
+def test_train_feature_batched_vs_oracle(E, cfg_name):
+    """--train_feature: per-utterance CNN/projection weights and the reference's duplicate-parameter Adam semantics; on the
+    lv60 family also the conv biases (x4) and the conv LayerNorms (x5: once as LayerNorm, four times as feature extractor)."""
+    for name, m in E.check_tiny_feat_batch(cfg_name=cfg_name).items():
+        print(cfg_name, name, m)
         _assert_parity(m)
         for k, v in m.items():
             if k.startswith("delta:"):
                 assert v < 0.25, (name, k, v)
 
 
-@pytest.mark.parametrize("case", ["tiny_feat", "base_feat_2s", "base_feat_5s", "tiny_feat_noise20", "tiny_feat_sgd"])
+@pytest.mark.parametrize("case", ["tiny_feat", "base_feat_2s", "base_feat_5s", "tiny_feat_noise20", "tiny_feat_sgd", "tiny_lv60_feat"])
 def test_train_feature_against_reference_golden_vectors(E, case):
     """--train_feature incl. BASELINE.json configs[1]'s shape (base, 10 steps: base_feat_5s) and configs[4]'s recipe
     (20 steps, extra_noise 0.01: tiny_feat_noise20).  Here the adaptation moves the logits far above the forward's
