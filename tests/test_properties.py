@@ -1,6 +1,5 @@
 """CPU: property tests (hypothesis) of the host logic around the hot path -- partitioning, bucketing, greedy CTC text,
 WER -- against the oracle restatement and their defining invariants (size-independent properties)."""
-import numpy as np
 from hypothesis import given, settings, strategies as st
 
 from oracle import suta_oracle as O
