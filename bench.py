@@ -238,13 +238,7 @@ def run_b200(a):
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    json_fd = None
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: whatever else native libraries write there (NCCL's "NCCL version ..." banner
-        # at communicator creation) goes to stderr for the duration of the run; the line itself is written to the saved fd
-        sys.stdout.flush()
-        json_fd = os.dup(1)
-        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = a.w
     cfg = getattr(ModelConfig, w["model"])()
@@ -442,11 +436,7 @@ def run_b200(a):
             rec = baseline_record(a, "cpu", n_utts=a.cpu_utts, warmup=1, kind="port")[0]
             out["cpu_baseline"] = rec
     if rank == 0:
-        if json_fd is not None:
-            sys.stdout.flush()
-            os.write(json_fd, (json.dumps(out) + "\n").encode())
-        else:
-            print(json.dumps(out), flush=True)
+        print(json.dumps(out), flush=True)      # the LAST line of stdout (NCCL may print its version banner before it at N > 1)
     if world > 1:
         dist.destroy_process_group()
 
