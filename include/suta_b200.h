@@ -19,7 +19,7 @@ extern "C" {
 
 #define SUTA_MAX_LAYERS 48
 #define SUTA_MAX_CONV 8
-#define SUTA_ABI_VERSION 3
+#define SUTA_ABI_VERSION 4
 
 typedef struct suta_engine suta_engine;
 
@@ -65,10 +65,13 @@ typedef struct suta_weights {
 } suta_weights;
 
 /* One segment of the per-utterance trainable vector. kind: 0 LN gamma, 1 LN beta, 2 GroupNorm gamma, 3 GroupNorm beta,
- * 4 conv weight (layer index in `index`), 5 projection weight, 6 projection bias, 7 conv bias (feat_norm_layer + TRAIN_FEATURE).
+ * 4 conv weight (layer index in `index`), 5 linear weight [out,in], 6 linear / conv bias, 7 conv bias (feat_norm_layer +
+ * TRAIN_FEATURE), 8 weight_norm magnitude g [K] and 9 weight_norm direction v [H, H/G, K] of the positional conv (TRAIN_ALL).
  * module: 0 feature_projection.layer_norm, 1 encoder.layer_norm, 2 layers[index].layer_norm,
  *         3 layers[index].final_layer_norm, 4 feature_extractor.conv_layers[index], 5 feature_projection.projection,
- *         6 feature_extractor.conv_layers[index].layer_norm (feat_norm_layer: kinds 0 / 1) */
+ *         6 feature_extractor.conv_layers[index].layer_norm (feat_norm_layer: kinds 0 / 1),
+ *         TRAIN_ALL only: 7 / 8 / 9 / 10 layers[index].attention.{q,k,v,out}_proj, 11 layers[index].feed_forward.intermediate_dense,
+ *         12 layers[index].feed_forward.output_dense, 13 lm_head, 14 encoder.pos_conv_embed.conv */
 typedef struct suta_param_seg {
   int32_t kind, module, index;
   int64_t offset, size;
@@ -92,6 +95,9 @@ int suta_device_sm_count(void);
  *      collect_params, REF/main.py:302-307; train_feature as REF/main.py:88-94) ---------------------------- */
 #define SUTA_FLAG_TRAIN_FEATURE 1          /* REF/main.py:88-94: CNN front end + projection adapted per utterance */
 #define SUTA_FLAG_PSEUDO_LABEL 2           /* REF/main_SDPL.py: reserve the CTC scratch (alpha lattice) in every batch workspace */
+#define SUTA_FLAG_TRAIN_ALL 4              /* REF/main.py:96-100: EVERY parameter of the model is the utterance's own (implies
+                                            * TRAIN_FEATURE's layout; GroupNorm / post-LN family; one utterance per batch, as
+                                            * the reference adapts: nothing is shared between utterances any more) */
 int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_engine** out);
 void suta_engine_destroy(suta_engine* e);
 int64_t suta_engine_param_count(const suta_engine* e);

@@ -64,13 +64,13 @@ class ReferenceLoop:
 
     def __init__(self, cfg: O.W2V2Config, sd: Dict[str, torch.Tensor], device: str = "cpu", train_feature: bool = False,
                  bias_only: bool = False, opt: str = "AdamW", lr: float = 2e-5, beta: float = 0.9,
-                 sched_gamma: Optional[float] = None):
+                 sched_gamma: Optional[float] = None, train_all: bool = False):
         self.device = device
         self.model = build_model(cfg, sd, device)
         self.model.requires_grad_(False)                                       # configure_model, REF/main.py:167-170
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")                                    # torch warns about duplicate parameters
-            self.params, self.names = collect_params(self.model, bias_only, train_feature)
+            self.params, self.names = collect_params(self.model, bias_only, train_feature, train_all)
             kw = dict(betas=(beta, 0.999)) if opt == "Adam" else {}            # REF/main.py:12-18
             self.optimizer = getattr(torch.optim, opt)(self.params, lr=lr, weight_decay=0.0, **kw)
         self.scheduler = (torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=1, gamma=sched_gamma)
@@ -119,7 +119,9 @@ class ReferenceLoop:
             if (i + 1) in O.CHECKPOINT_STEPS:
                 res.texts[i + 1] = O.ctc_greedy_decode(res.logits[i + 1])
         msd = self.model.state_dict()
-        res.params = {n: msd[n].detach().cpu().numpy().copy() for n in dict.fromkeys(self.names)}
+        # (train_all lists the root module's parameters as ".<name>" and wav2vec2.masked_spec_embed, which the state dict of
+        #  an eval-mode model may not carry: every real parameter is also listed under its full name)
+        res.params = {n: msd[n].detach().cpu().numpy().copy() for n in dict.fromkeys(self.names) if n in msd}
         return res
 
 

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "libsuta_b200.so")
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_fwd2_tc.cu", "attention_bwd_tc.cu", "norm.cu", "loss.cu", "ctc.cu", "optim.cu", "decode.cu", "frontend.cu", "posconv.cu", "posconv_tc.cu", "convbwd.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_fwd2_tc.cu", "attention_bwd_tc.cu", "norm.cu", "loss.cu", "ctc.cu", "optim.cu", "decode.cu", "frontend.cu", "posconv.cu", "posconv_tc.cu", "convbwd.cu", "trainall.cu"]
 NVCC_FLAGS = (["-DATTN_TIMING"] if os.environ.get("ATTN_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

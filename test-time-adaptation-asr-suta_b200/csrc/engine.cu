@@ -68,6 +68,19 @@ struct suta_engine {
   // cnn_bwd = the batch layout / tables / buffers a backward through the CNN needs (train_feature or conv_ln)
   int conv_ln = 0, stable = 0, cnn_bwd = 0;
   int pseudo_label = 0;                            // SUTA_FLAG_PSEUDO_LABEL: CTC scratch is part of every batch workspace
+  // SUTA_FLAG_TRAIN_ALL (REF/main.py:96-100): every weight and bias of the model lives in the trainable vector (train_feature's
+  // layout plus the segments below); the GEMM operands are bf16 copies of that vector (Pb) and transposed copies for the
+  // dgrads, refreshed after every update; one utterance per batch (nothing is shared between utterances any more)
+  int train_all = 0;
+  std::vector<long long> wqkv_off, bqkv_off, wo_off, bo_off, w1_off, b1_off, w2_off, b2_off;
+  long long lm_w_off = 0, lm_b_off = 0, pos_g_off = 0, pos_v_off = 0, pos_b_off = 0;
+  struct TaLayer {
+    bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;             // [H,3H], [H,H], [H,I], [I,H]
+    bf16 *xa, *xf, *gl;                            // saved GEMM inputs of the layer: LayerNorm outputs [M,H] x2, GELU output [M,I]
+  };
+  std::vector<TaLayer> ta;
+  bf16 *Pb = nullptr, *lm_w_t_sh = nullptr, *pos_w_sh = nullptr, *pos_w_t_sh = nullptr, *x_last16 = nullptr, *xg_grad = nullptr;
+  float *pos_dW = nullptr, *wn_scratch = nullptr;
   suta_weights w{};
   bool have_weights = false;
   std::vector<Seg> segs;
@@ -222,6 +235,30 @@ int build_layout(suta_engine* e) {
       for (int l = 0; l < c.n_conv; ++l) e->conv_b_off[l] = add(7, 4, l, c.conv_dim[l]);
     e->proj_w_off = add(5, 5, 0, (long long)H * C);
     e->proj_b_off = add(6, 5, 0, H);
+  }
+  if (e->train_all) {
+    const int I = c.intermediate, K = c.pos_k, CG = H / c.pos_groups;
+    e->pos_g_off = add(8, 14, 0, K);                               // weight_norm: g [1,1,K], v [H, H/G, K] (HF layout), bias [H]
+    e->pos_v_off = add(9, 14, 0, (long long)H * CG * K);
+    e->pos_b_off = add(6, 14, 0, H);
+    auto v = [&](std::vector<long long>& x) { x.assign(c.layers, 0); };
+    v(e->wqkv_off); v(e->bqkv_off); v(e->wo_off); v(e->bo_off); v(e->w1_off); v(e->b1_off); v(e->w2_off); v(e->b2_off);
+    for (int l = 0; l < c.layers; ++l) {
+      e->wqkv_off[l] = add(5, 7, l, (long long)H * H);             // q, k, v weights back to back = the fused [3H, H] operand
+      add(5, 8, l, (long long)H * H);
+      add(5, 9, l, (long long)H * H);
+      e->bqkv_off[l] = add(6, 7, l, H);
+      add(6, 8, l, H);
+      add(6, 9, l, H);
+      e->wo_off[l] = add(5, 10, l, (long long)H * H);
+      e->bo_off[l] = add(6, 10, l, H);
+      e->w1_off[l] = add(5, 11, l, (long long)I * H);
+      e->b1_off[l] = add(6, 11, l, I);
+      e->w2_off[l] = add(5, 12, l, (long long)H * I);
+      e->b2_off[l] = add(6, 12, l, H);
+    }
+    e->lm_w_off = add(5, 13, 0, (long long)c.vocab * H);
+    e->lm_b_off = add(6, 13, 0, c.vocab);
   }
   e->n_params = o;
   return SUTA_OK;
@@ -425,6 +462,7 @@ void carve(suta_engine* e, Bump& b) {
     }
     e->d_feat = b.take<float>((size_t)M * C);
   }
+  if (e->train_all) e->Pb = b.take<bf16>((size_t)e->n_params);      // U == 1: the conv / projection operand copies live in it too
   if (e->train_feature) {
     size_t zmax = 0;
     for (int l = 0; l < c.n_conv; ++l) {
@@ -436,21 +474,65 @@ void carve(suta_engine* e, Bump& b) {
         e->conv_dpre[l] = b.take<bf16>((size_t)(rows + 256) * c.conv_dim[l]) + (size_t)128 * c.conv_dim[l];
       }
       if (l >= 1) {
-        e->w_shadow[l] = b.take<bf16>((size_t)U * e->conv_w_size[l]);
+        e->w_shadow[l] = e->train_all ? e->Pb + e->conv_w_off[l] : b.take<bf16>((size_t)U * e->conv_w_size[l]);
         size_t z = dgrad_fused(e, l) ? 0 : (size_t)(rows + 128) * c.conv_kernel[l] * c.conv_dim[l - 1];
         zmax = z > zmax ? z : zmax;
       }
     }
     e->zbuf = b.take<bf16>(zmax);
-    e->proj_shadow = b.take<bf16>((size_t)U * H * C);
+    e->proj_shadow = e->train_all ? e->Pb + e->proj_w_off : b.take<bf16>((size_t)U * H * C);
     e->dh0_pad = b.take<bf16>((size_t)(e->R64 + 128) * H);
     if (!e->conv_ln) e->d_feat = b.take<float>((size_t)M * C);
     e->c0_scratch = b.take<float>((size_t)conv0_bwd_scratch_floats(U, c.conv_dim[0], c.conv_kernel[0], e->max_L0));
+  }
+  if (e->train_all) {
+    const size_t K = c.pos_k, CG = H / c.pos_groups;
+    e->ta.resize(c.layers);
+    for (int l = 0; l < c.layers; ++l) {
+      suta_engine::TaLayer& t = e->ta[l];
+      t.wqkv_t = b.take<bf16>((size_t)3 * H * H); t.wo_t = b.take<bf16>((size_t)H * H);
+      t.w1_t = b.take<bf16>((size_t)I * H); t.w2_t = b.take<bf16>((size_t)H * I);
+      t.xa = b.take<bf16>((size_t)M * H); t.xf = b.take<bf16>((size_t)M * H); t.gl = b.take<bf16>((size_t)M * I);
+    }
+    e->x_last16 = b.take<bf16>((size_t)M * H);
+    e->lm_w_t_sh = b.take<bf16>((size_t)H * V);
+    e->pos_w_sh = b.take<bf16>((size_t)H * K * CG); e->pos_w_t_sh = b.take<bf16>((size_t)H * K * CG);
+    e->xg_grad = b.take<bf16>((size_t)(e->R + 8) * H);
+    e->pos_dW = b.take<float>((size_t)H * K * CG);
+    e->wn_scratch = b.take<float>((size_t)posconv_weight_norm_scratch_floats(c.pos_k));
   }
   b.off = align_up(b.off, 256);
 }
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Where the encoder's GEMM operands live: the frozen shared weights handed over by suta_engine_set_weights, or (train_all)
+// the bf16 copies of the utterance's own trainable vector (Pb, transposed copies) and fp32 biases inside P (U == 1).
+struct LayerW {
+  const bf16 *wqkv, *wqkv_t, *wo, *wo_t, *w1, *w1_t, *w2, *w2_t;
+  const float *bqkv, *bo, *b1, *b2;
+};
+inline const bf16* B16(const void* p) { return reinterpret_cast<const bf16*>(p); }
+LayerW layer_w(const suta_engine* e, int l) {
+  if (!e->train_all) {
+    const suta_layer_weights& w = e->w.layer[l];
+    return {B16(w.wqkv), B16(w.wqkv_t), B16(w.wo), B16(w.wo_t), B16(w.w1), B16(w.w1_t), B16(w.w2), B16(w.w2_t), w.bqkv, w.bo, w.b1, w.b2};
+  }
+  const suta_engine::TaLayer& t = e->ta[l];
+  return {e->Pb + e->wqkv_off[l], t.wqkv_t, e->Pb + e->wo_off[l], t.wo_t, e->Pb + e->w1_off[l], t.w1_t, e->Pb + e->w2_off[l], t.w2_t,
+          e->P + e->bqkv_off[l], e->P + e->bo_off[l], e->P + e->b1_off[l], e->P + e->b2_off[l]};
+}
+inline const bf16* lm_w(const suta_engine* e) { return e->train_all ? e->Pb + e->lm_w_off : B16(e->w.lm_w); }
+inline const bf16* lm_w_t(const suta_engine* e) { return e->train_all ? e->lm_w_t_sh : B16(e->w.lm_w_t); }
+inline const float* lm_b(const suta_engine* e) { return e->train_all ? e->P + e->lm_b_off : e->w.lm_b; }
+inline const bf16* pos_w(const suta_engine* e) { return e->train_all ? e->pos_w_sh : B16(e->w.pos_w); }
+inline const bf16* pos_w_t(const suta_engine* e) { return e->train_all ? e->pos_w_t_sh : B16(e->w.pos_w_t); }
+inline const float* pos_b(const suta_engine* e) { return e->train_all ? e->P + e->pos_b_off : e->w.pos_b; }
+// bf16 GEMM inputs the weight gradients of train_all need again in the backward: kept per layer instead of in the shared
+// b16 / gelu16 scratch.  act_xa(l): input of layer l's q/k/v projections (l == layers: of lm_head); act_xf: of FFN1; act_gl: of FFN2
+inline bf16* act_xa(const suta_engine* e, int l) { return !e->train_all ? e->b16 : (l < e->cfg.layers ? e->ta[l].xa : e->x_last16); }
+inline bf16* act_xf(const suta_engine* e, int l) { return e->train_all ? e->ta[l].xf : e->b16; }
+inline bf16* act_gl(const suta_engine* e, int l) { return e->train_all ? e->ta[l].gl : e->gelu16; }
 
 // CUDA-event pair around one launch (or group of launches) when profiling is on; records (tag, flops) for the report
 struct ProfScope {
@@ -538,21 +620,46 @@ GemmProblem dense(const bf16* A, long long M, int K, const bf16* B, int N) {
   return p;
 }
 
+// train_all: gradient of one Linear of the encoder, written whole into the gradient vector (U == 1):
+//   d W [n_out, n_in] = d Y^T X   (both operands MN-major, the reduction runs over the utterance's frames; rows past the
+//                                  last frame are out of bounds of the tensor maps and read as zeros)
+//   d b [n_out]       = column sums of d Y   (bf16 rows, fixed order)
+int linear_param_grads(suta_engine* e, const bf16* dY, int n_out, const bf16* X, int n_in, long long w_off, long long b_off,
+                       cudaStream_t st) {
+  GemmProblem p;
+  p.a = {dY, e->M, n_out, 1, n_out};
+  p.b = {X, e->M, n_in, 1, n_in};
+  p.M = n_out; p.N = n_in; p.K = 0; p.nz = 1;
+  p.ztab = e->d_ztab[e->cfg.n_conv];               // U == 1: {0, 0, T}
+  p.epi.out_f32 = e->G + w_off; p.epi.out_ld = n_in; p.out_z_stride = e->n_params;
+  p.flops = 2.0 * n_out * n_in * (double)e->M;
+  SUTA_TRY(gemm(e, p, st));
+  PROF("colsum", colsum_per_utt_bf16(dY, e->d_tok_off, e->d_T, e->G, e->n_params, b_off, n_out, e->U, st));
+  e->launches += 1;
+  return SUTA_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
 // C ABI
 // =================================================================================================
 extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_engine** out) {
-  SUTA_CHECK_ARG(cfg && out && (flags & ~(SUTA_FLAG_TRAIN_FEATURE | SUTA_FLAG_PSEUDO_LABEL)) == 0);
+  SUTA_CHECK_ARG(cfg && out && (flags & ~(SUTA_FLAG_TRAIN_FEATURE | SUTA_FLAG_PSEUDO_LABEL | SUTA_FLAG_TRAIN_ALL)) == 0);
   SUTA_TRY(check_cfg(*cfg));
   suta_engine* e = new suta_engine();
   e->cfg = *cfg;
-  e->train_feature = (flags & SUTA_FLAG_TRAIN_FEATURE) ? 1 : 0;
+  e->train_all = (flags & SUTA_FLAG_TRAIN_ALL) ? 1 : 0;
+  e->train_feature = (flags & (SUTA_FLAG_TRAIN_FEATURE | SUTA_FLAG_TRAIN_ALL)) ? 1 : 0;
   e->pseudo_label = (flags & SUTA_FLAG_PSEUDO_LABEL) ? 1 : 0;
   e->conv_ln = cfg->feat_norm_layer ? 1 : 0;
   e->stable = cfg->stable_layer_norm ? 1 : 0;
   e->cnn_bwd = e->train_feature || e->conv_ln;
+  if (e->train_all && (e->conv_ln || e->stable)) {       // REF/main_SDPL.py (the script of the lv60 checkpoints) has no --train_all
+    suta_set_last_error("SUTA_FLAG_TRAIN_ALL is built for the GroupNorm / post-LN family (wav2vec2-base-960h, REF/main.py)");
+    delete e;
+    return SUTA_ERR_ARG;
+  }
   if (e->conv_ln)
     for (int l = 1; l < cfg->n_conv; ++l)
       if (!dgrad_fused(e, l)) {
@@ -608,6 +715,10 @@ extern "C" int64_t suta_batch_workspace_bytes(suta_engine* e, int n_utts, const 
 extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_samples, void* workspace, int64_t bytes,
                                 void* stream) {
   SUTA_CHECK_ARG(e && workspace && e->have_weights);
+  if (e->train_all && n_utts != 1) {
+    suta_set_last_error("SUTA_FLAG_TRAIN_ALL adapts one utterance per batch (got %d): every weight is the utterance's own", n_utts);
+    return SUTA_ERR_ARG;
+  }
   SUTA_TRY(plan_batch(e, n_utts, n_samples));
   Bump b;
   b.base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 256));
@@ -726,6 +837,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
       SUTA_TRY(fill_row_utt(e->d_conv_row_utt[l], e->rows_total[l] + 128, e->d_off[l], e->d_L[l], U, e->max_L[l], st));
   // zero rows of the padded positional-conv slabs never get written afterwards
   CUDA_TRY(cudaMemsetAsync(e->xg, 0, sizeof(bf16) * (size_t)(e->R + 8) * c.hidden, st));
+  if (e->train_all) CUDA_TRY(cudaMemsetAsync(e->xg_grad, 0, sizeof(bf16) * (size_t)(e->R + 8) * c.hidden, st));
   // conv buffers carry 128 slack rows read (never used) by partial implicit-GEMM tiles
   for (int l = 0; l < c.n_conv; ++l)
     CUDA_TRY(cudaMemsetAsync(e->conv_out[l] + (size_t)e->rows_total[l] * c.conv_dim[l], 0, sizeof(bf16) * 128 * c.conv_dim[l], st));
@@ -797,9 +909,34 @@ extern "C" int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t
 extern "C" const char* suta_profile_report(const suta_engine* e) { return e ? e->prof_report.c_str() : ""; }
 
 // bf16 GEMM-operand copies of the per-utterance trainable matrices (train_feature): refreshed after every update
+// train_all: everything derived from the trainable vector beyond its plain bf16 copy -- W^T of every encoder Linear and of
+// lm_head (B operands of the dgrads) and the folded weight_norm weight of the positional conv in its two layouts
+static int refresh_train_all(suta_engine* e, cudaStream_t st) {
+  const suta_model_cfg& c = e->cfg;
+  const int H = c.hidden, I = c.intermediate;
+  for (int l = 0; l < c.layers; ++l) {
+    const suta_engine::TaLayer& t = e->ta[l];
+    SUTA_TRY(transpose_cast_bf16(e->P + e->wqkv_off[l], t.wqkv_t, 3 * H, H, st));
+    SUTA_TRY(transpose_cast_bf16(e->P + e->wo_off[l], t.wo_t, H, H, st));
+    SUTA_TRY(transpose_cast_bf16(e->P + e->w1_off[l], t.w1_t, I, H, st));
+    SUTA_TRY(transpose_cast_bf16(e->P + e->w2_off[l], t.w2_t, H, I, st));
+  }
+  SUTA_TRY(transpose_cast_bf16(e->P + e->lm_w_off, e->lm_w_t_sh, c.vocab, H, st));
+  PROF("weight_norm_fwd", posconv_weight_norm_forward(e->P + e->pos_g_off, e->P + e->pos_v_off, e->wn_scratch, e->pos_w_sh, e->pos_w_t_sh, H,
+                                                      H / c.pos_groups, c.pos_k, st));
+  e->launches += 4 * c.layers + 4;
+  e->frontend_done = false;
+  return SUTA_OK;
+}
+
 static int refresh_shadows(suta_engine* e, cudaStream_t st) {
   if (!e->train_feature) return SUTA_OK;
   const suta_model_cfg& c = e->cfg;
+  if (e->train_all) {            // one cast of the whole vector (the conv / projection operand copies are slices of Pb)
+    PROF("cast_shadow", cast_params_bf16(e->P, e->n_params, 0, e->n_params, e->U, e->Pb, st));
+    e->launches += 1;
+    return refresh_train_all(e, st);
+  }
   for (int l = 1; l < c.n_conv; ++l) {
     PROF("cast_shadow", cast_params_bf16(e->P, e->n_params, e->conv_w_off[l], e->conv_w_size[l], e->U, e->w_shadow[l], st));
     e->launches += 1;
@@ -1045,15 +1182,15 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   // positional conv embedding + GELU + residual               HF/modeling_wav2vec2.py:360-368, :690-691
   PROF("posconv_pack", posconv_pack(e->h0, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, st));
   if (use_posconv_tc(e)) {
-    PROF("posconv_tc", posconv_tc(e->xg, reinterpret_cast<const bf16*>(e->w.pos_w), e->w.pos_b, e->cpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
+    PROF("posconv_tc", posconv_tc(e->xg, pos_w(e), pos_b(e), e->cpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
     e->launches += 1;
   } else {
     GemmProblem p;
     p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
-    p.b = {reinterpret_cast<const bf16*>(e->w.pos_w), H, (long long)c.pos_k * CG};
+    p.b = {pos_w(e), H, (long long)c.pos_k * CG};
     p.M = (int)e->Rm; p.N = CG; p.K = c.pos_k * CG;
     p.nz = G; p.a_z_rows = e->R; p.b_z_rows = CG; p.c_z_cols = CG;
-    p.epi.bias = e->w.pos_b; p.epi.out_f32 = e->cpos; p.epi.out_ld = H;
+    p.epi.bias = pos_b(e); p.epi.out_f32 = e->cpos; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
   // pre-LN ("stable") encoder: no LayerNorm here -- h0 + pos-conv IS the residual stream entering layer 0 (HF:760-762)
@@ -1068,14 +1205,14 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   // the next pre-LayerNorm sum (lb[l].h1 / h2, kept per layer for the backward), and the following GEMM accumulates
   // "+= x W^T + b" into it with a TMA reduce-add -- the GEMM epilogue never loads the residual.
   // (the bias of that GEMM is added by the LayerNorm too, so its fp32 epilogue needs no bias and keeps 4 stages)
-  PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, e->b16, e->enc_mean,
-                             e->enc_rstd, M, H, c.ln_eps, st, e->w.layer[0].bo));
+  PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, e->lb[0].h1, act_xa(e, 0), e->enc_mean,
+                             e->enc_rstd, M, H, c.ln_eps, st, layer_w(e, 0).bo));
   e->launches += 5;
   for (int l = 0; l < c.layers; ++l) {
-    const suta_layer_weights& w = e->w.layer[l];
+    const LayerW w = layer_w(e, l);
     LayerBufs& x = e->lb[l];
     {  // q,k,v projections fused to one N=3H GEMM            HF:500-507
-      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
+      GemmProblem p = dense(act_xa(e, l), M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
       p.epi.bias = w.bqkv; p.epi.out_bf16 = x.qkv; p.epi.out_ld = 3 * H;
       SUTA_TRY(gemm(e, p, st));
     }
@@ -1085,26 +1222,26 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
       p.epi.accumulate = 1; p.epi.out_f32 = x.h1; p.epi.out_ld = H;      // + bo: already in h1 (added by the LayerNorm)
       SUTA_TRY(gemm(e, p, st));
     }
-    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, act_xf(e, l),
                                x.mean1, x.rstd1, M, H, c.ln_eps, st, w.b2));
     {  // intermediate_dense + GELU (pre-activation kept for the backward)      HF:565-566
-      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
-      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->gelu16; p.epi.out_ld = I;
+      GemmProblem p = dense(act_xf(e, l), M, H, reinterpret_cast<const bf16*>(w.w1), I);
+      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = act_gl(e, l); p.epi.out_ld = I;
       SUTA_TRY(gemm(e, p, st));
     }
     {  // output_dense + residual                                HF:569, :600
-      GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
+      GemmProblem p = dense(act_gl(e, l), M, I, reinterpret_cast<const bf16*>(w.w2), H);
       p.epi.accumulate = 1; p.epi.out_f32 = x.h2; p.epi.out_ld = H;      // + b2: already in h2
       SUTA_TRY(gemm(e, p, st));
     }
     PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
-                               l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, e->b16, x.mean2, x.rstd2, M, H, c.ln_eps, st,
-                               l + 1 < c.layers ? e->w.layer[l + 1].bo : nullptr));
+                               l + 1 < c.layers ? e->lb[l + 1].h1 : e->fa, act_xa(e, l + 1), x.mean2, x.rstd2, M, H, c.ln_eps, st,
+                               l + 1 < c.layers ? layer_w(e, l + 1).bo : nullptr));
     e->launches += 3;
   }
   {  // lm_head                                                   HF:1708
-    GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.lm_w), V);
-    p.epi.bias = e->w.lm_b; p.epi.out_f32 = e->logits; p.epi.out_ld = V;
+    GemmProblem p = dense(act_xa(e, c.layers), M, H, lm_w(e), V);
+    p.epi.bias = lm_b(e); p.epi.out_f32 = e->logits; p.epi.out_ld = V;
     SUTA_TRY(gemm(e, p, st));
   }
   return SUTA_OK;
@@ -1151,10 +1288,11 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   float* da = e->fa;   // gradient w.r.t. the current LayerNorm output
   float* db = e->fb;   // gradient w.r.t. the pre-LayerNorm sum
   {  // lm_head dgrad
-    GemmProblem p = dense(e->dlogits16, M, V, reinterpret_cast<const bf16*>(e->w.lm_w_t), H);
+    GemmProblem p = dense(e->dlogits16, M, V, lm_w_t(e), H);
     p.epi.out_f32 = da; p.epi.out_ld = H;
     SUTA_TRY(gemm(e, p, st));
   }
+  if (e->train_all) SUTA_TRY(linear_param_grads(e, e->dlogits16, V, act_xa(e, c.layers), H, e->lm_w_off, e->lm_b_off, st));
   if (e->stable) {
     // Pre-LN encoder (HF:638-645, :790).  db carries d(residual stream); every branch gradient comes back through its
     // LayerNorm's backward, which adds it onto db in place (dx_add = dx = db) and emits the bf16 operand of the next dgrad.
@@ -1195,11 +1333,12 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     }
   }
   for (int l = e->stable ? -1 : c.layers - 1; l >= 0; --l) {
-    const suta_layer_weights& w = e->w.layer[l];
+    const LayerW w = layer_w(e, l);
     LayerBufs& x = e->lb[l];
     PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
                                 e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
     lnred.n += 1;
+    if (e->train_all) SUTA_TRY(linear_param_grads(e, e->b16, H, act_gl(e, l), I, e->w2_off[l], e->b2_off[l], st));      // output_dense
     {  // output_dense dgrad, times GELU'(pre)
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
       p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
@@ -1210,9 +1349,11 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.accumulate = 1; p.epi.out_f32 = db; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
+    if (e->train_all) SUTA_TRY(linear_param_grads(e, e->dpre16, I, act_xf(e, l), H, e->w1_off[l], e->b1_off[l], st));   // intermediate_dense
     PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 2), layernorm_backward(db, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
                                 e->G, da, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
     lnred.n += 1;
+    if (e->train_all) SUTA_TRY(linear_param_grads(e, e->b16, H, x.attn, H, e->wo_off[l], e->bo_off[l], st));            // out_proj
     {  // out_proj dgrad
       GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
       p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
@@ -1224,6 +1365,7 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
       p.epi.accumulate = 1; p.epi.out_f32 = da; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
+    if (e->train_all) SUTA_TRY(linear_param_grads(e, e->dqkv16, 3 * H, act_xa(e, l), H, e->wqkv_off[l], e->bqkv_off[l], st));   // q, k, v
     e->launches += 5;             // 2 x LayerNorm backward, attention backward (3 launches)
   }
   // encoder.layer_norm (post-LN: in front of the layers)
@@ -1233,14 +1375,37 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
     lnred.n += 1;
   }
   // positional conv: d h0 = d hE + conv^T (d hE * GELU'(cpos))
-  PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, e->xg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
+  // (train_all keeps the forward's padded input slabs in xg for the weight gradient and packs the gradient beside them)
+  bf16* xgg = e->train_all ? e->xg_grad : e->xg;
+  PROF("posconv_pack_grad", posconv_pack_grad(db, e->cpos, e->d_row_utt, e->d_tok_off, e->d_pad_off, xgg, M, H, G, CG, e->R, -(c.pos_k / 2), st));
+  if (e->train_all) {
+    // d w[co][tap][ci] = sum_t d conv[t, co] * x_pad[t + tap, ci]: per group, d conv^T (rows K/2 .. of the gradient slab) times
+    // the overlapping K-tap windows of the input slab, both MN-major over the utterance's frames; d bias = column sums;
+    // then through the weight_norm parametrisation (HF:344-352) into d g, d v
+    const int K = c.pos_k;
+    for (int g = 0; g < G; ++g) {
+      GemmProblem p;
+      p.a = {xgg + ((long long)g * e->R + K / 2) * CG, M, CG, 1, CG};
+      p.b = {e->xg + (long long)g * e->R * CG, M, CG, 1, (long long)K * CG};
+      p.M = CG; p.N = K * CG; p.K = 0; p.nz = 1;
+      p.ztab = e->d_ztab[c.n_conv];
+      p.epi.out_f32 = e->pos_dW + (long long)g * CG * K * CG; p.epi.out_ld = K * CG;
+      p.flops = 2.0 * CG * K * CG * (double)M;
+      SUTA_TRY(gemm(e, p, st));
+      PROF("colsum", colsum_per_utt_bf16(xgg + (long long)g * e->R * CG, e->d_pad_off, e->d_T, e->G, e->n_params, e->pos_b_off + (long long)g * CG,
+                                         CG, e->U, st));
+    }
+    PROF("weight_norm_bwd", posconv_weight_norm_backward(e->P + e->pos_v_off, e->pos_dW, e->wn_scratch, e->G + e->pos_g_off, e->G + e->pos_v_off,
+                                                         H, CG, K, st));
+    e->launches += G + 3;
+  }
   if (use_posconv_tc(e)) {
-    PROF("posconv_tc", posconv_tc(e->xg, reinterpret_cast<const bf16*>(e->w.pos_w_t), nullptr, e->dcpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
+    PROF("posconv_tc", posconv_tc(xgg, pos_w_t(e), nullptr, e->dcpos, H, G, CG, e->R, e->Rm, c.pos_k, st));
     e->launches += 1;
   } else {
     GemmProblem p;
-    p.a = {e->xg, (long long)G * e->R - c.pos_k + 1, CG};
-    p.b = {reinterpret_cast<const bf16*>(e->w.pos_w_t), H, (long long)c.pos_k * CG};
+    p.a = {xgg, (long long)G * e->R - c.pos_k + 1, CG};
+    p.b = {pos_w_t(e), H, (long long)c.pos_k * CG};
     p.M = (int)e->Rm; p.N = CG; p.K = c.pos_k * CG;
     p.nz = G; p.a_z_rows = e->R; p.b_z_rows = CG; p.c_z_cols = CG;
     p.epi.out_f32 = e->dcpos; p.epi.out_ld = H;
@@ -1472,7 +1637,10 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
   a.n = e->n_params; a.n_utts = e->U; a.step_index = e->opt_steps;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps; a.weight_decay = h->weight_decay;
   a.kind = h->opt_kind; a.shadow = nullptr;
-  if (e->train_feature) {        // the update also refreshes the bf16 GEMM-operand copies of the trainable matrices
+  if (e->train_all) {
+    a.shadow = e->Pb;            // the update writes the bf16 copy of the whole vector
+    e->frontend_done = false;
+  } else if (e->train_feature) {        // the update also refreshes the bf16 GEMM-operand copies of the trainable matrices
     const suta_model_cfg& c = e->cfg;
     for (int l = 1; l < c.n_conv; ++l) a.seg[a.n_seg++] = {e->conv_w_off[l], e->conv_w_size[l], e->w_shadow[l]};
     a.seg[a.n_seg++] = {e->proj_w_off, (long long)c.hidden * c.conv_dim[c.n_conv - 1], e->proj_shadow};
@@ -1482,9 +1650,11 @@ extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* st
   cudaStream_t st = S(stream);
   double shadow_elems = 0.0;
   for (int i = 0; i < a.n_seg; ++i) shadow_elems += (double)a.seg[i].size;
+  if (a.shadow) shadow_elems = (double)e->n_params;
   PROF_B("adam", (double)e->U * ((double)e->n_params * 28.0 + shadow_elems * 2.0), optimizer_step(a, st));
   e->opt_steps += 1;
   e->launches += 1;
+  if (e->train_all) SUTA_TRY(refresh_train_all(e, st));
   return SUTA_OK;
 }
 

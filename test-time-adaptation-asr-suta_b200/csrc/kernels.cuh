@@ -140,6 +140,18 @@ int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float
 int colsum_per_utt_bf16(const bf16* x, const long long* row_off, const int* L, float* G, long long gstride, long long g_off,
                         int C, int n_utts, cudaStream_t stream);
 
+// ---- trainall.cu (SUTA_FLAG_TRAIN_ALL) --------------------------------------------------------
+// dst [C][R] bf16 = transpose of src [R][C] fp32
+int transpose_cast_bf16(const float* src, bf16* dst, int R, int C, cudaStream_t stream);
+// positional conv weight_norm (HF/modeling_wav2vec2.py:344-352, dim = 2): g [K], v [H][CG][K] fp32 inside the trainable vector
+// -> w_fwd [H][(tap, ci)], w_bwd [g*CG + ci][(K-1-tap, co)] bf16; scratch keeps ||v|| and g / ||v|| for the backward
+long long posconv_weight_norm_scratch_floats(int K);
+int posconv_weight_norm_forward(const float* g, const float* v, float* scratch, bf16* w_fwd, bf16* w_bwd, int H, int CG, int K,
+                                cudaStream_t stream);
+// dW fp32 [H][(tap, ci)] = gradient of the folded weight -> dg [K], dv [H][CG][K]
+int posconv_weight_norm_backward(const float* v, const float* dW, float* scratch, float* dg, float* dv, int H, int CG, int K,
+                                 cudaStream_t stream);
+
 // ---- posconv_tc.cu --------------------------------------------------------------------------
 // grouped positional conv on tcgen05 with a shared-memory-resident input window (CG = H/G in {48, 64})
 bool posconv_tc_supported(int CG, int pos_k);

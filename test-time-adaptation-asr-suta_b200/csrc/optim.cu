@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int MAXK = 6;     // largest multiplicity: 5 = a conv LayerNorm of the lv60 family under train_feature (REF/main.py:81-94)
+constexpr int MAXK = 12;    // largest multiplicity: 7 = an encoder Linear under train_all, 10 = a conv weight under train_all + train_feature (REF/main.py:81-100: once per enclosing module and flag)
 struct AdamConsts {
   float step_size[MAXK + 1][MAXK];   // [k][j]: lr / (1 - beta1^s), s = k*step_index + j + 1
   float bc2_sqrt[MAXK + 1][MAXK];    // sqrt(1 - beta2^s)

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SUTA_B200_LIB") or os.path.join(os.path.dirname(_HERE
 
 MAX_LAYERS = 48
 MAX_CONV = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 

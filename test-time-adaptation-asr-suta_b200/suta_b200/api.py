@@ -75,11 +75,84 @@ def _module_order(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
     return mods
 
 
-def reference_multiplicities(cfg, bias_only: bool = False, train_feature: bool = False, train_LN: bool = True) -> Dict[str, int]:
+def _module_tree_all(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
+    """EVERY module of HF's Wav2Vec2ForCTC in named_modules() order with its own parameter leaves (GroupNorm / post-LN
+    family, the one REF/main.py loads): what --train_all walks (REF/main.py:96-100).  tests/test_host.py checks it against
+    the real HF module tree."""
+    if cfg.feat_extract_norm == "layer" or cfg.do_stable_layer_norm:
+        raise NotImplementedError("--train_all is built for the GroupNorm / post-LN family (REF/main.py's wav2vec2-base-960h)")
+    mods = [("", "container", []), ("wav2vec2", "container", ["masked_spec_embed"]),
+            ("wav2vec2.feature_extractor", "container", []), ("wav2vec2.feature_extractor.conv_layers", "container", [])]
+    for i in range(len(cfg.conv_dim)):
+        b = f"wav2vec2.feature_extractor.conv_layers.{i}"
+        mods += [(b, "container", []), (b + ".conv", "conv", ["weight", "bias"] if cfg.conv_bias else ["weight"]),
+                 (b + ".activation", "none", [])]
+        if i == 0:
+            mods.append((b + ".layer_norm", "groupnorm", ["weight", "bias"]))
+    e = "wav2vec2.encoder"
+    mods += [("wav2vec2.feature_projection", "container", []),
+             ("wav2vec2.feature_projection.layer_norm", "layernorm", ["weight", "bias"]),
+             ("wav2vec2.feature_projection.projection", "linear", ["weight", "bias"]),
+             ("wav2vec2.feature_projection.dropout", "none", []),
+             (e, "container", []), (e + ".pos_conv_embed", "container", []), (e + ".pos_conv_embed.conv", "conv", ["bias"]),
+             (e + ".pos_conv_embed.conv.parametrizations", "container", []),
+             (e + ".pos_conv_embed.conv.parametrizations.weight", "container", ["original0", "original1"]),
+             (e + ".pos_conv_embed.conv.parametrizations.weight.0", "none", []),
+             (e + ".pos_conv_embed.padding", "none", []), (e + ".pos_conv_embed.activation", "none", []),
+             (e + ".layer_norm", "layernorm", ["weight", "bias"]), (e + ".dropout", "none", []), (e + ".layers", "container", [])]
+    for l in range(cfg.num_hidden_layers):
+        b = f"{e}.layers.{l}"
+        mods += [(b, "container", []), (b + ".attention", "container", [])]
+        mods += [(b + f".attention.{n}_proj", "linear", ["weight", "bias"]) for n in ("k", "v", "q", "out")]
+        mods += [(b + ".dropout", "none", []), (b + ".layer_norm", "layernorm", ["weight", "bias"]),
+                 (b + ".feed_forward", "container", []), (b + ".feed_forward.intermediate_dropout", "none", []),
+                 (b + ".feed_forward.intermediate_dense", "linear", ["weight", "bias"]),
+                 (b + ".feed_forward.intermediate_act_fn", "none", []),
+                 (b + ".feed_forward.output_dense", "linear", ["weight", "bias"]),
+                 (b + ".feed_forward.output_dropout", "none", []), (b + ".final_layer_norm", "layernorm", ["weight", "bias"])]
+    mods += [("dropout", "none", []), ("lm_head", "linear", ["weight", "bias"])]
+    return mods
+
+
+def _walk_all(cfg: ModelConfig, bias_only: bool, train_feature: bool, train_all: bool, train_LN: bool):
+    """REF/main.py:62-103 over the full module tree: yields (module name, listed name, full parameter name) in the
+    reference's order (module name None marks the visit of a module, for the reference's print)."""
+    trainable = ['bias'] if bias_only else ['weight', 'bias']
+    tree = _module_tree_all(cfg)
+
+    def below(nm):          # m.named_parameters(): own parameters first, then the sub-modules', pre-order
+        for nm2, _k, leaves in tree:
+            if nm == "" or nm2 == nm or nm2.startswith(nm + "."):
+                for leaf in leaves:
+                    full = f"{nm2}.{leaf}" if nm2 else leaf
+                    yield (full[len(nm) + 1:] if nm else full), full
+
+    for nm, kind, leaves in tree:
+        yield nm, None, None
+        if train_LN and kind == "layernorm":
+            for leaf in leaves:
+                if leaf in trainable:
+                    yield nm, f"{nm}.{leaf}", f"{nm}.{leaf}"
+        if train_feature and len(nm.split('.')) > 1 and nm.split('.')[1] in ('feature_extractor', 'feature_projection'):
+            for rel, full in below(nm):
+                yield nm, f"{nm}.{rel}", full
+        if train_all:
+            for rel, full in below(nm):
+                yield nm, f"{nm}.{rel}", full
+
+
+def reference_multiplicities(cfg, bias_only: bool = False, train_feature: bool = False, train_LN: bool = True,
+                             train_all: bool = False) -> Dict[str, int]:
     """How many times REF/main.py:62-103 would list each parameter (0 = not trainable): LayerNorm affine once, and under
     train_feature every parameter of feature_extractor / feature_projection once per enclosing module (recursive
     named_parameters), e.g. conv weights x4, feature_projection.layer_norm x3, projection x2."""
     cfg = ModelConfig.from_any(cfg)
+    if train_all:           # every parameter once per enclosing module: up to 7 for an encoder Linear or LayerNorm
+        mult = {}
+        for _nm, listed, full in _walk_all(cfg, bias_only, train_feature, True, train_LN):
+            if listed is not None:
+                mult[full] = mult.get(full, 0) + 1
+        return mult
     trainable = ['bias'] if bias_only else ['weight', 'bias']
     tree = _module_order(cfg)
     mult: Dict[str, int] = {f"{nm}.{leaf}": 0 for nm, _k, leaves in tree for leaf in leaves}
@@ -100,11 +173,14 @@ class SutaModel:
     """Engine-backed stand-in for the HF model object the reference functions touch."""
 
     def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False, device=None,
-                 pseudo_label: bool = False):
+                 pseudo_label: bool = False, train_all: bool = False):
         self.cfg = ModelConfig.from_any(cfg)
         self.engine = SutaEngine(self.cfg, state_dict, train_feature=train_feature, trainable_mult={}, device=device,
-                                 pseudo_label=pseudo_label)
+                                 pseudo_label=pseudo_label, train_all=train_all)
         self._params = {name: SutaParam(self, name, off, size) for name, off, size in self.engine.segments}
+        if train_all:       # listed by the reference's walk, never given a gradient (eval mode: no SpecAugment mask), so
+            #                 torch.optim skips it: an empty handle keeps the parameter list and its names identical
+            self._params["wav2vec2.masked_spec_embed"] = SutaParam(self, "wav2vec2.masked_spec_embed", 0, 0)
         self._x_ref = None              # strong reference to the bound input: its address cannot be recycled while bound
         self._x_version = -1
         self._logits_valid = False
@@ -314,7 +390,18 @@ def div_loss(x, non_blank=None, L_thd=64):
 def collect_params(model: SutaModel, bias_only=False, train_feature=False, train_all=False, train_LN=True):
     """REF/main.py:62-103: same walk over named_modules(), same duplicates, same names."""
     if train_all:
-        raise NotImplementedError("train_all is outside the hot path built here (SURVEY.md 8f rank 4)")
+        if not model.engine.train_all:
+            raise _lib.SutaError("model was not created with train_all=True")
+        params, names = [], []
+        for nm, listed, full in _walk_all(model.cfg, bias_only, train_feature, True, train_LN):
+            if listed is None:
+                print(nm)
+                continue
+            p = model._params[full]
+            p.requires_grad = True
+            params.append(p)
+            names.append(listed)
+        return params, names
     if train_feature and not model.engine.train_feature:
         raise _lib.SutaError("model was not created with train_feature=True")
     trainable = ['bias'] if bias_only else ['weight', 'bias']

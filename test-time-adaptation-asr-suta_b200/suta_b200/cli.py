@@ -105,7 +105,7 @@ def main(argv=None, sdpl: bool = False):
         sd = random_state_dict(cfg, seed=0, blank_bias=1.75, special_bias=-10.0 if sdpl else 0.0)
     else:
         cfg, sd = load_checkpoint(asr)
-    model = api.SutaModel(cfg, sd, train_feature=train_feature, pseudo_label=sdpl)
+    model = api.SutaModel(cfg, sd, train_feature=train_feature, pseudo_label=sdpl, train_all=train_all)
 
     # set up for tent
     model = api.configure_model(model)
@@ -123,6 +123,9 @@ def main(argv=None, sdpl: bool = False):
         # batched extension: many utterances per adaptation step, each with its own parameters
         # (independent utterances = the reference's --episodic semantics; carrying state between utterances serialises them)
         from .runner import SutaRunner
+        if train_all:
+            raise SystemExit("--train_all makes every weight the utterance's own: one utterance per step, as the reference "
+                             "adapts (drop --batch_utts)")
         if not episodic:
             raise SystemExit("--batch_utts adapts independent utterances: pass --episodic (without it the reference carries "
                              "model and optimizer state from one utterance to the next, which cannot be batched)")

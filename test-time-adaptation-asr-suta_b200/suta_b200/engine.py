@@ -21,9 +21,16 @@ CHECKPOINT_STEPS = (1, 3, 5, 10, 20, 40)       # REF/main.py:350-398
 _MODULE_NAMES = {0: "wav2vec2.feature_projection.layer_norm", 1: "wav2vec2.encoder.layer_norm",
                  2: "wav2vec2.encoder.layers.{i}.layer_norm", 3: "wav2vec2.encoder.layers.{i}.final_layer_norm",
                  4: "wav2vec2.feature_extractor.conv_layers.{i}", 5: "wav2vec2.feature_projection.projection",
-                 6: "wav2vec2.feature_extractor.conv_layers.{i}.layer_norm"}
+                 6: "wav2vec2.feature_extractor.conv_layers.{i}.layer_norm",
+                 # SUTA_FLAG_TRAIN_ALL (REF/main.py:96-100)
+                 7: "wav2vec2.encoder.layers.{i}.attention.q_proj", 8: "wav2vec2.encoder.layers.{i}.attention.k_proj",
+                 9: "wav2vec2.encoder.layers.{i}.attention.v_proj", 10: "wav2vec2.encoder.layers.{i}.attention.out_proj",
+                 11: "wav2vec2.encoder.layers.{i}.feed_forward.intermediate_dense",
+                 12: "wav2vec2.encoder.layers.{i}.feed_forward.output_dense", 13: "lm_head",
+                 14: "wav2vec2.encoder.pos_conv_embed.conv"}
 _KIND_LEAF = {0: "weight", 1: "bias", 2: "layer_norm.weight", 3: "layer_norm.bias", 4: "conv.weight", 5: "weight", 6: "bias",
-              7: "conv.bias"}
+              7: "conv.bias", 8: "parametrizations.weight.original0", 9: "parametrizations.weight.original1"}
+MAX_MULTIPLICITY = 12                           # csrc/optim.cu MAXK
 
 
 @dataclass
@@ -60,14 +67,18 @@ class SutaEngine:
 
     def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], train_feature: bool = False,
                  trainable_mult: Optional[Dict[str, int]] = None, device: Optional[torch.device] = None,
-                 pseudo_label: bool = False):
+                 pseudo_label: bool = False, train_all: bool = False):
         if not torch.cuda.is_available():
             raise _lib.SutaError("suta_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.cfg = ModelConfig.from_any(cfg)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.train_feature = bool(train_feature)
+        self.train_all = bool(train_all)         # REF/main.py:96-100: every parameter is the utterance's own; one utterance per batch
+        self.train_feature = bool(train_feature) or self.train_all      # (its layout contains train_feature's)
         c = self.cfg
+        if self.train_all and (c.feat_extract_norm == "layer" or c.do_stable_layer_norm):
+            raise NotImplementedError("--train_all is built for the GroupNorm / post-LN family (REF/main.py's wav2vec2-base-960h); "
+                                      "REF/main_SDPL.py, the script of the lv60 checkpoints, has no such flag")
         cc = ModelCfg()
         cc.hidden, cc.layers, cc.heads, cc.intermediate, cc.vocab = (c.hidden_size, c.num_hidden_layers,
                                                                       c.num_attention_heads, c.intermediate_size, c.vocab_size)
@@ -80,7 +91,8 @@ class SutaEngine:
             raise NotImplementedError("--train_feature on a LayerNorm feature extractor without conv bias (no checkpoint has one)")
         h = C.c_void_p()
         self.pseudo_label = bool(pseudo_label)         # SDPL: reserves the CTC lattice scratch in every batch workspace
-        check(self.lib.suta_engine_create(C.byref(cc), int(self.train_feature) | (2 if self.pseudo_label else 0), C.byref(h)))
+        flags = int(self.train_feature) | (2 if self.pseudo_label else 0) | (4 if self.train_all else 0)
+        check(self.lib.suta_engine_create(C.byref(cc), flags, C.byref(h)))
         self._h = h
         self.n_params = int(self.lib.suta_engine_param_count(h))
         n = C.c_int()
@@ -158,6 +170,11 @@ class SutaEngine:
         a, at = mat(g("lm_head.weight")); w.lm_w, w.lm_w_t = p(a), p(at)
         w.lm_b = p(self._dev(g("lm_head.bias"), f32))
         # pristine trainable vector + per-element multiplicity (REF/main.py:62-103 lists some tensors several times)
+        if self.train_all and pre + "parametrizations.weight.original0" not in sd:
+            # a folded positional-conv weight: weight_norm's own initialisation (g = ||w|| per tap, v = w) reproduces it
+            sd = dict(sd)
+            sd[pre + "parametrizations.weight.original0"] = pcw.norm(dim=(0, 1), keepdim=True)
+            sd[pre + "parametrizations.weight.original1"] = pcw.clone()
         p0 = torch.empty(self.n_params, dtype=f32)
         mult = torch.zeros(self.n_params, dtype=torch.uint8)
         self._hf_shapes = {name: tuple(sd[name].shape) for name, _o, _s in self.segments}
@@ -185,8 +202,8 @@ class SutaEngine:
 
     def set_trainable(self, mult_by_name: Dict[str, int]):
         """Re-select what the optimizer updates (collect_params' result): name -> multiplicity (0 = frozen)."""
-        if max(list(mult_by_name.values()) + [0]) > 6:
-            raise ValueError("a parameter listed more than 6 times (csrc/optim.cu MAXK)")
+        if max(list(mult_by_name.values()) + [0]) > MAX_MULTIPLICITY:
+            raise ValueError(f"a parameter listed more than {MAX_MULTIPLICITY} times (csrc/optim.cu MAXK)")
         m = torch.zeros(self.n_params, dtype=torch.uint8)
         for name, off, size in self.segments:
             m[off:off + size] = int(mult_by_name.get(name, 0))

@@ -28,13 +28,13 @@ def _rel(a, b):
 
 
 def run_engine(cfg_name, sd, wavs, steps, hp=None, keep_grads=False, train_feature=False, mult=None, sched_gamma=None,
-               pseudo_label=False):
+               pseudo_label=False, train_all=False):
     """Batched SUTA on the GPU: returns per-utterance dicts (logits at checkpoints, losses, params, ids).
     sched_gamma: StepLR(step_size=1) factor, applied by the caller between steps like REF/main.py:207-208."""
     _, mcfg = _cfgs(cfg_name)
     hp = hp or AdaptHyper()
     lr0 = hp.lr
-    eng = SutaEngine(mcfg, sd, train_feature=train_feature, trainable_mult=mult, pseudo_label=pseudo_label)
+    eng = SutaEngine(mcfg, sd, train_feature=train_feature, trainable_mult=mult, pseudo_label=pseudo_label, train_all=train_all)
     eng.begin_batch(wavs)
     eng.reset()
     res = [dict(logits={}, losses=[], ids={}, pl_losses=[]) for _ in wavs]
@@ -198,9 +198,9 @@ def _grad_rel(flat, segments, g0, to_layout):
     return float(np.sqrt(num / max(den, 1e-300)))
 
 
-def _mult(ocfg, train_feature, bias_only=False):
+def _mult(ocfg, train_feature, bias_only=False, train_all=False):
     m = {}
-    for n in O.collect_param_names(ocfg, bias_only=bias_only, train_feature=train_feature):
+    for n in O.collect_param_names(ocfg, bias_only=bias_only, train_feature=train_feature, train_all=train_all):
         m[n] = m.get(n, 0) + 1
     return m
 
@@ -342,12 +342,14 @@ def check_golden(case, with_grad0=True):
     hp = AdaptHyper(**{k: meta["hyper"][k] for k in ("lr", "em_coef", "reweight", "temp", "not_blank")},
                     opt=meta.get("opt", "AdamW"), beta1=meta.get("beta", 0.9) if meta.get("opt") == "Adam" else 0.9,
                     div_coef=meta.get("div_coef", 0.0))
-    tf, bo = bool(meta["train_feature"]), bool(meta.get("bias_only", False))
-    res = run_engine(meta["cfg"], sd, [wav], meta["steps"], hp, keep_grads=True, train_feature=tf, mult=_mult(ocfg, tf, bo),
-                     sched_gamma=meta.get("sched_gamma"))[0]
+    tf, bo, ta = bool(meta["train_feature"]), bool(meta.get("bias_only", False)), bool(meta.get("train_all", False))
+    res = run_engine(meta["cfg"], sd, [wav], meta["steps"], hp, keep_grads=True, train_feature=tf, mult=_mult(ocfg, tf, bo, ta),
+                     sched_gamma=meta.get("sched_gamma"), train_all=ta)[0]
     hp.lr = meta["hyper"]["lr"]
     ref_logits = {int(k.split("_")[1]): z[k] for k in z.files if k.startswith("logits_")}
-    ref_params = {k[6:]: z[k] for k in z.files if k.startswith("param:") and z[k].dtype == np.float32}
+    # (train_all: the gradient of a key bias is identically zero -- it shifts every score of a softmax row alike -- so Adam
+    #  random-walks on rounding noise there, in the reference as well: tests/golden/make_golden.py)
+    ref_params = {k[6:]: z[k] for k in z.files if k.startswith("param:") and z[k].dtype == np.float32 and not k.endswith("k_proj.bias")}
     x = O.normalize_audio(wav)
     m = compare(res, ref_logits, z["losses"], ref_params, sd, ref_ids=True, ocfg=ocfg, x=x)
     # big tensors are stored as (sum, sum|.|, sum .^2, first 4096 values): compare the head and the moments of the DELTA
@@ -360,8 +362,12 @@ def check_golden(case, with_grad0=True):
     if big:
         m["big_param_head_delta_rel"] = float(np.sqrt(num / max(den, 1e-300)))
     if with_grad0:
-        g0 = oracle_grad0(ocfg, sd, x, hp, meta["names"], meta.get("div_coef", 0.0))
+        names = [n.lstrip(".") for n in meta["names"]]          # (train_all lists the root module's parameters as ".<name>")
+        g0 = oracle_grad0(ocfg, sd, x, hp, [n for n in names if n in sd and not n.endswith("k_proj.bias")], meta.get("div_coef", 0.0))
         m["grad0_rel"] = _grad_rel(res["grad0"], res["segments"], g0, res["to_layout"])
+        if ta:              # per-tensor gradient errors localise a broken weight-gradient path
+            m["grad0_by_tensor"] = {n: _grad_rel(res["grad0"], [sg for sg in res["segments"] if sg[0] == n], g0, res["to_layout"])
+                                    for n in g0}
     m["texts_equal"] = {k: (O.ctc_ids_to_text(res["ids"][int(k)]) == v) for k, v in meta["texts"].items() if int(k) in res["ids"]}
     a0 = np.argmax(res["logits"][0], -1); r0 = np.argmax(ref_logits[0], -1)
     m["argmax_agree0"] = float((a0 == r0).mean())

@@ -161,6 +161,32 @@ def test_train_feature_against_reference_golden_vectors(E, case):
         assert m["big_param_head_delta_rel"] < 0.15
 
 
+@pytest.mark.parametrize("case", ["tiny_all", "base_all_2s"])
+def test_train_all_against_reference_golden_vectors(E, case):
+    """--train_all (REF/main.py:96-100): every weight and bias of the model is the utterance's own -- encoder Linears (x7),
+    LayerNorms, the CNN, lm_head and the weight_norm g / v of the positional conv -- with the reference's multiplicities.
+    The step-0 gradient of EVERY tensor is compared with fp32 autograd through the oracle."""
+    m = E.check_golden(case)
+    by = m.pop("grad0_by_tensor")
+    worst = sorted(by.items(), key=lambda kv: -kv[1])[:12]
+    print(case, m, "worst gradients:", worst)
+    assert m["logits0_maxabs"] < LOGIT_TOL and m["argmax_agree0"] > 0.95
+    assert m["loss_rel_max"] < 2e-3 and m["decode_equal_given_logits"]
+    # step 0: the whole gradient and every tensor of it (the CNN sits at the far end of the bf16 backward chain)
+    assert m["grad0_rel"] < 0.05, worst
+    for n, v in by.items():
+        assert v < (0.15 if "feature_extractor" in n else 0.1), (n, v)
+    # after the fixture's steps; a non-blank decision of a later step that the reference takes by less than the engine's
+    # logit error changes that step's entropy gradient by 1 / n_M (see _assert_parity)
+    loose = 2.5 if m["mask_margin"] < 2 * m["logitsN_maxabs"] else 1.0
+    assert m["param_delta_rel"] < 0.15 * loose and m["param_delta_rel"] < 0.5
+    if "big_param_head_delta_rel" in m:
+        assert m["big_param_head_delta_rel"] < 0.15 * loose
+    assert m["dlogits_via_oracle_rel"] < 0.15 * loose
+    if m["logit_change_maxabs"] > 10 * m["logits0_maxabs"]:
+        assert m["dlogits_rel"] < 0.15 * loose
+
+
 @pytest.mark.parametrize("case", ["tiny_sdpl", "tiny_sdpl_mix", "tiny_lv60_sdpl"])
 def test_sdpl_pseudo_label_baseline_against_reference_golden_vectors(E, case):
     """REF/main_SDPL.py (the README's comparison row): adaptation by the CTC pseudo-label loss alone (pl_coef = 1, Adam,
@@ -216,6 +242,40 @@ def test_drop_in_api_single_utterance(E, capsys, cfg_name):
     assert np.allclose(ent.cpu().numpy(), O.softmax_entropy(torch.tensor(out.cpu().numpy()) / 2.5).numpy(), atol=1e-5)
     mc = api.mcc_loss(out / 2.5, True)
     assert abs(float(mc) - float(O.mcc_loss(torch.tensor(out.cpu().numpy()) / 2.5, True))) < 1e-5
+    capsys.readouterr()
+
+
+def test_drop_in_api_train_all(E, capsys):
+    """`main.py --train_all` through the reference's function surface: collect_params lists every parameter once per
+    enclosing module (names and order of the reference's walk, tests/test_host.py), the optimizer applies those
+    multiplicities, the episodic restore brings every weight back, a second utterance in one call is refused."""
+    from oracle import suta_oracle as O
+    from suta_b200 import ModelConfig, api
+    ocfg = O.W2V2Config.tiny()
+    sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1)
+    wav = O.synth_audio(12000, 119)
+    model = api.configure_model(api.SutaModel(ModelConfig.tiny(), sd, train_all=True))
+    params, names = api.collect_params(model, False, False, True, True)
+    assert sorted(n.lstrip(".") for n in names) == sorted(O.collect_param_names(ocfg, train_all=True))
+    opt, sched = api.setup_optimizer(params, "AdamW", 2e-5)
+    assert opt.mult["wav2vec2.encoder.layers.1.feed_forward.output_dense.weight"] == 7 and opt.mult["lm_head.bias"] == 2
+    snap = api.copy_model_and_optimizer(model, opt, sched)
+    x = torch.from_numpy(O.normalize_audio(wav))[None].cuda()
+    ref = O.adapt_utterance(ocfg, sd, O.normalize_audio(wav), steps=3, train_all=True)
+    for rep in range(2):                      # second pass checks the episodic restore of ALL weights
+        model, opt, sched = api.load_model_and_optimizer(model, opt, *snap)
+        out0 = model(x).logits
+        assert np.abs(out0[0].cpu().numpy() - ref.logits0).max() < 0.05
+        for i in range(3):
+            out = api.forward_and_adapt(x, model, opt, 0.3, True, 2.5, True, sched, 0)
+        assert np.abs(out[0].cpu().numpy() - ref.logits[3]).max() < 0.05 + 0.15 * np.abs(ref.logits[3] - ref.logits0).max()
+        got = {p.name: p.data[0].cpu().numpy() for p in params if p.size and not p.name.endswith("k_proj.bias")}
+        eng = model.engine
+        num = sum(float(((got[n] - eng.to_engine_layout(n, torch.from_numpy(ref.params[n])).numpy()) ** 2).sum()) for n in got)
+        den = sum(float(((ref.params[n] - sd[n].numpy()) ** 2).sum()) for n in got)
+        assert (num / den) ** 0.5 < 0.3, (num / den) ** 0.5
+    with pytest.raises(Exception, match="one utterance per batch"):
+        model(torch.cat([x, x], 0))
     capsys.readouterr()
 
 
