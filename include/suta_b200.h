@@ -150,6 +150,10 @@ int suta_opt_steps(const suta_engine* e);
 int suta_set_opt_steps(suta_engine* e, int steps);
 const void* suta_debug_buffer(const suta_engine* e, const char* name, int64_t* rows, int64_t* cols, int* dtype);
 int64_t suta_launch_count(const suta_engine* e); /* kernels launched by this engine since creation */
+/* Small batches (<= 4096 frames: the reference's one-utterance-at-a-time operating point, REF/main.py:319-402) are
+ * launch-bound; suta_forward / suta_loss_backward record their launch chain as a CUDA graph the second time it runs in a
+ * batch and replay it afterwards (SUTA_NO_GRAPH=1: never; SUTA_GRAPH_MAX_TOKENS=n moves the bound).  Number of replays so far: */
+int64_t suta_graph_replays(const suta_engine* e);
 /* per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg). Reads and clears the counters collected
  * so far (any pointer may be NULL), then switches collection on/off. */
 int suta_profile(suta_engine* e, int enable, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);

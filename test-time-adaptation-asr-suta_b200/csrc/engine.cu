@@ -184,11 +184,27 @@ struct suta_engine {
   int *ids = nullptr, *collapsed = nullptr, *out_len = nullptr;
   // every device table of a batch lives in one contiguous region at the start of the workspace and is uploaded by ONE
   // host-to-device copy from this pinned mirror (no pageable copies, no stream synchronisation in suta_batch_begin)
+  // CUDA graphs of the two launch chains of an adaptation step.  A small batch (the reference's operating point: one
+  // utterance at a time) is launch-bound -- ~250 kernels of a few microseconds per step -- and its launch sequence does
+  // not change between the steps of a batch: the second call with the same key records the chain on a side stream
+  // (the caller's may be the legacy default stream, which cannot be captured), later calls replay it.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long key = 0, seen_key = 0;      // what the recorded chain depends on besides the batch layout
+    bool seen = false;
+    long long launches = 0;                        // launch-counter increment of one replay
+    bool post_frontend_done = false, post_moments_done = false, post_z0_done = false;   // host state after the chain (forward)
+  };
+  GraphSlot g_fwd, g_bwd;
+  cudaStream_t cap_stream = nullptr;
+  long long graph_replays = 0;                     // chains launched as graphs since the engine was created
   size_t tables_bytes = 0;
   uint8_t* h_stage = nullptr;
   size_t h_stage_cap = 0;
   cudaEvent_t stage_ev = nullptr;                  // recorded after the upload: the mirror may be rewritten once it fired
 };
+
+static void drop_graphs(suta_engine* e);
 
 namespace {
 
@@ -673,6 +689,8 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_eng
 }
 extern "C" void suta_engine_destroy(suta_engine* e) {
   if (!e) return;
+  drop_graphs(e);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->stage_ev) cudaEventDestroy(e->stage_ev);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -705,7 +723,9 @@ extern "C" int suta_engine_set_weights(suta_engine* e, const suta_weights* w) {
 }
 
 extern "C" int64_t suta_batch_workspace_bytes(suta_engine* e, int n_utts, const int32_t* n_samples) {
-  if (!e || plan_batch(e, n_utts, n_samples) != SUTA_OK) return -1;
+  if (!e) return -1;
+  drop_graphs(e);                 // planning invalidates the live batch
+  if (plan_batch(e, n_utts, n_samples) != SUTA_OK) return -1;
   Bump b;
   carve(e, b);
   e->U = 0;   // planning only: the batch is not live until suta_batch_begin
@@ -719,6 +739,7 @@ extern "C" int suta_batch_begin(suta_engine* e, int n_utts, const int32_t* n_sam
     suta_set_last_error("SUTA_FLAG_TRAIN_ALL adapts one utterance per batch (got %d): every weight is the utterance's own", n_utts);
     return SUTA_ERR_ARG;
   }
+  drop_graphs(e);                 // recorded chains point into the previous batch's layout
   SUTA_TRY(plan_batch(e, n_utts, n_samples));
   Bump b;
   b.base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 256));
@@ -1156,7 +1177,7 @@ static int forward_stable(suta_engine* e, cudaStream_t st) {
   return SUTA_OK;
 }
 
-extern "C" int suta_forward(suta_engine* e, void* stream) {
+static int forward_eager(suta_engine* e, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0);
   if (!e->frontend_done) SUTA_TRY(suta_frontend(e, stream));
   const suta_model_cfg& c = e->cfg;
@@ -1247,7 +1268,7 @@ extern "C" int suta_forward(suta_engine* e, void* stream) {
   return SUTA_OK;
 }
 
-extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* stream) {
+static int loss_backward_eager(suta_engine* e, const suta_hyper* h, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0 && h);
   const suta_model_cfg& c = e->cfg;
   cudaStream_t st = S(stream);
@@ -1630,6 +1651,78 @@ extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* str
   return SUTA_OK;
 }
 
+// ---- CUDA graphs of the forward / backward launch chains (small batches) ---------------------------------------
+static void drop_graphs(suta_engine* e) {
+  for (suta_engine::GraphSlot* g : {&e->g_fwd, &e->g_bwd}) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    *g = suta_engine::GraphSlot();
+  }
+}
+// Launch-bound batches only: at the benched batch sizes (M ~ 20 k tokens, ~90 us per kernel) the stream launches keep
+// the GPU fed and the chains stay eager.  SUTA_NO_GRAPH=1 switches the graphs off, SUTA_GRAPH_MAX_TOKENS moves the bound.
+static bool graph_eligible(const suta_engine* e) {
+  static const bool off = getenv("SUTA_NO_GRAPH") != nullptr || getenv("SUTA_GEMM_LOG") != nullptr;
+  static const long long max_tokens = getenv("SUTA_GRAPH_MAX_TOKENS") ? atoll(getenv("SUTA_GRAPH_MAX_TOKENS")) : 4096;
+  return !off && !e->profile && e->M <= max_tokens;
+}
+// run `chain` (a launch sequence on the stream it is given) eagerly the first time a key is seen, record + replay it the
+// second time, replay it afterwards
+template <typename F>
+static int run_chain(suta_engine* e, suta_engine::GraphSlot& g, unsigned long long key, void* stream, bool is_fwd, F chain) {
+  if (!graph_eligible(e)) return chain(stream);
+  cudaStream_t st = S(stream);
+  if (!(g.exec && g.key == key)) {
+    if (!(g.seen && g.seen_key == key)) {        // first call with this key: eager (also runs every one-time kernel set-up)
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      g.seen = true; g.seen_key = key;
+      return chain(stream);
+    }
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (!e->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    const bool fd = e->frontend_done, md = e->moments_done, zd = e->z0_done;
+    const long long l0 = e->launches;
+    CUDA_TRY(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = chain(e->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc != SUTA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CUDA_TRY(ce);
+    const cudaError_t ci = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_TRY(ci);
+    g.key = key;
+    g.launches = e->launches - l0;
+    g.post_frontend_done = e->frontend_done; g.post_moments_done = e->moments_done; g.post_z0_done = e->z0_done;
+    e->frontend_done = fd; e->moments_done = md; e->z0_done = zd;      // nothing ran yet: the replay below does
+    e->launches = l0;
+  }
+  CUDA_TRY(cudaGraphLaunch(g.exec, st));
+  e->launches += g.launches;
+  e->graph_replays += 1;
+  if (is_fwd) { e->frontend_done = g.post_frontend_done; e->moments_done = g.post_moments_done; e->z0_done = g.post_z0_done; }
+  return SUTA_OK;
+}
+
+extern "C" int suta_forward(suta_engine* e, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0);
+  // the chain depends on which parts of the front end are still valid (LayerNorm-only mode runs the CNN once per batch)
+  const unsigned long long key = 1ull | (e->frontend_done ? 2ull : 0ull) | (e->moments_done ? 4ull : 0ull) | (e->z0_done ? 8ull : 0ull);
+  return run_chain(e, e->g_fwd, key, stream, true, [&](void* s2) { return forward_eager(e, s2); });
+}
+
+extern "C" int suta_loss_backward(suta_engine* e, const suta_hyper* h, void* stream) {
+  SUTA_CHECK_ARG(e && e->U > 0 && h);
+  // the loss kernels take their hyper-parameters by value: part of the recorded chain (the optimizer's are not: it stays eager)
+  unsigned long long key = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) {
+    for (size_t i = 0; i < n; ++i) key = (key ^ reinterpret_cast<const unsigned char*>(p)[i]) * 1099511628211ull;
+  };
+  mix(&h->em_coef, sizeof(float)); mix(&h->temp, sizeof(float)); mix(&h->reweight, sizeof(int32_t)); mix(&h->not_blank, sizeof(int32_t));
+  mix(&h->div_coef, sizeof(float)); mix(&h->pl_coef, sizeof(float));
+  const suta_hyper hc = *h;
+  return run_chain(e, e->g_bwd, key | 1ull, stream, false, [&, hc](void* s2) { return loss_backward_eager(e, &hc, s2); });
+}
+
 extern "C" int suta_optimizer_step(suta_engine* e, const suta_hyper* h, void* stream) {
   SUTA_CHECK_ARG(e && e->U > 0 && h);
   AdamArgs a{};
@@ -1679,6 +1772,7 @@ extern "C" int32_t* suta_argmax_ids(const suta_engine* e) { return e->ids; }
 extern "C" int32_t* suta_collapsed_ids(const suta_engine* e) { return e->collapsed; }
 extern "C" int32_t* suta_collapsed_len(const suta_engine* e) { return e->out_len; }
 extern "C" int64_t suta_launch_count(const suta_engine* e) { return e->launches; }
+extern "C" int64_t suta_graph_replays(const suta_engine* e) { return e ? e->graph_replays : 0; }
 extern "C" float* suta_adam_exp_avg(const suta_engine* e) { return e->Mom; }
 extern "C" float* suta_adam_exp_avg_sq(const suta_engine* e) { return e->Var; }
 extern "C" int suta_opt_steps(const suta_engine* e) { return e ? e->opt_steps : 0; }

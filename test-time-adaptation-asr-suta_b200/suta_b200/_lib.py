@@ -88,6 +88,7 @@ SIGNATURES = {
     "suta_set_opt_steps": (c_int, [c_void_p, c_int]),
     "suta_debug_buffer": (c_void_p, [c_void_p, C.c_char_p, C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(c_int)]),
     "suta_launch_count": (c_int64, [c_void_p]),
+    "suta_graph_replays": (c_int64, [c_void_p]),
     "suta_profile": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
     "suta_profile_report": (C.c_char_p, [c_void_p]),
     "suta_debug_set_gemm_trace": (None, [c_void_p, c_int]),

@@ -376,6 +376,11 @@ class SutaEngine:
     def launch_count(self) -> int:
         return int(self.lib.suta_launch_count(self._h))
 
+    @property
+    def graph_replays(self) -> int:
+        """Forward / backward launch chains replayed as CUDA graphs so far (small, launch-bound batches only)."""
+        return int(self.lib.suta_graph_replays(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.suta_engine_destroy(self._h)

@@ -360,6 +360,32 @@ def test_alternative_cuda_paths_keep_parity(switches):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_cuda_graph_chains_give_the_same_bits(tmp_path):
+    """Small batches replay the forward / backward launch chains as CUDA graphs (csrc/engine.cu::run_chain).  The same
+    batches adapted with the graphs switched off (SUTA_NO_GRAPH=1, read once per process) must give the same BITS -- logits,
+    adapted parameters, transcripts -- and the same launch count, for LayerNorm-only, train_feature, the lv60 family (CNN in
+    every chain), the SDPL loss and train_all; the graph run must really have replayed."""
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    here = os.path.dirname(os.path.abspath(__file__))
+    outs = []
+    for name, extra in (("graph", {}), ("eager", {"SUTA_NO_GRAPH": "1"})):
+        path = str(tmp_path / (name + ".npz"))
+        r = subprocess.run([sys.executable, os.path.join(here, "graph_probe.py"), path], env=dict(os.environ, **extra),
+                           capture_output=True, text=True, cwd=os.path.dirname(here), timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(np.load(path))
+    g, e = outs
+    for k in g.files:
+        if k.endswith("_replays"):
+            assert int(g[k]) >= 16 and int(e[k]) == 0, (k, int(g[k]), int(e[k]))     # 2 batches x 2 chains x (6 - 2) steps
+        else:
+            assert np.array_equal(g[k], e[k]), k
+
+
 def test_full_size_batch_is_reproducible_and_utterances_are_independent(E):
     """BASELINE.json configs[1] at full size (wav2vec2-base, --train_feature, one 64-utterance batch of the
     LibriSpeech-shaped set: ~20 k frames, CTA-pair GEMMs, tail split, fused conv dgrad): the oracle cannot follow at

@@ -1,0 +1,76 @@
+"""--train_all at the reference's operating point: one utterance at a time (REF/main.py:319-402 with :96-100).
+
+Times, per utterance of a duration-stratified sample of the LibriSpeech-shaped set: reset + vanilla forward + S x (loss,
+backward, AdamW over every weight with the reference's multiplicities, forward) + the greedy decodes -- through this
+repo's engine (wav2vec2-base, SUTA_FLAG_TRAIN_ALL) and through the reference's eager fp32 loop on the same GPU
+(oracle/hf_reference.py over HF Wav2Vec2ForCTC + torch.optim.AdamW, `collect_params(train_all=True)`).  One JSON line.
+
+    python tools/train_all_latency.py [--steps 10] [--utts 5] [--no-eager]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "test-time-adaptation-asr-suta_b200")]
+
+from oracle import hf_reference as HR  # noqa: E402
+from oracle import suta_oracle as O  # noqa: E402
+from suta_b200 import AdaptHyper, ModelConfig, SutaEngine  # noqa: E402
+from suta_b200.data import librispeech_shaped  # noqa: E402
+from suta_b200.runner import adapt_batch  # noqa: E402
+from suta_b200.text import CTCVocab  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--utts", type=int, default=5)
+    ap.add_argument("--no-eager", action="store_true")
+    a = ap.parse_args()
+    utts = sorted(librispeech_shaped(2939), key=lambda u: u.n_samples)
+    sample = [utts[int((i + 0.5) * len(utts) / a.utts)] for i in range(a.utts)]
+    ocfg, mcfg = O.W2V2Config.base(), ModelConfig.base()
+    sd = O.init_weights(ocfg, 0, blank_bias=1.75)
+    mult = {}
+    for n in O.collect_param_names(ocfg, train_all=True):
+        mult[n] = mult.get(n, 0) + 1
+    eng = SutaEngine(mcfg, sd, train_all=True, trainable_mult=mult)
+    hp, vocab = AdaptHyper(), CTCVocab()
+    ms, secs = [], []
+    for j, u in enumerate([sample[len(sample) // 2]] + sample):          # first = warm-up
+        wav = u.audio()
+        host = torch.zeros((len(wav) + 3) & ~3, dtype=torch.float32).pin_memory()       # the engine's packed layout (16-byte rows)
+        host[:len(wav)] = torch.from_numpy(np.ascontiguousarray(wav, dtype=np.float32))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        eng.begin_batch_lengths(np.asarray([len(wav)], dtype=np.int32))
+        adapt_batch(eng, host, np.asarray([len(wav)]), a.steps, hp, vocab)
+        e1.record()
+        torch.cuda.synchronize()
+        if j:
+            ms.append(e0.elapsed_time(e1))
+            secs.append(u.duration)
+    out = {"what": "train_all, one utterance per step (REF/main.py:96-100), wav2vec2-base, %d-step SUTA" % a.steps,
+           "utt_seconds": secs, "ms_per_utt": ms, "audio_s_per_s": sum(secs) / (sum(ms) * 1e-3),
+           "rtf_median": float(np.median([m * 1e-3 / s for m, s in zip(ms, secs)])), "params_per_utt": int(eng.n_params),
+           "launches": int(eng.launch_count)}
+    eng.close()
+    if not a.no_eager:
+        loop = HR.ReferenceLoop(ocfg, sd, "cuda", train_all=True)
+        t = HR.time_utterances(loop, [sample[len(sample) // 2].audio()] + [u.audio() for u in sample], steps=a.steps, warmup=1)
+        out["gpu_eager_reference"] = {"s_per_utt": t, "audio_s_per_s": sum(secs) / sum(t),
+                                      "kind": "oracle/hf_reference.py ReferenceLoop(train_all=True) on cuda:0, fp32 eager"}
+        out["speedup_vs_eager"] = out["audio_s_per_s"] / out["gpu_eager_reference"]["audio_s_per_s"]
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    main()
