@@ -96,8 +96,8 @@ int suta_device_sm_count(void);
 #define SUTA_FLAG_TRAIN_FEATURE 1          /* REF/main.py:88-94: CNN front end + projection adapted per utterance */
 #define SUTA_FLAG_PSEUDO_LABEL 2           /* REF/main_SDPL.py: reserve the CTC scratch (alpha lattice) in every batch workspace */
 #define SUTA_FLAG_TRAIN_ALL 4              /* REF/main.py:96-100: EVERY parameter of the model is the utterance's own (implies
-                                            * TRAIN_FEATURE's layout; GroupNorm / post-LN family; one utterance per batch, as
-                                            * the reference adapts: nothing is shared between utterances any more) */
+                                            * TRAIN_FEATURE's layout; one utterance per batch, as the reference adapts:
+                                            * nothing is shared between utterances any more) */
 int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_engine** out);
 void suta_engine_destroy(suta_engine* e);
 int64_t suta_engine_param_count(const suta_engine* e);

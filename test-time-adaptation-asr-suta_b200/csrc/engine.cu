@@ -671,8 +671,8 @@ extern "C" int suta_engine_create(const suta_model_cfg* cfg, int flags, suta_eng
   e->conv_ln = cfg->feat_norm_layer ? 1 : 0;
   e->stable = cfg->stable_layer_norm ? 1 : 0;
   e->cnn_bwd = e->train_feature || e->conv_ln;
-  if (e->train_all && (e->conv_ln || e->stable)) {       // REF/main_SDPL.py (the script of the lv60 checkpoints) has no --train_all
-    suta_set_last_error("SUTA_FLAG_TRAIN_ALL is built for the GroupNorm / post-LN family (wav2vec2-base-960h, REF/main.py)");
+  if (e->train_all && e->conv_ln != e->stable) {         // the two families HF ships: GroupNorm + post-LN, LayerNorm conv + pre-LN
+    suta_set_last_error("SUTA_FLAG_TRAIN_ALL: feat_norm_layer and stable_layer_norm must be set together");
     delete e;
     return SUTA_ERR_ARG;
   }
@@ -1135,12 +1135,12 @@ static int forward_stable(suta_engine* e, cudaStream_t st) {
   const long long M = e->M;
   UttParams prm{e->P, e->n_params};
   for (int l = 0; l < c.layers; ++l) {
-    const suta_layer_weights& w = e->w.layer[l];
+    const LayerW w = layer_w(e, l);
     LayerBufs& x = e->lb[l];
-    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, e->b16,
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h1, nullptr, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l], x.h2, act_xa(e, l),
                                x.mean1, x.rstd1, M, H, c.ln_eps, st, w.bo, LN_KEEP_INPUT));
     {
-      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
+      GemmProblem p = dense(act_xa(e, l), M, H, reinterpret_cast<const bf16*>(w.wqkv), 3 * H);
       p.epi.bias = w.bqkv; p.epi.out_bf16 = x.qkv; p.epi.out_ld = 3 * H;
       SUTA_TRY(gemm(e, p, st));
     }
@@ -1151,27 +1151,27 @@ static int forward_stable(suta_engine* e, cudaStream_t st) {
       SUTA_TRY(gemm(e, p, st));
     }
     float* next = l + 1 < c.layers ? e->lb[l + 1].h1 : e->hE;        // hE: the residual stream after the last layer
-    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], next, e->b16,
+    PROF_B("ln_fwd", (double)M * H * (4 + 4 + 2), layernorm_forward(x.h2, nullptr, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l], next, act_xf(e, l),
                                x.mean2, x.rstd2, M, H, c.ln_eps, st, w.b2, LN_KEEP_INPUT));
     {
-      GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w1), I);
-      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->gelu16; p.epi.out_ld = I;
+      GemmProblem p = dense(act_xf(e, l), M, H, reinterpret_cast<const bf16*>(w.w1), I);
+      p.epi.bias = w.b1; p.epi.act = 1; p.epi.aux_out = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = act_gl(e, l); p.epi.out_ld = I;
       SUTA_TRY(gemm(e, p, st));
     }
     {
-      GemmProblem p = dense(e->gelu16, M, I, reinterpret_cast<const bf16*>(w.w2), H);
+      GemmProblem p = dense(act_gl(e, l), M, I, reinterpret_cast<const bf16*>(w.w2), H);
       p.epi.accumulate = 1; p.epi.out_f32 = next; p.epi.out_ld = H;
       SUTA_TRY(gemm(e, p, st));
     }
     e->launches += 3;
   }
   // encoder.layer_norm AFTER the layers (HF:790): only the bf16 operand of lm_head is needed
-  PROF_B("ln_fwd", (double)M * H * (4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, nullptr, e->b16,
+  PROF_B("ln_fwd", (double)M * H * (4 + 2), layernorm_forward(e->hE, nullptr, e->d_row_utt, prm, (int)e->enc_g, (int)e->enc_b, nullptr, act_xa(e, c.layers),
                              e->enc_mean, e->enc_rstd, M, H, c.ln_eps, st));
   e->launches += 1;
   {
-    GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(e->w.lm_w), V);
-    p.epi.bias = e->w.lm_b; p.epi.out_f32 = e->logits; p.epi.out_ld = V;
+    GemmProblem p = dense(act_xa(e, c.layers), M, H, lm_w(e), V);
+    p.epi.bias = lm_b(e); p.epi.out_f32 = e->logits; p.epi.out_ld = V;
     SUTA_TRY(gemm(e, p, st));
   }
   return SUTA_OK;
@@ -1321,8 +1321,11 @@ static int loss_backward_eager(suta_engine* e, const suta_hyper* h, void* stream
                                 e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n]));
     lnred.n += 1;
     for (int l = c.layers - 1; l >= 0; --l) {
-      const suta_layer_weights& w = e->w.layer[l];
+      const LayerW w = layer_w(e, l);
       LayerBufs& x = e->lb[l];
+      // (train_all: b16 = bf16 of d(residual stream) = the gradient of output_dense's result; after the LayerNorm backward
+      //  below, of out_proj's)
+      if (e->train_all) SUTA_TRY(linear_param_grads(e, e->b16, H, act_gl(e, l), I, e->w2_off[l], e->b2_off[l], st));
       {  // output_dense dgrad, times GELU'(pre)
         GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.w2_t), I);
         p.epi.act = 2; p.epi.aux_in = x.pre; p.epi.aux_ld = I; p.epi.out_bf16 = e->dpre16; p.epi.out_ld = I;
@@ -1333,9 +1336,11 @@ static int loss_backward_eager(suta_engine* e, const suta_hyper* h, void* stream
         p.epi.out_f32 = da; p.epi.out_ld = H;
         SUTA_TRY(gemm(e, p, st));
       }
+      if (e->train_all) SUTA_TRY(linear_param_grads(e, e->dpre16, I, act_xf(e, l), H, e->w1_off[l], e->b1_off[l], st));
       PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 4 + 2), layernorm_backward(da, x.h2, nullptr, x.mean2, x.rstd2, e->d_row_utt, prm, (int)e->ln2_g[l], (int)e->ln2_b[l],
                                   e->G, db, e->b16, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n], db));
       lnred.n += 1;
+      if (e->train_all) SUTA_TRY(linear_param_grads(e, e->b16, H, x.attn, H, e->wo_off[l], e->bo_off[l], st));
       {  // out_proj dgrad
         GemmProblem p = dense(e->b16, M, H, reinterpret_cast<const bf16*>(w.wo_t), H);
         p.epi.out_bf16 = e->dO16; p.epi.out_ld = H;
@@ -1347,6 +1352,7 @@ static int loss_backward_eager(suta_engine* e, const suta_hyper* h, void* stream
         p.epi.out_f32 = da; p.epi.out_ld = H;
         SUTA_TRY(gemm(e, p, st));
       }
+      if (e->train_all) SUTA_TRY(linear_param_grads(e, e->dqkv16, 3 * H, act_xa(e, l), H, e->wqkv_off[l], e->bqkv_off[l], st));
       PROF_B("ln_bwd", (double)M * H * (4 + 4 + 4 + 4 + 2), layernorm_backward(da, x.h1, nullptr, x.mean1, x.rstd1, e->d_row_utt, prm, (int)e->ln1_g[l], (int)e->ln1_b[l],
                                   e->G, db, l > 0 ? e->b16 : nullptr, M, H, e->d_tok_off, e->d_T, e->U, ln_slot(), st, &lnred.item[lnred.n], db));
       lnred.n += 1;

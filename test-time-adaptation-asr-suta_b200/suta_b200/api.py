@@ -76,17 +76,21 @@ def _module_order(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
 
 
 def _module_tree_all(cfg: ModelConfig) -> List[Tuple[str, str, List[str]]]:
-    """EVERY module of HF's Wav2Vec2ForCTC in named_modules() order with its own parameter leaves (GroupNorm / post-LN
-    family, the one REF/main.py loads): what --train_all walks (REF/main.py:96-100).  tests/test_host.py checks it against
-    the real HF module tree."""
-    if cfg.feat_extract_norm == "layer" or cfg.do_stable_layer_norm:
-        raise NotImplementedError("--train_all is built for the GroupNorm / post-LN family (REF/main.py's wav2vec2-base-960h)")
+    """EVERY module of HF's Wav2Vec2ForCTC in named_modules() order with its own parameter leaves: what --train_all
+    walks (REF/main.py:96-100).  Both families (the module ORDER of the two encoders is the same; the LayerNorm feature
+    extractor registers conv, layer_norm, activation per layer, HF:281-289).  tests/test_host.py checks it against the real
+    HF module trees."""
+    if (cfg.feat_extract_norm == "layer") != bool(cfg.do_stable_layer_norm):
+        raise NotImplementedError("--train_all: GroupNorm + post-LN or LayerNorm feature extractor + pre-LN (the two shipped families)")
     mods = [("", "container", []), ("wav2vec2", "container", ["masked_spec_embed"]),
             ("wav2vec2.feature_extractor", "container", []), ("wav2vec2.feature_extractor.conv_layers", "container", [])]
     for i in range(len(cfg.conv_dim)):
         b = f"wav2vec2.feature_extractor.conv_layers.{i}"
-        mods += [(b, "container", []), (b + ".conv", "conv", ["weight", "bias"] if cfg.conv_bias else ["weight"]),
-                 (b + ".activation", "none", [])]
+        mods += [(b, "container", []), (b + ".conv", "conv", ["weight", "bias"] if cfg.conv_bias else ["weight"])]
+        if cfg.feat_extract_norm == "layer":
+            mods += [(b + ".layer_norm", "layernorm", ["weight", "bias"]), (b + ".activation", "none", [])]
+            continue
+        mods.append((b + ".activation", "none", []))
         if i == 0:
             mods.append((b + ".layer_norm", "groupnorm", ["weight", "bias"]))
     e = "wav2vec2.encoder"

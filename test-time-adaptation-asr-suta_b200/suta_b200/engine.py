@@ -76,9 +76,8 @@ class SutaEngine:
         self.train_all = bool(train_all)         # REF/main.py:96-100: every parameter is the utterance's own; one utterance per batch
         self.train_feature = bool(train_feature) or self.train_all      # (its layout contains train_feature's)
         c = self.cfg
-        if self.train_all and (c.feat_extract_norm == "layer" or c.do_stable_layer_norm):
-            raise NotImplementedError("--train_all is built for the GroupNorm / post-LN family (REF/main.py's wav2vec2-base-960h); "
-                                      "REF/main_SDPL.py, the script of the lv60 checkpoints, has no such flag")
+        if self.train_all and (c.feat_extract_norm == "layer") != bool(c.do_stable_layer_norm):
+            raise NotImplementedError("--train_all: GroupNorm + post-LN or LayerNorm feature extractor + pre-LN (the two shipped families)")
         cc = ModelCfg()
         cc.hidden, cc.layers, cc.heads, cc.intermediate, cc.vocab = (c.hidden_size, c.num_hidden_layers,
                                                                       c.num_attention_heads, c.intermediate_size, c.vocab_size)

@@ -72,6 +72,7 @@ CASES = {
     # (audio seed chosen so that the reference's non-blank decisions at step 0 stand clear of the engine's logit error)
     "tiny_all": _case("tiny", 12000, 119, 3, 0.5, 0.1, 5, train_all=True),
     "base_all_2s": _case("base", 32000, 77, 0, 1.75, 0.0, 2, train_all=True),
+    "tiny_lv60_all": _case("tiny_lv60", 12000, 124, 3, 0.5, 0.1, 5, train_all=True),      # the lv60 family: conv biases, conv LayerNorms, pre-LN encoder
 }
 BIG = 1 << 16      # tensors above this many elements are stored as (checksum, head) only
 

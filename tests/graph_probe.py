@@ -20,7 +20,7 @@ def main(out_path):
     out = {}
     for tag, cfg_name, kw, lens in (("ln", "tiny", {}, [9000, 4000, 12345]), ("feat", "tiny", dict(train_feature=True), [9000, 5000]),
                                     ("lv60", "tiny_lv60", {}, [7000, 9000]), ("sdpl", "tiny", dict(pseudo_label=True), [9000]),
-                                    ("all", "tiny", dict(train_all=True), [12000])):
+                                    ("all", "tiny", dict(train_all=True), [12000]), ("lv60all", "tiny_lv60", dict(train_all=True), [9000])):
         ocfg, mcfg = E._cfgs(cfg_name)
         sd = O.init_weights(ocfg, 3, blank_bias=0.5, ln_jitter=0.1, **({"special_bias": -10.0} if tag == "sdpl" else {}))
         mult = E._mult(ocfg, kw.get("train_feature", False), False, kw.get("train_all", False))

@@ -161,10 +161,11 @@ def test_train_feature_against_reference_golden_vectors(E, case):
         assert m["big_param_head_delta_rel"] < 0.15
 
 
-@pytest.mark.parametrize("case", ["tiny_all", "base_all_2s"])
+@pytest.mark.parametrize("case", ["tiny_all", "base_all_2s", "tiny_lv60_all"])
 def test_train_all_against_reference_golden_vectors(E, case):
     """--train_all (REF/main.py:96-100): every weight and bias of the model is the utterance's own -- encoder Linears (x7),
-    LayerNorms, the CNN, lm_head and the weight_norm g / v of the positional conv -- with the reference's multiplicities.
+    LayerNorms, the CNN, lm_head and the weight_norm g / v of the positional conv -- with the reference's multiplicities;
+    on the lv60 family (LayerNorm feature extractor + pre-LN encoder) also the conv biases and conv LayerNorms.
     The step-0 gradient of EVERY tensor is compared with fp32 autograd through the oracle."""
     m = E.check_golden(case)
     by = m.pop("grad0_by_tensor")

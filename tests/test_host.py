@@ -87,9 +87,6 @@ def test_collect_params_names_and_duplicates_match_reference_walk(capsys):
                 assert sorted(names) == sorted(O.collect_param_names(ocfg, bias_only=bias_only, train_feature=tf))
                 assert [p.name for p in params] == names
     capsys.readouterr()
-    with pytest.raises(NotImplementedError):          # --train_all: GroupNorm / post-LN family only (REF/main.py's model)
-        model.engine.train_all = True
-        api.collect_params(model, False, False, True, True)
 
 
 def test_train_all_walk_matches_the_hf_module_tree_and_the_reference_walk(capsys):
@@ -100,28 +97,29 @@ def test_train_all_walk_matches_the_hf_module_tree_and_the_reference_walk(capsys
     from transformers import Wav2Vec2ForCTC
     from oracle import hf_reference as HR
     from suta_b200 import api
-    cfg, ocfg = ModelConfig.tiny(), O.W2V2Config.tiny()
-    hf = Wav2Vec2ForCTC(ocfg.to_hf()).eval()
-    assert [(nm, leaves) for nm, _k, leaves in api._module_tree_all(cfg)] == \
-        [(nm, [n for n, _ in m.named_parameters(recurse=False)]) for nm, m in hf.named_modules()]
-    names_all = {(f"{nm}.{leaf}" if nm else leaf) for nm, _k, leaves in api._module_tree_all(cfg) for leaf in leaves}
-    model = types.SimpleNamespace(cfg=cfg, engine=types.SimpleNamespace(train_feature=True, train_all=True),
-                                  _params={n: types.SimpleNamespace(name=n, requires_grad=False) for n in names_all})
-    for bias_only, tf, train_LN in ((False, False, True), (False, True, True), (True, False, True), (False, False, False)):
-        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            _, ref_names = HR.collect_params(hf, bias_only, tf, True, train_LN)
-        params, names = api.collect_params(model, bias_only, tf, True, train_LN)
-        assert names == ref_names
-        mult = api.reference_multiplicities(cfg, bias_only, tf, train_LN, train_all=True)
-        want = {}
-        for p in params:
-            want[p.name] = want.get(p.name, 0) + 1
-        assert mult == want
-        assert sorted(n for n in (x.lstrip(".") for x in ref_names)) == \
-            sorted(O.collect_param_names(ocfg, bias_only=bias_only, train_feature=tf, train_LN=train_LN, train_all=True))
-    assert mult["wav2vec2.encoder.layers.0.attention.q_proj.weight"] == 7 and mult["lm_head.weight"] == 2
-    assert mult["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original1"] == 7
+    for cfg, ocfg in ((ModelConfig.tiny(), O.W2V2Config.tiny()), (ModelConfig.tiny_lv60(), O.W2V2Config.tiny_lv60())):
+        hf = Wav2Vec2ForCTC(ocfg.to_hf()).eval()
+        assert [(nm, leaves) for nm, _k, leaves in api._module_tree_all(cfg)] == \
+            [(nm, [n for n, _ in m.named_parameters(recurse=False)]) for nm, m in hf.named_modules()]
+        names_all = {(f"{nm}.{leaf}" if nm else leaf) for nm, _k, leaves in api._module_tree_all(cfg) for leaf in leaves}
+        model = types.SimpleNamespace(cfg=cfg, engine=types.SimpleNamespace(train_feature=True, train_all=True),
+                                      _params={n: types.SimpleNamespace(name=n, requires_grad=False) for n in names_all})
+        for bias_only, tf, train_LN in ((False, False, True), (False, True, True), (True, False, True), (False, False, False)):
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                _, ref_names = HR.collect_params(hf, bias_only, tf, True, train_LN)
+            params, names = api.collect_params(model, bias_only, tf, True, train_LN)
+            assert names == ref_names
+            mult = api.reference_multiplicities(cfg, bias_only, tf, train_LN, train_all=True)
+            want = {}
+            for p in params:
+                want[p.name] = want.get(p.name, 0) + 1
+            assert mult == want
+            assert sorted(n for n in (x.lstrip(".") for x in ref_names)) == \
+                sorted(O.collect_param_names(ocfg, bias_only=bias_only, train_feature=tf, train_LN=train_LN, train_all=True))
+        assert mult["wav2vec2.encoder.layers.0.attention.q_proj.weight"] == 7 and mult["lm_head.weight"] == 2
+        assert mult["wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original1"] == 7
+    assert mult["wav2vec2.feature_extractor.conv_layers.3.layer_norm.weight"] == 6       # lv60: 6 enclosing modules, train_LN off in the last pass
     capsys.readouterr()
 
 

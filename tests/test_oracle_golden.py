@@ -12,7 +12,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TINY = ["tiny_ln", "tiny_feat", "tiny_short", "tiny_feat_noise20", "tiny_sgd", "tiny_feat_sgd", "tiny_adam_beta", "tiny_steplr",
         "tiny_bias_only", "tiny_div", "tiny_em_only", "tiny_mcc_plain", "tiny_temp1_allframes",
         "tiny_lv60_ln", "tiny_lv60_short", "tiny_lv60_feat",      # lv60: LayerNorm feature extractor + conv bias + pre-LN encoder
-        "tiny_all"]                                               # --train_all (REF/main.py:96-100)
+        "tiny_all", "tiny_lv60_all"]                              # --train_all (REF/main.py:96-100), both families
 CASES = TINY + ["base_all_2s", "base_ln_5s", "base_ln_5s_noblank", "base_feat_2s", "base_feat_5s", "base_ln_30s", "large_ln_2s", "large_lv60_2s"]
 
 
