@@ -10,7 +10,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "test-time-adaptation-asr-suta_b200"), 
 
 import e2e_checks as E  # noqa: E402
 from oracle import suta_oracle as O  # noqa: E402
-from suta_b200 import AdaptHyper, ModelConfig, SutaEngine  # noqa: E402
+from suta_b200 import AdaptHyper, SutaEngine  # noqa: E402
 from suta_b200.runner import adapt_batch  # noqa: E402
 from suta_b200.text import CTCVocab  # noqa: E402
 import torch  # noqa: E402

@@ -1,5 +1,4 @@
 """CPU: host-side logic of the package (no CUDA calls)."""
-import re
 import types
 
 import numpy as np

@@ -11,7 +11,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -72,5 +71,4 @@ def main():
 
 
 if __name__ == "__main__":
-    t0 = time.time()
     main()
