@@ -4,6 +4,8 @@ Times, per utterance of a duration-stratified sample of the LibriSpeech-shaped s
 backward, AdamW over every weight with the reference's multiplicities, forward) + the greedy decodes -- through this
 repo's engine (wav2vec2-base, SUTA_FLAG_TRAIN_ALL) and through the reference's eager fp32 loop on the same GPU
 (oracle/hf_reference.py over HF Wav2Vec2ForCTC + torch.optim.AdamW, `collect_params(train_all=True)`).  One JSON line.
+The engine leg imports the product only; the oracle is imported by the baseline leg alone (as in bench.py's
+`gpu_eager_baseline`), never on the measured product path.
 
     python tools/train_all_latency.py [--steps 10] [--utts 5] [--no-eager]
 """
@@ -18,12 +20,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "test-time-adaptation-asr-suta_b200")]
 
-from oracle import hf_reference as HR  # noqa: E402
-from oracle import suta_oracle as O  # noqa: E402
-from suta_b200 import AdaptHyper, ModelConfig, SutaEngine  # noqa: E402
+from suta_b200 import AdaptHyper, ModelConfig, SutaEngine, api  # noqa: E402
 from suta_b200.data import librispeech_shaped  # noqa: E402
 from suta_b200.runner import adapt_batch  # noqa: E402
 from suta_b200.text import CTCVocab  # noqa: E402
+from suta_b200.weights import random_state_dict  # noqa: E402
 
 
 def main():
@@ -34,12 +35,9 @@ def main():
     a = ap.parse_args()
     utts = sorted(librispeech_shaped(2939), key=lambda u: u.n_samples)
     sample = [utts[int((i + 0.5) * len(utts) / a.utts)] for i in range(a.utts)]
-    ocfg, mcfg = O.W2V2Config.base(), ModelConfig.base()
-    sd = O.init_weights(ocfg, 0, blank_bias=1.75)
-    mult = {}
-    for n in O.collect_param_names(ocfg, train_all=True):
-        mult[n] = mult.get(n, 0) + 1
-    eng = SutaEngine(mcfg, sd, train_all=True, trainable_mult=mult)
+    mcfg = ModelConfig.base()
+    sd = random_state_dict(mcfg, seed=0, blank_bias=1.75)
+    eng = SutaEngine(mcfg, sd, train_all=True, trainable_mult=api.reference_multiplicities(mcfg, train_all=True))
     hp, vocab = AdaptHyper(), CTCVocab()
     ms, secs = [], []
     for j, u in enumerate([sample[len(sample) // 2]] + sample):          # first = warm-up
@@ -62,6 +60,15 @@ def main():
            "launches": int(eng.launch_count)}
     eng.close()
     if not a.no_eager:
+        from oracle import hf_reference as HR            # baseline leg only
+        from oracle import suta_oracle as O
+        ocfg = O.W2V2Config.base()
+        # HF's positional conv is weight_norm-parametrised: g / v from the folded weight of random_state_dict
+        pre = "wav2vec2.encoder.pos_conv_embed.conv."
+        sd = dict(sd)
+        w = sd.pop(pre + "weight")
+        sd[pre + "parametrizations.weight.original0"] = w.norm(dim=(0, 1), keepdim=True)
+        sd[pre + "parametrizations.weight.original1"] = w.clone()
         loop = HR.ReferenceLoop(ocfg, sd, "cuda", train_all=True)
         t = HR.time_utterances(loop, [sample[len(sample) // 2].audio()] + [u.audio() for u in sample], steps=a.steps, warmup=1)
         out["gpu_eager_reference"] = {"s_per_utt": t, "audio_s_per_s": sum(secs) / sum(t),
