@@ -418,12 +418,13 @@ def check_ctc(Ts=(249, 37, 1, 6, 700), seed=10, blank_bias=1.0, all_blank_utt=1)
                 bit_equal=bool(torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])))
 
 
-def check_adam(n=5000, U=3, steps=4, seed=8, opt="AdamW", lr=2e-5, beta1=0.9, wd=0.0):
-    """The fused update vs oracle.adam_update (= torch's single-tensor CPU loop, k sub-steps for multiplicity k)."""
+def check_adam(n=5000, U=3, steps=4, seed=8, opt="AdamW", lr=2e-5, beta1=0.9, wd=0.0, max_mult=4):
+    """The fused update vs oracle.adam_update (= torch's single-tensor CPU loop, k sub-steps for multiplicity k).
+    max_mult: 4 = --train_feature's conv weights, 7 = an encoder Linear under --train_all, 10 = a conv weight under both."""
     lib = _lib.load()
     rng = np.random.default_rng(seed)
     p0 = rng.standard_normal((U, n)).astype(np.float32)
-    mult = rng.integers(0, 5, n).astype(np.uint8)
+    mult = rng.integers(0, max_mult + 1, n).astype(np.uint8)
     Pd = torch.tensor(p0, device=DEV); Md = torch.zeros(U, n, device=DEV); Vd = torch.zeros(U, n, device=DEV)
     multd = torch.tensor(mult, device=DEV)
     h = Hyper(0.3, 2.5, 1, 1, {"AdamW": 0, "SGD": 1, "Adam": 2}[opt], lr, beta1, 0.999, 1e-8, wd, 0.0)
@@ -434,7 +435,7 @@ def check_adam(n=5000, U=3, steps=4, seed=8, opt="AdamW", lr=2e-5, beta1=0.9, wd
         Gd = torch.tensor(gnp, device=DEV)
         check(lib.suta_op_adam(P(Pd), P(Gd), P(Md), P(Vd), P(multd), n, U, s, C.byref(h), None, stream()))
         gt = torch.tensor(gnp)
-        for k in range(1, 5):
+        for k in range(1, max_mult + 1):
             idx = torch.tensor(np.nonzero(mult == k)[0])
             if len(idx) == 0:
                 continue

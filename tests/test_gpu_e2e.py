@@ -275,6 +275,19 @@ def test_drop_in_api_train_all(E, capsys):
         num = sum(float(((got[n] - eng.to_engine_layout(n, torch.from_numpy(ref.params[n])).numpy()) ** 2).sum()) for n in got)
         den = sum(float(((ref.params[n] - sd[n].numpy()) ** 2).sum()) for n in got)
         assert (num / den) ** 0.5 < 0.3, (num / den) ** 0.5
+    # continual mode (no --episodic, the reference's default): all weights and the optimizer state flow into the next utterance
+    wav2 = O.synth_audio(9000, 115)
+    x2 = torch.from_numpy(O.normalize_audio(wav2))[None].cuda()
+    ref2 = O.adapt_utterance(ocfg, sd, O.normalize_audio(wav2), steps=2, train_all=True, carry=ref.carry)
+    out0 = model(x2).logits
+    assert np.abs(out0[0].cpu().numpy() - ref2.logits0).max() < 0.1
+    for i in range(2):
+        out = api.forward_and_adapt(x2, model, opt, 0.3, True, 2.5, True, sched, 0)
+    assert model.engine.opt_steps == 5
+    got = {p.name: p.data[0].cpu().numpy() for p in params if p.size and not p.name.endswith("k_proj.bias")}
+    num = sum(float(((got[n] - eng.to_engine_layout(n, torch.from_numpy(ref2.params[n])).numpy()) ** 2).sum()) for n in got)
+    den = sum(float(((ref2.params[n] - sd[n].numpy()) ** 2).sum()) for n in got)
+    assert (num / den) ** 0.5 < 0.3, (num / den) ** 0.5
     with pytest.raises(Exception, match="one utterance per batch"):
         model(torch.cat([x, x], 0))
     capsys.readouterr()

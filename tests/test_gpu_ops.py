@@ -144,6 +144,9 @@ def test_gemm_mn_major_operands(K):
 def test_adam_with_multiplicities(K):
     r = K.check_adam()
     assert r["frozen_moved"] == 0.0 and r["delta_rel"] < 1e-4 and r["m_rel"] < 1e-5 and r["v_rel"] < 1e-4
+    # --train_all lists an encoder Linear 7 times, --train_all --train_feature a conv weight 10 times (REF/main.py:88-100)
+    r = K.check_adam(max_mult=12, seed=18)
+    assert r["frozen_moved"] == 0.0 and r["delta_rel"] < 1e-4 and r["m_rel"] < 1e-5 and r["v_rel"] < 1e-4
 
 
 def test_ctc_decode_bit_exact(K):
