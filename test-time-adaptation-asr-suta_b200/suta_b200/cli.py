@@ -123,15 +123,14 @@ def main(argv=None, sdpl: bool = False):
         # batched extension: many utterances per adaptation step, each with its own parameters
         # (independent utterances = the reference's --episodic semantics; carrying state between utterances serialises them)
         from .runner import SutaRunner
-        if train_all:
-            raise SystemExit("--train_all makes every weight the utterance's own: one utterance per step, as the reference "
-                             "adapts (drop --batch_utts)")
         if not episodic:
             raise SystemExit("--batch_utts adapts independent utterances: pass --episodic (without it the reference carries "
                              "model and optimizer state from one utterance to the next, which cannot be batched)")
         hp = optimizer.hp                      # the optimizer built by setup_optimizer above (opt, lr, betas, weight decay)
         hp.em_coef, hp.temp, hp.reweight, hp.not_blank, hp.div_coef, hp.pl_coef = em_coef, temp, reweight, non_blank, div_coef, pl_coef
-        out = SutaRunner(model.engine, steps, hp, max_utts=args.batch_utts, vocab=vocab,
+        # --train_all makes every weight the utterance's own: the runner (sharding over ranks, device-side noise, gather) then
+        # adapts batches of ONE utterance, as the reference does
+        out = SutaRunner(model.engine, steps, hp, max_utts=1 if train_all else args.batch_utts, vocab=vocab,
                          sched_gamma=scheduler.gamma if scheduler is not None else None,
                          sched_step=scheduler.step_size if scheduler is not None else 1, extra_noise=extra_noise).run(dataset)
         for k, d in out["texts"].items():

@@ -118,18 +118,17 @@ def test_main_cli_rejects_batching_without_episodic(tmp_path):
 def test_main_cli_train_all(tmp_path):
     """`main.py --train_all` (REF/main.py:96-100, :267 exp_name, :449 log line): the whole model adapted per utterance, one
     utterance at a time (what the adaptation does to the model is checked by test_gpu_e2e.py::test_train_all_* and
-    test_drop_in_api_train_all); combined with the batching extension it is refused."""
+    test_drop_in_api_train_all).  Through the runner (`--batch_utts`: sharding, gather) the batches hold ONE utterance each
+    and the results are the sequential loop's."""
     _need_gpu()
-    out, name, log, _csv = _run_main(tmp_path, "--train_all")
+    out, name, log, csv = _run_main(tmp_path, "--train_all")
     assert name.endswith("_feat_False_all_True_LN_True")
     assert "train_all = True" in log.splitlines()
     assert "wav2vec2.encoder.layers.1.attention.q_proj.weight" in out          # print(param_names), REF/main.py:311
     _, _, log_ln, _ = _run_main(tmp_path / "ln")
     assert log.splitlines()[0] == log_ln.splitlines()[0]                        # original WER: the same un-adapted model
-    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--asr", "random-tiny", "--num_utts", "3", "--steps", "3", "--episodic",
-           "--train_all", "--batch_utts", "2", "--log_dir", str(tmp_path / "x")]
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
-    assert r.returncode != 0 and "--train_all" in (r.stdout + r.stderr)
+    _, _, log_run, csv_run = _run_main(tmp_path / "runner", "--train_all", "--batch_utts", "4")
+    assert log_run == log and csv_run == csv
 
 
 def test_device_side_noise_and_truncation():
