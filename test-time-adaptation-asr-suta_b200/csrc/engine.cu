@@ -935,17 +935,28 @@ extern "C" const char* suta_profile_report(const suta_engine* e) { return e ? e-
 static int refresh_train_all(suta_engine* e, cudaStream_t st) {
   const suta_model_cfg& c = e->cfg;
   const int H = c.hidden, I = c.intermediate;
+  TransposeJobs jobs;                         // <= 100 per launch: 24 layers x 4 + lm_head = 97
+  auto flush = [&]() -> int {
+    if (jobs.n == 0) return SUTA_OK;
+    e->launches += 1;
+    PROF("transpose_cast", transpose_cast_bf16(jobs, st));
+    jobs.n = 0;
+    return SUTA_OK;
+  };
   for (int l = 0; l < c.layers; ++l) {
     const suta_engine::TaLayer& t = e->ta[l];
-    SUTA_TRY(transpose_cast_bf16(e->P + e->wqkv_off[l], t.wqkv_t, 3 * H, H, st));
-    SUTA_TRY(transpose_cast_bf16(e->P + e->wo_off[l], t.wo_t, H, H, st));
-    SUTA_TRY(transpose_cast_bf16(e->P + e->w1_off[l], t.w1_t, I, H, st));
-    SUTA_TRY(transpose_cast_bf16(e->P + e->w2_off[l], t.w2_t, H, I, st));
+    if (jobs.n + 4 > TransposeJobs::MAX) SUTA_TRY(flush());
+    jobs.add(e->P + e->wqkv_off[l], t.wqkv_t, 3 * H, H);
+    jobs.add(e->P + e->wo_off[l], t.wo_t, H, H);
+    jobs.add(e->P + e->w1_off[l], t.w1_t, I, H);
+    jobs.add(e->P + e->w2_off[l], t.w2_t, H, I);
   }
-  SUTA_TRY(transpose_cast_bf16(e->P + e->lm_w_off, e->lm_w_t_sh, c.vocab, H, st));
+  if (jobs.n + 1 > TransposeJobs::MAX) SUTA_TRY(flush());
+  jobs.add(e->P + e->lm_w_off, e->lm_w_t_sh, c.vocab, H);
+  SUTA_TRY(flush());
   PROF("weight_norm_fwd", posconv_weight_norm_forward(e->P + e->pos_g_off, e->P + e->pos_v_off, e->wn_scratch, e->pos_w_sh, e->pos_w_t_sh, H,
                                                       H / c.pos_groups, c.pos_k, st));
-  e->launches += 4 * c.layers + 4;
+  e->launches += 3;
   e->frontend_done = false;
   return SUTA_OK;
 }

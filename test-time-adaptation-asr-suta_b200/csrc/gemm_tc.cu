@@ -677,8 +677,13 @@ int gemm_bf16_tc(const GemmProblem& p, cudaStream_t stream) {
   if (p.a.mn_major || p.b.mn_major) {
     SUTA_CHECK_ARG(p.N % 64 == 0 && (!p.a.mn_major || p.b.mn_major) && !p.epi.accumulate);
     if (p.a.mn_major) {
-      if (p.N % 256 == 0) return launch<256, true, true, false>(p, stream);
-      if (p.N % 128 == 0) return launch<128, true, true, false>(p, stream);
+      // Weight gradients.  With few tiles (ONE utterance's gradient under train_all: K = its ~300 frames, 4-5 k-blocks) the
+      // row-masked fp32 epilogue of a 128 x 256 tile outlasts the mainloop and most SMs idle: take the widest tile that still
+      // gives every SM one.  The sum over k of an output element does not depend on the tile width (same bits).
+      const long long mb = p.mblk ? p.num_mblk : ceil_div(p.M, BM);
+      auto fills = [&](int bn) { return p.N % bn == 0 && mb * (p.N / bn) * p.nz >= gemm_num_sms(); };
+      if (fills(256)) return launch<256, true, true, false>(p, stream);
+      if (fills(128)) return launch<128, true, true, false>(p, stream);
       return launch<64, true, true, false>(p, stream);
     }
     // SUTA_NO_LEAN_BMN=1: the 3-stage variant (two epilogue patches) instead of the 4-stage LEAN one (debug switch)

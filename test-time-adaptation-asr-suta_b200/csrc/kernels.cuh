@@ -141,8 +141,15 @@ int colsum_per_utt_bf16(const bf16* x, const long long* row_off, const int* L, f
                         int C, int n_utts, cudaStream_t stream);
 
 // ---- trainall.cu (SUTA_FLAG_TRAIN_ALL) --------------------------------------------------------
-// dst [C][R] bf16 = transpose of src [R][C] fp32
-int transpose_cast_bf16(const float* src, bf16* dst, int R, int C, cudaStream_t stream);
+// dst [C][R] bf16 = transpose of src [R][C] fp32, for every job of the list in ONE launch (the list rides in the kernel
+// parameters: 4 matrices per encoder layer + lm_head, launched MAX jobs at a time)
+struct TransposeJobs {
+  static constexpr int MAX = 100;
+  struct Job { const float* src; bf16* dst; int R, C, tile0; } job[MAX];
+  int n = 0;
+  void add(const float* src, bf16* dst, int R, int C) { job[n].src = src; job[n].dst = dst; job[n].R = R; job[n].C = C; job[n].tile0 = 0; ++n; }
+};
+int transpose_cast_bf16(TransposeJobs& jobs, cudaStream_t stream);
 // positional conv weight_norm (HF/modeling_wav2vec2.py:344-352, dim = 2): g [K], v [H][CG][K] fp32 inside the trainable vector
 // -> w_fwd [H][(tap, ci)], w_bwd [g*CG + ci][(K-1-tap, co)] bf16; scratch keeps ||v|| and g / ||v|| for the backward
 long long posconv_weight_norm_scratch_floats(int K);

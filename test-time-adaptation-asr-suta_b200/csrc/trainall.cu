@@ -12,17 +12,24 @@ namespace {
 
 constexpr int WN_BLOCKS = 256;
 
-__global__ void transpose_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int C) {
+// one launch for all the matrices of an update: block -> (job, 32 x 32 tile) through the jobs' running tile counts
+__global__ void transpose_cast_kernel(TransposeJobs jobs) {
   __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].tile0) ++j;
+  const float* __restrict__ src = jobs.job[j].src;
+  bf16* __restrict__ dst = jobs.job[j].dst;
+  const int R = jobs.job[j].R, C = jobs.job[j].C;
+  const int tx = (C + 31) / 32, t = blockIdx.x - jobs.job[j].tile0;
+  const int c0 = (t % tx) * 32, r0 = (t / tx) * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int r = r0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, r = r0 + threadIdx.x;
-    if (c < C && r < R) dst[(long long)c * R + r] = __float2bfloat16(tile[threadIdx.x][j]);
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int c = c0 + y, r = r0 + threadIdx.x;
+    if (c < C && r < R) dst[(long long)c * R + r] = __float2bfloat16(tile[threadIdx.x][y]);
   }
 }
 
@@ -96,9 +103,15 @@ __global__ void wn_dv_kernel(const float* __restrict__ v, const float* __restric
 
 }  // namespace
 
-int transpose_cast_bf16(const float* src, bf16* dst, int R, int C, cudaStream_t stream) {
-  SUTA_CHECK_ARG(src && dst && R > 0 && C > 0);
-  transpose_cast_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), dim3(32, 8), 0, stream>>>(src, dst, R, C);
+int transpose_cast_bf16(TransposeJobs& jobs, cudaStream_t stream) {
+  SUTA_CHECK_ARG(jobs.n > 0 && jobs.n <= TransposeJobs::MAX);
+  int tiles = 0;
+  for (int j = 0; j < jobs.n; ++j) {
+    SUTA_CHECK_ARG(jobs.job[j].src && jobs.job[j].dst && jobs.job[j].R > 0 && jobs.job[j].C > 0);
+    jobs.job[j].tile0 = tiles;
+    tiles += ceil_div(jobs.job[j].C, 32) * ceil_div(jobs.job[j].R, 32);
+  }
+  transpose_cast_kernel<<<tiles, dim3(32, 8), 0, stream>>>(jobs);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
