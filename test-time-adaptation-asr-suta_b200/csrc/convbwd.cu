@@ -261,19 +261,22 @@ __global__ void colsum_kernel(const float* __restrict__ x, const long long* __re
   G[(long long)u * gstride + g_off + c] = s;
 }
 
-// 8 row lanes x 32 column pairs per CTA; every lane sums its rows in order, the lanes are added in order: same bits every run
-__global__ void __launch_bounds__(256)
+// 32 row lanes x 8 column pairs per CTA; every lane sums its rows in order, the lanes are added in order: same bits every
+// run.  (8 lanes x 32 pairs before: with ONE utterance of ~300 rows per launch -- the bias gradients of train_all -- a 12-CTA
+// grid walked 33 dependent loads per lane, 8.6 us per launch and 9 % of a train_all step; a warp still reads whole 32-byte sectors)
+constexpr int CS_LANES = 32, CS_PAIRS = 8;
+__global__ void __launch_bounds__(CS_LANES * CS_PAIRS)
 colsum_bf16_kernel(const bf16* __restrict__ x, const long long* __restrict__ row_off, const int* __restrict__ L,
                    float* __restrict__ G, long long gstride, long long g_off, int C) {
-  __shared__ float2 red[8][32];
+  __shared__ float2 red[CS_LANES][CS_PAIRS];
   const int u = blockIdx.y;
-  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
-  const int c = (blockIdx.x * 32 + cp) * 2;
+  const int cp = threadIdx.x & (CS_PAIRS - 1), lane_r = threadIdx.x / CS_PAIRS;
+  const int c = (blockIdx.x * CS_PAIRS + cp) * 2;
   float2 s = make_float2(0.f, 0.f);
   if (c < C) {
     const bf16* p = x + row_off[u] * C + c;
     const int n = L[u];
-    for (int t = lane_r; t < n; t += 8) {
+    for (int t = lane_r; t < n; t += CS_LANES) {
       const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(p + (long long)t * C)));
       s.x += v.x; s.y += v.y;
     }
@@ -282,7 +285,7 @@ colsum_bf16_kernel(const bf16* __restrict__ x, const long long* __restrict__ row
   __syncthreads();
   if (lane_r == 0 && c < C) {
     float2 a = red[0][cp];
-    for (int r = 1; r < 8; ++r) { a.x += red[r][cp].x; a.y += red[r][cp].y; }
+    for (int r = 1; r < CS_LANES; ++r) { a.x += red[r][cp].x; a.y += red[r][cp].y; }
     *reinterpret_cast<float2*>(G + (long long)u * gstride + g_off + c) = a;
   }
 }
@@ -342,7 +345,7 @@ int colsum_per_utt(const float* x, const long long* tok_off, const int* T, float
 int colsum_per_utt_bf16(const bf16* x, const long long* row_off, const int* L, float* G, long long gstride, long long g_off,
                         int C, int n_utts, cudaStream_t stream) {
   SUTA_CHECK_ARG(C % 2 == 0 && g_off % 2 == 0 && gstride % 2 == 0);
-  colsum_bf16_kernel<<<dim3(ceil_div(C, 64), n_utts), 256, 0, stream>>>(x, row_off, L, G, gstride, g_off, C);
+  colsum_bf16_kernel<<<dim3(ceil_div(C, 2 * CS_PAIRS), n_utts), CS_LANES * CS_PAIRS, 0, stream>>>(x, row_off, L, G, gstride, g_off, C);
   CUDA_TRY(cudaGetLastError());
   return SUTA_OK;
 }
