@@ -169,3 +169,26 @@ def test_load_checkpoint_reads_a_local_hf_directory(tmp_path):
     Wav2Vec2Config(feat_extract_norm="group", conv_bias=True).save_pretrained(str(d4))
     with pytest.raises(NotImplementedError):
         load_checkpoint(str(d4))
+
+
+def test_preset_launcher_builds_the_reference_presets():
+    """scripts/suta.sh = REF/scripts/{LS,CH,CV,TD}.sh as one launcher: same flags, LibriSpeech at the three noise levels."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["bash", os.path.join(root, "scripts", "suta.sh"), "LS", "/data/LibriSpeech", "--", "--num_utts", "5"],
+                       env=dict(os.environ, DRY_RUN="1", BATCH_UTTS="0"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cmds = [ln for ln in r.stderr.splitlines() if ln.startswith("+ ")]
+    assert [c.split("--extra_noise ")[1].split()[0] for c in cmds] == ["0", "0.005", "0.01"]
+    for c in cmds:
+        for flag in ("--asr facebook/wav2vec2-base-960h", "--dataset_name librispeech", "--dataset_dir /data/LibriSpeech", "--steps 10",
+                     "--episodic", "--lr 2e-5", "--temp 2.5", "--em_coef 0.3", "--reweight", "--non_blank", "--train_feature",
+                     "--log_dir exps", "--num_utts 5"):
+            assert flag in c, (flag, c)
+        assert "--batch_utts" not in c
+    r = subprocess.run(["bash", os.path.join(root, "scripts", "suta.sh"), "TD", "/data/ted", "0.01"], env=dict(os.environ, DRY_RUN="1"),
+                       capture_output=True, text=True)
+    cmds = [ln for ln in r.stderr.splitlines() if ln.startswith("+ ")]
+    assert len(cmds) == 1 and "--dataset_name ted" in cmds[0] and "--extra_noise 0.01" in cmds[0] and "--batch_utts 64" in cmds[0]
+    assert subprocess.run(["bash", os.path.join(root, "scripts", "suta.sh"), "XX", "/d"], capture_output=True).returncode == 2
