@@ -139,3 +139,43 @@ def test_create_dataset_dispatch_and_cli_flag(libri, capsys):
     with pytest.raises(NotImplementedError):                     # REF/data.py:62-63
         corpus.create_dataset(None, "switchboard", str(libri))
     assert "There are 5 samples" in capsys.readouterr().out
+
+
+def test_ted_preprocessing_cuts_talks_like_the_reference(tmp_path, capsys):
+    """REF/preprocess/preprocess_ted.sh + preprocess_ted.py without sox / soundfile: one talk as NIST SPHERE, one as the
+    reference's intermediate WAV; segments [int(s * sr), int(e * sr)), names built from the STM's own strings, normalised
+    transcripts, gap lines skipped -- and the result is what the TED reader (REF/corpus/ted.py) lists."""
+    from suta_b200 import preprocess_ted as P
+    split = tmp_path / "test"
+    for d in ("stm", "sph", "wav"):
+        os.makedirs(split / d)
+    rng = np.random.default_rng(5)
+    a = (rng.standard_normal(16000 * 4) * 3000).astype("<i2")
+    head = ("NIST_1A\n   1024\nchannel_count -i 1\nsample_rate -i 16000\nsample_n_bytes -i 2\nsample_byte_format -s2 01\n"
+            f"sample_coding -s3 pcm\nsample_count -i {len(a)}\nend_head\n").encode()
+    (split / "sph" / "TalkA_2010.sph").write_bytes(head + b" " * (1024 - len(head)) + a.tobytes())
+    b = _wav(split / "wav" / "TalkB_2011.wav", n=16000 * 3, seed=6)
+    (split / "stm" / "TalkA_2010.stm").write_text(
+        "TalkA_2010 1 inter_segment_gap 0 0.5 <o,,unknown> ignore_time_segment_in_scoring\n"
+        "TalkA_2010 1 TalkA_2010 0.5 1.75 <o,f0,male> it 's a well-known fact (laughter) that 3 birds\n"
+        "TalkA_2010 1 TalkA_2010 2.01 3.9 <o,f0,male> so i said  yes\n")
+    (split / "stm" / "TalkB_2011.stm").write_text("TalkB_2011 1 TalkB_2011 0.25 2.5 <o,f0,female> thank you\n")
+    files = P.preprocess(str(split))
+    capsys.readouterr()
+    assert sorted(os.path.basename(f) for f in files) == ["TalkA_2010-0.5-1.75.wav", "TalkA_2010-2.01-3.9.wav", "TalkB_2011-0.25-2.5.wav"]
+    assert (split / "transcription" / "TalkA_2010-0.5-1.75.txt").read_text() == "IT'S A WELL KNOWN FACT LAUGHTER THAT BIRDS"
+    assert (split / "transcription" / "TalkA_2010-2.01-3.9.txt").read_text() == "SO I SAID YES"
+
+    def seg(name):
+        with wave.open(str(split / "wav_segment" / name), "rb") as f:
+            assert (f.getframerate(), f.getnchannels(), f.getsampwidth()) == (16000, 1, 2)
+            return np.frombuffer(f.readframes(f.getnframes()), dtype="<i2")
+    s0, s1, s2 = seg("TalkA_2010-0.5-1.75.wav"), seg("TalkA_2010-2.01-3.9.wav"), seg("TalkB_2011-0.25-2.5.wav")
+    assert len(s0) == int(1.75 * 16000) - int(0.5 * 16000) and len(s1) == int(3.9 * 16000) - int(2.01 * 16000) and len(s2) == 36000
+    want = np.rint(a[8000:28000].astype(np.float64) / 32768 * 32767).astype(np.int16)       # soundfile's read / write round trip
+    assert np.array_equal(s0, want) and np.abs(s0.astype(int) - a[8000:28000]).max() <= 1
+    assert np.abs(s2.astype(int) - b[4000:40000]).max() <= 1
+    listing = corpus.ted(str(split))                       # REF/corpus/ted.py order: shortest transcript first
+    assert [t for _f, t in listing] == ["THANK YOU", "SO I SAID YES", "IT'S A WELL KNOWN FACT LAUGHTER THAT BIRDS"]
+    x = corpus.read_audio(str(listing[0][0]))
+    assert x.dtype == np.float32 and len(x) == 36000
